@@ -1,0 +1,285 @@
+"""Synthetic models and GGUF files.
+
+There are no real checkpoints and no network, so every test and benchmark runs on
+seeded synthetic weights with the real architectures' shapes.  The GGUF files written
+here only use what the reference loader accepts (read_ggml.f90:663-685: KV value types
+4,5,6,8,9; tensor types 0 and 1 -- plus 2 for the q4_0 extension), so an f32 file from
+this module is loadable by the unmodified reference.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Iterable
+
+import numpy as np
+
+from .layout import (Config, Weights, F32, F16, Q4_0, GGML_TYPE, QK4_0, row_bytes)
+
+GGUF_MAGIC = 1179993927  # read_ggml.f90:122
+GGUF_VERSION = 3
+ALIGNMENT = 32           # read_ggml.f90:104
+
+KV_U32, KV_I32, KV_F32, KV_STR, KV_ARR = 4, 5, 6, 8, 9
+
+
+# --------------------------------------------------------------------------- quantisation
+def quantize_q4_0(w: np.ndarray) -> np.ndarray:
+    """f32 [rows, n] -> uint8 [rows, n/32*18] ggml q4_0 blocks (public ggml algorithm:
+    d = (signed value of largest magnitude) / -8, q = min(15, trunc(x/d + 8.5)))."""
+    rows, n = w.shape
+    assert n % QK4_0 == 0
+    blk = np.ascontiguousarray(w, dtype=np.float32).reshape(rows, n // QK4_0, QK4_0)
+    idx = np.argmax(np.abs(blk), axis=-1)
+    mx = np.take_along_axis(blk, idx[..., None], axis=-1)[..., 0]
+    d = mx / -8.0
+    with np.errstate(divide="ignore"):
+        inv = np.where(d != 0, 1.0 / d, 0.0).astype(np.float32)
+    q = np.minimum(15, (blk * inv[..., None] + 8.5).astype(np.int32)).astype(np.uint8)
+    packed = (q[..., :16] | (q[..., 16:] << 4)).astype(np.uint8)
+    out = np.empty((rows, n // QK4_0, 18), dtype=np.uint8)
+    out[..., 0:2] = d.astype(np.float16).view(np.uint8).reshape(rows, n // QK4_0, 2)
+    out[..., 2:] = packed
+    return out.reshape(rows, n // QK4_0 * 18)
+
+
+def dequantize_q4_0(b: np.ndarray, n: int) -> np.ndarray:
+    """uint8 [rows, n/32*18] -> f32 [rows, n], exact (value = d*(q-8))."""
+    rows = b.shape[0]
+    blk = b.reshape(rows, n // QK4_0, 18)
+    d = blk[..., 0:2].copy().view(np.float16).astype(np.float32)  # [rows, nb, 1]
+    qs = blk[..., 2:]
+    lo = (qs & 0x0F).astype(np.int32) - 8
+    hi = (qs >> 4).astype(np.int32) - 8
+    vals = np.concatenate([lo, hi], axis=-1).astype(np.float32) * d
+    return vals.reshape(rows, n)
+
+
+def encode_matrix(w: np.ndarray, wtype: int) -> np.ndarray:
+    """f32 [rows, n] -> storage array for ``wtype`` (f32 array, f16 array, or q4_0 bytes)."""
+    if wtype == F32:
+        return np.ascontiguousarray(w, dtype=np.float32)
+    if wtype == F16:
+        return np.ascontiguousarray(w.astype(np.float16))
+    return quantize_q4_0(w)
+
+
+def decode_matrix(a: np.ndarray, wtype: int, n: int) -> np.ndarray:
+    """Storage array -> exact f32 values [rows, n]."""
+    if wtype == F32:
+        return a.reshape(-1, n).astype(np.float32)
+    if wtype == F16:
+        return a.reshape(-1, n).astype(np.float32)
+    return dequantize_q4_0(a.reshape(-1, row_bytes(Q4_0, n)), n)
+
+
+# --------------------------------------------------------------------------- weights
+def _normal(rng: np.random.Generator, shape, std: float) -> np.ndarray:
+    a = rng.standard_normal(shape, dtype=np.float32)
+    a *= np.float32(std)
+    return a
+
+
+def synth_tensors(cfg: Config, seed: int = 0) -> dict[str, np.ndarray]:
+    """Per-tensor f32 arrays keyed by their GGUF names (read_ggml.f90:238-410).
+    Matrices ~ N(0, 1/fan_in), norm weights = 1 + N(0, 0.02^2), embeddings ~ N(0, 1)."""
+    cfg.validate()
+    rng = np.random.default_rng(seed)
+    e, h, V, kv = cfg.emb_dim, cfg.hidden_dim, cfg.vocab_size, cfg.kv_head_size
+    t: dict[str, np.ndarray] = {}
+    t["token_embd.weight"] = _normal(rng, (V, e), 1.0)
+    for l in range(cfg.n_layers):
+        p = f"blk.{l}."
+        t[p + "attn_norm.weight"] = 1.0 + _normal(rng, (e,), 0.02)
+        t[p + "attn_q.weight"] = _normal(rng, (e, e), e ** -0.5)
+        t[p + "attn_k.weight"] = _normal(rng, (kv, e), e ** -0.5)
+        t[p + "attn_v.weight"] = _normal(rng, (kv, e), e ** -0.5)
+        t[p + "attn_output.weight"] = _normal(rng, (e, e), e ** -0.5)
+        t[p + "ffn_norm.weight"] = 1.0 + _normal(rng, (e,), 0.02)
+        t[p + "ffn_gate.weight"] = _normal(rng, (h, e), e ** -0.5)
+        t[p + "ffn_down.weight"] = _normal(rng, (e, h), h ** -0.5)
+        t[p + "ffn_up.weight"] = _normal(rng, (h, e), e ** -0.5)
+    t["output_norm.weight"] = 1.0 + _normal(rng, (e,), 0.02)
+    t["output.weight"] = _normal(rng, (V, e), e ** -0.5)
+    return t
+
+
+def fuse_tensors(cfg: Config, t: dict[str, np.ndarray]) -> Weights:
+    """GGUF-named f32 tensors -> ``Weights`` in the fused weight_module layout, stored as
+    ``cfg.wtype`` (the same mapping load_ggml performs, read_ggml.f90:238-410)."""
+    L, wt = cfg.n_layers, cfg.wtype
+    enc = lambda a: encode_matrix(a, wt)
+
+    def per_layer(names: Iterable[str]) -> np.ndarray:
+        return np.stack([np.concatenate([enc(t[f"blk.{l}.{n}.weight"]) for n in names], axis=0)
+                         for l in range(L)])
+
+    return Weights(
+        cfg,
+        token_embedding_table=enc(t["token_embd.weight"]),
+        rms_att_weight=np.stack([t[f"blk.{l}.attn_norm.weight"] for l in range(L)]),
+        wqkv=per_layer(["attn_q", "attn_k", "attn_v"]),
+        wo=per_layer(["attn_output"]),
+        rms_ffn_weight=np.stack([t[f"blk.{l}.ffn_norm.weight"] for l in range(L)]),
+        w13=per_layer(["ffn_gate", "ffn_up"]),
+        w2=per_layer(["ffn_down"]),
+        rms_final_weight=t["output_norm.weight"],
+        wcls=enc(t["output.weight"]),
+    )
+
+
+def synth_weights(cfg: Config, seed: int = 0) -> Weights:
+    return fuse_tensors(cfg, synth_tensors(cfg, seed))
+
+
+def synth_weights_fast(cfg: Config, seed: int = 0) -> Weights:
+    """Full-size synthetic weights directly in the fused layout, generated tensor by tensor
+    with a cheap generator (used by bench.py / full-size tests where building per-tensor
+    f32 copies first would need several times the model size in host RAM)."""
+    cfg.validate()
+    rng = np.random.default_rng(seed)
+    e, h, L, V, wt = cfg.emb_dim, cfg.hidden_dim, cfg.n_layers, cfg.vocab_size, cfg.wtype
+
+    def mat(rows: int, n: int, std: float) -> np.ndarray:
+        out = np.empty((rows, row_bytes(wt, n)), dtype=np.uint8)
+        step = max(1, (1 << 24) // n)
+        for r0 in range(0, rows, step):
+            r1 = min(rows, r0 + step)
+            blk = _normal(rng, (r1 - r0, n), std)
+            out[r0:r1] = encode_matrix(blk, wt).reshape(r1 - r0, -1).view(np.uint8)
+        if wt == F32:
+            return out.view(np.float32)
+        if wt == F16:
+            return out.view(np.float16)
+        return out
+
+    def stack(rows: int, n: int, std: float) -> np.ndarray:
+        m = mat(L * rows, n, std)
+        return m.reshape(L, rows, -1)
+
+    return Weights(
+        cfg,
+        token_embedding_table=mat(V, e, 1.0),
+        rms_att_weight=1.0 + _normal(rng, (L, e), 0.02),
+        wqkv=stack(cfg.n_qkv, e, e ** -0.5),
+        wo=stack(e, e, e ** -0.5),
+        rms_ffn_weight=1.0 + _normal(rng, (L, e), 0.02),
+        w13=stack(2 * h, e, e ** -0.5),
+        w2=stack(e, h, h ** -0.5),
+        rms_final_weight=1.0 + _normal(rng, (e,), 0.02),
+        wcls=mat(V, e, e ** -0.5),
+    )
+
+
+# --------------------------------------------------------------------------- vocabulary
+def synth_vocab(vocab_size: int) -> tuple[list[bytes], np.ndarray]:
+    """A llama-style vocabulary: <unk>, <s>, </s>, the 95 printable ASCII characters with
+    the space spelled as U+2581 (the loader rewrites a leading U+2581 to ' ',
+    read_ggml.f90:483-503), then deterministic multi-character merges, some with a leading
+    U+2581.  scores = -index, so earlier merges win (llama2.f90:691-703)."""
+    assert vocab_size >= 3 + 95
+    sp = "▁".encode("utf-8")
+    toks: list[bytes] = [b"<unk>", b"<s>", b"</s>", sp]
+    toks += [bytes([c]) for c in range(33, 127)]
+    seen = set(toks)
+    letters = "etaoinshrdlucmfwypvbgkqjxz"
+
+    def gen():
+        n = 2
+        while True:
+            idx = [0] * n
+            while True:
+                w = "".join(letters[i] for i in idx).encode()
+                yield w
+                yield sp + w
+                k = n - 1
+                while k >= 0:
+                    idx[k] += 1
+                    if idx[k] < len(letters):
+                        break
+                    idx[k] = 0
+                    k -= 1
+                if k < 0:
+                    break
+            n += 1
+
+    g = gen()
+    while len(toks) < vocab_size:
+        w = next(g)
+        if w not in seen and len(w) <= 48:
+            seen.add(w)
+            toks.append(w)
+    scores = -np.arange(vocab_size, dtype=np.float32)
+    return toks, scores
+
+
+# --------------------------------------------------------------------------- GGUF writer
+def _s(b: bytes) -> bytes:
+    return struct.pack("<Q", len(b)) + b
+
+
+def _kv(key: str, vtype: int, payload: bytes) -> bytes:
+    return _s(key.encode()) + struct.pack("<I", vtype) + payload
+
+
+def write_gguf(path: str, cfg: Config, tensors: dict[str, np.ndarray],
+               vocab: list[bytes] | None = None, scores: np.ndarray | None = None,
+               alignment: int = ALIGNMENT, name: str = "synthetic") -> None:
+    """Write a GGUF v3 file.  ``tensors`` are f32 arrays by GGUF name; 2-D ones are stored as
+    ``cfg.wtype``, 1-D ones as f32.  Framing per read_ggml.f90:112-196,600-718."""
+    if vocab is None:
+        vocab, scores = synth_vocab(cfg.vocab_size)
+    assert len(vocab) == cfg.vocab_size
+    kvs = [
+        _kv("general.architecture", KV_STR, _s(b"llama")),
+        _kv("general.name", KV_STR, _s(name.encode())),
+        _kv("llama.context_length", KV_U32, struct.pack("<I", cfg.seq_len)),
+        _kv("llama.embedding_length", KV_U32, struct.pack("<I", cfg.emb_dim)),
+        _kv("llama.block_count", KV_U32, struct.pack("<I", cfg.n_layers)),
+        _kv("llama.feed_forward_length", KV_U32, struct.pack("<I", cfg.hidden_dim)),
+        _kv("llama.rope.dimension_count", KV_U32, struct.pack("<I", cfg.head_size)),
+        _kv("llama.attention.head_count", KV_U32, struct.pack("<I", cfg.n_heads)),
+        _kv("llama.attention.head_count_kv", KV_U32, struct.pack("<I", cfg.n_kv_heads)),
+        _kv("llama.attention.layer_norm_rms_epsilon", KV_F32, struct.pack("<f", 1e-5)),
+        _kv("tokenizer.ggml.model", KV_STR, _s(b"llama")),
+        _kv("tokenizer.ggml.tokens", KV_ARR,
+            struct.pack("<IQ", KV_STR, len(vocab)) + b"".join(_s(t) for t in vocab)),
+        _kv("tokenizer.ggml.scores", KV_ARR,
+            struct.pack("<IQ", KV_F32, len(vocab)) + np.asarray(scores, "<f4").tobytes()),
+        _kv("tokenizer.ggml.token_type", KV_ARR,
+            struct.pack("<IQ", KV_I32, len(vocab)) + np.ones(len(vocab), "<i4").tobytes()),
+        _kv("tokenizer.ggml.bos_token_id", KV_U32, struct.pack("<I", 1)),
+        _kv("tokenizer.ggml.eos_token_id", KV_U32, struct.pack("<I", 2)),
+    ]
+    if alignment != ALIGNMENT:
+        kvs.insert(2, _kv("general.alignment", KV_U32, struct.pack("<I", alignment)))
+
+    infos, blobs, off = [], [], 0
+    for tname, a in tensors.items():
+        if a.ndim == 2:
+            ttype, data = GGML_TYPE[cfg.wtype], encode_matrix(a, cfg.wtype)
+            dims = (a.shape[1], a.shape[0])  # innermost (contraction) dimension first
+        else:
+            ttype, data = GGML_TYPE[F32], np.ascontiguousarray(a, dtype=np.float32)
+            dims = (a.shape[0],)
+        raw = data.tobytes()
+        infos.append(_s(tname.encode()) + struct.pack("<I", len(dims))
+                     + b"".join(struct.pack("<Q", d) for d in dims)
+                     + struct.pack("<IQ", ttype, off))
+        pad = (-len(raw)) % alignment
+        blobs.append(raw + b"\0" * pad)
+        off += len(raw) + pad
+
+    head = struct.pack("<IIQQ", GGUF_MAGIC, GGUF_VERSION, len(infos), len(kvs))
+    meta = head + b"".join(kvs) + b"".join(infos)
+    meta += b"\0" * ((-len(meta)) % alignment)
+    with open(path, "wb") as f:
+        f.write(meta)
+        for b in blobs:
+            f.write(b)
+
+
+def write_synth_gguf(path: str, cfg: Config, seed: int = 0, **kw) -> Weights:
+    """Write a synthetic model to ``path`` and return the fused ``Weights`` it must load to."""
+    t = synth_tensors(cfg, seed)
+    write_gguf(path, cfg, t, **kw)
+    return fuse_tensors(cfg, t)
