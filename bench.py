@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- tokens/s of a 128-position greedy decode (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model tinyllama|llama2-7b|small]
+                    [--wtype f32|f16|q4_0] [--impl ours|reference]
+
+One "step" = one 128-position greedy generation (BOS + forced prompt + greedy picks,
+llama2.f90:376-402) on synthetic weights of the named architecture.
+
+  value        tokens/s with everything resident in HBM: the device-side greedy loop
+               (llmf90_b200_generate_greedy; one kernel launch per token, next token never leaves
+               the device), timed with CUDA events on the engine's stream.
+  e2e          the same 128 positions through the reference-facing call
+               llmf90_b200_transformer(token, pos, logits) with HOST logits every token and the
+               host picking the next token (what the Fortran loop does), wall clock between
+               device synchronisations.
+  roofline     the decode kernel (one launch = one token): algorithmic bytes per token
+                / mean launch duration vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline the C restatement of llama2.f90 (oracle/, 1 thread like the reference) on a bounded
+               sample of the same workload, on this box's host cores.
+
+--impl reference times that CPU restatement with all host threads (the Fortran binary cannot be
+built: no Fortran compiler in the image).  Under torchrun only rank 0 runs it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POS = 128
+PROMPT = "I stopped posting on knitting forums because"  # README.md:42
+METRIC = "tokens/sec decode (128-tok gen)"
+
+
+def model_config(name: str, wtype: str):
+    from llm.f90_b200.layout import Config, TINYLLAMA, LLAMA2_7B, SMALL, WTYPE_BY_NAME
+    dims = {"tinyllama": TINYLLAMA, "llama2-7b": LLAMA2_7B, "small": SMALL}[name]
+    return Config(**dims, wtype=WTYPE_BY_NAME[wtype])
+
+
+def prompt_tokens(cfg) -> list[int]:
+    """Tokenise PROMPT with the synthetic vocabulary (byte-level + merges, llama2.f90:658-724).
+    Falls back to a fixed id sequence when the host tokenizer is not built."""
+    try:
+        from llm.f90_b200 import hostapi
+        return hostapi.encode_with_synth_vocab(PROMPT, cfg.vocab_size)
+    except Exception:
+        rng = np.random.default_rng(42)
+        return [int(t) for t in rng.integers(4, cfg.vocab_size, size=9)]
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self.how = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.how = "nvml"
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        if nv:
+            for n in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap", "HwPowerBrakeSlowdown"):
+                v = getattr(nv, "nvmlClocksEventReason" + n, None) or getattr(nv, "nvmlClocksThrottleReason" + n, None)
+                if v is not None:
+                    names[v] = n
+        while not self._stop.is_set():
+            try:
+                if nv:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, n in names.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}",
+                                          "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                                          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                                          "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append(int(out[0]))
+                    self.max_mhz = int(out[1])
+                    for n, v in zip(("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap"), out[2:]):
+                        if v.strip().lower().startswith("active"):
+                            self.reasons.add(n)
+                    self.how = "nvidia-smi"
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=5)
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s), "how": self.how}
+
+
+# ------------------------------------------------------------------ CPU legs
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_run(weights, prompt, n_pos: int, threads: int, arch: str = "native"):
+    """tokens/s of the C restatement by the reference's formula (n-1)/(t_end - t_after_first)."""
+    from oracle import oracle_c
+    try:
+        o = oracle_c.Oracle(weights, n_threads=threads, arch=arch)
+    except Exception:
+        o = oracle_c.Oracle(weights, n_threads=threads)
+    t0 = time.perf_counter()
+    _, _, ms_after_first = o.generate(prompt, n_pos)
+    wall = time.perf_counter() - t0
+    o.close()
+    return (n_pos - 1) / (ms_after_first / 1000.0), wall
+
+
+def peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(model: str, wtype: str):
+    """dram bytes per launch of the decode kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(f"{model}-{wtype}")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--wtype", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-pos", type=int, default=0, help="positions of the CPU sample (0 = auto)")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus != world and world > 1:
+        a.gpus = world
+    # workload: configs[1] at N=1 (TinyLlama f32 fits one GPU); the 8-GPU config is Llama-2-7B f16
+    model = a.model or "tinyllama"
+    wtype = a.wtype or "f32"
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+
+    from llm.f90_b200 import fixtures as fx
+    from llm.f90_b200.layout import active_weight_bytes
+    cfg = model_config(model, wtype)
+    workload = f"{model}-{wtype} {N_POS}-position greedy decode, synthetic weights (seed 0)"
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = host_cores()
+        w = fx.synth_weights_fast(cfg, 0)
+        prompt = prompt_tokens(cfg)
+        n_pos = a.cpu_sample_pos or {"tinyllama": 12, "llama2-7b": 4, "small": N_POS}[model]
+        for _ in range(a.warmup):
+            cpu_oracle_run(w, prompt, min(n_pos, 3), cores)
+        tps, walls = [], []
+        for _ in range(a.steps):
+            t, wall = cpu_oracle_run(w, prompt, n_pos, cores)
+            tps.append(t)
+            walls.append(wall)
+        val = float(len(tps) * (n_pos - 1) / sum((n_pos - 1) / t for t in tps))
+        sample = f"{n_pos} positions per step (of the {N_POS}-position workload), (n-1)/(t_end-t_after_first)"
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * sum(walls) / len(walls),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": workload},
+                "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample,
+                                 "note": "C restatement of llama2.f90 (oracle/), OpenMP over rows; the Fortran "
+                                         "binary cannot be built in this image (no Fortran compiler)"},
+                "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------- our arm
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this engine has no CPU fallback"}))
+        return 2
+    from llm.f90_b200 import capi
+    capi.load()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+
+    w = fx.synth_weights_fast(cfg, 0)
+    prompt = prompt_tokens(cfg)
+    eng = capi.make_engine(w, device=dev, tp_rank=rank, tp_size=world)
+    act_bytes = active_weight_bytes(cfg)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: device-resident loop
+    for _ in range(a.warmup):
+        eng.generate_greedy(prompt, N_POS)
+    barrier()
+    l0 = eng.stats()["kernel_launches"]
+    dev_ms, after_first = [], []
+    t0 = time.perf_counter()
+    with ClockSampler(dev) as clk:
+        for _ in range(a.steps):
+            toks, af = eng.generate_greedy(prompt, N_POS)
+            st = eng.stats()
+            dev_ms.append(st["last_loop_total_ms"])
+            after_first.append(af)
+        barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    launches = eng.stats()["kernel_launches"] - l0
+    tot_ms = float(sum(dev_ms))
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([tot_ms], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms = float(t.item())
+    value = a.steps * N_POS / (tot_ms / 1000.0)
+    ref_formula = a.steps * (N_POS - 1) / (sum(after_first) / 1000.0)
+
+    # ---- e2e: the reference-facing per-token call with host logits
+    for _ in range(2):
+        eng.reset()
+        capi.host_generate(eng, prompt, N_POS)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(a.steps, 5))
+    for _ in range(e2e_steps):
+        toks_h, _ = capi.host_generate(eng, prompt, N_POS)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_s], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = e2e_steps * N_POS / e2e_s
+    tokens_agree = bool((np.asarray(toks_h) == np.asarray(toks)).all())
+
+    if rank != 0:
+        eng.close()
+        return 0
+
+    peak, peak_src = peaks()
+    st = eng.stats()
+    per_launch_ms = tot_ms / max(1, a.steps * N_POS)
+    per_gpu_bytes = st["active_bytes_per_token"]
+    achieved = per_gpu_bytes / (per_launch_ms / 1000.0) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "emb_dim": cfg.emb_dim, "hidden_dim": cfg.hidden_dim,
+                   "n_layers": cfg.n_layers, "n_heads": cfg.n_heads, "n_kv_heads": cfg.n_kv_heads,
+                   "vocab_size": cfg.vocab_size, "weight_storage": wtype, "positions_per_step": N_POS,
+                   "prompt_tokens": len(prompt), "parallelism": f"tp{world}",
+                   "l2": f"inputs larger than L2: {act_bytes / 1e6:.0f} MB of weights streamed per token vs 126 MB L2",
+                   "tokens_per_s_reference_formula": ref_formula,
+                   "wall_ms_timed_region": wall_ms},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8 * N_POS,
+                "d2h_bytes_per_step": 4 * cfg.vocab_size * N_POS, "steps": e2e_steps,
+                "api": "llmf90_b200_transformer(token,pos,logits) per position, host argmax",
+                "tokens_match_device_loop": tokens_agree},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(model, wtype), "peak_source": peak_src,
+                     "kernel": "stream_decode_kernel (1 launch = 1 token)" if st["stream_slots"] else "granular graph",
+                     "algorithmic_bytes_per_launch": int(per_gpu_bytes), "launch_ms": per_launch_ms},
+    }
+    if not a.no_cpu_baseline and world == 1:
+        n_pos = a.cpu_sample_pos or {"tinyllama": 64, "llama2-7b": 6, "small": N_POS}[model]
+        tps, wall = cpu_oracle_run(w, prompt, n_pos, 1)
+        line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": 1, "kind": "port",
+                                "sample": f"first {n_pos} of the {N_POS} positions, 1 thread, {wall:.1f} s wall; "
+                                          f"C restatement of llama2.f90 (no Fortran compiler in the image); "
+                                          f"box has {host_cores()} host cores"}
+    eng.close()
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,145 @@
+/*
+ * llmf90_b200.h -- C ABI of the B200-native decode engine that replaces the
+ * forward pass of rbitr/llm.f90.
+ *
+ * Drop-in boundary: the single call site
+ *     logits = transformer(token, pos, s, weights)        (llama2.f90:380)
+ * and the inner subroutines it uses (rmsnorm llama2.f90:450-457, softmax
+ * :468-478, the inline mat-vec loops :529-531/:603-605/:610-612/:618-620/
+ * :634-636, RoPE :543-559).  Everything above that call (CLI, GGUF loader,
+ * tokenizer, sampler, token loop) stays on the host.  The reference has no FFI
+ * today; these are the entry points an ISO_C_BINDING interface block binds
+ * (fortran/llmf90_b200_iface.f90), following the author's own
+ * bind(C) convention (load.f90:123-152: scalar `value` args, c_float/c_int).
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success, non-zero on error;
+ *    llmf90_b200_last_error() then describes it (the reference's convention is
+ *    `print *, msg; stop`, read_ggml.f90:122-125 -- the host prints and stops).
+ *  - `token` and `pos` are 1-based, exactly what the Fortran loop passes
+ *    (llama2.f90:376-380); BOS = 2.
+ *  - weight pointers are the base addresses of the TransformerWeights
+ *    allocatables (weight_module.f90:13-26).  Column-major Fortran == row-major C
+ *    with reversed index order: wqkv(emb, emb+2kv, L) is [L][emb+2kv][emb] etc.
+ *    The library copies (and re-lays-out / shards) them to the device in init and
+ *    never frees or mutates host memory.
+ *  - the engine is a process-wide singleton (the reference is a single-model
+ *    program); the caller is single-threaded; calls are synchronous -- on return
+ *    of llmf90_b200_transformer the logits are in host memory (llama2.f90:388-391
+ *    reads them immediately).
+ *  - RunState (weight_module.f90:33-40: att, key_cache, value_cache, times) lives
+ *    on the device and is owned by the library.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with an error.
+ */
+#ifndef LLMF90_B200_H
+#define LLMF90_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* storage of the 2-D weight tensors (ggml tensor type ids, read_ggml.f90:613-635) */
+#define LLMF90_WTYPE_F32  0   /* what the reference's master branch runs                */
+#define LLMF90_WTYPE_F16  1   /* ggml type 1 (the optimize16 branch's storage)          */
+#define LLMF90_WTYPE_Q4_0 2   /* ggml type 2: 18-byte blocks of 32 (four_bit_dev branch) */
+
+/* flags */
+#define LLMF90_FLAG_GRANULAR 1u  /* run the forward as separate kernels (rmsnorm, matvec, rope,
+                                    attention ...) instead of the fused weight-streaming kernel */
+
+/* mirror of `type Config` (weight_module.f90:28-31) + dtype and placement */
+typedef struct llmf90_b200_config {
+    int32_t emb_dim;      /* llama2.f90:102 */
+    int32_t hidden_dim;   /* :103 */
+    int32_t n_layers;     /* :104 */
+    int32_t n_heads;      /* :105 */
+    int32_t n_kv_heads;   /* :106 */
+    int32_t vocab_size;   /* :107 */
+    int32_t seq_len;      /* :108 -- size of the KV cache in positions */
+    int32_t wtype;        /* LLMF90_WTYPE_* */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t tp_rank;      /* tensor-parallel rank of this process (0 when tp_size == 1) */
+    int32_t tp_size;      /* number of GPUs the heads / FFN rows are sharded over (1,2,4,8) */
+    uint32_t flags;       /* LLMF90_FLAG_* */
+} llmf90_b200_config;
+
+/* replaces the allocation + load of `weights` and `s` (llama2.f90:151, :311-319).
+ * Norm vectors are always f32; the other tensors are `wtype` rows. */
+int llmf90_b200_init(const llmf90_b200_config *cfg,
+                     const void *token_embedding_table, /* [V][emb]            */
+                     const float *rms_att_weight,       /* [L][emb]            */
+                     const void *wqkv,                  /* [L][emb+2kv][emb]   */
+                     const void *wo,                    /* [L][emb][emb]       */
+                     const float *rms_ffn_weight,       /* [L][emb]            */
+                     const void *w13,                   /* [L][2*hid][emb]     */
+                     const void *w2,                    /* [L][emb][hid]       */
+                     const float *rms_final_weight,     /* [emb]               */
+                     const void *wcls);                 /* [V][emb]            */
+
+/* replaces `function transformer(token,pos,s,w) result(logits)` (llama2.f90:480-640).
+ * logits[vocab_size] is host memory. */
+int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits);
+
+/* s%times(1:5) in milliseconds, accumulated since init/reset (llama2.f90:526-638, :407-410).
+ * Bucket 2 (RoPE) is fused into bucket 1's kernel phase and reported as 0. */
+int llmf90_b200_times(float t[5]);
+
+/* zero the KV cache and the timers (the state llama2.f90:316-319 initialises) */
+int llmf90_b200_reset(void);
+
+int llmf90_b200_free(void);
+
+const char *llmf90_b200_last_error(void);
+
+/* The whole generation loop of llama2.f90:376-402 for temperature == 0 kept on the device
+ * (argmax fused after the classifier, next token never leaves HBM).  out_tokens[i] is the
+ * 1-based token chosen after position i+1 (forced prompt token or greedy pick); elapsed_ms
+ * is device time from after the first token to the end (llama2.f90:399-406). */
+int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, int32_t n,
+                                int32_t *out_tokens, float *elapsed_ms);
+
+/* ---- the inner subroutines as separately callable operators (host pointers in/out) ---- */
+/* y(ix) = dot_product(x, w(:,ix)), ix = 1..rows; w is `rows` rows of `cols` weights of `wtype` */
+int llmf90_b200_matvec(const void *w, int32_t wtype, int32_t rows, int32_t cols, const float *x,
+                       float *y);
+/* llama2.f90:450-457 */
+int llmf90_b200_rmsnorm(const float *x, const float *w, int32_t n, float *out);
+/* llama2.f90:468-478: softmax over x(1:s), zeros in p(s+1:n) */
+int llmf90_b200_softmax(const float *x, int32_t n, int32_t s, float *p);
+/* llama2.f90:543-559, in place on q(1:emb) and k(1:kv); pos is 1-based */
+int llmf90_b200_rope(float *q, float *k, int32_t emb, int32_t kv, int32_t head_size, int32_t pos);
+
+/* ---- tensor parallelism plumbing (one process per GPU) ---- */
+/* rank 0 creates a 128-byte id, the host distributes it, every rank passes it to init_tp
+ * BEFORE llmf90_b200_init with tp_size > 1. */
+int llmf90_b200_tp_unique_id(void *id128);
+int llmf90_b200_tp_connect(const void *id128, int32_t rank, int32_t size, int32_t device);
+
+/* ---- introspection used by the benchmark harness ---- */
+typedef struct llmf90_b200_stats {
+    uint64_t kernel_launches;     /* kernels of this library launched since init/reset */
+    uint64_t forward_calls;
+    uint64_t weight_bytes_device; /* bytes of weights resident in HBM on this GPU      */
+    uint64_t active_bytes_per_token; /* weight bytes one token streams on this GPU      */
+    float last_forward_ms;        /* CUDA-event time of the most recent forward kernel(s) */
+    int32_t n_sms;
+    int32_t stream_slots, stream_slot_bytes, stream_smem_bytes, stream_threads;
+    float last_loop_total_ms;       /* device loop (generate_greedy / bench_device_loop): all positions */
+    float last_loop_after_first_ms; /* same, from after the first token (llama2.f90:399-406)            */
+} llmf90_b200_stats;
+int llmf90_b200_get_stats(llmf90_b200_stats *out);
+
+/* device-resident variant used for the HBM-resident measurement: runs `n_steps` forwards for
+ * positions pos0..pos0+n_steps-1 feeding each one the greedy pick of the previous one, without
+ * any host<->device traffic; returns the device time in ms. */
+int llmf90_b200_bench_device_loop(int32_t first_token, int32_t pos0, int32_t n_steps,
+                                  float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLMF90_B200_H */

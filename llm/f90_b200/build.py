@@ -1,0 +1,81 @@
+"""Build the native artefacts in-tree (they travel to the GPU box with the repo snapshot).
+
+    libllmf90_b200.so   CUDA kernels for sm_100a + the C ABI (include/llmf90_b200.h)
+    libllmf90_host.so   C++ mirror of the reference's host program (loader, tokenizer, sampler)
+    llm                 the `./llm -m <gguf>` command-line program
+
+nvcc cross-compiles sm_100a without a GPU, so this runs in the CPU container too.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+CUDA_SRCS = ["ops.cu", "stream.cu", "engine.cu"]
+CUDA_HDRS = ["common.cuh", "kernels.cuh", os.path.join(ROOT, "include", "llmf90_b200.h")]
+CUDA_LIB = os.path.join(HERE, "libllmf90_b200.so")
+HOST_LIB = os.path.join(HERE, "libllmf90_host.so")
+HOST_SRCS = ["host/gguf_loader.cpp", "host/tokenizer.cpp", "host/host_api.cpp"]
+HOST_HDRS = ["host/host.hpp", os.path.join(ROOT, "include", "llmf90_host.h")]
+LLM_BIN = os.path.join(HERE, "bin", "llm")
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _abs(names):
+    return [n if os.path.isabs(n) else os.path.join(CSRC, n) for n in names]
+
+
+def _cxx() -> str:
+    for c in ("/usr/bin/g++", shutil.which("g++") or ""):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("no g++ found")
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    deps = _abs(CUDA_SRCS) + _abs(CUDA_HDRS)
+    if force or _newer(CUDA_LIB, deps):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB] + _abs(CUDA_SRCS)
+        subprocess.run(cmd, check=True, cwd=CSRC)
+    return CUDA_LIB
+
+
+def build_host(force: bool = False) -> str:
+    srcs = _abs(HOST_SRCS)
+    if not all(os.path.exists(s) for s in srcs):
+        return ""
+    if force or _newer(HOST_LIB, srcs + _abs(HOST_HDRS)):
+        cmd = [_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB] + srcs
+        subprocess.run(cmd, check=True, cwd=CSRC)
+    main = os.path.join(CSRC, "host", "llm_main.cpp")
+    if os.path.exists(main) and (force or _newer(LLM_BIN, [main, HOST_LIB, CUDA_LIB])):
+        os.makedirs(os.path.dirname(LLM_BIN), exist_ok=True)
+        cmd = [_cxx(), "-O2", "-std=c++17", "-Wall", "-o", LLM_BIN, main, "-L" + HERE, "-lllmf90_host",
+               "-lllmf90_b200", "-Wl,-rpath,$ORIGIN/..", "-Wl,--allow-shlib-undefined"]
+        subprocess.run(cmd, check=True, cwd=CSRC)
+    return HOST_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_cuda(force, verbose)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built:", CUDA_LIB, HOST_LIB if os.path.exists(HOST_LIB) else "(host lib pending)")

@@ -1,0 +1,207 @@
+"""ctypes binding of libllmf90_b200.so (include/llmf90_b200.h).
+
+Plumbing for the tests and the benchmark: it passes numpy host buffers straight through the
+C ABI, exactly as the Fortran host would pass its allocatables.  If the library is missing it
+raises -- there is no Python or CPU fallback for any operator.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .layout import Config, Weights
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libllmf90_b200.so")
+
+FLAG_GRANULAR = 1
+
+EXPORTS = [
+    "llmf90_b200_init", "llmf90_b200_transformer", "llmf90_b200_times", "llmf90_b200_reset",
+    "llmf90_b200_free", "llmf90_b200_last_error", "llmf90_b200_generate_greedy",
+    "llmf90_b200_matvec", "llmf90_b200_rmsnorm", "llmf90_b200_softmax", "llmf90_b200_rope",
+    "llmf90_b200_tp_unique_id", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
+    "llmf90_b200_bench_device_loop",
+]
+
+
+class CConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("emb_dim", "hidden_dim", "n_layers", "n_heads", "n_kv_heads",
+                                         "vocab_size", "seq_len", "wtype", "device", "tp_rank",
+                                         "tp_size")] + [("flags", C.c_uint32)]
+
+
+class CStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("forward_calls", C.c_uint64),
+                ("weight_bytes_device", C.c_uint64), ("active_bytes_per_token", C.c_uint64),
+                ("last_forward_ms", C.c_float), ("n_sms", C.c_int32), ("stream_slots", C.c_int32),
+                ("stream_slot_bytes", C.c_int32), ("stream_smem_bytes", C.c_int32),
+                ("stream_threads", C.c_int32), ("last_loop_total_ms", C.c_float),
+                ("last_loop_after_first_ms", C.c_float)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building it is __graft_entry__.build()'s job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: run `python -m llm.f90_b200.build` "
+                          "(there is no fallback implementation)")
+    L = C.CDLL(LIB_PATH)
+    vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    L.llmf90_b200_init.argtypes = [C.POINTER(CConfig)] + [vp] * 9
+    L.llmf90_b200_transformer.argtypes = [C.c_int32, C.c_int32, fp]
+    L.llmf90_b200_times.argtypes = [fp]
+    L.llmf90_b200_last_error.restype = C.c_char_p
+    L.llmf90_b200_generate_greedy.argtypes = [ip, C.c_int32, C.c_int32, ip, fp]
+    L.llmf90_b200_matvec.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, fp]
+    L.llmf90_b200_rmsnorm.argtypes = [fp, fp, C.c_int32, fp]
+    L.llmf90_b200_softmax.argtypes = [fp, C.c_int32, C.c_int32, fp]
+    L.llmf90_b200_rope.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.llmf90_b200_tp_unique_id.argtypes = [vp]
+    L.llmf90_b200_tp_connect.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.llmf90_b200_get_stats.argtypes = [C.POINTER(CStats)]
+    L.llmf90_b200_bench_device_loop.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp]
+    for name in EXPORTS:
+        if name != "llmf90_b200_last_error":
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise EngineError(load().llmf90_b200_last_error().decode())
+
+
+def _fp(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Engine:
+    """The process-wide engine singleton behind the C ABI."""
+
+    def __init__(self, weights: Weights, device: int = 0, granular: bool = False):
+        self.L = load()
+        c = weights.cfg
+        self.cfg = c
+        cc = CConfig(c.emb_dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads, c.vocab_size,
+                     c.seq_len, c.wtype, device, 0, 1, FLAG_GRANULAR if granular else 0)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        _check(self.L.llmf90_b200_init(C.byref(cc), ptr(weights.token_embedding_table),
+                                       ptr(weights.rms_att_weight), ptr(weights.wqkv), ptr(weights.wo),
+                                       ptr(weights.rms_ffn_weight), ptr(weights.w13), ptr(weights.w2),
+                                       ptr(weights.rms_final_weight), ptr(weights.wcls)))
+        self._logits = np.empty(c.vocab_size, np.float32)
+        self.open = True
+
+    def transformer(self, token: int, pos: int, out: np.ndarray | None = None) -> np.ndarray:
+        """logits = transformer(token, pos) with 1-based token/pos (llama2.f90:380)."""
+        if out is None:
+            out = np.empty(self.cfg.vocab_size, np.float32)
+        _check(self.L.llmf90_b200_transformer(token, pos, _fp(out)))
+        return out
+
+    def generate_greedy(self, prompt_tokens, n: int):
+        pt = np.ascontiguousarray(prompt_tokens, np.int32)
+        out = np.empty(n, np.int32)
+        ms = C.c_float(0)
+        _check(self.L.llmf90_b200_generate_greedy(_ip(pt) if len(pt) else None, len(pt), n, _ip(out),
+                                                  C.byref(ms)))
+        return out, ms.value
+
+    def bench_device_loop(self, first_token: int, pos0: int, n_steps: int) -> float:
+        ms = C.c_float(0)
+        _check(self.L.llmf90_b200_bench_device_loop(first_token, pos0, n_steps, C.byref(ms)))
+        return ms.value
+
+    def times(self) -> np.ndarray:
+        t = np.zeros(5, np.float32)
+        _check(self.L.llmf90_b200_times(_fp(t)))
+        return t
+
+    def reset(self) -> None:
+        _check(self.L.llmf90_b200_reset())
+
+    def stats(self) -> dict:
+        s = CStats()
+        _check(self.L.llmf90_b200_get_stats(C.byref(s)))
+        return {n: getattr(s, n) for n, _ in CStats._fields_}
+
+    def close(self) -> None:
+        if getattr(self, "open", False):
+            self.L.llmf90_b200_free()
+            self.open = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def host_generate(engine: Engine, prompt_tokens, n: int, want_logits: bool = False):
+    """The reference's token loop (llama2.f90:376-393, temperature 0) driving the C ABI one
+    token at a time with host logits -- what the Fortran host does."""
+    V = engine.cfg.vocab_size
+    toks = np.empty(n, np.int32)
+    lg_all = np.empty((n, V), np.float32) if want_logits else None
+    buf = np.empty(V, np.float32)
+    token = 2
+    for pos in range(1, n + 1):
+        engine.transformer(token, pos, buf)
+        if want_logits:
+            lg_all[pos - 1] = buf
+        token = int(prompt_tokens[pos - 1]) if pos <= len(prompt_tokens) else int(np.argmax(buf)) + 1
+        toks[pos - 1] = token
+    return toks, lg_all
+
+
+# ---- operators
+def matvec(w: np.ndarray, wtype: int, rows: int, cols: int, x: np.ndarray) -> np.ndarray:
+    y = np.empty(rows, np.float32)
+    w = np.ascontiguousarray(w)
+    _check(load().llmf90_b200_matvec(w.ctypes.data_as(C.c_void_p), wtype, rows, cols, _fp(x), _fp(y)))
+    return y
+
+
+def rmsnorm(x: np.ndarray, w: np.ndarray) -> np.ndarray:
+    out = np.empty_like(x)
+    _check(load().llmf90_b200_rmsnorm(_fp(x), _fp(w), len(x), _fp(out)))
+    return out
+
+
+def softmax(x: np.ndarray, s: int) -> np.ndarray:
+    out = np.empty_like(x)
+    _check(load().llmf90_b200_softmax(_fp(x), len(x), s, _fp(out)))
+    return out
+
+
+def rope(q: np.ndarray, k: np.ndarray, head_size: int, pos: int):
+    q, k = q.copy(), k.copy()
+    _check(load().llmf90_b200_rope(_fp(q), _fp(k), len(q), len(k), head_size, pos))
+    return q, k
+
+
+def make_engine(weights: Weights, device: int = 0, tp_rank: int = 0, tp_size: int = 1,
+                granular: bool = False) -> Engine:
+    """Engine factory used by bench.py: single GPU, or one tensor-parallel rank of `tp_size`."""
+    if tp_size == 1:
+        return Engine(weights, device=device, granular=granular)
+    raise EngineError("tensor-parallel engine: use llm.f90_b200.tp.TPEngine (not built yet)")

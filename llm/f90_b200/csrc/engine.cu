@@ -1,0 +1,613 @@
+// engine.cu -- the C ABI of libllmf90_b200.so (include/llmf90_b200.h): device state, weight
+// upload / re-layout, the two forward drivers (fused streaming kernel; granular kernels in a
+// CUDA graph) and the operator wrappers.  Host logic only -- every computation is a kernel in
+// ops.cu / stream.cu.  There is deliberately no CPU fallback: if CUDA is unavailable every
+// entry point fails with an error string.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/llmf90_b200.h"
+#include "kernels.cuh"
+
+using namespace llmf90;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int MAX_SPLITS = 8;
+
+struct Engine {
+    bool ready = false;
+    llmf90_b200_config cfg{};
+    int hs = 0, kv = 0, nqkv = 0, kv_mul = 0;
+    int n_sms = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    // weights (device row format)
+    uint8_t *d_emb = nullptr, *d_wqkv = nullptr, *d_wo = nullptr, *d_w13 = nullptr, *d_w2 = nullptr,
+            *d_wcls = nullptr;
+    float *d_rms_att = nullptr, *d_rms_ffn = nullptr, *d_rms_final = nullptr;
+    float2 *d_rope = nullptr;
+    // RunState + activations
+    float *d_kc = nullptr, *d_vc = nullptr;
+    float *d_x = nullptr, *d_xb = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_att_part = nullptr,
+          *d_h13 = nullptr, *d_hb = nullptr, *d_logits = nullptr, *d_times = nullptr;
+    int *d_tokpos = nullptr, *d_forced = nullptr, *d_out_tokens = nullptr, *d_amax = nullptr;
+    unsigned long long *d_bar = nullptr;
+    unsigned long long bar_base = 0;
+    float *h_logits = nullptr;  // pinned
+    int *h_tokpos = nullptr;    // pinned
+    // drivers
+    bool use_stream = true;
+    StreamParams sp{};
+    StreamPlan plan{};
+    cudaGraphExec_t graph = nullptr;
+    int graph_kernels = 0;
+    // stats
+    uint64_t launches = 0, forwards = 0, weight_bytes = 0, active_bytes = 0;
+    float last_ms = 0.f, loop_total_ms = 0.f, loop_after_first_ms = 0.f;
+    float host_times[5] = {0, 0, 0, 0, 0};
+};
+
+Engine E;
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n)
+{
+    return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 1);
+}
+
+void release_all()
+{
+    if (E.graph) cudaGraphExecDestroy(E.graph);
+    void *ptrs[] = {E.d_emb, E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls, E.d_rms_att, E.d_rms_ffn,
+                    E.d_rms_final, E.d_rope, E.d_kc, E.d_vc, E.d_x, E.d_xb, E.d_qkv, E.d_att,
+                    E.d_att_part, E.d_h13, E.d_hb, E.d_logits, E.d_times, E.d_tokpos, E.d_forced,
+                    E.d_out_tokens, E.d_amax, E.d_bar};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (E.h_logits) cudaFreeHost(E.h_logits);
+    if (E.h_tokpos) cudaFreeHost(E.h_tokpos);
+    if (E.ev0) cudaEventDestroy(E.ev0);
+    if (E.ev1) cudaEventDestroy(E.ev1);
+    if (E.ev2) cudaEventDestroy(E.ev2);
+    if (E.st) cudaStreamDestroy(E.st);
+    E = Engine{};
+}
+
+// Copy `src_rows` host-format rows to a staging buffer on the device, then re-lay them out into
+// `dst` (device row format): dst row r = src row map(r), columns [col0, col0+ncols).
+int upload_matrix(uint8_t *dst, const void *src_host, int wtype, int src_rows, int src_cols,
+                  int dst_rows, int col0, int ncols, int map_kind, int row0, int half,
+                  uint8_t *stage, size_t stage_bytes)
+{
+    const size_t src_bytes = (size_t)src_rows * host_row_bytes(wtype, src_cols);
+    if (src_bytes > stage_bytes) return fail("internal: staging buffer too small");
+    CK(cudaMemcpyAsync(stage, src_host, src_bytes, cudaMemcpyHostToDevice, E.st));
+    CK(launch_repack(stage, wtype, src_cols, dst, dst_rows, col0, ncols, map_kind, row0, half, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    return 0;
+}
+
+int n_splits_for(int pos)
+{
+    int s = (pos + 63) / 64;
+    return std::max(1, std::min(MAX_SPLITS, s));
+}
+
+int ensure_device(int dev)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail("no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (dev < 0 || dev >= n) return fail("device %d out of range (have %d)", dev, n);
+    CK(cudaSetDevice(dev));
+    return 0;
+}
+
+// ------------------------------------------------------------------ granular forward
+// One kernel per step of llama2.f90:520-636, captured once into a CUDA graph.  d_tokpos holds
+// {token, pos}; kernels that need them read them from there, so the graph is position-agnostic.
+int enqueue_granular(bool count)
+{
+    const auto &c = E.cfg;
+    const int emb = c.emb_dim, hid = c.hidden_dim, L = c.n_layers, wt = c.wtype;
+    const size_t rs_e = row_stride_bytes(wt, emb), rs_h = row_stride_bytes(wt, hid);
+    int k = 0;
+    CK(launch_embed(E.d_emb, wt, emb, E.d_tokpos, E.d_x, E.st)); k++;
+    for (int l = 0; l < L; l++) {
+        float *kc = E.d_kc + (size_t)l * c.seq_len * E.kv, *vc = E.d_vc + (size_t)l * c.seq_len * E.kv;
+        CK(launch_rmsnorm(E.d_x, E.d_rms_att + (size_t)l * emb, E.d_xb, emb, E.st)); k++;
+        CK(launch_matvec(E.d_wqkv + (size_t)l * E.nqkv * rs_e, wt, E.nqkv, emb, E.d_xb, nullptr,
+                         E.d_qkv, E.st)); k++;
+        CK(launch_rope_kv(E.d_qkv, emb, E.kv, E.hs, E.d_rope, E.d_tokpos, kc, vc, E.st)); k++;
+        CK(launch_attention(E.d_qkv, kc, vc, E.d_tokpos, E.d_att, c.n_heads, E.kv_mul, E.hs, E.kv,
+                            c.seq_len, E.st)); k++;
+        CK(launch_matvec(E.d_wo + (size_t)l * emb * rs_e, wt, emb, emb, E.d_att, E.d_x, E.d_x, E.st)); k++;
+        CK(launch_rmsnorm(E.d_x, E.d_rms_ffn + (size_t)l * emb, E.d_xb, emb, E.st)); k++;
+        CK(launch_matvec(E.d_w13 + (size_t)l * 2 * hid * rs_e, wt, 2 * hid, emb, E.d_xb, nullptr,
+                         E.d_h13, E.st)); k++;
+        CK(launch_swiglu(E.d_h13, E.d_hb, hid, E.st)); k++;
+        CK(launch_matvec(E.d_w2 + (size_t)l * emb * rs_h, wt, emb, hid, E.d_hb, E.d_x, E.d_x, E.st)); k++;
+    }
+    CK(launch_rmsnorm(E.d_x, E.d_rms_final, E.d_xb, emb, E.st)); k++;
+    CK(launch_matvec(E.d_wcls, wt, c.vocab_size, emb, E.d_xb, nullptr, E.d_logits, E.st)); k++;
+    if (count) E.graph_kernels = k;
+    return 0;
+}
+
+int build_granular_graph()
+{
+    // warm-up pass outside capture so that every kernel's attributes are set before capturing
+    E.h_tokpos[0] = 1; E.h_tokpos[1] = 1;
+    CK(cudaMemcpyAsync(E.d_tokpos, E.h_tokpos, 8, cudaMemcpyHostToDevice, E.st));
+    if (enqueue_granular(true)) return 1;
+    CK(cudaStreamSynchronize(E.st));
+    cudaGraph_t g;
+    CK(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_granular(false);
+    cudaError_t e = cudaStreamEndCapture(E.st, &g);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&E.graph, g, 0));
+    CK(cudaGraphDestroy(g));
+    // the warm-up pass wrote position 1 of the caches; restore the zeroed RunState
+    const size_t cache = (size_t)E.cfg.n_layers * E.cfg.seq_len * E.kv;
+    CK(cudaMemsetAsync(E.d_kc, 0, cache * 4, E.st));
+    CK(cudaMemsetAsync(E.d_vc, 0, cache * 4, E.st));
+    return 0;
+}
+
+__global__ void advance_kernel(int *tokpos, const int *amax, const int *forced, int *out_tokens)
+{
+    const int pos = tokpos[1];
+    int next = amax[0];
+    if (forced && forced[pos - 1] > 0) next = forced[pos - 1];
+    if (out_tokens) out_tokens[pos - 1] = next;
+    tokpos[0] = next;
+    tokpos[1] = pos + 1;
+}
+
+// enqueue one forward on the stream.  token > 0: inputs by value; token < 0: read d_tokpos.
+int enqueue_forward(int token, int pos, bool device_loop, const int *forced, int *out_tokens)
+{
+    if (E.use_stream) {
+        StreamParams &p = E.sp;
+        p.token = device_loop ? -1 : token;
+        p.pos = pos;
+        p.n_splits = n_splits_for(pos);
+        p.do_argmax = device_loop ? 1 : 0;
+        p.forced = forced;
+        p.out_tokens = out_tokens;
+        p.bar_base = E.bar_base;
+        CK(launch_stream(p, E.plan, E.st));
+        E.bar_base += (unsigned long long)stream_barriers_per_launch(p) * E.plan.grid;
+        E.launches += 1;
+    } else {
+        if (!device_loop) {
+            E.h_tokpos[0] = token; E.h_tokpos[1] = pos;
+            CK(cudaMemcpyAsync(E.d_tokpos, E.h_tokpos, 8, cudaMemcpyHostToDevice, E.st));
+        }
+        CK(cudaGraphLaunch(E.graph, E.st));
+        E.launches += E.graph_kernels;
+        if (device_loop) {
+            CK(launch_argmax(E.d_logits, E.cfg.vocab_size, E.d_amax, E.st));
+            advance_kernel<<<1, 1, 0, E.st>>>(E.d_tokpos, E.d_amax, forced, out_tokens);
+            CK(cudaGetLastError());
+            E.launches += 2;
+        }
+    }
+    E.forwards++;
+    return 0;
+}
+
+int device_loop(int first_token, int pos0, int n, const int *d_forced, int *d_out, float *ms_after_first,
+                float *ms_total)
+{
+    E.h_tokpos[0] = first_token; E.h_tokpos[1] = pos0;
+    CK(cudaMemcpyAsync(E.d_tokpos, E.h_tokpos, 8, cudaMemcpyHostToDevice, E.st));
+    CK(cudaEventRecord(E.ev0, E.st));
+    for (int i = 0; i < n; i++) {
+        if (enqueue_forward(-1, pos0 + i, true, d_forced, d_out)) return 1;
+        if (i == 0) CK(cudaEventRecord(E.ev1, E.st));
+    }
+    CK(cudaEventRecord(E.ev2, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, E.ev0, E.ev2));
+    CK(cudaEventElapsedTime(&b, E.ev1, E.ev2));
+    E.loop_total_ms = a;
+    E.loop_after_first_ms = b;
+    if (ms_total) *ms_total = a;
+    if (ms_after_first) *ms_after_first = b;
+    return 0;
+}
+
+}  // namespace
+
+// helpers of the operator wrappers
+namespace {
+struct TmpStream {
+    cudaStream_t s = nullptr;
+    std::vector<void *> bufs;
+    ~TmpStream()
+    {
+        for (void *b : bufs) cudaFree(b);
+        if (s) cudaStreamDestroy(s);
+    }
+};
+int op_begin(TmpStream &t)
+{
+    if (ensure_device(E.ready ? E.cfg.device : 0)) return 1;
+    CK(cudaStreamCreate(&t.s));
+    return 0;
+}
+template <typename T>
+int op_buf(TmpStream &t, T **p, size_t n, const void *host)
+{
+    CK(cudaMalloc((void **)p, std::max<size_t>(n * sizeof(T), 16)));
+    t.bufs.push_back(*p);
+    if (host) CK(cudaMemcpyAsync(*p, host, n * sizeof(T), cudaMemcpyHostToDevice, t.s));
+    return 0;
+}
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *llmf90_b200_last_error(void) { return g_err.c_str(); }
+
+int llmf90_b200_free(void)
+{
+    if (E.st) cudaStreamSynchronize(E.st);
+    release_all();
+    return 0;
+}
+
+int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const float *rms_att,
+                     const void *wqkv, const void *wo, const float *rms_ffn, const void *w13,
+                     const void *w2, const float *rms_final, const void *wcls)
+{
+    if (!cfg) return fail("config is null");
+    if (E.ready || E.st) llmf90_b200_free();
+    const llmf90_b200_config c = *cfg;
+    if (c.emb_dim <= 0 || c.hidden_dim <= 0 || c.n_layers <= 0 || c.n_heads <= 0 || c.n_kv_heads <= 0 ||
+        c.vocab_size <= 0 || c.seq_len <= 0)
+        return fail("config: non-positive dimension");
+    if (c.wtype < 0 || c.wtype > 2) return fail("config: unknown wtype %d", c.wtype);
+    if (c.emb_dim % c.n_heads || c.n_heads % c.n_kv_heads) return fail("config: heads do not divide");
+    const int hs = c.emb_dim / c.n_heads;
+    if (hs != 32 && hs != 64 && hs != 128) return fail("config: head size %d not in {32,64,128}", hs);
+    const int colmul = c.wtype == WT_Q4_0 ? 32 : (c.wtype == WT_F16 ? 8 : 4);
+    if (c.emb_dim % colmul || c.hidden_dim % colmul)
+        return fail("config: emb_dim/hidden_dim must be multiples of %d for this wtype", colmul);
+    if (c.tp_size != 1 && c.tp_size != 0)
+        return fail("tensor parallel init must go through llmf90_b200_tp_connect (tp_size=%d)", c.tp_size);
+    if (!tok_emb || !rms_att || !wqkv || !wo || !rms_ffn || !w13 || !w2 || !rms_final || !wcls)
+        return fail("null weight pointer");
+    if (ensure_device(c.device)) return 1;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major < 10)
+        return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device,
+                    prop.major, prop.minor);
+
+    E.cfg = c;
+    E.cfg.tp_size = 1; E.cfg.tp_rank = 0;
+    E.hs = hs; E.kv = c.n_kv_heads * hs; E.nqkv = c.emb_dim + 2 * E.kv; E.kv_mul = c.n_heads / c.n_kv_heads;
+    E.n_sms = prop.multiProcessorCount;
+    E.use_stream = !(c.flags & LLMF90_FLAG_GRANULAR);
+    const int emb = c.emb_dim, hid = c.hidden_dim, L = c.n_layers, V = c.vocab_size, wt = c.wtype;
+    const size_t rs_e = row_stride_bytes(wt, emb), rs_h = row_stride_bytes(wt, hid);
+
+    CK(cudaStreamCreateWithFlags(&E.st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&E.ev0)); CK(cudaEventCreate(&E.ev1)); CK(cudaEventCreate(&E.ev2));
+
+    // ---- weights
+    CK(dalloc(&E.d_emb, (size_t)V * rs_e));
+    CK(dalloc(&E.d_wqkv, (size_t)L * E.nqkv * rs_e));
+    CK(dalloc(&E.d_wo, (size_t)L * emb * rs_e));
+    CK(dalloc(&E.d_w13, (size_t)L * 2 * hid * rs_e));
+    CK(dalloc(&E.d_w2, (size_t)L * emb * rs_h));
+    CK(dalloc(&E.d_wcls, (size_t)V * rs_e));
+    CK(dalloc(&E.d_rms_att, (size_t)L * emb));
+    CK(dalloc(&E.d_rms_ffn, (size_t)L * emb));
+    CK(dalloc(&E.d_rms_final, (size_t)emb));
+    E.weight_bytes = (size_t)V * rs_e * 2 + (size_t)L * (E.nqkv * rs_e + emb * rs_e + 2 * hid * rs_e + emb * rs_h) +
+                     (size_t)(2 * L + 1) * emb * 4;
+    // algorithmic bytes per token, host row sizes
+    {
+        const size_t hb_e = host_row_bytes(wt, emb), hb_h = host_row_bytes(wt, hid);
+        E.active_bytes = (size_t)L * ((size_t)(E.nqkv + emb + 2 * hid) * hb_e + (size_t)emb * hb_h + 2 * emb * 4) +
+                         (size_t)V * hb_e + emb * 4 + hb_e;
+    }
+    {
+        const size_t hb_e = host_row_bytes(wt, emb), hb_h = host_row_bytes(wt, hid);
+        size_t stage_bytes = std::max({(size_t)V * hb_e, (size_t)2 * hid * hb_e, (size_t)emb * hb_h,
+                                       (size_t)E.nqkv * hb_e});
+        uint8_t *stage = nullptr;
+        CK(dalloc(&stage, stage_bytes));
+        int rc = 0;
+        rc |= upload_matrix(E.d_emb, tok_emb, wt, V, emb, V, 0, emb, 0, 0, 0, stage, stage_bytes);
+        rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, V, 0, emb, 0, 0, 0, stage, stage_bytes);
+        for (int l = 0; l < L && !rc; l++) {
+            const uint8_t *s_qkv = (const uint8_t *)wqkv + (size_t)l * E.nqkv * hb_e;
+            const uint8_t *s_wo = (const uint8_t *)wo + (size_t)l * emb * hb_e;
+            const uint8_t *s_w13 = (const uint8_t *)w13 + (size_t)l * 2 * hid * hb_e;
+            const uint8_t *s_w2 = (const uint8_t *)w2 + (size_t)l * emb * hb_h;
+            rc |= upload_matrix(E.d_wqkv + (size_t)l * E.nqkv * rs_e, s_qkv, wt, E.nqkv, emb, E.nqkv, 0,
+                                emb, 0, 0, 0, stage, stage_bytes);
+            rc |= upload_matrix(E.d_wo + (size_t)l * emb * rs_e, s_wo, wt, emb, emb, emb, 0, emb, 0, 0, 0,
+                                stage, stage_bytes);
+            // gate/up rows interleaved so that row 2i = W1 row i, row 2i+1 = W3 row i
+            rc |= upload_matrix(E.d_w13 + (size_t)l * 2 * hid * rs_e, s_w13, wt, 2 * hid, emb, 2 * hid, 0,
+                                emb, 1, 0, hid, stage, stage_bytes);
+            rc |= upload_matrix(E.d_w2 + (size_t)l * emb * rs_h, s_w2, wt, emb, hid, emb, 0, hid, 0, 0, 0,
+                                stage, stage_bytes);
+        }
+        cudaFree(stage);
+        if (rc) { release_all(); return 1; }
+    }
+    CK(cudaMemcpy(E.d_rms_att, rms_att, (size_t)L * emb * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(E.d_rms_ffn, rms_ffn, (size_t)L * emb * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(E.d_rms_final, rms_final, (size_t)emb * 4, cudaMemcpyHostToDevice));
+
+    // ---- RunState, activations
+    const size_t cache = (size_t)L * c.seq_len * E.kv;
+    CK(dalloc(&E.d_kc, cache)); CK(dalloc(&E.d_vc, cache));
+    CK(cudaMemsetAsync(E.d_kc, 0, cache * 4, E.st)); CK(cudaMemsetAsync(E.d_vc, 0, cache * 4, E.st));
+    CK(dalloc(&E.d_rope, (size_t)c.seq_len * (hs / 2)));
+    CK(launch_rope_table(E.d_rope, c.seq_len, hs, E.st));
+    CK(dalloc(&E.d_x, (size_t)emb)); CK(dalloc(&E.d_xb, (size_t)emb)); CK(dalloc(&E.d_qkv, (size_t)E.nqkv));
+    CK(dalloc(&E.d_att, (size_t)emb));
+    CK(dalloc(&E.d_att_part, (size_t)c.n_heads * MAX_SPLITS * (hs + 2)));
+    CK(dalloc(&E.d_h13, (size_t)2 * hid)); CK(dalloc(&E.d_hb, (size_t)hid));
+    CK(dalloc(&E.d_logits, (size_t)V)); CK(dalloc(&E.d_times, (size_t)8));
+    CK(cudaMemsetAsync(E.d_times, 0, 8 * 4, E.st));
+    CK(dalloc(&E.d_tokpos, (size_t)2)); CK(dalloc(&E.d_forced, (size_t)c.seq_len));
+    CK(dalloc(&E.d_out_tokens, (size_t)c.seq_len)); CK(dalloc(&E.d_amax, (size_t)2 * 1024));
+    CK(dalloc(&E.d_bar, (size_t)2));
+    CK(cudaMemsetAsync(E.d_bar, 0, 16, E.st));
+    E.bar_base = 0;
+    CK(cudaMallocHost((void **)&E.h_logits, (size_t)V * 4));
+    CK(cudaMallocHost((void **)&E.h_tokpos, 64));
+
+    if (E.use_stream) {
+        int coop = 0, smem_optin = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
+        CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
+        if (!coop) { release_all(); return fail("device does not support cooperative launch"); }
+        StreamParams &p = E.sp;
+        p = StreamParams{};
+        p.emb = emb; p.hid = hid; p.L = L; p.H = c.n_heads; p.KVH = c.n_kv_heads; p.V = V;
+        p.seq = c.seq_len; p.hs = hs; p.kv = E.kv; p.kv_mul = E.kv_mul; p.nqkv = E.nqkv; p.wtype = wt;
+        auto mk = [&](const uint8_t *base, int rows, int cols, int unit) {
+            PhaseW w{};
+            w.base = base; w.rows = rows; w.cols = cols; w.unit = unit;
+            w.rs = (unsigned)row_stride_bytes(wt, cols);
+            w.layer_stride = (unsigned long long)rows * w.rs;
+            return w;
+        };
+        p.ph[0] = mk(E.d_wqkv, E.nqkv, emb, 2);
+        p.ph[1] = mk(E.d_wo, emb, emb, 1);
+        p.ph[2] = mk(E.d_w13, 2 * hid, emb, 2);
+        p.ph[3] = mk(E.d_w2, emb, hid, 1);
+        p.ph[4] = mk(E.d_wcls, V, emb, 1);
+        int target_slot = 24576, max_slots = 8;
+        if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
+        if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
+        if (plan_stream(p, E.n_sms, smem_optin, target_slot, max_slots, &E.plan)) {
+            release_all();
+            return fail("model rows do not fit the shared-memory ring (row stride too large)");
+        }
+        if (const char *s = getenv("LLMF90_WPS")) {
+            int w = atoi(s);
+            if (w >= 1 && w * E.plan.n_slots <= 15) { E.plan.wps = w; E.plan.threads = (E.plan.n_slots * w + 1) * 32; }
+        }
+        for (int i = 0; i < 5; i++) p.ph[i].rps = std::max(1, E.plan.slot_bytes / (int)p.ph[i].rs);
+        p.emb_table = E.d_emb;
+        p.rms_att = E.d_rms_att; p.rms_ffn = E.d_rms_ffn; p.rms_final = E.d_rms_final;
+        p.rope_tab = E.d_rope;
+        p.x = E.d_x; p.q = E.d_qkv; p.att_part = E.d_att_part; p.hb = E.d_hb; p.logits = E.d_logits;
+        p.kc = E.d_kc; p.vc = E.d_vc;
+        p.bar_ctr = E.d_bar; p.times_dev = E.d_times; p.tokpos = E.d_tokpos; p.amax_scratch = E.d_amax;
+        p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.wps = E.plan.wps;
+        p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
+        if (E.plan.grid > 1024) { release_all(); return fail("grid larger than argmax scratch"); }
+        CK(prepare_stream_kernel(wt, E.plan.smem_bytes));
+    } else {
+        if (build_granular_graph()) { release_all(); return 1; }
+    }
+    CK(cudaStreamSynchronize(E.st));
+    E.ready = true;
+    return 0;
+}
+
+int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
+{
+    if (!E.ready) return fail("llmf90_b200_transformer: engine not initialised");
+    if (token < 1 || token > E.cfg.vocab_size) return fail("token %d out of range 1..%d", token, E.cfg.vocab_size);
+    if (pos < 1 || pos > E.cfg.seq_len) return fail("pos %d out of range 1..%d", pos, E.cfg.seq_len);
+    if (!logits) return fail("logits is null");
+    CK(cudaEventRecord(E.ev0, E.st));
+    if (enqueue_forward(token, pos, false, nullptr, nullptr)) return 1;
+    CK(cudaEventRecord(E.ev1, E.st));
+    CK(cudaMemcpyAsync(E.h_logits, E.d_logits, (size_t)E.cfg.vocab_size * 4, cudaMemcpyDeviceToHost, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    memcpy(logits, E.h_logits, (size_t)E.cfg.vocab_size * 4);
+    CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
+    if (!E.use_stream) E.host_times[3] += E.last_ms;  // granular path: whole forward in bucket 4
+    return 0;
+}
+
+int llmf90_b200_times(float t[5])
+{
+    if (!E.ready) return fail("engine not initialised");
+    float d[5];
+    CK(cudaMemcpy(d, E.d_times, sizeof d, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; i++) t[i] = d[i] + E.host_times[i];
+    return 0;
+}
+
+int llmf90_b200_reset(void)
+{
+    if (!E.ready) return fail("engine not initialised");
+    const size_t cache = (size_t)E.cfg.n_layers * E.cfg.seq_len * E.kv;
+    CK(cudaMemsetAsync(E.d_kc, 0, cache * 4, E.st));
+    CK(cudaMemsetAsync(E.d_vc, 0, cache * 4, E.st));
+    CK(cudaMemsetAsync(E.d_times, 0, 8 * 4, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    for (float &h : E.host_times) h = 0;
+    E.launches = 0; E.forwards = 0;
+    return 0;
+}
+
+int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, int32_t n,
+                                int32_t *out_tokens, float *elapsed_ms)
+{
+    if (!E.ready) return fail("engine not initialised");
+    if (n < 1 || n > E.cfg.seq_len) return fail("n %d out of range 1..%d", n, E.cfg.seq_len);
+    if (n_prompt < 0 || (n_prompt > 0 && !prompt_tokens)) return fail("bad prompt");
+    std::vector<int> forced(E.cfg.seq_len, 0);
+    for (int i = 0; i < n_prompt && i < n; i++) {
+        if (prompt_tokens[i] < 1 || prompt_tokens[i] > E.cfg.vocab_size) return fail("prompt token out of range");
+        forced[i] = prompt_tokens[i];
+    }
+    CK(cudaMemcpyAsync(E.d_forced, forced.data(), (size_t)E.cfg.seq_len * 4, cudaMemcpyHostToDevice, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    float after_first = 0.f;
+    if (device_loop(2 /* BOS, llama2.f90:376 */, 1, n, E.d_forced, E.d_out_tokens, &after_first, nullptr))
+        return 1;
+    CK(cudaMemcpy(out_tokens, E.d_out_tokens, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (elapsed_ms) *elapsed_ms = after_first;
+    return 0;
+}
+
+int llmf90_b200_bench_device_loop(int32_t first_token, int32_t pos0, int32_t n_steps, float *elapsed_ms)
+{
+    if (!E.ready) return fail("engine not initialised");
+    if (pos0 < 1 || n_steps < 1 || pos0 + n_steps - 1 > E.cfg.seq_len) return fail("bad position range");
+    if (first_token < 1 || first_token > E.cfg.vocab_size) return fail("bad token");
+    float total = 0.f;
+    if (device_loop(first_token, pos0, n_steps, nullptr, nullptr, nullptr, &total)) return 1;
+    if (elapsed_ms) *elapsed_ms = total;
+    return 0;
+}
+
+int llmf90_b200_get_stats(llmf90_b200_stats *out)
+{
+    if (!out) return fail("null");
+    memset(out, 0, sizeof *out);
+    if (!E.ready) return fail("engine not initialised");
+    out->kernel_launches = E.launches;
+    out->forward_calls = E.forwards;
+    out->weight_bytes_device = E.weight_bytes;
+    out->active_bytes_per_token = E.active_bytes;
+    out->last_forward_ms = E.last_ms;
+    out->n_sms = E.n_sms;
+    out->last_loop_total_ms = E.loop_total_ms;
+    out->last_loop_after_first_ms = E.loop_after_first_ms;
+    if (E.use_stream) {
+        out->stream_slots = E.plan.n_slots; out->stream_slot_bytes = E.plan.slot_bytes;
+        out->stream_smem_bytes = E.plan.smem_bytes; out->stream_threads = E.plan.threads;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- operator wrappers
+
+int llmf90_b200_matvec(const void *w, int32_t wtype, int32_t rows, int32_t cols, const float *x, float *y)
+{
+    if (!w || !x || !y || rows <= 0 || cols <= 0) return fail("matvec: bad argument");
+    if (wtype < 0 || wtype > 2) return fail("matvec: unknown wtype");
+    const int colmul = wtype == WT_Q4_0 ? 32 : (wtype == WT_F16 ? 8 : 4);
+    if (cols % colmul) return fail("matvec: cols must be a multiple of %d", colmul);
+    TmpStream t;
+    if (op_begin(t)) return 1;
+    uint8_t *d_src, *d_w; float *d_x, *d_y;
+    if (op_buf(t, &d_src, (size_t)rows * host_row_bytes(wtype, cols), w)) return 1;
+    if (op_buf(t, &d_w, (size_t)rows * row_stride_bytes(wtype, cols), nullptr)) return 1;
+    if (op_buf(t, &d_x, (size_t)cols, x)) return 1;
+    if (op_buf(t, &d_y, (size_t)rows, nullptr)) return 1;
+    CK(launch_repack(d_src, wtype, cols, d_w, rows, 0, cols, 0, 0, 0, t.s));
+    CK(launch_matvec(d_w, wtype, rows, cols, d_x, nullptr, d_y, t.s));
+    CK(cudaMemcpyAsync(y, d_y, (size_t)rows * 4, cudaMemcpyDeviceToHost, t.s));
+    CK(cudaStreamSynchronize(t.s));
+    return 0;
+}
+
+int llmf90_b200_rmsnorm(const float *x, const float *w, int32_t n, float *out)
+{
+    if (!x || !w || !out || n <= 0) return fail("rmsnorm: bad argument");
+    TmpStream t;
+    if (op_begin(t)) return 1;
+    float *d_x, *d_w, *d_o;
+    if (op_buf(t, &d_x, (size_t)n, x) || op_buf(t, &d_w, (size_t)n, w) || op_buf(t, &d_o, (size_t)n, nullptr)) return 1;
+    CK(launch_rmsnorm(d_x, d_w, d_o, n, t.s));
+    CK(cudaMemcpyAsync(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, t.s));
+    CK(cudaStreamSynchronize(t.s));
+    return 0;
+}
+
+int llmf90_b200_softmax(const float *x, int32_t n, int32_t s, float *p)
+{
+    if (!x || !p || n <= 0 || s <= 0 || s > n) return fail("softmax: bad argument");
+    TmpStream t;
+    if (op_begin(t)) return 1;
+    float *d_x, *d_p;
+    if (op_buf(t, &d_x, (size_t)n, x) || op_buf(t, &d_p, (size_t)n, nullptr)) return 1;
+    CK(launch_softmax(d_x, d_p, n, s, t.s));
+    CK(cudaMemcpyAsync(p, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost, t.s));
+    CK(cudaStreamSynchronize(t.s));
+    return 0;
+}
+
+int llmf90_b200_rope(float *q, float *k, int32_t emb, int32_t kv, int32_t head_size, int32_t pos)
+{
+    if (!q || !k || emb <= 0 || kv <= 0 || kv > emb || head_size <= 0 || (head_size & 1) || emb % head_size ||
+        kv % head_size || pos < 1)
+        return fail("rope: bad argument");
+    TmpStream t;
+    if (op_begin(t)) return 1;
+    float *d_q, *d_k;
+    if (op_buf(t, &d_q, (size_t)emb, q) || op_buf(t, &d_k, (size_t)kv, k)) return 1;
+    CK(launch_rope(d_q, d_k, emb, kv, head_size, pos, t.s));
+    CK(cudaMemcpyAsync(q, d_q, (size_t)emb * 4, cudaMemcpyDeviceToHost, t.s));
+    CK(cudaMemcpyAsync(k, d_k, (size_t)kv * 4, cudaMemcpyDeviceToHost, t.s));
+    CK(cudaStreamSynchronize(t.s));
+    return 0;
+}
+
+int llmf90_b200_tp_unique_id(void *) { return fail("tensor parallelism is not built in this revision"); }
+int llmf90_b200_tp_connect(const void *, int32_t, int32_t, int32_t)
+{
+    return fail("tensor parallelism is not built in this revision");
+}
+
+}  // extern "C"

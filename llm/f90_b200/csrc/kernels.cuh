@@ -1,0 +1,88 @@
+// kernels.cuh -- host-side launch interface of the sm_100a kernels (ops.cu, stream.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace llmf90 {
+
+// ---------------------------------------------------------------- granular operators (ops.cu)
+// All pointers are device pointers; kernels run on `st`.  Each returns the launch error.
+cudaError_t launch_rmsnorm(const float *x, const float *w, float *out, int n, cudaStream_t st);
+cudaError_t launch_softmax(const float *x, float *p, int n, int s, cudaStream_t st);
+// y[r] = (residual ? residual[r] : 0) + dot(W[r,:], x), W in device row format
+cudaError_t launch_matvec(const uint8_t *W, int wtype, int rows, int cols, const float *x,
+                          const float *residual, float *y, cudaStream_t st);
+// standalone RoPE with on-the-fly trig (llama2.f90:543-559); pos is read from *pos_dev if given
+cudaError_t launch_rope(float *q, float *k, int emb, int kv, int hs, int pos, cudaStream_t st);
+// rope table: tab[(p*hs/2 + j)] = (cos, sin)((p+1) * 10000^-((2j+1)/hs)),  p = 0..seq-1
+cudaError_t launch_rope_table(float2 *tab, int seq, int hs, cudaStream_t st);
+// x = dequant(table row token-1); tokpos = {token, pos} on the device
+cudaError_t launch_embed(const uint8_t *table, int wtype, int cols, const int *tokpos, float *x,
+                         cudaStream_t st);
+// rotate q (in place) and k with the table, append k,v at position pos-1 of this layer's cache
+cudaError_t launch_rope_kv(float *qkv, int emb, int kv, int hs, const float2 *tab,
+                           const int *tokpos, float *kc_layer, float *vc_layer, cudaStream_t st);
+// GQA decode attention for one layer: out[h*hs + d] (llama2.f90:574-598)
+cudaError_t launch_attention(const float *q, const float *kc_layer, const float *vc_layer,
+                             const int *tokpos, float *out, int n_heads, int kv_mul, int hs, int kv,
+                             int seq, cudaStream_t st);
+// hb[i] = silu(h13[2i]) * h13[2i+1]   (rows interleaved gate/up at upload)
+cudaError_t launch_swiglu(const float *h13, float *hb, int hid, cudaStream_t st);
+// out[0] = 1-based index of the first maximum (maxloc, llama2.f90:388); also tokpos update
+cudaError_t launch_argmax(const float *v, int n, int *out_token, cudaStream_t st);
+
+// ---------------------------------------------------------------- upload helpers (ops.cu)
+// dst row r (device format) = src row rowmap(r), columns [col0, col0+ncols) of a host-format
+// matrix already copied to the device.  map_kind: 0 identity (+row0), 1 interleave halves
+// (dst 2i = src i, dst 2i+1 = src half + i).
+cudaError_t launch_repack(const uint8_t *src, int wtype, int src_cols, uint8_t *dst, int dst_rows,
+                          int col0, int ncols, int map_kind, int row0, int half, cudaStream_t st);
+
+// ---------------------------------------------------------------- fused streaming kernel (stream.cu)
+struct PhaseW {
+    const uint8_t *base;     // layer 0 base, device row format
+    unsigned long long layer_stride;  // bytes between layers
+    unsigned int rs;         // row stride in bytes
+    int rows, cols;
+    int unit;                // rows are assigned to CTAs in multiples of `unit`
+    int rps;                 // rows per ring stage
+};
+
+struct StreamParams {
+    int emb, hid, L, H, KVH, V, seq, hs, kv, kv_mul, nqkv, wtype;
+    PhaseW ph[5];            // 0 QKV, 1 WO, 2 W13 (interleaved), 3 W2, 4 CLS
+    const uint8_t *emb_table;  // [V][rs_emb] device row format
+    const float *rms_att, *rms_ffn, *rms_final;
+    const float2 *rope_tab;  // [seq][hs/2]
+    float *x, *q, *att_part, *hb, *logits;  // activations in global memory
+    float *kc, *vc;          // [L][seq][kv]
+    unsigned long long *bar_ctr;
+    unsigned long long bar_base;
+    float *times_dev;        // [5] ms accumulators
+    const int *tokpos;       // device {token, pos} (1-based); used when token < 0
+    int token, pos;          // by-value inputs (token >= 1) -- no H2D copy needed
+    int n_splits;            // attention position splits
+    int do_argmax;           // fuse maxloc after the classifier and write tokpos = {argmax, pos+1}
+    int *amax_scratch;       // [2*grid] per-CTA (value bits, index)
+    const int *forced;       // optional device array of forced next tokens (prompt), or null
+    int *out_tokens;         // optional device array: out_tokens[pos-1] = chosen token
+    // ring geometry
+    int n_slots, slot_bytes, wps;  // wps = consumer warps per slot
+    int xs_floats, res_floats;
+};
+
+struct StreamPlan {
+    int n_slots, slot_bytes, wps, threads, smem_bytes, grid;
+    int xs_floats, res_floats;
+};
+
+// Decide ring geometry for a model on this device; returns non-zero if it cannot fit.
+int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target_slot_bytes,
+                int max_slots, StreamPlan *out);
+cudaError_t prepare_stream_kernel(int wtype, int smem_bytes);
+cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st);
+int stream_barriers_per_launch(const StreamParams &p);
+
+}  // namespace llmf90

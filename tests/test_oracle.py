@@ -1,0 +1,165 @@
+"""The oracle against everything that can pin it without the (uncompilable) Fortran binary:
+the float64 numpy restatement, the Hugging Face golden vectors (canonical mode), the gguf
+package's Q4_0 codec and hand-derived values for the reference's quirks."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from llm.f90_b200 import fixtures as fx
+from llm.f90_b200.layout import Config, TINY, SMALL, F32, F16, Q4_0, row_bytes, active_weight_bytes, \
+    TINYLLAMA, LLAMA2_7B
+from oracle import oracle_c as oc
+from oracle.oracle_np import OracleNP
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "hf_tiny_logits.npz")
+
+
+def test_hf_golden_canonical_mode():
+    """Structure pin: canonical-RoPE oracle == Hugging Face LlamaForCausalLM (f32) to 5e-6."""
+    g = np.load(GOLD)
+    cfg = Config(**TINY, wtype=F32)
+    w = fx.synth_weights(cfg, int(g["seed"]))
+    o = oc.Oracle(w, canonical=True)
+    n = OracleNP(w, canonical=True)
+    for i, t in enumerate(g["tokens_0based"]):
+        lg = o.transformer(int(t) + 1, i + 1)
+        assert rel_err(lg, g["logits"][i]) < 5e-6
+        assert rel_err(n.transformer(int(t) + 1, i + 1), g["logits"][i]) < 5e-6
+
+
+def test_reference_mode_differs_from_canonical():
+    """The quirks are real: reference-mode logits must NOT equal the canonical ones after pos 1."""
+    g = np.load(GOLD)
+    cfg = Config(**TINY, wtype=F32)
+    w = fx.synth_weights(cfg, int(g["seed"]))
+    o = oc.Oracle(w)
+    errs = [rel_err(o.transformer(int(t) + 1, i + 1), g["logits"][i]) for i, t in enumerate(g["tokens_0based"])]
+    assert max(errs[1:]) > 1e-3
+
+
+@pytest.mark.parametrize("wt", [F32, F16, Q4_0])
+@pytest.mark.parametrize("shape", [TINY, SMALL])
+def test_c_oracle_matches_float64(wt, shape):
+    cfg = Config(**shape, wtype=wt)
+    w = fx.synth_weights(cfg, seed=7)
+    prompt = [5, 6, 7, 8, 9]
+    n = 14
+    toks, lg, _ = oc.Oracle(w).generate(prompt, n, want_logits=True)
+    toks64, lg64 = OracleNP(w).generate(prompt, n)
+    assert (toks == toks64).all()
+    assert rel_err(lg, lg64) < 5e-6
+
+
+def test_oracle_threads_do_not_change_results():
+    cfg = Config(**SMALL, wtype=F32)
+    w = fx.synth_weights(cfg, seed=1)
+    a = oc.Oracle(w, n_threads=1).generate([3, 4], 8, want_logits=True)
+    b = oc.Oracle(w, n_threads=4).generate([3, 4], 8, want_logits=True)
+    assert (a[0] == b[0]).all() and np.array_equal(a[1], b[1])
+
+
+def test_rmsnorm_formula():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(257).astype(np.float32)
+    w = rng.standard_normal(257).astype(np.float32)
+    ref = x.astype(np.float64) * w / math.sqrt(float(x.astype(np.float64) @ x) / 257 + 1e-5)
+    assert rel_err(oc.rmsnorm(x, w), ref) < 1e-6
+
+
+def test_softmax_prefix_and_zero_tail():
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(64) * 5).astype(np.float32)
+    p = oc.softmax(x, 10)
+    e = np.exp(x[:10].astype(np.float64) - x[:10].max())
+    assert rel_err(p[:10], e / e.sum()) < 1e-6
+    assert (p[10:] == 0).all()
+    assert abs(float(p.sum()) - 1) < 1e-6
+
+
+def test_rope_quirks_q1_q2():
+    """Q1: exponent (2j+1)/hs; Q2: angle = pos*freq with the 1-based pos (llama2.f90:543-548)."""
+    hs, emb, kv = 8, 16, 8
+    q = np.arange(1, emb + 1, dtype=np.float32)
+    k = np.arange(1, kv + 1, dtype=np.float32) * 0.5
+    pos = 3
+    q2, k2 = oc.rope(q, k, hs, pos)
+    for i in range(0, emb, 2):
+        j = (i // 2) % (hs // 2)
+        ang = pos * 10000.0 ** (-(2 * j + 1) / hs)
+        c, s = math.cos(ang), math.sin(ang)
+        assert abs(q2[i] - (q[i] * c - q[i + 1] * s)) < 1e-5
+        assert abs(q2[i + 1] - (q[i] * s + q[i + 1] * c)) < 1e-5
+        if i < kv:
+            assert abs(k2[i] - (k[i] * c - k[i + 1] * s)) < 1e-5
+    qc, _ = oc.rope(q, k, hs, 1, canonical=True)  # canonical position 0 -> identity
+    assert np.allclose(qc, q)
+
+
+def test_gqa_head_mapping_q3():
+    """Q3: query head h reads kv head h // kv_mul.  Make kv heads distinguishable via Wv."""
+    cfg = Config(emb_dim=32, hidden_dim=32, n_layers=1, n_heads=4, n_kv_heads=2, vocab_size=32, seq_len=8)
+    t = fx.synth_tensors(cfg, 0)
+    w = fx.fuse_tensors(cfg, t)
+    a = OracleNP(w).transformer(3, 1)
+    b = oc.Oracle(w).transformer(3, 1)
+    assert rel_err(b, a) < 5e-6
+
+
+def test_q4_0_codec_matches_gguf_package():
+    gguf = pytest.importorskip("gguf")
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal((6, 128)).astype(np.float32)
+    ours = fx.quantize_q4_0(w)
+    theirs = gguf.quants.quantize(w, gguf.GGMLQuantizationType.Q4_0)
+    assert np.array_equal(ours, theirs.reshape(ours.shape))
+    deq = gguf.quants.dequantize(theirs, gguf.GGMLQuantizationType.Q4_0)
+    assert np.array_equal(fx.dequantize_q4_0(ours, 128), deq.reshape(6, 128))
+    for r in range(6):
+        assert np.array_equal(oc.dequant_row(ours[r], Q4_0, 128), deq.reshape(6, 128)[r])
+
+
+def test_f16_dequant_exact():
+    rng = np.random.default_rng(2)
+    h = rng.standard_normal(64).astype(np.float16)
+    assert np.array_equal(oc.dequant_row(h, F16, 64), h.astype(np.float32))
+
+
+@pytest.mark.parametrize("wt", [F32, F16, Q4_0])
+def test_matvec_operator(wt):
+    rng = np.random.default_rng(3)
+    rows, cols = 37, 96
+    wf = rng.standard_normal((rows, cols)).astype(np.float32)
+    enc = fx.encode_matrix(wf, wt)
+    x = rng.standard_normal(cols).astype(np.float32)
+    ref = fx.decode_matrix(enc, wt, cols).astype(np.float64) @ x
+    assert rel_err(oc.matvec(enc, wt, rows, cols, x), ref) < 1e-6
+
+
+def test_argmax_first_maximum_wins():
+    v = np.array([1, 5, 5, 2, 5], np.float32)
+    assert oc.lib().oracle_argmax1(oc._fp(v), 5) == 2  # maxloc -> 1-based first max (llama2.f90:388)
+
+
+def test_roofline_numerators_match_baseline_md():
+    """BASELINE.md section 2 / SURVEY.md 8a: algorithmic bytes per token."""
+    assert active_weight_bytes(Config(**TINYLLAMA, wtype=F32)) == 4_138_057_728
+    assert active_weight_bytes(Config(**TINYLLAMA, wtype=F16)) == 2_069_213_184
+    assert active_weight_bytes(Config(**LLAMA2_7B, wtype=Q4_0)) == 3_717_548_288
+    assert active_weight_bytes(Config(**LLAMA2_7B, wtype=F16)) == 13_215_227_904
+    assert row_bytes(Q4_0, 4096) == 4096 // 32 * 18
+
+
+def test_forced_prompt_then_greedy():
+    """llama2.f90:376-393: BOS=2 fed first, prompt tokens forced, then maxloc."""
+    cfg = Config(**TINY, wtype=F32)
+    w = fx.synth_weights(cfg, seed=9)
+    o = oc.Oracle(w)
+    toks, lg, _ = o.generate([40, 41, 42], 8, want_logits=True)
+    assert list(toks[:3]) == [40, 41, 42]
+    assert all(int(np.argmax(lg[i])) + 1 == toks[i] for i in range(3, 8))
+    o2 = oc.Oracle(w)
+    assert np.array_equal(o2.transformer(2, 1), lg[0])
+    assert np.array_equal(o2.transformer(40, 2), lg[1])
