@@ -88,6 +88,18 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits);
  * Bucket 2 (RoPE) is fused into bucket 1's kernel phase and reported as 0. */
 int llmf90_b200_times(float t[5]);
 
+/* profiling aid: the fused kernel's fine-grained phase timers in ms (17 buckets per layer loop:
+ * qkv prologue, qkv mat-vec, rope+barrier, attention, barrier, wo prologue, wo mat-vec, barrier,
+ * w13 prologue, w13 mat-vec, swiglu+barrier, w2 prologue, w2 mat-vec, barrier, cls prologue,
+ * cls mat-vec, argmax), measured on CTA 0, accumulated since init/reset. */
+#define LLMF90_N_PHASES 17
+int llmf90_b200_phase_times(float *ms, int32_t n);
+
+/* profiling aid: run one forward and record, for every CTA of the fused kernel, globaltimer stamps
+ * (ns) at the 15 phase edges of `layer` (entries 0..14) and the cycles warp 0 waited for ring data
+ * in the four mat-vec phases (entries 16..19); out is [n_ctas][32]. */
+int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t *out, int32_t n_ctas);
+
 /* zero the KV cache and the timers (the state llama2.f90:316-319 initialises) */
 int llmf90_b200_reset(void);
 

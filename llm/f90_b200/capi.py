@@ -23,7 +23,7 @@ EXPORTS = [
     "llmf90_b200_free", "llmf90_b200_last_error", "llmf90_b200_generate_greedy",
     "llmf90_b200_matvec", "llmf90_b200_rmsnorm", "llmf90_b200_softmax", "llmf90_b200_rope",
     "llmf90_b200_tp_unique_id", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
-    "llmf90_b200_bench_device_loop",
+    "llmf90_b200_bench_device_loop", "llmf90_b200_phase_times", "llmf90_b200_debug_trace",
 ]
 
 
@@ -62,6 +62,8 @@ def load() -> C.CDLL:
     L.llmf90_b200_init.argtypes = [C.POINTER(CConfig)] + [vp] * 9
     L.llmf90_b200_transformer.argtypes = [C.c_int32, C.c_int32, fp]
     L.llmf90_b200_times.argtypes = [fp]
+    L.llmf90_b200_phase_times.argtypes = [fp, C.c_int32]
+    L.llmf90_b200_debug_trace.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]
     L.llmf90_b200_last_error.restype = C.c_char_p
     L.llmf90_b200_generate_greedy.argtypes = [ip, C.c_int32, C.c_int32, ip, fp]
     L.llmf90_b200_matvec.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, fp]
@@ -135,6 +137,20 @@ class Engine:
         t = np.zeros(5, np.float32)
         _check(self.L.llmf90_b200_times(_fp(t)))
         return t
+
+    PHASES = ("qkv_pro", "qkv_mv", "rope_bar", "att", "att_bar", "wo_pro", "wo_mv", "wo_bar", "w13_pro",
+              "w13_mv", "w13_bar", "w2_pro", "w2_mv", "w2_bar", "cls_pro", "cls_mv", "argmax")
+
+    def phase_times(self) -> dict:
+        t = np.zeros(len(self.PHASES), np.float32)
+        _check(self.L.llmf90_b200_phase_times(_fp(t), len(t)))
+        return dict(zip(self.PHASES, (float(v) for v in t)))
+
+    def debug_trace(self, token: int, pos: int, layer: int) -> np.ndarray:
+        n = self.stats()["n_sms"]
+        out = np.zeros((n, 32), np.uint64)
+        _check(self.L.llmf90_b200_debug_trace(token, pos, layer, out.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+        return out
 
     def reset(self) -> None:
         _check(self.L.llmf90_b200_reset())

@@ -55,7 +55,8 @@ struct Engine {
     // RunState + activations
     float *d_kc = nullptr, *d_vc = nullptr;
     float *d_x = nullptr, *d_xb = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_att_part = nullptr,
-          *d_h13 = nullptr, *d_hb = nullptr, *d_logits = nullptr, *d_times = nullptr;
+          *d_h13 = nullptr, *d_hb = nullptr, *d_logits = nullptr;
+    unsigned long long *d_times = nullptr;  // [PH_COUNT + 2]
     int *d_tokpos = nullptr, *d_forced = nullptr, *d_out_tokens = nullptr, *d_amax = nullptr;
     unsigned long long *d_bar = nullptr;
     unsigned long long bar_base = 0;
@@ -86,7 +87,7 @@ void release_all()
     if (E.graph) cudaGraphExecDestroy(E.graph);
     void *ptrs[] = {E.d_emb, E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls, E.d_rms_att, E.d_rms_ffn,
                     E.d_rms_final, E.d_rope, E.d_kc, E.d_vc, E.d_x, E.d_xb, E.d_qkv, E.d_att,
-                    E.d_att_part, E.d_h13, E.d_hb, E.d_logits, E.d_times, E.d_tokpos, E.d_forced,
+                    E.d_att_part, E.d_h13, E.d_hb, E.d_logits, (void *)E.d_times, E.d_tokpos, E.d_forced,
                     E.d_out_tokens, E.d_amax, E.d_bar};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -115,7 +116,7 @@ int upload_matrix(uint8_t *dst, const void *src_host, int wtype, int src_rows, i
 
 int n_splits_for(int pos)
 {
-    int s = (pos + 63) / 64;
+    int s = (pos + 255) / 256;
     return std::max(1, std::min(MAX_SPLITS, s));
 }
 
@@ -386,10 +387,10 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     CK(launch_rope_table(E.d_rope, c.seq_len, hs, E.st));
     CK(dalloc(&E.d_x, (size_t)emb)); CK(dalloc(&E.d_xb, (size_t)emb)); CK(dalloc(&E.d_qkv, (size_t)E.nqkv));
     CK(dalloc(&E.d_att, (size_t)emb));
-    CK(dalloc(&E.d_att_part, (size_t)c.n_heads * MAX_SPLITS * (hs + 2)));
+    CK(dalloc(&E.d_att_part, (size_t)c.n_heads * MAX_SPLITS * (hs + 4)));
     CK(dalloc(&E.d_h13, (size_t)2 * hid)); CK(dalloc(&E.d_hb, (size_t)hid));
-    CK(dalloc(&E.d_logits, (size_t)V)); CK(dalloc(&E.d_times, (size_t)8));
-    CK(cudaMemsetAsync(E.d_times, 0, 8 * 4, E.st));
+    CK(dalloc(&E.d_logits, (size_t)V)); CK(dalloc(&E.d_times, (size_t)(PH_COUNT + 2)));
+    CK(cudaMemsetAsync(E.d_times, 0, (PH_COUNT + 2) * 8, E.st));
     CK(dalloc(&E.d_tokpos, (size_t)2)); CK(dalloc(&E.d_forced, (size_t)c.seq_len));
     CK(dalloc(&E.d_out_tokens, (size_t)c.seq_len)); CK(dalloc(&E.d_amax, (size_t)2 * 1024));
     CK(dalloc(&E.d_bar, (size_t)2));
@@ -419,13 +420,15 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.ph[2] = mk(E.d_w13, 2 * hid, emb, 2);
         p.ph[3] = mk(E.d_w2, emb, hid, 1);
         p.ph[4] = mk(E.d_wcls, V, emb, 1);
-        int target_slot = 24576, max_slots = 8;
+        int target_slot = 24576, max_slots = (wt == WT_Q4_0) ? 7 : 7;
         if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
         if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
-        if (plan_stream(p, E.n_sms, smem_optin, target_slot, max_slots, &E.plan)) {
+        if (plan_stream(p, E.n_sms, smem_optin - 1024 /* static smem */, target_slot, max_slots, &E.plan)) {
             release_all();
             return fail("model rows do not fit the shared-memory ring (row stride too large)");
         }
+        p.pf_stages = 0;
+        if (const char *s = getenv("LLMF90_PF_STAGES")) p.pf_stages = std::max(0, atoi(s));
         if (const char *s = getenv("LLMF90_WPS")) {
             int w = atoi(s);
             if (w >= 1 && w * E.plan.n_slots <= 15) { E.plan.wps = w; E.plan.threads = (E.plan.n_slots * w + 1) * 32; }
@@ -434,13 +437,13 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.emb_table = E.d_emb;
         p.rms_att = E.d_rms_att; p.rms_ffn = E.d_rms_ffn; p.rms_final = E.d_rms_final;
         p.rope_tab = E.d_rope;
-        p.x = E.d_x; p.q = E.d_qkv; p.att_part = E.d_att_part; p.hb = E.d_hb; p.logits = E.d_logits;
+        p.x = E.d_x; p.q = E.d_qkv; p.att = E.d_att; p.att_part = E.d_att_part; p.hb = E.d_hb; p.logits = E.d_logits;
         p.kc = E.d_kc; p.vc = E.d_vc;
-        p.bar_ctr = E.d_bar; p.times_dev = E.d_times; p.tokpos = E.d_tokpos; p.amax_scratch = E.d_amax;
+        p.bar_ctr = E.d_bar; p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos; p.amax_scratch = E.d_amax;
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.wps = E.plan.wps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
         if (E.plan.grid > 1024) { release_all(); return fail("grid larger than argmax scratch"); }
-        CK(prepare_stream_kernel(wt, E.plan.smem_bytes));
+        CK(prepare_stream_kernel(wt, E.plan.threads, E.plan.smem_bytes));
     } else {
         if (build_granular_graph()) { release_all(); return 1; }
     }
@@ -466,11 +469,48 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
     return 0;
 }
 
+int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t *out, int32_t n_ctas)
+{
+    if (!E.ready || !E.use_stream) return fail("debug_trace: needs the fused streaming engine");
+    if (!out || n_ctas < E.plan.grid) return fail("debug_trace: buffer must hold %d x 32 entries", E.plan.grid);
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc((void **)&d, (size_t)E.plan.grid * 32 * 8));
+    CK(cudaMemset(d, 0, (size_t)E.plan.grid * 32 * 8));
+    E.sp.trace = d; E.sp.trace_layer = layer;
+    int rc = enqueue_forward(token, pos, false, nullptr, nullptr);
+    E.sp.trace = nullptr;
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(E.st);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)E.plan.grid * 32 * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail("debug_trace: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int llmf90_b200_phase_times(float *ms, int32_t n)
+{
+    if (!E.ready) return fail("engine not initialised");
+    if (!ms || n < 1) return fail("phase_times: bad argument");
+    unsigned long long c[PH_COUNT + 2];
+    CK(cudaStreamSynchronize(E.st));
+    CK(cudaMemcpy(c, E.d_times, sizeof c, cudaMemcpyDeviceToHost));
+    // cycles -> ms with the kernel's own (globaltimer ns / clock64 cycles) ratio
+    const double ns_per_cycle = c[PH_COUNT] ? (double)c[PH_COUNT + 1] / (double)c[PH_COUNT] : 0.0;
+    for (int i = 0; i < n; i++) ms[i] = i < PH_COUNT ? (float)((double)c[i] * ns_per_cycle * 1e-6) : 0.f;
+    return 0;
+}
+
 int llmf90_b200_times(float t[5])
 {
     if (!E.ready) return fail("engine not initialised");
-    float d[5];
-    CK(cudaMemcpy(d, E.d_times, sizeof d, cudaMemcpyDeviceToHost));
+    float ph[PH_COUNT];
+    if (llmf90_b200_phase_times(ph, PH_COUNT)) return 1;
+    // the reference's five buckets (llama2.f90:526-638): 1 rmsnorm+QKV, 2 RoPE+KV append,
+    // 3 attention, 4 Wo+FFN, 5 final norm+classifier
+    float d[5] = {ph[PH_QKV_PRO] + ph[PH_QKV_MV], ph[PH_ROPE_BAR], ph[PH_ATT] + ph[PH_ATT_BAR], 0.f,
+                  ph[PH_CLS_PRO] + ph[PH_CLS_MV] + ph[PH_ARGMAX]};
+    for (int i = PH_WO_PRO; i <= PH_W2_BAR; i++) d[3] += ph[i];
     for (int i = 0; i < 5; i++) t[i] = d[i] + E.host_times[i];
     return 0;
 }
@@ -481,7 +521,7 @@ int llmf90_b200_reset(void)
     const size_t cache = (size_t)E.cfg.n_layers * E.cfg.seq_len * E.kv;
     CK(cudaMemsetAsync(E.d_kc, 0, cache * 4, E.st));
     CK(cudaMemsetAsync(E.d_vc, 0, cache * 4, E.st));
-    CK(cudaMemsetAsync(E.d_times, 0, 8 * 4, E.st));
+    CK(cudaMemsetAsync(E.d_times, 0, (PH_COUNT + 2) * 8, E.st));
     CK(cudaStreamSynchronize(E.st));
     for (float &h : E.host_times) h = 0;
     E.launches = 0; E.forwards = 0;

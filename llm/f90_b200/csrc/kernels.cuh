@@ -41,6 +41,14 @@ cudaError_t launch_repack(const uint8_t *src, int wtype, int src_cols, uint8_t *
                           int col0, int ncols, int map_kind, int row0, int half, cudaStream_t st);
 
 // ---------------------------------------------------------------- fused streaming kernel (stream.cu)
+// fine-grained phase timers of the streaming kernel (CTA 0); _PRO = prologue (activation
+// vector load / rmsnorm / attention merge), _MV = ring consumption, _BAR = epilogue + grid barrier
+enum {
+    PH_QKV_PRO, PH_QKV_MV, PH_ROPE_BAR, PH_ATT, PH_ATT_BAR, PH_WO_PRO, PH_WO_MV, PH_WO_BAR,
+    PH_W13_PRO, PH_W13_MV, PH_W13_BAR, PH_W2_PRO, PH_W2_MV, PH_W2_BAR, PH_CLS_PRO, PH_CLS_MV,
+    PH_ARGMAX, PH_COUNT
+};
+
 struct PhaseW {
     const uint8_t *base;     // layer 0 base, device row format
     unsigned long long layer_stride;  // bytes between layers
@@ -56,14 +64,17 @@ struct StreamParams {
     const uint8_t *emb_table;  // [V][rs_emb] device row format
     const float *rms_att, *rms_ffn, *rms_final;
     const float2 *rope_tab;  // [seq][hs/2]
-    float *x, *q, *att_part, *hb, *logits;  // activations in global memory
+    float *x, *q, *att, *att_part, *hb, *logits;  // activations in global memory
     float *kc, *vc;          // [L][seq][kv]
     unsigned long long *bar_ctr;
     unsigned long long bar_base;
-    float *times_dev;        // [5] ms accumulators
+    unsigned long long *phase_cycles;  // [PH_COUNT + 2] SM-cycle accumulators (+ total cycles, total ns)
     const int *tokpos;       // device {token, pos} (1-based); used when token < 0
     int token, pos;          // by-value inputs (token >= 1) -- no H2D copy needed
     int n_splits;            // attention position splits
+    unsigned long long *trace;  // optional [grid][32] debug trace of layer `trace_layer` (or null)
+    int trace_layer;
+    int pf_stages;           // L2 prefetch distance beyond the shared-memory ring, in stages
     int do_argmax;           // fuse maxloc after the classifier and write tokpos = {argmax, pos+1}
     int *amax_scratch;       // [2*grid] per-CTA (value bits, index)
     const int *forced;       // optional device array of forced next tokens (prompt), or null
@@ -81,7 +92,7 @@ struct StreamPlan {
 // Decide ring geometry for a model on this device; returns non-zero if it cannot fit.
 int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target_slot_bytes,
                 int max_slots, StreamPlan *out);
-cudaError_t prepare_stream_kernel(int wtype, int smem_bytes);
+cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes);
 cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st);
 int stream_barriers_per_launch(const StreamParams &p);
 

@@ -6,14 +6,16 @@
 // token and does ~0.5 flop per byte, so the only thing that matters is keeping HBM busy
 // across the ~110 dependent mat-vec phases of a token.  One persistent cooperative CTA per SM:
 //
-//   * a PRODUCER warp walks the CTA's private, fully static weight schedule -- for every layer
-//     its contiguous row range of Wqkv, Wo, W13 (gate/up rows interleaved at upload), W2 and
-//     finally Wcls -- and streams it with 1-D TMA bulk copies (cp.async.bulk, mbarrier
-//     complete_tx) into a ring of shared-memory slots.  Weights do not depend on activations,
-//     so the producer never waits for a grid barrier: while the consumers finish a phase,
-//     synchronise the grid and rebuild the activation vector, the ring keeps filling.
+//   * a PRODUCER warp walks the CTA's private, fully static schedule -- the token's embedding
+//     row, then for every layer the rms_att vector, its contiguous row range of Wqkv and Wo, the
+//     rms_ffn vector, its rows of W13 (gate/up rows interleaved at upload) and W2, finally the
+//     rms_final vector and its rows of Wcls -- and streams it with 1-D TMA bulk copies
+//     (cp.async.bulk, mbarrier complete_tx) into a ring of shared-memory slots.  Nothing in the
+//     schedule depends on activations, so the producer never waits for a grid barrier: while
+//     the consumers finish a phase, synchronise the grid and rebuild the activation vector, the
+//     ring keeps filling.
 //   * CONSUMER warps each own one ring slot: wait on its `full` mbarrier, do the dot products
-//     of the rows in the slot against the activation vector held in shared memory (f16 and
+//     of the rows in the slot against the activation vector (registers / shared memory; f16 and
 //     q4_0 dequantisation fused into the load, f32 accumulation, warp-shuffle reduction),
 //     release the slot with an `empty` mbarrier arrive.
 //   * Between phases the consumers run the tiny epilogues in place -- RoPE + KV-cache append,
@@ -21,7 +23,12 @@
 //     (release/acquire counter in L2); the next phase's prologue re-reads the full vector
 //     (rmsnorm recomputed redundantly per CTA: 8-16 KB from L2).
 //   * Attention (scores, softmax, value gather) is a phase of the same kernel: (head, split)
-//     items over the CTAs, online softmax, combined in the Wo prologue.
+//     items over the CTAs, online softmax, merged in the Wo prologue when there are splits.
+//
+// All ring bookkeeping is incremental (no integer division on the hot path), the big pieces
+// are deliberately NOT inlined (one copy of the mat-vec code serves all five weight phases: the
+// whole kernel stays within the instruction cache), and the per-CTA row ranges are computed
+// once per launch into shared memory.
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
@@ -30,12 +37,18 @@ namespace llmf90 {
 
 constexpr int MAX_SLOTS = 16;
 constexpr int MAX_CONS_WARPS = 15;  // + 1 producer warp = 512 threads -> 128 registers/thread
-constexpr int CONS_BAR = 1;  // named barrier id used by the consumer warps
+constexpr int CONS_BAR = 1;         // named barrier id used by the consumer warps
 
 struct SmemView {
     uint8_t *ring;
     float *xs, *res, *red;
     uint64_t *full, *empty;
+};
+
+// per-launch constants of this CTA, computed once into shared memory
+struct CtaPlan {
+    PhaseW ph[5];
+    int r0[5], r1[5], nst[5];
 };
 
 __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
@@ -47,7 +60,7 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
     v.xs = reinterpret_cast<float *>(smem + off);
     off += (size_t)P.xs_floats * 4;
     v.res = reinterpret_cast<float *>(smem + off);
-    off += (size_t)P.res_floats * 4;
+    off += (size_t)P.res_floats * 4 * 2;
     v.red = reinterpret_cast<float *>(smem + off);
     off += 64 * 4;
     v.full = reinterpret_cast<uint64_t *>(smem + off);
@@ -57,7 +70,7 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
 
 static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats)
 {
-    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 + 64 * 4 +
+    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 * 2 + 64 * 4 +
            2 * MAX_SLOTS * 8;
 }
 
@@ -68,23 +81,90 @@ __host__ __device__ inline void cta_rows(const PhaseW &ph, int cta, int G, int &
     r1 = (int)((long long)(cta + 1) * U / G) * ph.unit;
 }
 
-// ------------------------------------------------------------------ producer
-__device__ __forceinline__ void produce_phase(const PhaseW &ph, int layer, const StreamParams &P,
-                                              const SmemView &sv, uint32_t &s, uint64_t pol)
+// stage index = div * n_slots + mod, advanced without division
+struct RingPos {
+    uint32_t mod, div;
+};
+__device__ __forceinline__ void ring_advance(RingPos &p, uint32_t n, uint32_t ns)
 {
-    int r0, r1;
-    cta_rows(ph, blockIdx.x, gridDim.x, r0, r1);
-    const int nrows = r1 - r0;
-    const uint8_t *src = ph.base + (size_t)layer * ph.layer_stride + (size_t)r0 * ph.rs;
-    for (int r = 0; r < nrows; r += ph.rps) {
-        const int n = min(ph.rps, nrows - r);
-        const uint32_t bytes = (uint32_t)n * ph.rs;
-        const uint32_t slot = s % (uint32_t)P.n_slots, k = s / (uint32_t)P.n_slots;
+    p.mod += n;
+    while (p.mod >= ns) { p.mod -= ns; p.div++; }
+}
+
+// ------------------------------------------------------------------ producer
+// Segment order (linear index q): 0 = embedding row of the token; per layer l, base 1 + 6l:
+// +0 rms_att vector, +1 QKV, +2 WO, +3 rms_ffn vector, +4 W13, +5 W2; then rms_final vector, CLS.
+// The small f32 vectors and the embedding row travel through the ring like weights ("vector
+// stages", one stage each, read by all consumer warps in the prologue) so that no prologue waits
+// for a demand miss queued behind megabytes of in-flight weight requests.
+struct StageIter {
+    int q, q_end, k6, layer;  // k6 = position inside the layer's six segments
+    int r, nrows, rps;
+    unsigned int rs;
+    const uint8_t *src;
+    const CtaPlan *cp;
+    int token;
+
+    __device__ __forceinline__ void vec(const void *p, unsigned int bytes)
+    {
+        r = 0; nrows = 1; rps = 1; rs = bytes;
+        src = reinterpret_cast<const uint8_t *>(p);
+    }
+    __device__ __forceinline__ bool rows(int ph, int l)
+    {
+        const int n = cp->r1[ph] - cp->r0[ph];
+        if (n <= 0) return false;
+        const PhaseW &w = cp->ph[ph];
+        r = 0; nrows = n; rps = w.rps; rs = w.rs;
+        src = w.base + (size_t)l * w.layer_stride + (size_t)cp->r0[ph] * w.rs;
+        return true;
+    }
+    // position on the next non-empty segment at or after q
+    __device__ __forceinline__ void settle(const StreamParams &P)
+    {
+        const int qf = 1 + 6 * P.L;
+        for (; q < q_end; q++, k6++) {
+            if (k6 == 6) { k6 = 0; layer++; }
+            if (q == 0) { vec(P.emb_table + (size_t)(token - 1) * cp->ph[0].rs, cp->ph[0].rs); return; }
+            if (q == qf) { vec(P.rms_final, (unsigned)P.emb * 4u); return; }
+            if (q > qf) { if (rows(4, 0)) return; continue; }
+            if (k6 == 0) { vec(P.rms_att + (size_t)layer * P.emb, (unsigned)P.emb * 4u); return; }
+            if (k6 == 3) { vec(P.rms_ffn + (size_t)layer * P.emb, (unsigned)P.emb * 4u); return; }
+            if (rows(k6 < 3 ? k6 - 1 : k6 - 2, layer)) return;
+        }
+    }
+    __device__ __forceinline__ void init(const StreamParams &P, const CtaPlan *plan, int tok)
+    {
+        cp = plan; token = tok; q = 0; q_end = 3 + 6 * P.L; k6 = -1; layer = 0;
+        settle(P);
+    }
+    __device__ __forceinline__ bool next(const StreamParams &P, const uint8_t *&p, uint32_t &bytes)
+    {
+        if (q >= q_end) return false;
+        const int n = min(rps, nrows - r);
+        p = src + (size_t)r * rs;
+        bytes = (uint32_t)n * rs;
+        r += n;
+        if (r >= nrows) { q++; k6++; settle(P); }
+        return true;
+    }
+};
+
+__device__ __forceinline__ void producer_loop(const StreamParams &P, const SmemView &sv, const CtaPlan *cp,
+                                              int token)
+{
+    const uint64_t pol = l2_policy_evict_first();
+    StageIter it;
+    it.init(P, cp, token);
+    const uint32_t ns = (uint32_t)P.n_slots;
+    uint32_t slot = 0, k = 0;
+    const uint8_t *src;
+    uint32_t bytes;
+    while (it.next(P, src, bytes)) {
         mbar_wait(&sv.empty[slot], (k & 1u) ^ 1u);
         mbar_arrive_expect_tx(&sv.full[slot], bytes);
-        bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, src + (size_t)r * ph.rs, bytes,
-                 &sv.full[slot], pol);
-        s++;
+        bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, src, bytes, &sv.full[slot], pol);
+        if (++slot == ns) { slot = 0; k++; }
     }
 }
 
@@ -92,6 +172,13 @@ __device__ __forceinline__ void produce_phase(const PhaseW &ph, int layer, const
 struct Cons {
     int tid, warp, lane, nt, nw;  // within the consumer group
     int slot, sub;                // ring slot this warp serves, sub-warp index within the slot
+};
+
+// ring cursor of the consumer side: `pos` = next stage of the schedule, `my_div` = how many times
+// this warp's slot has been consumed (so its next stage is my_div * n_slots + slot)
+struct CState {
+    RingPos pos;
+    uint32_t my_div;
 };
 
 __device__ __forceinline__ void cons_sync(const Cons &c) { named_bar_sync(CONS_BAR, c.nt); }
@@ -122,210 +209,426 @@ __device__ __forceinline__ void rows_to_res(const uint8_t *sp, size_t rs, const 
     }
 }
 
+// consume the `nst` stages of one weight phase: res[i] = dot(row r0 + i, xs)
 template <int WT>
-__device__ __forceinline__ void consume_phase(const PhaseW &ph, const StreamParams &P,
-                                              const SmemView &sv, const Cons &c, uint32_t &s)
+__device__ __forceinline__ void consume_phase(const PhaseW *ph, int nrows, int nst, const StreamParams &P,
+                                              const SmemView &sv, const Cons &c, CState &cs,
+                                              long long *wait_cycles)
 {
-    int r0, r1;
-    cta_rows(ph, blockIdx.x, gridDim.x, r0, r1);
-    const int nrows = r1 - r0;
-    const uint32_t nst = (uint32_t)((nrows + ph.rps - 1) / ph.rps);
-    const uint32_t ns = (uint32_t)P.n_slots;
-    uint32_t st = s + (((uint32_t)c.slot + ns - s % ns) % ns);
+    const int ns = P.n_slots, rps = ph->rps, cols = ph->cols;
+    const size_t rs = ph->rs;
     const uint8_t *slot_ptr = sv.ring + (size_t)c.slot * P.slot_bytes;
-    for (; st < s + nst; st += ns) {
-        mbar_wait(&sv.full[c.slot], (st / ns) & 1u);
-        const int rbase = (int)(st - s) * ph.rps;
-        const int n = min(ph.rps, nrows - rbase);
-        // rows of this stage are split between the wps warps that share the slot
-        const int per = (n + P.wps - 1) / P.wps;
-        int i = c.sub * per;
-        const int iend = min(n, i + per);
-        for (; i + 4 <= iend; i += 4)
-            rows_to_res<WT, 4>(slot_ptr + (size_t)i * ph.rs, ph.rs, sv.xs, ph.cols, c.lane,
-                               sv.res + rbase + i);
-        if (i + 2 <= iend) {
-            rows_to_res<WT, 2>(slot_ptr + (size_t)i * ph.rs, ph.rs, sv.xs, ph.cols, c.lane,
-                               sv.res + rbase + i);
-            i += 2;
+    // offset of this warp's next stage from the start of the phase
+    int off = ((int)cs.my_div - (int)cs.pos.div) * ns + (c.slot - (int)cs.pos.mod);
+    for (; off < nst; off += ns) {
+        if (wait_cycles) {
+            const long long w0 = clock64();
+            mbar_wait(&sv.full[c.slot], cs.my_div & 1u);
+            wait_cycles[0] += clock64() - w0;
+        } else {
+            mbar_wait(&sv.full[c.slot], cs.my_div & 1u);
         }
-        if (i < iend)
-            rows_to_res<WT, 1>(slot_ptr + (size_t)i * ph.rs, ph.rs, sv.xs, ph.cols, c.lane,
-                               sv.res + rbase + i);
+        const long long tc0 = wait_cycles ? clock64() : 0ll;
+        const int rbase = off * rps;
+        const int n = min(rps, nrows - rbase);
+        if constexpr (WT != WT_Q4_0) {
+            // two warps per slot split the COLUMNS: each writes its own plane of partial results
+            const int nunits = cols >> (WT == WT_F32 ? 2 : 3);
+            int ub = 0, nu = nunits;
+            if (P.wps == 2) {
+                const int h = min(nunits, ((nunits + 63) >> 6) << 5);  // first half, a multiple of 32 units
+                ub = c.sub * h;
+                nu = c.sub ? nunits - h : h;
+            }
+            stage_rows<WT>(slot_ptr, rs, n, sv.xs, ub, nu, c.lane, sv.res + c.sub * P.res_floats + rbase);
+        } else {
+            // q4_0: the wps warps that share the slot split the ROWS
+            int i = 0, iend = n;
+            if (P.wps == 2) {
+                const int h = (n + 1) >> 1;
+                i = c.sub * h;
+                iend = min(n, i + h);
+            }
+            for (; i + 4 <= iend; i += 4)
+                rows_to_res<WT, 4>(slot_ptr + (size_t)i * rs, rs, sv.xs, cols, c.lane, sv.res + rbase + i);
+            if (i + 2 <= iend) {
+                rows_to_res<WT, 2>(slot_ptr + (size_t)i * rs, rs, sv.xs, cols, c.lane, sv.res + rbase + i);
+                i += 2;
+            }
+            if (i < iend)
+                rows_to_res<WT, 1>(slot_ptr + (size_t)i * rs, rs, sv.xs, cols, c.lane, sv.res + rbase + i);
+        }
         __syncwarp();
+        if (wait_cycles) { wait_cycles[4] += clock64() - tc0; wait_cycles[8] += 1; }
         if (c.lane == 0) mbar_arrive(&sv.empty[c.slot]);
+        cs.my_div++;
     }
-    s += nst;
+    ring_advance(cs.pos, (uint32_t)nst, (uint32_t)ns);
 }
 
-// grid-wide barrier over the consumer groups of all CTAs (the producers never join)
+// grid-wide barrier over the consumer groups of all CTAs (the producers never join).  bar.sync
+// orders the CTA's writes before thread 0's gpu-scope release; the acquire load + bar.sync
+// make every other CTA's writes visible to all consumer threads.
 __device__ __forceinline__ void grid_sync(const StreamParams &P, const Cons &c, uint32_t &nbar)
 {
     cons_sync(c);
     if (c.tid == 0) {
-        __threadfence();
         red_release_add_u64(P.bar_ctr, 1ull);
         const unsigned long long target = P.bar_base + (unsigned long long)(nbar + 1) * gridDim.x;
         while (ld_acquire_u64(P.bar_ctr) < target) {
         }
-        __threadfence();
     }
     cons_sync(c);
     nbar++;
 }
 
-// xs = rmsnorm(src) * w   (llama2.f90:450-457); src is read through L2 (written by other CTAs)
-template <int WT>
-__device__ __forceinline__ void load_x_norm(const float *src, const uint8_t *emb_row,
-                                            const float *__restrict__ wn, const StreamParams &P,
-                                            const SmemView &sv, const Cons &c)
+// ---- vector stages: every consumer thread waits for the stage and reads what it needs; after
+// the consumer-wide barrier that ends the prologue the warps that own the slot hand it back
+__device__ __forceinline__ const uint8_t *vec_stage_wait(const StreamParams &P, const SmemView &sv,
+                                                         const RingPos &at)
 {
-    const int n = P.emb;
-    float ss = 0.f;
-    for (int e = c.tid; e < n; e += c.nt) {
-        const float v = emb_row ? row_elem(emb_row, P.wtype, n, e) : __ldcg(src + e);
-        sv.xs[xs_index<WT>(e)] = v;
-        ss = fmaf(v, v, ss);
+    mbar_wait(&sv.full[at.mod], at.div & 1u);
+    return sv.ring + (size_t)at.mod * P.slot_bytes;
+}
+// call in stage order, after a cons_sync that follows the last read of the stage
+__device__ __forceinline__ void vec_stage_release(const StreamParams &P, const SmemView &sv, const Cons &c,
+                                                  CState &cs)
+{
+    if ((uint32_t)c.slot == cs.pos.mod) {
+        if (c.lane == 0) mbar_arrive(&sv.empty[cs.pos.mod]);
+        cs.my_div++;
     }
-    const float tot = cons_sum(ss, c, sv.red);
-    const float xn = sqrtf(tot / (float)n + 1e-5f);
-    for (int e = c.tid; e < n; e += c.nt) {
-        const int ix = xs_index<WT>(e);
-        sv.xs[ix] = sv.xs[ix] * wn[e] / xn;
+    ring_advance(cs.pos, 1u, (uint32_t)P.n_slots);
+}
+
+// ---- activation-vector prologues.  Every CTA needs the whole vector; it is 8-44 KB and was
+// just written by the other CTAs, so it comes from L2.  All loads of a thread are issued
+// before the first use (PRO_V independent 128-bit requests in flight per thread): one L2 round
+// trip per prologue instead of one per element.
+template <int WT>
+__device__ __forceinline__ void store_x4(float *xs, int j4, const float4 v)
+{
+    int idx = j4;
+    if (WT == WT_Q4_0) idx = (j4 & ~7) | ((j4 & 7) ^ ((j4 >> 3) & 7));  // == xs_index<WT> per float4
+    reinterpret_cast<float4 *>(xs)[idx] = v;
+}
+
+__device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int cols, int j4)
+{
+    return make_float4(row_elem(row, wtype, cols, 4 * j4), row_elem(row, wtype, cols, 4 * j4 + 1),
+                       row_elem(row, wtype, cols, 4 * j4 + 2), row_elem(row, wtype, cols, 4 * j4 + 3));
+}
+
+// xs = rmsnorm(x) * w   (llama2.f90:450-457).  x comes from global memory (L2) or, for layer 0,
+// from the embedding row in a ring slot; w from a ring slot.  With an embedding row the CTA also
+// writes its own residual slice x[wr0..wr1) for the Wo epilogue (llama2.f90:520).
+template <int WT, int PRO_V>
+__device__ __forceinline__ void load_x_norm(const float *src, const uint8_t *emb_row,
+                                            const float *wn /* shared */, const StreamParams &P,
+                                            const SmemView &sv, const Cons &c, int wr0, int wr1)
+{
+    const int n = P.emb, n4 = n >> 2;
+    const float4 *src4 = reinterpret_cast<const float4 *>(src);
+    const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
+    if (n4 <= PRO_V * c.nt) {
+        float4 v[PRO_V], wv[PRO_V];
+#pragma unroll
+        for (int k = 0; k < PRO_V; k++) {
+            const int j = c.tid + k * c.nt;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[k] = v[k];
+            if (j < n4) {
+                v[k] = emb_row ? emb_row4(emb_row, P.wtype, n, j) : __ldcg(src4 + j);
+                wv[k] = wn4[j];
+            }
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < PRO_V; k++) {
+            ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss);
+            ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+        }
+        if (emb_row) {
+#pragma unroll
+            for (int k = 0; k < PRO_V; k++) {
+                const int e = 4 * (c.tid + k * c.nt);
+                if (e + 3 >= wr0 && e < wr1) {
+                    if (e >= wr0 && e < wr1) P.x[e] = v[k].x;
+                    if (e + 1 >= wr0 && e + 1 < wr1) P.x[e + 1] = v[k].y;
+                    if (e + 2 >= wr0 && e + 2 < wr1) P.x[e + 2] = v[k].z;
+                    if (e + 3 >= wr0 && e + 3 < wr1) P.x[e + 3] = v[k].w;
+                }
+            }
+        }
+        const float tot = cons_sum(ss, c, sv.red);
+        const float inv = 1.0f / sqrtf(tot / (float)n + 1e-5f);
+#pragma unroll
+        for (int k = 0; k < PRO_V; k++) {
+            const int j = c.tid + k * c.nt;
+            if (j < n4)
+                store_x4<WT>(sv.xs, j, make_float4(v[k].x * wv[k].x * inv, v[k].y * wv[k].y * inv,
+                                                   v[k].z * wv[k].z * inv, v[k].w * wv[k].w * inv));
+        }
+    } else {  // very wide models: two passes through shared memory
+        float ss = 0.f;
+        for (int j = c.tid; j < n4; j += c.nt) {
+            const float4 v = emb_row ? emb_row4(emb_row, P.wtype, n, j) : __ldcg(src4 + j);
+            store_x4<WT>(sv.xs, j, v);
+            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+            if (emb_row) {
+                const int e = 4 * j;
+                if (e >= wr0 && e < wr1) P.x[e] = v.x;
+                if (e + 1 >= wr0 && e + 1 < wr1) P.x[e + 1] = v.y;
+                if (e + 2 >= wr0 && e + 2 < wr1) P.x[e + 2] = v.z;
+                if (e + 3 >= wr0 && e + 3 < wr1) P.x[e + 3] = v.w;
+            }
+        }
+        const float tot = cons_sum(ss, c, sv.red);
+        const float inv = 1.0f / sqrtf(tot / (float)n + 1e-5f);
+        for (int e = c.tid; e < n; e += c.nt) {
+            const int ix = xs_index<WT>(e);
+            sv.xs[ix] = sv.xs[ix] * wn[e] * inv;
+        }
+    }
+    cons_sync(c);
+}
+
+template <int WT, int PRO_V>
+__device__ __forceinline__ void load_x_plain(const float *src, int n, const SmemView &sv, const Cons &c)
+{
+    const int n4 = n >> 2;
+    const float4 *src4 = reinterpret_cast<const float4 *>(src);
+    for (int base = 0; base < n4; base += PRO_V * c.nt) {
+        float4 v[PRO_V];
+#pragma unroll
+        for (int k = 0; k < PRO_V; k++) {
+            const int j = base + c.tid + k * c.nt;
+            if (j < n4) v[k] = __ldcg(src4 + j);
+        }
+#pragma unroll
+        for (int k = 0; k < PRO_V; k++) {
+            const int j = base + c.tid + k * c.nt;
+            if (j < n4) store_x4<WT>(sv.xs, j, v[k]);
+        }
     }
     cons_sync(c);
 }
 
 // ------------------------------------------------------------------ attention phase
-// (head, split) items over the CTAs.  Within an item the consumer warps take positions
-// round-robin, keep an online-softmax state (m, l, acc) and merge through shared memory.
-// Partial result layout in global memory: att_part[(h*S + sp)*(hs+2)] = {m, l, acc[hs]}.
-__device__ __forceinline__ void attention_phase(const StreamParams &P, const SmemView &sv,
-                                                const Cons &c, int layer, int pos)
+// (head, split) items over the CTAs (llama2.f90:574-598); a split is a run of positions (<= 256
+// up to 2048 positions of context).  Inside an item each consumer warp takes groups of 8
+// positions; lane = 4 * (position in group) + (quarter of the head dimension):
+//   scores : each lane dots its quarter of q_h with its quarter of one K row (q, K and V requests
+//            are all issued up front: ONE L2 round trip per group), two shuffles finish the dot
+//   softmax: online (running max / sum) over the 8 positions, three shuffles each
+//   values : lane <-> head dimension (hs/32 consecutive dims), p_t broadcast by shuffle
+// Warp partials merge through shared memory.  With one split the normalised head output goes
+// straight to P.att; otherwise {m, l, acc} partials go to P.att_part and the Wo prologue merges.
+constexpr int ATT_PSTRIDE_PAD = 4;  // partial record = {m, l, -, -, acc[hs]}
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 {
-    const int hs = P.hs, S = P.n_splits, vec = hs >> 5;  // hs in {32, 64, 128}
+    if (VEC == 4) {
+        const float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else if (VEC == 2) {
+        const float2 t = __ldcg(reinterpret_cast<const float2 *>(p));
+        o[0] = t.x; o[1] = t.y;
+    } else {
+        o[0] = __ldcg(p);
+    }
+}
+
+template <int HS>
+__device__ __forceinline__ void attention_phase_t(const StreamParams &P, const SmemView &sv, const Cons &c,
+                                                  int layer, int pos)
+{
+    constexpr int hs = HS, vec = HS >> 5;  // HS in {32, 64, 128}
+    constexpr int q4n = HS >> 4;           // float4 per lane of a quarter head: 2, 4, 8
+    const int S = P.n_splits;
     const int items = P.H * S;
-    const int chunk = (pos + S - 1) / S;
+    const int chunk = (((pos + S - 1) / S) + 7) & ~7;
+    const int pstride = hs + ATT_PSTRIDE_PAD;
     const float scale = sqrtf((float)hs);
-    float *sc = sv.xs;  // [nw][hs + 2] scratch (xs is dead between weight phases)
+    float *sc = sv.xs;  // [nw][pstride]  (xs is dead between weight phases)
     const float *kc = P.kc + (size_t)layer * P.seq * P.kv;
     const float *vc = P.vc + (size_t)layer * P.seq * P.kv;
+    const int pl = c.lane >> 2, dq = c.lane & 3;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int h = item / S, sp = item % S, g = h / P.kv_mul;
+        const int h = item / S, sp = item - h * S, g = h / P.kv_mul;
         const int t0 = sp * chunk, t1 = min(pos, t0 + chunk);
-        float qv[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float m = -INFINITY, l = 0.f, acc[vec];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            qv[i] = i < vec ? __ldcg(P.q + (size_t)h * hs + c.lane * vec + i) : 0.f;
-        float m = -INFINITY, l = 0.f;
-        for (int t = t0 + c.warp; t < t1; t += c.nw) {
-            const float *kt = kc + (size_t)t * P.kv + (size_t)g * hs + c.lane * vec;
-            const float *vt = vc + (size_t)t * P.kv + (size_t)g * hs + c.lane * vec;
-            float kk[4], vv[4];
+        for (int i = 0; i < vec; i++) acc[i] = 0.f;
+        const float4 *qp = reinterpret_cast<const float4 *>(P.q + (size_t)h * hs + dq * (hs >> 2));
+        for (int tb = t0 + 8 * c.warp; tb < t1; tb += 8 * c.nw) {
+            const int t = tb + pl;
+            const bool valid = t < t1;
+            const int cnt = min(8, t1 - tb);
+            const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)min(t, t1 - 1) * P.kv + (size_t)g * hs +
+                                                                dq * (hs >> 2));
+            const float *vb = vc + (size_t)tb * P.kv + (size_t)g * hs + c.lane * vec;
+            float4 qq[q4n], kk[q4n];
+            float vv[8][vec];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                kk[i] = i < vec ? __ldcg(kt + i) : 0.f;
-                vv[i] = i < vec ? __ldcg(vt + i) : 0.f;
+            for (int i = 0; i < q4n; i++) qq[i] = __ldcg(qp + i);
+#pragma unroll
+            for (int i = 0; i < q4n; i++) kk[i] = __ldcg(kr + i);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (u < cnt) load_vec<vec>(vb + (size_t)u * P.kv, vv[u]);
+                else
+#pragma unroll
+                    for (int i = 0; i < vec; i++) vv[u][i] = 0.f;
             }
             float sdot = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; i++) sdot = fmaf(qv[i], kk[i], sdot);
-            sdot = warp_sum(sdot) / scale;  // dot_product(q_t,k_t)/sqrt(head_size), :582
-            const float mn = fmaxf(m, sdot);
-            const float corr = expf(m - mn), p = expf(sdot - mn);
-            l = l * corr + p;
-#pragma unroll
-            for (int i = 0; i < 4; i++) acc[i] = acc[i] * corr + p * vv[i];
+            for (int i = 0; i < q4n; i++) {
+                sdot = fmaf(qq[i].x, kk[i].x, sdot); sdot = fmaf(qq[i].y, kk[i].y, sdot);
+                sdot = fmaf(qq[i].z, kk[i].z, sdot); sdot = fmaf(qq[i].w, kk[i].w, sdot);
+            }
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot = valid ? sdot / scale : -INFINITY;  // dot_product(q_t,k_t)/sqrt(head_size), :582
+            float bm = sdot;
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+            const float mn = fmaxf(m, bm);
+            const float corr = expf(m - mn);
+            const float p = valid ? expf(sdot - mn) : 0.f;
+            float ps = p;  // every position is held by 4 lanes: sum over the position bits only
+            ps += __shfl_xor_sync(0xffffffffu, ps, 4);
+            ps += __shfl_xor_sync(0xffffffffu, ps, 8);
+            ps += __shfl_xor_sync(0xffffffffu, ps, 16);
+            l = fmaf(l, corr, ps);
             m = mn;
+#pragma unroll
+            for (int i = 0; i < vec; i++) acc[i] *= corr;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float pt = __shfl_sync(0xffffffffu, p, 4 * u);
+#pragma unroll
+                for (int i = 0; i < vec; i++) acc[i] = fmaf(pt, vv[u][i], acc[i]);
+            }
         }
-        float *mine = sc + (size_t)c.warp * (hs + 2);
+        float *mine = sc + (size_t)c.warp * pstride;
         if (c.lane == 0) { mine[0] = m; mine[1] = l; }
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (i < vec) mine[2 + c.lane * vec + i] = acc[i];
+        for (int i = 0; i < vec; i++) mine[ATT_PSTRIDE_PAD + c.lane * vec + i] = acc[i];
         cons_sync(c);
-        float *out = P.att_part + (size_t)(h * S + sp) * (hs + 2);
         for (int d = c.tid; d < hs; d += c.nt) {
             float M = -INFINITY;
-            for (int w = 0; w < c.nw; w++) M = fmaxf(M, sc[(size_t)w * (hs + 2)]);
+            for (int w = 0; w < c.nw; w++) M = fmaxf(M, sc[(size_t)w * pstride]);
             float L = 0.f, A = 0.f;
             for (int w = 0; w < c.nw; w++) {
-                const float mw = sc[(size_t)w * (hs + 2)];
+                const float mw = sc[(size_t)w * pstride];
                 if (mw > -INFINITY) {
                     const float e = expf(mw - M);
-                    L = fmaf(sc[(size_t)w * (hs + 2) + 1], e, L);
-                    A = fmaf(sc[(size_t)w * (hs + 2) + 2 + d], e, A);
+                    L = fmaf(sc[(size_t)w * pstride + 1], e, L);
+                    A = fmaf(sc[(size_t)w * pstride + ATT_PSTRIDE_PAD + d], e, A);
                 }
             }
-            out[2 + d] = A;
-            if (d == 0) { out[0] = M; out[1] = L; }
+            if (S == 1) {
+                P.att[(size_t)h * hs + d] = A / L;
+            } else {
+                float *out = P.att_part + (size_t)(h * S + sp) * pstride;
+                out[ATT_PSTRIDE_PAD + d] = A;
+                if (d == 0) { out[0] = M; out[1] = L; }
+            }
         }
         cons_sync(c);
     }
 }
 
-// xs = attention output (all heads), merging the position splits
-template <int WT>
-__device__ __forceinline__ void load_x_attn(const StreamParams &P, const SmemView &sv, const Cons &c)
+__device__ __forceinline__ void attention_phase(const StreamParams &P, const SmemView &sv, const Cons &c,
+                                                int layer, int pos)
 {
-    const int hs = P.hs, S = P.n_splits;
-    for (int e = c.tid; e < P.emb; e += c.nt) {
-        const int h = e / hs, d = e % hs;
-        const float *part = P.att_part + (size_t)h * S * (hs + 2);
-        float M = -INFINITY;
-        for (int s = 0; s < S; s++) M = fmaxf(M, __ldcg(part + (size_t)s * (hs + 2)));
-        float num = 0.f, den = 0.f;
-        for (int s = 0; s < S; s++) {
-            const float ms = __ldcg(part + (size_t)s * (hs + 2));
-            if (ms > -INFINITY) {
-                const float w = expf(ms - M);
-                den = fmaf(__ldcg(part + (size_t)s * (hs + 2) + 1), w, den);
-                num = fmaf(__ldcg(part + (size_t)s * (hs + 2) + 2 + d), w, num);
-            }
-        }
-        sv.xs[xs_index<WT>(e)] = num / den;
-    }
-    cons_sync(c);
+    if (P.hs == 64) attention_phase_t<64>(P, sv, c, layer, pos);
+    else if (P.hs == 128) attention_phase_t<128>(P, sv, c, layer, pos);
+    else attention_phase_t<32>(P, sv, c, layer, pos);
 }
 
-template <int WT>
-__device__ __forceinline__ void load_x_plain(const float *src, int n, const SmemView &sv, const Cons &c)
+// xs = attention output (all heads), merging the position splits (n_splits > 1)
+template <int WT, int PRO_V>
+__device__ __forceinline__ void load_x_attn(const StreamParams &P, const SmemView &sv, const Cons &c)
 {
-    for (int e = c.tid; e < n; e += c.nt) sv.xs[xs_index<WT>(e)] = __ldcg(src + e);
+    const int S = P.n_splits;
+    const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.emb >> 2;
+    const int hs_shift = hs == 64 ? 6 : (hs == 128 ? 7 : 5);
+    for (int j = c.tid; j < n4; j += c.nt) {
+        const int h = (4 * j) >> hs_shift, d = (4 * j) & (hs - 1);
+        const float *part = P.att_part + (size_t)h * S * pstride;
+        float ms[8], ls[8];
+        float4 av[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            if (s < S) {
+                ms[s] = __ldcg(part + (size_t)s * pstride);
+                ls[s] = __ldcg(part + (size_t)s * pstride + 1);
+                av[s] = __ldcg(reinterpret_cast<const float4 *>(part + (size_t)s * pstride + ATT_PSTRIDE_PAD + d));
+            }
+        float M = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            if (s < S) M = fmaxf(M, ms[s]);
+        float den = 0.f;
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            if (s < S && ms[s] > -INFINITY) {
+                const float w = expf(ms[s] - M);
+                den = fmaf(ls[s], w, den);
+                num.x = fmaf(av[s].x, w, num.x); num.y = fmaf(av[s].y, w, num.y);
+                num.z = fmaf(av[s].z, w, num.z); num.w = fmaf(av[s].w, w, num.w);
+            }
+        store_x4<WT>(sv.xs, j, make_float4(num.x / den, num.y / den, num.z / den, num.w / den));
+    }
     cons_sync(c);
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int WT>
-__global__ void __launch_bounds__((MAX_CONS_WARPS + 1) * 32, 1)
+// MAXT = 512: up to 15 consumer warps + the producer warp, 128 registers per thread.  Two warps
+// share a ring slot (f32 / f16: column halves, q4_0: row halves): the shared-memory load->FMA
+// latency is hidden by thread-level parallelism rather than by deep per-thread unrolling.
+template <int WT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 stream_decode_kernel(const __grid_constant__ StreamParams P)
 {
+    constexpr int PRO_V = MAXT <= 256 ? 8 : 4;
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemView sv = carve(smem, P);
     const int n_cons_warps = P.n_slots * P.wps;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0) {
+    __shared__ CtaPlan cp;
+    __shared__ float2 rope[64];
+    __shared__ long long tacc[PH_COUNT];  // phase timers, touched by the timer thread only
+    if (threadIdx.x < 5) {
+        const int i = threadIdx.x;
+        cp.ph[i] = P.ph[i];
+        int r0, r1;
+        cta_rows(P.ph[i], blockIdx.x, gridDim.x, r0, r1);
+        cp.r0[i] = r0; cp.r1[i] = r1;
+        cp.nst[i] = (r1 - r0 + P.ph[i].rps - 1) / P.ph[i].rps;
+    }
+    if (threadIdx.x == 32) {
         for (int i = 0; i < P.n_slots; i++) {
             mbar_init(&sv.full[i], 1);
             mbar_init(&sv.empty[i], (uint32_t)P.wps);
         }
         fence_mbar_init();
     }
-    __syncthreads();
-
     const int token = P.token > 0 ? P.token : P.tokpos[0];
     const int pos = P.token > 0 ? P.pos : P.tokpos[1];
+    // this position's RoPE row (a cold HBM read, issued first thing, used after the QKV phase)
+    if (threadIdx.x < (P.hs >> 1)) rope[threadIdx.x] = P.rope_tab[(size_t)(pos - 1) * (P.hs >> 1) + threadIdx.x];
+    __syncthreads();
 
     if (warp == n_cons_warps) {
         // ===================== producer warp =====================
-        if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
-            uint32_t s = 0;
-            for (int l = 0; l < P.L; l++)
-                for (int ph = 0; ph < 4; ph++) produce_phase(P.ph[ph], l, P, sv, s, pol);
-            produce_phase(P.ph[4], 0, P, sv, s, pol);
-        }
+        if (lane == 0) producer_loop(P, sv, &cp, token);
         return;
     }
 
@@ -333,109 +636,141 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     Cons c;
     c.tid = threadIdx.x; c.warp = warp; c.lane = lane;
     c.nw = n_cons_warps; c.nt = n_cons_warps * 32;
-    c.slot = warp / P.wps; c.sub = warp % P.wps;
-    uint32_t s = 0, nbar = 0;
+    c.slot = P.wps == 2 ? warp >> 1 : warp;
+    c.sub = P.wps == 2 ? warp & 1 : 0;
+    CState cs;
+    cs.pos.mod = 0; cs.pos.div = 0; cs.my_div = 0;
+    uint32_t nbar = 0;
+    // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh
     const bool timer = (blockIdx.x == 0 && c.tid == 0);
-    unsigned long long tmark = timer ? globaltimer_ns() : 0ull;
-    float tacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    long long tmark = timer ? clock64() : 0ll;
+    const unsigned long long t_ns0 = timer ? globaltimer_ns() : 0ull;
+    const long long t_c0 = tmark;
+    if (timer)
+        for (int i = 0; i < PH_COUNT; i++) tacc[i] = 0;
+    // optional per-CTA trace of one layer (debug/profiling): globaltimer stamps at every phase edge
+    // + per mat-vec phase the cycles warp 0 waited for ring data / computed, and its stage count
+    const bool tracer = (P.trace != nullptr && c.tid == 0);
+    __shared__ long long twait[12];
+    if (tracer)
+        for (int i = 0; i < 12; i++) twait[i] = 0;
+    auto stamp = [&](int l, int k) {
+        if (tracer && l == P.trace_layer) P.trace[(size_t)blockIdx.x * 32 + k] = globaltimer_ns();
+    };
     auto lap = [&](int bucket) {
         if (timer) {
-            const unsigned long long now = globaltimer_ns();
-            tacc[bucket] += (float)(now - tmark) * 1e-6f;
+            const long long now = clock64();
+            tacc[bucket] += now - tmark;
             tmark = now;
         }
     };
+    // phase results: one plane per warp of a slot when the columns are split (f32 / f16)
+    const int res_planes = (WT != WT_Q4_0) ? P.wps : 1;
+    auto resv = [&](int i) -> float { return res_planes == 2 ? sv.res[i] + sv.res[P.res_floats + i] : sv.res[i]; };
+    const int wr0 = cp.r0[1], wr1 = cp.r1[1];  // this CTA's Wo rows = its residual slice
+    const int half_mask = (P.hs >> 1) - 1;
+    const uint32_t ns = (uint32_t)P.n_slots;
+    float best = -INFINITY;  // running maxloc of this thread's logits (classifier epilogue)
+    int bidx = 0x7fffffff;
 
-    const uint8_t *emb_row = P.emb_table + (size_t)(token - 1) * P.ph[0].rs;
-    const float2 *rope = P.rope_tab + (size_t)(pos - 1) * (P.hs >> 1);
-    int r0, r1;
+    // One loop over the 4 L + 1 weight phases (q = 4 l + {0 QKV, 1 WO, 2 W13, 3 W2}; q = 4 L is the
+    // classifier): prologue -> ring consumption -> epilogue -> grid barrier.  A single inlined
+    // copy of every piece serves all phases, so the hot code is small and call-free.
+    const int nq = 4 * P.L + 1;
+    for (int q = 0; q < nq; q++) {
+        const int ph = q < 4 * P.L ? (q & 3) : 4, l = q >> 2;
+        const int tb = ph == 0 ? 0 : 2 + 3 * ph;  // timer bucket / trace stamp base of this phase
+        if (ph == 0) stamp(l, 0);
 
-    for (int l = 0; l < P.L; l++) {
-        // ---- phase A: rmsnorm + fused QKV mat-vec + RoPE + KV append (llama2.f90:527-565)
-        load_x_norm<WT>(P.x, l == 0 ? emb_row : nullptr, P.rms_att + (size_t)l * P.emb, P, sv, c);
-        consume_phase<WT>(P.ph[0], P, sv, c, s);
+        // ---- prologue: the activation vector of this phase, in shared memory
+        if (ph == 0 || ph == 2 || ph == 4) {
+            // rmsnorm (llama2.f90:527, :608, :627); layer 0 starts from the embedding row (:520)
+            const uint8_t *emb_row = nullptr;
+            RingPos at = cs.pos;
+            if (q == 0) {
+                emb_row = vec_stage_wait(P, sv, at);
+                ring_advance(at, 1u, ns);
+            }
+            const float *wn = reinterpret_cast<const float *>(vec_stage_wait(P, sv, at));
+            load_x_norm<WT, PRO_V>(P.x, emb_row, wn, P, sv, c, wr0, wr1);
+            if (q == 0) vec_stage_release(P, sv, c, cs);
+            vec_stage_release(P, sv, c, cs);
+        } else if (ph == 1 && P.n_splits > 1) {
+            load_x_attn<WT, PRO_V>(P, sv, c);
+        } else {
+            load_x_plain<WT, PRO_V>(ph == 1 ? P.att : P.hb, ph == 1 ? P.emb : P.hid, sv, c);
+        }
+        lap(tb);
+        stamp(l, ph == 0 ? 1 : 3 + 3 * ph);
+
+        // ---- the mat-vec: consume this CTA's stages of the phase from the ring
+        const int r0 = cp.r0[ph], nr = cp.r1[ph] - cp.r0[ph];
+        consume_phase<WT>(&cp.ph[ph], nr, cp.nst[ph], P, sv, c, cs,
+                          (tracer && l == P.trace_layer && ph < 4) ? &twait[ph] : nullptr);
+        stamp(l, ph == 0 ? 2 : 4 + 3 * ph);
         cons_sync(c);
-        cta_rows(P.ph[0], blockIdx.x, gridDim.x, r0, r1);
-        {
+        lap(tb + 1);
+
+        // ---- epilogue
+        if (ph == 0) {
+            // RoPE on q and k (reference quirks Q1/Q2 are in the table), KV append (llama2.f90:543-565)
             float *kc = P.kc + ((size_t)l * P.seq + (pos - 1)) * P.kv;
             float *vc = P.vc + ((size_t)l * P.seq + (pos - 1)) * P.kv;
-            const int half = P.hs >> 1;
-            for (int i = 2 * c.tid; i < r1 - r0; i += 2 * c.nt) {
+            for (int i = 2 * c.tid; i < nr; i += 2 * c.nt) {
                 const int r = r0 + i;
-                const float a = sv.res[i], b = sv.res[i + 1];
+                const float a = resv(i), b = resv(i + 1);
                 if (r < P.emb) {
-                    const float2 cs = rope[(r >> 1) % half];
-                    P.q[r] = a * cs.x - b * cs.y;
-                    P.q[r + 1] = a * cs.y + b * cs.x;
+                    const float2 cs2 = rope[(r >> 1) & half_mask];
+                    P.q[r] = a * cs2.x - b * cs2.y;
+                    P.q[r + 1] = a * cs2.y + b * cs2.x;
                 } else if (r < P.emb + P.kv) {
                     const int rk = r - P.emb;
-                    const float2 cs = rope[(rk >> 1) % half];
-                    kc[rk] = a * cs.x - b * cs.y;
-                    kc[rk + 1] = a * cs.y + b * cs.x;
+                    const float2 cs2 = rope[(rk >> 1) & half_mask];
+                    kc[rk] = a * cs2.x - b * cs2.y;
+                    kc[rk + 1] = a * cs2.y + b * cs2.x;
                 } else {
                     const int rv = r - P.emb - P.kv;
                     vc[rv] = a;
                     vc[rv + 1] = b;
                 }
             }
+        } else if (ph == 2) {
+            // SwiGLU on the interleaved gate/up rows (llama2.f90:613-616)
+            for (int i = 2 * c.tid; i < nr; i += 2 * c.nt) {
+                const float g = resv(i), u = resv(i + 1);
+                P.hb[(r0 + i) >> 1] = (g * (1.0f / (1.0f + expf(-g)))) * u;
+            }
+        } else if (ph == 4) {
+            for (int i = c.tid; i < nr; i += c.nt) {
+                const float v = resv(i);
+                P.logits[r0 + i] = v;
+                if (v > best) { best = v; bidx = r0 + i; }
+            }
+        } else {
+            // residual add after Wo / W2 (llama2.f90:603-605, :618-620)
+            for (int i = c.tid; i < nr; i += c.nt) {
+                const int r = r0 + i;
+                P.x[r] = __ldcg(P.x + r) + resv(i);
+            }
         }
+        if (ph == 4) break;
         grid_sync(P, c, nbar);
-        lap(0);
+        lap(tb + 2);
+        stamp(l, ph == 0 ? 3 : 5 + 3 * ph);
 
-        // ---- phase B: attention (llama2.f90:574-598)
-        attention_phase(P, sv, c, l, pos);
-        grid_sync(P, c, nbar);
-        lap(2);
-
-        // ---- phase C: x += Wo * att (llama2.f90:603-605)
-        load_x_attn<WT>(P, sv, c);
-        consume_phase<WT>(P.ph[1], P, sv, c, s);
-        cons_sync(c);
-        cta_rows(P.ph[1], blockIdx.x, gridDim.x, r0, r1);
-        for (int i = c.tid; i < r1 - r0; i += c.nt) {
-            const int r = r0 + i;
-            const float base = (l == 0) ? row_elem(emb_row, P.wtype, P.emb, r) : __ldcg(P.x + r);
-            P.x[r] = base + sv.res[i];
+        if (ph == 0) {
+            // ---- attention (llama2.f90:574-598)
+            attention_phase(P, sv, c, l, pos);
+            lap(PH_ATT);
+            stamp(l, 4);
+            grid_sync(P, c, nbar);
+            lap(PH_ATT_BAR);
+            stamp(l, 5);
         }
-        grid_sync(P, c, nbar);
-
-        // ---- phase D: rmsnorm + fused W1|W3 mat-vec + SwiGLU (llama2.f90:608-616)
-        load_x_norm<WT>(P.x, nullptr, P.rms_ffn + (size_t)l * P.emb, P, sv, c);
-        consume_phase<WT>(P.ph[2], P, sv, c, s);
-        cons_sync(c);
-        cta_rows(P.ph[2], blockIdx.x, gridDim.x, r0, r1);
-        for (int i = 2 * c.tid; i < r1 - r0; i += 2 * c.nt) {
-            const float g = sv.res[i], u = sv.res[i + 1];
-            P.hb[(r0 + i) >> 1] = (g * (1.0f / (1.0f + expf(-g)))) * u;
-        }
-        grid_sync(P, c, nbar);
-
-        // ---- phase E: x += W2 * hb (llama2.f90:618-620)
-        load_x_plain<WT>(P.hb, P.hid, sv, c);
-        consume_phase<WT>(P.ph[3], P, sv, c, s);
-        cons_sync(c);
-        cta_rows(P.ph[3], blockIdx.x, gridDim.x, r0, r1);
-        for (int i = c.tid; i < r1 - r0; i += c.nt) {
-            const int r = r0 + i;
-            P.x[r] = __ldcg(P.x + r) + sv.res[i];
-        }
-        grid_sync(P, c, nbar);
-        lap(3);
+        if (ph == 3 && tracer && l == P.trace_layer)
+            for (int i = 0; i < 12; i++) P.trace[(size_t)blockIdx.x * 32 + 16 + i] = (unsigned long long)twait[i];
     }
-
-    // ---- final rmsnorm + classifier (llama2.f90:627-636)
-    load_x_norm<WT>(P.x, nullptr, P.rms_final, P, sv, c);
-    consume_phase<WT>(P.ph[4], P, sv, c, s);
-    cons_sync(c);
-    cta_rows(P.ph[4], blockIdx.x, gridDim.x, r0, r1);
-    float best = -INFINITY;
-    int bidx = 0x7fffffff;
-    for (int i = c.tid; i < r1 - r0; i += c.nt) {
-        const float v = sv.res[i];
-        P.logits[r0 + i] = v;
-        if (v > best) { best = v; bidx = r0 + i; }
-    }
-    lap(4);
+    lap(PH_CLS_MV);
 
     if (P.do_argmax) {
         // maxloc(logits) (llama2.f90:388): first maximum wins at every reduction level
@@ -479,8 +814,12 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             }
         }
     }
-    if (timer)
-        for (int i = 0; i < 5; i++) P.times_dev[i] += tacc[i];
+    if (timer) {
+        lap(PH_ARGMAX);
+        for (int i = 0; i < PH_COUNT; i++) P.phase_cycles[i] += (unsigned long long)tacc[i];
+        P.phase_cycles[PH_COUNT] += (unsigned long long)(clock64() - t_c0);
+        P.phase_cycles[PH_COUNT + 1] += globaltimer_ns() - t_ns0;
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -497,11 +836,12 @@ int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target
         const int per = ((U + n_sms - 1) / n_sms + 1) * p.ph[i].unit;
         if (per > max_rows) max_rows = per;
     }
+    if ((unsigned)p.emb * 4u > rs_max) rs_max = (unsigned)p.emb * 4u;  // f32 vector stages
     int slot = target_slot_bytes > (int)rs_max ? target_slot_bytes : (int)rs_max;
     slot = (slot + 127) & ~127;
     int xs_floats = p.emb > p.hid ? p.emb : p.hid;
-    // attention scratch [consumer warps][hs+2] also lives in xs
-    const int att_scratch = MAX_SLOTS * (p.hs + 2);
+    // attention scratch ([consumer warps][hs+4] partials) also lives in xs
+    const int att_scratch = MAX_SLOTS * (p.hs + 4);
     if (att_scratch > xs_floats) xs_floats = att_scratch;
     xs_floats = (xs_floats + 31) & ~31;
     const int res_floats = (max_rows + 31) & ~31;
@@ -513,7 +853,7 @@ int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target
     if (n_slots < 2) return 1;
     out->n_slots = n_slots;
     out->slot_bytes = slot;
-    out->wps = (p.wtype == WT_Q4_0 && 2 * n_slots <= MAX_CONS_WARPS) ? 2 : 1;
+    out->wps = (2 * n_slots <= MAX_CONS_WARPS) ? 2 : 1;
     out->threads = (n_slots * out->wps + 1) * 32;
     out->smem_bytes = (int)smem_bytes_for(n_slots, slot, xs_floats, res_floats);
     out->grid = n_sms;
@@ -523,29 +863,33 @@ int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target
 }
 
 template <int WT>
-static cudaError_t prepare_t(int smem_bytes)
+static const void *kernel_for(int threads)
 {
-    return cudaFuncSetAttribute(stream_decode_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                smem_bytes);
+    (void)threads;
+    return (const void *)stream_decode_kernel<WT, 512>;
 }
 
-cudaError_t prepare_stream_kernel(int wtype, int smem_bytes)
+static const void *kernel_for(int wtype, int threads)
 {
-    if (wtype == WT_F32) return prepare_t<WT_F32>(smem_bytes);
-    if (wtype == WT_F16) return prepare_t<WT_F16>(smem_bytes);
-    if (wtype == WT_Q4_0) return prepare_t<WT_Q4_0>(smem_bytes);
-    return cudaErrorInvalidValue;
+    if (wtype == WT_F32) return kernel_for<WT_F32>(threads);
+    if (wtype == WT_F16) return kernel_for<WT_F16>(threads);
+    if (wtype == WT_Q4_0) return kernel_for<WT_Q4_0>(threads);
+    return nullptr;
+}
+
+cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes)
+{
+    const void *fn = kernel_for(wtype, threads);
+    if (!fn) return cudaErrorInvalidValue;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 
 cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st)
 {
     StreamParams q = p;
     void *args[] = {(void *)&q};
-    const void *fn = nullptr;
-    if (p.wtype == WT_F32) fn = (const void *)stream_decode_kernel<WT_F32>;
-    else if (p.wtype == WT_F16) fn = (const void *)stream_decode_kernel<WT_F16>;
-    else if (p.wtype == WT_Q4_0) fn = (const void *)stream_decode_kernel<WT_Q4_0>;
-    else return cudaErrorInvalidValue;
+    const void *fn = kernel_for(p.wtype, plan.threads);
+    if (!fn) return cudaErrorInvalidValue;
     // cooperative launch: guarantees all CTAs are co-resident (the grid barrier needs it)
     return cudaLaunchCooperativeKernel(fn, dim3(plan.grid), dim3(plan.threads), args,
                                        (size_t)plan.smem_bytes, st);
