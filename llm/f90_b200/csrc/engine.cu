@@ -58,8 +58,8 @@ struct Engine {
           *d_h13 = nullptr, *d_hb = nullptr, *d_logits = nullptr;
     unsigned long long *d_times = nullptr;  // [PH_COUNT + 2]
     int *d_tokpos = nullptr, *d_forced = nullptr, *d_out_tokens = nullptr, *d_amax = nullptr;
-    unsigned long long *d_bar = nullptr;
-    unsigned long long bar_base = 0;
+    unsigned long long *d_ll = nullptr;  // all LL buffers of the fused kernel, one allocation
+    unsigned int launch_seq = 0;
     float *h_logits = nullptr;  // pinned
     int *h_tokpos = nullptr;    // pinned
     // drivers
@@ -88,7 +88,7 @@ void release_all()
     void *ptrs[] = {E.d_emb, E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls, E.d_rms_att, E.d_rms_ffn,
                     E.d_rms_final, E.d_rope, E.d_kc, E.d_vc, E.d_x, E.d_xb, E.d_qkv, E.d_att,
                     E.d_att_part, E.d_h13, E.d_hb, E.d_logits, (void *)E.d_times, E.d_tokpos, E.d_forced,
-                    E.d_out_tokens, E.d_amax, E.d_bar};
+                    E.d_out_tokens, E.d_amax, E.d_ll};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (E.h_logits) cudaFreeHost(E.h_logits);
@@ -206,9 +206,9 @@ int enqueue_forward(int token, int pos, bool device_loop, const int *forced, int
         p.do_argmax = device_loop ? 1 : 0;
         p.forced = forced;
         p.out_tokens = out_tokens;
-        p.bar_base = E.bar_base;
+        E.launch_seq++;
+        p.ep_base = E.launch_seq * (unsigned)(E.cfg.n_layers + 1);
         CK(launch_stream(p, E.plan, E.st));
-        E.bar_base += (unsigned long long)stream_barriers_per_launch(p) * E.plan.grid;
         E.launches += 1;
     } else {
         if (!device_loop) {
@@ -393,9 +393,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     CK(cudaMemsetAsync(E.d_times, 0, (PH_COUNT + 2) * 8, E.st));
     CK(dalloc(&E.d_tokpos, (size_t)2)); CK(dalloc(&E.d_forced, (size_t)c.seq_len));
     CK(dalloc(&E.d_out_tokens, (size_t)c.seq_len)); CK(dalloc(&E.d_amax, (size_t)2 * 1024));
-    CK(dalloc(&E.d_bar, (size_t)2));
-    CK(cudaMemsetAsync(E.d_bar, 0, 16, E.st));
-    E.bar_base = 0;
+    E.launch_seq = 0;
     CK(cudaMallocHost((void **)&E.h_logits, (size_t)V * 4));
     CK(cudaMallocHost((void **)&E.h_tokpos, 64));
 
@@ -429,6 +427,8 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         }
         p.pf_stages = 0;
         if (const char *s = getenv("LLMF90_PF_STAGES")) p.pf_stages = std::max(0, atoi(s));
+        p.pace = 38;  // ~1.15x the per-SM fair share of the measured HBM bandwidth (23 B/cycle)
+        if (const char *s = getenv("LLMF90_PACE")) p.pace = std::max(0, atoi(s));
         if (const char *s = getenv("LLMF90_WPS")) {
             int w = atoi(s);
             if (w >= 1 && w * E.plan.n_slots <= 15) { E.plan.wps = w; E.plan.threads = (E.plan.n_slots * w + 1) * 32; }
@@ -437,9 +437,25 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.emb_table = E.d_emb;
         p.rms_att = E.d_rms_att; p.rms_ffn = E.d_rms_ffn; p.rms_final = E.d_rms_final;
         p.rope_tab = E.d_rope;
-        p.x = E.d_x; p.q = E.d_qkv; p.att = E.d_att; p.att_part = E.d_att_part; p.hb = E.d_hb; p.logits = E.d_logits;
+        {
+            // LL buffers (64-bit words), zero-filled: epoch 0 is never expected
+            const size_t n_part = (size_t)c.n_heads * MAX_SPLITS * (hs + 4);
+            const size_t words = 4 * (size_t)emb + hid + 2 * (size_t)E.kv + n_part + 2 * (size_t)E.n_sms + 64;
+            CK(dalloc(&E.d_ll, words));
+            CK(cudaMemsetAsync(E.d_ll, 0, words * 8, E.st));
+            unsigned long long *w = E.d_ll;
+            p.ll_x1 = w; w += emb;
+            p.ll_x2 = w; w += emb;
+            p.ll_q = w; w += emb;
+            p.ll_att = w; w += emb;
+            p.ll_hb = w; w += (hid + 1) & ~1;
+            p.ll_kv = w; w += 2 * E.kv;
+            p.ll_part = w; w += n_part;
+            p.ll_amax = w;
+        }
+        p.logits = E.d_logits;
         p.kc = E.d_kc; p.vc = E.d_vc;
-        p.bar_ctr = E.d_bar; p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos; p.amax_scratch = E.d_amax;
+        p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.wps = E.plan.wps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
         if (E.plan.grid > 1024) { release_all(); return fail("grid larger than argmax scratch"); }

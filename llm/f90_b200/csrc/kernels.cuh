@@ -64,10 +64,20 @@ struct StreamParams {
     const uint8_t *emb_table;  // [V][rs_emb] device row format
     const float *rms_att, *rms_ffn, *rms_final;
     const float2 *rope_tab;  // [seq][hs/2]
-    float *x, *q, *att, *att_part, *hb, *logits;  // activations in global memory
+    // Activations between phases travel in "LL" buffers: every float is one 64-bit word
+    // {value, epoch} written and read atomically, so a reader that sees the expected epoch has
+    // the value -- no grid barrier, no fence (see stream.cu).  Sizes in 64-bit words.
+    unsigned long long *ll_x1;    // [emb]   residual stream after Wo
+    unsigned long long *ll_x2;    // [emb]   residual stream after W2 (input of the next layer)
+    unsigned long long *ll_hb;    // [hid]   SwiGLU output
+    unsigned long long *ll_q;     // [emb]   rotated query
+    unsigned long long *ll_kv;    // [2 kv]  this position's rotated key and value rows
+    unsigned long long *ll_att;   // [emb]   attention output (n_splits == 1)
+    unsigned long long *ll_part;  // [H][MAX_SPLITS][hs + 4] split partials {m, l, -, -, acc[hs]}
+    unsigned long long *ll_amax;  // [grid][2] per-CTA {max logit bits, index}
+    unsigned int ep_base;         // epoch of layer l of this launch = ep_base + l + 1
+    float *logits;
     float *kc, *vc;          // [L][seq][kv]
-    unsigned long long *bar_ctr;
-    unsigned long long bar_base;
     unsigned long long *phase_cycles;  // [PH_COUNT + 2] SM-cycle accumulators (+ total cycles, total ns)
     const int *tokpos;       // device {token, pos} (1-based); used when token < 0
     int token, pos;          // by-value inputs (token >= 1) -- no H2D copy needed
@@ -75,8 +85,8 @@ struct StreamParams {
     unsigned long long *trace;  // optional [grid][32] debug trace of layer `trace_layer` (or null)
     int trace_layer;
     int pf_stages;           // L2 prefetch distance beyond the shared-memory ring, in stages
+    int pace;                // producer pacing: SM cycles per KB issued (0 = unpaced)
     int do_argmax;           // fuse maxloc after the classifier and write tokpos = {argmax, pos+1}
-    int *amax_scratch;       // [2*grid] per-CTA (value bits, index)
     const int *forced;       // optional device array of forced next tokens (prompt), or null
     int *out_tokens;         // optional device array: out_tokens[pos-1] = chosen token
     // ring geometry
@@ -94,6 +104,5 @@ int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target
                 int max_slots, StreamPlan *out);
 cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes);
 cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st);
-int stream_barriers_per_launch(const StreamParams &p);
 
 }  // namespace llmf90

@@ -19,9 +19,11 @@
 //     q4_0 dequantisation fused into the load, f32 accumulation, warp-shuffle reduction),
 //     release the slot with an `empty` mbarrier arrive.
 //   * Between phases the consumers run the tiny epilogues in place -- RoPE + KV-cache append,
-//     SwiGLU, residual add -- publish their slice to global memory and meet at a grid barrier
-//     (release/acquire counter in L2); the next phase's prologue re-reads the full vector
-//     (rmsnorm recomputed redundantly per CTA: 8-16 KB from L2).
+//     SwiGLU, residual add -- and publish their slice as {value, epoch} 64-bit words ("LL"
+//     buffers, the protocol NCCL uses for small messages): the next phase's prologue polls the
+//     whole vector straight out of L2 until every word carries the expected epoch.  There is NO
+//     grid barrier and no fence anywhere in the token: a phase hand-over costs one store->load
+//     trip through L2 (rmsnorm is recomputed redundantly per CTA).
 //   * Attention (scores, softmax, value gather) is a phase of the same kernel: (head, split)
 //     items over the CTAs, online softmax, merged in the Wo prologue when there are splits.
 //
@@ -150,21 +152,45 @@ struct StageIter {
     }
 };
 
+// Two cursors walk the schedule: the copy cursor (TMA bulk copies into the ring) and, pf_stages
+// stages ahead of it, the L2-prefetch cursor (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2).  The
+// second cursor turns part of the 126 MB L2 into a deeper level of the ring: when the consumers
+// sit in a phase hand-over or in attention and every shared-memory slot is full, the requests
+// already queued for L2 keep the HBM channels busy, and the ring later refills at L2 latency.
 __device__ __forceinline__ void producer_loop(const StreamParams &P, const SmemView &sv, const CtaPlan *cp,
                                               int token)
 {
     const uint64_t pol = l2_policy_evict_first();
-    StageIter it;
+    StageIter it, ip;
     it.init(P, cp, token);
+    ip = it;
     const uint32_t ns = (uint32_t)P.n_slots;
-    uint32_t slot = 0, k = 0;
+    const uint32_t depth = ns + (uint32_t)P.pf_stages;
+    uint32_t slot = 0, k = 0, s = 0, pf = P.pf_stages > 0 ? 0u : 0xffffffffu;
     const uint8_t *src;
     uint32_t bytes;
+    // pacing: issue at most one KB per `pace` SM cycles (0 = unpaced).  Every byte in flight
+    // beyond bandwidth x latency only adds queueing delay in front of the latency-critical LL
+    // traffic of the phase hand-overs; a paced producer keeps the queues short.
+    long long next_ok = clock64();
     while (it.next(P, src, bytes)) {
         mbar_wait(&sv.empty[slot], (k & 1u) ^ 1u);
+        if (P.pace > 0) {
+            long long now = clock64();
+            while (now < next_ok) now = clock64();
+            next_ok = now + (((long long)bytes * P.pace) >> 10);
+        }
         mbar_arrive_expect_tx(&sv.full[slot], bytes);
         bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, src, bytes, &sv.full[slot], pol);
         if (++slot == ns) { slot = 0; k++; }
+        s++;
+        while (pf < s + depth) {
+            const uint8_t *psrc;
+            uint32_t pbytes;
+            if (!ip.next(P, psrc, pbytes)) { pf = 0xffffffffu; break; }
+            if (pf >= s + ns - 1) bulk_prefetch_l2(psrc, pbytes);  // nearer stages go straight to the ring
+            pf++;
+        }
     }
 }
 
@@ -266,20 +292,108 @@ __device__ __forceinline__ void consume_phase(const PhaseW *ph, int nrows, int n
     ring_advance(cs.pos, (uint32_t)nst, (uint32_t)ns);
 }
 
-// grid-wide barrier over the consumer groups of all CTAs (the producers never join).  bar.sync
-// orders the CTA's writes before thread 0's gpu-scope release; the acquire load + bar.sync
-// make every other CTA's writes visible to all consumer threads.
-__device__ __forceinline__ void grid_sync(const StreamParams &P, const Cons &c, uint32_t &nbar)
+// ------------------------------------------------------------------ LL buffers
+// One float per 64-bit word: low half = value bits, high half = epoch.  64-bit scalar accesses
+// are single-copy atomic, so value and epoch always arrive together; relaxed gpu-scope accesses
+// go to L2 (never a stale L1 line).  A buffer is rewritten one layer later at the earliest, and
+// a CTA can only get there after it has seen every other CTA's output of the phases in between,
+// i.e. after every reader of the old contents is done -- no write-after-read hazard.
+__device__ __forceinline__ void ll_store(unsigned long long *buf, int i, float v, uint32_t ep)
 {
-    cons_sync(c);
-    if (c.tid == 0) {
-        red_release_add_u64(P.bar_ctr, 1ull);
-        const unsigned long long target = P.bar_base + (unsigned long long)(nbar + 1) * gridDim.x;
-        while (ld_acquire_u64(P.bar_ctr) < target) {
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)ep << 32);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(buf + i), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ll_load2(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load1(const unsigned long long *p)
+{
+    unsigned long long a;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+__device__ __forceinline__ float ll_val(unsigned long long w) { return __uint_as_float((uint32_t)w); }
+__device__ __forceinline__ bool ll_ok(unsigned long long w, uint32_t ep) { return (uint32_t)(w >> 32) == ep; }
+// value only (own earlier write, no polling)
+__device__ __forceinline__ float ll_peek(const unsigned long long *buf, int i) { return ll_val(ll_load1(buf + i)); }
+// poll four consecutive floats (i % 4 == 0)
+__device__ __forceinline__ float4 ll_wait4(const unsigned long long *buf, int i, uint32_t ep)
+{
+    unsigned long long a, b, c, d;
+    do {
+        ll_load2(buf + i, a, b);
+        ll_load2(buf + i + 2, c, d);
+    } while (!(ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep)));
+    return make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
+}
+// poll N consecutive float4 (i % 4 == 0): all requests of a round in flight together
+template <int N>
+__device__ __forceinline__ void ll_wait4n(const unsigned long long *buf, int i, uint32_t ep, float4 (&o)[N])
+{
+    unsigned long long w[N][4];
+    bool ok;
+    do {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            ll_load2(buf + i + 4 * k, w[k][0], w[k][1]);
+            ll_load2(buf + i + 4 * k + 2, w[k][2], w[k][3]);
         }
+        ok = true;
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            ok = ok && ll_ok(w[k][0], ep) && ll_ok(w[k][1], ep) && ll_ok(w[k][2], ep) && ll_ok(w[k][3], ep);
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < N; k++) o[k] = make_float4(ll_val(w[k][0]), ll_val(w[k][1]), ll_val(w[k][2]), ll_val(w[k][3]));
+}
+// poll NV (<= 4) consecutive floats (i % NV == 0)
+template <int NV>
+__device__ __forceinline__ void ll_waitv(const unsigned long long *buf, int i, uint32_t ep, float (&o)[NV])
+{
+    if (NV == 4) {
+        const float4 t = ll_wait4(buf, i, ep);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else if (NV == 2) {
+        unsigned long long a, b;
+        do { ll_load2(buf + i, a, b); } while (!(ll_ok(a, ep) && ll_ok(b, ep)));
+        o[0] = ll_val(a); o[1] = ll_val(b);
+    } else {
+        unsigned long long a;
+        do { a = ll_load1(buf + i); } while (!ll_ok(a, ep));
+        o[0] = ll_val(a);
     }
-    cons_sync(c);
-    nbar++;
+}
+// a thread's batch of up to PRO_V float4: all requests of a polling round are issued before the
+// first check (one L2 round trip per round)
+template <int PRO_V>
+__device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4, int base, uint32_t ep,
+                                          const Cons &c, float4 (&v)[PRO_V])
+{
+    unsigned long long w[PRO_V][4];
+    bool ok;
+    do {
+#pragma unroll
+        for (int k = 0; k < PRO_V; k++) {
+            const int j = base + c.tid + k * c.nt;
+            if (j < n4) {
+                ll_load2(buf + 4 * j, w[k][0], w[k][1]);
+                ll_load2(buf + 4 * j + 2, w[k][2], w[k][3]);
+            }
+        }
+        ok = true;
+#pragma unroll
+        for (int k = 0; k < PRO_V; k++) {
+            const int j = base + c.tid + k * c.nt;
+            if (j < n4) ok = ok && ll_ok(w[k][0], ep) && ll_ok(w[k][1], ep) && ll_ok(w[k][2], ep) && ll_ok(w[k][3], ep);
+        }
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < PRO_V; k++) {
+        const int j = base + c.tid + k * c.nt;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < n4) v[k] = make_float4(ll_val(w[k][0]), ll_val(w[k][1]), ll_val(w[k][2]), ll_val(w[k][3]));
+    }
 }
 
 // ---- vector stages: every consumer thread waits for the stage and reads what it needs; after
@@ -319,92 +433,70 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
                        row_elem(row, wtype, cols, 4 * j4 + 2), row_elem(row, wtype, cols, 4 * j4 + 3));
 }
 
-// xs = rmsnorm(x) * w   (llama2.f90:450-457).  x comes from global memory (L2) or, for layer 0,
-// from the embedding row in a ring slot; w from a ring slot.  With an embedding row the CTA also
-// writes its own residual slice x[wr0..wr1) for the Wo epilogue (llama2.f90:520).
+// xs = rmsnorm(x) * w   (llama2.f90:450-457).  x is polled from an LL buffer or, for layer 0,
+// taken from the embedding row in a ring slot; w comes from a ring slot.  With an embedding row the
+// CTA also publishes its own residual slice x[wr0..wr1) (llama2.f90:520) for its Wo epilogue.
 template <int WT, int PRO_V>
-__device__ __forceinline__ void load_x_norm(const float *src, const uint8_t *emb_row,
+__device__ __forceinline__ void load_x_norm(const unsigned long long *src, uint32_t ep, const uint8_t *emb_row,
                                             const float *wn /* shared */, const StreamParams &P,
                                             const SmemView &sv, const Cons &c, int wr0, int wr1)
 {
     const int n = P.emb, n4 = n >> 2;
-    const float4 *src4 = reinterpret_cast<const float4 *>(src);
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
-    if (n4 <= PRO_V * c.nt) {
-        float4 v[PRO_V], wv[PRO_V];
-#pragma unroll
-        for (int k = 0; k < PRO_V; k++) {
-            const int j = c.tid + k * c.nt;
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            wv[k] = v[k];
-            if (j < n4) {
-                v[k] = emb_row ? emb_row4(emb_row, P.wtype, n, j) : __ldcg(src4 + j);
-                wv[k] = wn4[j];
-            }
-        }
-        float ss = 0.f;
-#pragma unroll
-        for (int k = 0; k < PRO_V; k++) {
-            ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss);
-            ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
-        }
+    float ss = 0.f;
+    for (int base = 0; base < n4; base += PRO_V * c.nt) {
+        float4 v[PRO_V];
         if (emb_row) {
 #pragma unroll
             for (int k = 0; k < PRO_V; k++) {
-                const int e = 4 * (c.tid + k * c.nt);
-                if (e + 3 >= wr0 && e < wr1) {
-                    if (e >= wr0 && e < wr1) P.x[e] = v[k].x;
-                    if (e + 1 >= wr0 && e + 1 < wr1) P.x[e + 1] = v[k].y;
-                    if (e + 2 >= wr0 && e + 2 < wr1) P.x[e + 2] = v[k].z;
-                    if (e + 3 >= wr0 && e + 3 < wr1) P.x[e + 3] = v[k].w;
+                const int j = base + c.tid + k * c.nt;
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < n4) {
+                    v[k] = emb_row4(emb_row, P.wtype, n, j);
+                    const int e = 4 * j;
+                    if (e + 3 >= wr0 && e < wr1) {
+                        if (e >= wr0 && e < wr1) ll_store(P.ll_x2, e, v[k].x, 0u);
+                        if (e + 1 >= wr0 && e + 1 < wr1) ll_store(P.ll_x2, e + 1, v[k].y, 0u);
+                        if (e + 2 >= wr0 && e + 2 < wr1) ll_store(P.ll_x2, e + 2, v[k].z, 0u);
+                        if (e + 3 >= wr0 && e + 3 < wr1) ll_store(P.ll_x2, e + 3, v[k].w, 0u);
+                    }
                 }
             }
+        } else {
+            ll_gather<PRO_V>(src, n4, base, ep, c, v);
         }
-        const float tot = cons_sum(ss, c, sv.red);
-        const float inv = 1.0f / sqrtf(tot / (float)n + 1e-5f);
 #pragma unroll
         for (int k = 0; k < PRO_V; k++) {
-            const int j = c.tid + k * c.nt;
-            if (j < n4)
-                store_x4<WT>(sv.xs, j, make_float4(v[k].x * wv[k].x * inv, v[k].y * wv[k].y * inv,
-                                                   v[k].z * wv[k].z * inv, v[k].w * wv[k].w * inv));
-        }
-    } else {  // very wide models: two passes through shared memory
-        float ss = 0.f;
-        for (int j = c.tid; j < n4; j += c.nt) {
-            const float4 v = emb_row ? emb_row4(emb_row, P.wtype, n, j) : __ldcg(src4 + j);
-            store_x4<WT>(sv.xs, j, v);
-            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-            if (emb_row) {
-                const int e = 4 * j;
-                if (e >= wr0 && e < wr1) P.x[e] = v.x;
-                if (e + 1 >= wr0 && e + 1 < wr1) P.x[e + 1] = v.y;
-                if (e + 2 >= wr0 && e + 2 < wr1) P.x[e + 2] = v.z;
-                if (e + 3 >= wr0 && e + 3 < wr1) P.x[e + 3] = v.w;
+            const int j = base + c.tid + k * c.nt;
+            ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss);
+            ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+            if (j < n4) {
+                const float4 w = wn4[j];
+                store_x4<WT>(sv.xs, j, make_float4(v[k].x * w.x, v[k].y * w.y, v[k].z * w.z, v[k].w * w.w));
             }
         }
-        const float tot = cons_sum(ss, c, sv.red);
-        const float inv = 1.0f / sqrtf(tot / (float)n + 1e-5f);
-        for (int e = c.tid; e < n; e += c.nt) {
-            const int ix = xs_index<WT>(e);
-            sv.xs[ix] = sv.xs[ix] * wn[e] * inv;
-        }
+    }
+    const float tot = cons_sum(ss, c, sv.red);
+    const float inv = 1.0f / sqrtf(tot / (float)n + 1e-5f);
+    // second pass over this thread's own elements: scale by 1 / rms
+    for (int j = c.tid; j < n4; j += c.nt) {
+        int idx = j;
+        if (WT == WT_Q4_0) idx = (j & ~7) | ((j & 7) ^ ((j >> 3) & 7));
+        float4 t = reinterpret_cast<float4 *>(sv.xs)[idx];
+        t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
+        reinterpret_cast<float4 *>(sv.xs)[idx] = t;
     }
     cons_sync(c);
 }
 
 template <int WT, int PRO_V>
-__device__ __forceinline__ void load_x_plain(const float *src, int n, const SmemView &sv, const Cons &c)
+__device__ __forceinline__ void load_x_plain(const unsigned long long *src, uint32_t ep, int n, const SmemView &sv,
+                                             const Cons &c)
 {
     const int n4 = n >> 2;
-    const float4 *src4 = reinterpret_cast<const float4 *>(src);
     for (int base = 0; base < n4; base += PRO_V * c.nt) {
         float4 v[PRO_V];
-#pragma unroll
-        for (int k = 0; k < PRO_V; k++) {
-            const int j = base + c.tid + k * c.nt;
-            if (j < n4) v[k] = __ldcg(src4 + j);
-        }
+        ll_gather<PRO_V>(src, n4, base, ep, c, v);
 #pragma unroll
         for (int k = 0; k < PRO_V; k++) {
             const int j = base + c.tid + k * c.nt;
@@ -442,13 +534,14 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 
 template <int HS>
 __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const SmemView &sv, const Cons &c,
-                                                  int layer, int pos)
+                                                  int layer, int pos, uint32_t ep)
 {
     constexpr int hs = HS, vec = HS >> 5;  // HS in {32, 64, 128}
     constexpr int q4n = HS >> 4;           // float4 per lane of a quarter head: 2, 4, 8
     const int S = P.n_splits;
     const int items = P.H * S;
-    const int chunk = (((pos + S - 1) / S) + 7) & ~7;
+    const int npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches)
+    const int chunk = (((npast + S - 1) / S) + 7) & ~7;
     const int pstride = hs + ATT_PSTRIDE_PAD;
     const float scale = sqrtf((float)hs);
     float *sc = sv.xs;  // [nw][pstride]  (xs is dead between weight phases)
@@ -457,11 +550,14 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
     const int pl = c.lane >> 2, dq = c.lane & 3;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int h = item / S, sp = item - h * S, g = h / P.kv_mul;
-        const int t0 = sp * chunk, t1 = min(pos, t0 + chunk);
+        const int t0 = sp * chunk, t1 = min(npast, t0 + chunk);
         float m = -INFINITY, l = 0.f, acc[vec];
 #pragma unroll
         for (int i = 0; i < vec; i++) acc[i] = 0.f;
-        const float4 *qp = reinterpret_cast<const float4 *>(P.q + (size_t)h * hs + dq * (hs >> 2));
+        // this lane's quarter of the query head (written by the QKV epilogues of this launch);
+        // polled after the first group's K / V requests are in flight
+        float4 qq[q4n];
+        bool have_q = false;
         for (int tb = t0 + 8 * c.warp; tb < t1; tb += 8 * c.nw) {
             const int t = tb + pl;
             const bool valid = t < t1;
@@ -469,10 +565,8 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
             const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)min(t, t1 - 1) * P.kv + (size_t)g * hs +
                                                                 dq * (hs >> 2));
             const float *vb = vc + (size_t)tb * P.kv + (size_t)g * hs + c.lane * vec;
-            float4 qq[q4n], kk[q4n];
+            float4 kk[q4n];
             float vv[8][vec];
-#pragma unroll
-            for (int i = 0; i < q4n; i++) qq[i] = __ldcg(qp + i);
 #pragma unroll
             for (int i = 0; i < q4n; i++) kk[i] = __ldcg(kr + i);
 #pragma unroll
@@ -481,6 +575,10 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
                 else
 #pragma unroll
                     for (int i = 0; i < vec; i++) vv[u][i] = 0.f;
+            }
+            if (!have_q) {
+                ll_wait4n<q4n>(P.ll_q, h * hs + dq * (hs >> 2), ep, qq);
+                have_q = true;
             }
             float sdot = 0.f;
 #pragma unroll
@@ -513,6 +611,29 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
                 for (int i = 0; i < vec; i++) acc[i] = fmaf(pt, vv[u][i], acc[i]);
             }
         }
+        if (sp == S - 1 && c.warp == 0) {
+            // the current position: its key / value rows were produced in this launch (LL buffer)
+            float4 kk[q4n];
+            float vv[vec];
+            if (!have_q) ll_wait4n<q4n>(P.ll_q, h * hs + dq * (hs >> 2), ep, qq);
+            ll_wait4n<q4n>(P.ll_kv, g * hs + dq * (hs >> 2), ep, kk);
+            ll_waitv<vec>(P.ll_kv, P.kv + g * hs + c.lane * vec, ep, vv);
+            float sdot = 0.f;
+#pragma unroll
+            for (int i = 0; i < q4n; i++) {
+                sdot = fmaf(qq[i].x, kk[i].x, sdot); sdot = fmaf(qq[i].y, kk[i].y, sdot);
+                sdot = fmaf(qq[i].z, kk[i].z, sdot); sdot = fmaf(qq[i].w, kk[i].w, sdot);
+            }
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot = sdot / scale;  // identical in every lane (all lanes hold the same position)
+            const float mn = fmaxf(m, sdot);
+            const float corr = expf(m - mn), p = expf(sdot - mn);
+            l = fmaf(l, corr, p);
+            m = mn;
+#pragma unroll
+            for (int i = 0; i < vec; i++) acc[i] = fmaf(acc[i], corr, p * vv[i]);
+        }
         float *mine = sc + (size_t)c.warp * pstride;
         if (c.lane == 0) { mine[0] = m; mine[1] = l; }
 #pragma unroll
@@ -531,11 +652,11 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
                 }
             }
             if (S == 1) {
-                P.att[(size_t)h * hs + d] = A / L;
+                ll_store(P.ll_att, h * hs + d, A / L, ep);
             } else {
-                float *out = P.att_part + (size_t)(h * S + sp) * pstride;
-                out[ATT_PSTRIDE_PAD + d] = A;
-                if (d == 0) { out[0] = M; out[1] = L; }
+                unsigned long long *out = P.ll_part + (size_t)(h * S + sp) * pstride;
+                ll_store(out, ATT_PSTRIDE_PAD + d, A, ep);
+                if (d == 0) { ll_store(out, 0, M, ep); ll_store(out, 1, L, ep); }
             }
         }
         cons_sync(c);
@@ -543,36 +664,34 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
 }
 
 __device__ __forceinline__ void attention_phase(const StreamParams &P, const SmemView &sv, const Cons &c,
-                                                int layer, int pos)
+                                                int layer, int pos, uint32_t ep)
 {
-    if (P.hs == 64) attention_phase_t<64>(P, sv, c, layer, pos);
-    else if (P.hs == 128) attention_phase_t<128>(P, sv, c, layer, pos);
-    else attention_phase_t<32>(P, sv, c, layer, pos);
+    if (P.hs == 64) attention_phase_t<64>(P, sv, c, layer, pos, ep);
+    else if (P.hs == 128) attention_phase_t<128>(P, sv, c, layer, pos, ep);
+    else attention_phase_t<32>(P, sv, c, layer, pos, ep);
 }
 
 // xs = attention output (all heads), merging the position splits (n_splits > 1)
 template <int WT, int PRO_V>
-__device__ __forceinline__ void load_x_attn(const StreamParams &P, const SmemView &sv, const Cons &c)
+__device__ __forceinline__ void load_x_attn(const StreamParams &P, uint32_t ep, const SmemView &sv, const Cons &c)
 {
     const int S = P.n_splits;
     const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.emb >> 2;
     const int hs_shift = hs == 64 ? 6 : (hs == 128 ? 7 : 5);
     for (int j = c.tid; j < n4; j += c.nt) {
         const int h = (4 * j) >> hs_shift, d = (4 * j) & (hs - 1);
-        const float *part = P.att_part + (size_t)h * S * pstride;
-        float ms[8], ls[8];
+        const unsigned long long *part = P.ll_part + (size_t)h * S * pstride;
+        float M = -INFINITY, ms[8], ls[8];
         float4 av[8];
 #pragma unroll
         for (int s = 0; s < 8; s++)
             if (s < S) {
-                ms[s] = __ldcg(part + (size_t)s * pstride);
-                ls[s] = __ldcg(part + (size_t)s * pstride + 1);
-                av[s] = __ldcg(reinterpret_cast<const float4 *>(part + (size_t)s * pstride + ATT_PSTRIDE_PAD + d));
+                float ml[2];
+                ll_waitv<2>(part + (size_t)s * pstride, 0, ep, ml);
+                ms[s] = ml[0]; ls[s] = ml[1];
+                av[s] = ll_wait4(part + (size_t)s * pstride, ATT_PSTRIDE_PAD + d, ep);
+                M = fmaxf(M, ms[s]);
             }
-        float M = -INFINITY;
-#pragma unroll
-        for (int s = 0; s < 8; s++)
-            if (s < S) M = fmaxf(M, ms[s]);
         float den = 0.f;
         float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -640,7 +759,6 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     c.sub = P.wps == 2 ? warp & 1 : 0;
     CState cs;
     cs.pos.mod = 0; cs.pos.div = 0; cs.my_div = 0;
-    uint32_t nbar = 0;
     // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh
     const bool timer = (blockIdx.x == 0 && c.tid == 0);
     long long tmark = timer ? clock64() : 0ll;
@@ -679,6 +797,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     const int nq = 4 * P.L + 1;
     for (int q = 0; q < nq; q++) {
         const int ph = q < 4 * P.L ? (q & 3) : 4, l = q >> 2;
+        const uint32_t ep = P.ep_base + (uint32_t)l + 1u;  // epoch of everything layer l publishes
         const int tb = ph == 0 ? 0 : 2 + 3 * ph;  // timer bucket / trace stamp base of this phase
         if (ph == 0) stamp(l, 0);
 
@@ -692,13 +811,21 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 ring_advance(at, 1u, ns);
             }
             const float *wn = reinterpret_cast<const float *>(vec_stage_wait(P, sv, at));
-            load_x_norm<WT, PRO_V>(P.x, emb_row, wn, P, sv, c, wr0, wr1);
+            // input: the residual stream after the previous layer's W2 (epoch of that layer)
+            load_x_norm<WT, PRO_V>(ph == 2 ? P.ll_x1 : P.ll_x2, ph == 2 ? ep : ep - 1u, emb_row, wn, P, sv, c, wr0, wr1);
             if (q == 0) vec_stage_release(P, sv, c, cs);
             vec_stage_release(P, sv, c, cs);
+        }
+        // residual phases: request the old value of this thread's output rows now (own earlier
+        // writes), so the epilogue does not pay an L2 round trip (rows per CTA <= threads)
+        unsigned long long x_old = 0ull;
+        if ((ph == 1 || ph == 3) && c.tid < cp.r1[ph] - cp.r0[ph])
+            x_old = ll_load1((ph == 1 ? P.ll_x2 : P.ll_x1) + cp.r0[ph] + c.tid);
+        if (ph == 0 || ph == 2 || ph == 4) {
         } else if (ph == 1 && P.n_splits > 1) {
-            load_x_attn<WT, PRO_V>(P, sv, c);
+            load_x_attn<WT, PRO_V>(P, ep, sv, c);
         } else {
-            load_x_plain<WT, PRO_V>(ph == 1 ? P.att : P.hb, ph == 1 ? P.emb : P.hid, sv, c);
+            load_x_plain<WT, PRO_V>(ph == 1 ? P.ll_att : P.ll_hb, ep, ph == 1 ? P.emb : P.hid, sv, c);
         }
         lap(tb);
         stamp(l, ph == 0 ? 1 : 3 + 3 * ph);
@@ -721,24 +848,30 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 const float a = resv(i), b = resv(i + 1);
                 if (r < P.emb) {
                     const float2 cs2 = rope[(r >> 1) & half_mask];
-                    P.q[r] = a * cs2.x - b * cs2.y;
-                    P.q[r + 1] = a * cs2.y + b * cs2.x;
+                    ll_store(P.ll_q, r, a * cs2.x - b * cs2.y, ep);
+                    ll_store(P.ll_q, r + 1, a * cs2.y + b * cs2.x, ep);
                 } else if (r < P.emb + P.kv) {
+                    // the cache row serves later launches, the LL copy this launch's attention
                     const int rk = r - P.emb;
                     const float2 cs2 = rope[(rk >> 1) & half_mask];
-                    kc[rk] = a * cs2.x - b * cs2.y;
-                    kc[rk + 1] = a * cs2.y + b * cs2.x;
+                    const float k0 = a * cs2.x - b * cs2.y, k1 = a * cs2.y + b * cs2.x;
+                    kc[rk] = k0;
+                    kc[rk + 1] = k1;
+                    ll_store(P.ll_kv, rk, k0, ep);
+                    ll_store(P.ll_kv, rk + 1, k1, ep);
                 } else {
                     const int rv = r - P.emb - P.kv;
                     vc[rv] = a;
                     vc[rv + 1] = b;
+                    ll_store(P.ll_kv, P.kv + rv, a, ep);
+                    ll_store(P.ll_kv, P.kv + rv + 1, b, ep);
                 }
             }
         } else if (ph == 2) {
             // SwiGLU on the interleaved gate/up rows (llama2.f90:613-616)
             for (int i = 2 * c.tid; i < nr; i += 2 * c.nt) {
                 const float g = resv(i), u = resv(i + 1);
-                P.hb[(r0 + i) >> 1] = (g * (1.0f / (1.0f + expf(-g)))) * u;
+                ll_store(P.ll_hb, (r0 + i) >> 1, (g * (1.0f / (1.0f + expf(-g)))) * u, ep);
             }
         } else if (ph == 4) {
             for (int i = c.tid; i < nr; i += c.nt) {
@@ -747,24 +880,24 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 if (v > best) { best = v; bidx = r0 + i; }
             }
         } else {
-            // residual add after Wo / W2 (llama2.f90:603-605, :618-620)
+            // residual add after Wo / W2 (llama2.f90:603-605, :618-620).  The old value of the
+            // slice is this thread's own earlier write (Wo and W2 have the same row partition).
+            unsigned long long *from = ph == 1 ? P.ll_x2 : P.ll_x1, *to = ph == 1 ? P.ll_x1 : P.ll_x2;
             for (int i = c.tid; i < nr; i += c.nt) {
                 const int r = r0 + i;
-                P.x[r] = __ldcg(P.x + r) + resv(i);
+                const float old = i == c.tid ? ll_val(x_old) : ll_peek(from, r);
+                ll_store(to, r, old + resv(i), ep);
             }
         }
         if (ph == 4) break;
-        grid_sync(P, c, nbar);
         lap(tb + 2);
         stamp(l, ph == 0 ? 3 : 5 + 3 * ph);
 
         if (ph == 0) {
             // ---- attention (llama2.f90:574-598)
-            attention_phase(P, sv, c, l, pos);
+            attention_phase(P, sv, c, l, pos, ep);
             lap(PH_ATT);
             stamp(l, 4);
-            grid_sync(P, c, nbar);
-            lap(PH_ATT_BAR);
             stamp(l, 5);
         }
         if (ph == 3 && tracer && l == P.trace_layer)
@@ -782,20 +915,22 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         }
         float *rv = sv.red;
         int *ri = reinterpret_cast<int *>(sv.red + 32);
+        const uint32_t epl = P.ep_base + (uint32_t)P.L + 1u;
         if (c.lane == 0) { rv[c.warp] = best; ri[c.warp] = bidx; }
         cons_sync(c);
         if (c.tid == 0) {
             for (int w = 1; w < c.nw; w++)
                 if (rv[w] > best || (rv[w] == best && ri[w] < bidx)) { best = rv[w]; bidx = ri[w]; }
-            P.amax_scratch[2 * blockIdx.x] = __float_as_int(best);
-            P.amax_scratch[2 * blockIdx.x + 1] = bidx;
+            ll_store(P.ll_amax, 2 * blockIdx.x, best, epl);
+            ll_store(P.ll_amax, 2 * blockIdx.x + 1, __int_as_float(bidx), epl);
         }
-        grid_sync(P, c, nbar);
         if (blockIdx.x == 0 && c.warp == 0) {
             best = -INFINITY; bidx = 0x7fffffff;
             for (int i = c.lane; i < (int)gridDim.x; i += 32) {
-                const float v = __int_as_float(__ldcg(P.amax_scratch + 2 * i));
-                const int ix = __ldcg(P.amax_scratch + 2 * i + 1);
+                float rec[2];
+                ll_waitv<2>(P.ll_amax, 2 * i, epl, rec);
+                const float v = rec[0];
+                const int ix = __float_as_int(rec[1]);
                 if (v > best || (v == best && ix < bidx)) { best = v; bidx = ix; }
             }
 #pragma unroll
@@ -823,8 +958,6 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
 }
 
 // ------------------------------------------------------------------ host side
-int stream_barriers_per_launch(const StreamParams &p) { return 5 * p.L + (p.do_argmax ? 1 : 0); }
-
 int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target_slot_bytes,
                 int max_slots, StreamPlan *out)
 {
