@@ -125,11 +125,19 @@ int llmf90_b200_softmax(const float *x, int32_t n, int32_t s, float *p);
 /* llama2.f90:543-559, in place on q(1:emb) and k(1:kv); pos is 1-based */
 int llmf90_b200_rope(float *q, float *k, int32_t emb, int32_t kv, int32_t head_size, int32_t pos);
 
-/* ---- tensor parallelism plumbing (one process per GPU) ---- */
-/* rank 0 creates a 128-byte id, the host distributes it, every rank passes it to init_tp
- * BEFORE llmf90_b200_init with tp_size > 1. */
-int llmf90_b200_tp_unique_id(void *id128);
-int llmf90_b200_tp_connect(const void *id128, int32_t rank, int32_t size, int32_t device);
+/* ---- tensor parallelism plumbing (one process per GPU) ----
+ * Every rank calls llmf90_b200_init with the FULL host weights and its tp_rank / tp_size: the
+ * library uploads only the rank's shard (its heads' Wq rows, their KV heads' Wk / Wv rows, the
+ * matching Wo columns, its FFN rows of W1 / W3 and columns of W2, its vocabulary rows).  The
+ * all-reduce after Wo and after W2 is fused into the decode kernel: every rank stores its partial
+ * vector straight into every other rank's hand-over buffer over NVLink.  For that the ranks
+ * exchange one 64-byte CUDA IPC handle each (any host transport: MPI, torch.distributed, a file):
+ *   llmf90_b200_tp_export(h)          -> this rank's handle
+ *   llmf90_b200_tp_connect(all, n)    <- the n = tp_size handles in rank order
+ * After connect every rank calls llmf90_b200_transformer / _generate_greedy with the same
+ * arguments in the same order; each returns the full, identical logits. */
+int llmf90_b200_tp_export(void *handle64);
+int llmf90_b200_tp_connect(const void *handles, int32_t n);
 
 /* ---- introspection used by the benchmark harness ---- */
 typedef struct llmf90_b200_stats {

@@ -22,7 +22,7 @@ EXPORTS = [
     "llmf90_b200_init", "llmf90_b200_transformer", "llmf90_b200_times", "llmf90_b200_reset",
     "llmf90_b200_free", "llmf90_b200_last_error", "llmf90_b200_generate_greedy",
     "llmf90_b200_matvec", "llmf90_b200_rmsnorm", "llmf90_b200_softmax", "llmf90_b200_rope",
-    "llmf90_b200_tp_unique_id", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
+    "llmf90_b200_tp_export", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
     "llmf90_b200_bench_device_loop", "llmf90_b200_phase_times", "llmf90_b200_debug_trace",
 ]
 
@@ -70,8 +70,8 @@ def load() -> C.CDLL:
     L.llmf90_b200_rmsnorm.argtypes = [fp, fp, C.c_int32, fp]
     L.llmf90_b200_softmax.argtypes = [fp, C.c_int32, C.c_int32, fp]
     L.llmf90_b200_rope.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
-    L.llmf90_b200_tp_unique_id.argtypes = [vp]
-    L.llmf90_b200_tp_connect.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.llmf90_b200_tp_export.argtypes = [vp]
+    L.llmf90_b200_tp_connect.argtypes = [vp, C.c_int32]
     L.llmf90_b200_get_stats.argtypes = [C.POINTER(CStats)]
     L.llmf90_b200_bench_device_loop.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp]
     for name in EXPORTS:
@@ -99,12 +99,14 @@ def _ip(a: np.ndarray):
 class Engine:
     """The process-wide engine singleton behind the C ABI."""
 
-    def __init__(self, weights: Weights, device: int = 0, granular: bool = False):
+    def __init__(self, weights: Weights, device: int = 0, granular: bool = False, tp_rank: int = 0,
+                 tp_size: int = 1):
         self.L = load()
         c = weights.cfg
         self.cfg = c
+        self.tp_rank, self.tp_size = tp_rank, tp_size
         cc = CConfig(c.emb_dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads, c.vocab_size,
-                     c.seq_len, c.wtype, device, 0, 1, FLAG_GRANULAR if granular else 0)
+                     c.seq_len, c.wtype, device, tp_rank, tp_size, FLAG_GRANULAR if granular else 0)
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
         _check(self.L.llmf90_b200_init(C.byref(cc), ptr(weights.token_embedding_table),
                                        ptr(weights.rms_att_weight), ptr(weights.wqkv), ptr(weights.wo),
@@ -112,6 +114,18 @@ class Engine:
                                        ptr(weights.rms_final_weight), ptr(weights.wcls)))
         self._logits = np.empty(c.vocab_size, np.float32)
         self.open = True
+
+    def tp_export(self) -> bytes:
+        """This rank's 64-byte CUDA IPC handle of the buffers the other ranks write into."""
+        buf = C.create_string_buffer(64)
+        _check(self.L.llmf90_b200_tp_export(buf))
+        return buf.raw
+
+    def tp_connect(self, handles: list[bytes]) -> None:
+        """Map the other ranks' buffers (handles in rank order, one per rank)."""
+        assert len(handles) == self.tp_size and all(len(h) == 64 for h in handles)
+        blob = C.create_string_buffer(b"".join(handles), 64 * len(handles))
+        _check(self.L.llmf90_b200_tp_connect(blob, len(handles)))
 
     def transformer(self, token: int, pos: int, out: np.ndarray | None = None) -> np.ndarray:
         """logits = transformer(token, pos) with 1-based token/pos (llama2.f90:380)."""
@@ -217,7 +231,14 @@ def rope(q: np.ndarray, k: np.ndarray, head_size: int, pos: int):
 
 def make_engine(weights: Weights, device: int = 0, tp_rank: int = 0, tp_size: int = 1,
                 granular: bool = False) -> Engine:
-    """Engine factory used by bench.py: single GPU, or one tensor-parallel rank of `tp_size`."""
-    if tp_size == 1:
-        return Engine(weights, device=device, granular=granular)
-    raise EngineError("tensor-parallel engine: use llm.f90_b200.tp.TPEngine (not built yet)")
+    """Single GPU, or one tensor-parallel rank of `tp_size` (one process per GPU).  For tp_size > 1
+    torch.distributed must be initialised: it carries the 64-byte IPC handles, nothing else -- the
+    all-reduces of the forward run inside the decode kernel over NVLink peer stores."""
+    eng = Engine(weights, device=device, granular=granular, tp_rank=tp_rank, tp_size=tp_size)
+    if tp_size > 1:
+        import torch.distributed as dist
+        handles: list = [None] * tp_size
+        dist.all_gather_object(handles, eng.tp_export())
+        eng.tp_connect(handles)
+        dist.barrier()
+    return eng

@@ -43,7 +43,11 @@ constexpr int MAX_SPLITS = 8;
 struct Engine {
     bool ready = false;
     llmf90_b200_config cfg{};
-    int hs = 0, kv = 0, nqkv = 0, kv_mul = 0;
+    int hs = 0, kv = 0, nqkv = 0, kv_mul = 0, hid_l = 0, att_dim = 0, v_l = 0;  // this rank's share
+    // peer-visible buffer (see init) and the mapped buffers of the other tensor-parallel ranks
+    uint8_t *d_shared = nullptr, *peer[MAX_TP] = {};
+    size_t sh_part1 = 0, sh_part2 = 0, sh_amax = 0, sh_done = 0, sh_logits = 0, sh_bytes = 0;
+    bool peers_ready = false;
     int n_sms = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -55,7 +59,7 @@ struct Engine {
     // RunState + activations
     float *d_kc = nullptr, *d_vc = nullptr;
     float *d_x = nullptr, *d_xb = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_att_part = nullptr,
-          *d_h13 = nullptr, *d_hb = nullptr, *d_logits = nullptr;
+          *d_h13 = nullptr, *d_hb = nullptr;
     unsigned long long *d_times = nullptr;  // [PH_COUNT + 2]
     int *d_tokpos = nullptr, *d_forced = nullptr, *d_out_tokens = nullptr, *d_amax = nullptr;
     unsigned long long *d_ll = nullptr;  // all LL buffers of the fused kernel, one allocation
@@ -87,10 +91,13 @@ void release_all()
     if (E.graph) cudaGraphExecDestroy(E.graph);
     void *ptrs[] = {E.d_emb, E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls, E.d_rms_att, E.d_rms_ffn,
                     E.d_rms_final, E.d_rope, E.d_kc, E.d_vc, E.d_x, E.d_xb, E.d_qkv, E.d_att,
-                    E.d_att_part, E.d_h13, E.d_hb, E.d_logits, (void *)E.d_times, E.d_tokpos, E.d_forced,
+                    E.d_att_part, E.d_h13, E.d_hb, (void *)E.d_times, E.d_tokpos, E.d_forced,
                     E.d_out_tokens, E.d_amax, E.d_ll};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (int k = 0; k < MAX_TP; k++)
+        if (E.peer[k] && E.peer[k] != E.d_shared) cudaIpcCloseMemHandle(E.peer[k]);
+    if (E.d_shared) cudaFree(E.d_shared);
     if (E.h_logits) cudaFreeHost(E.h_logits);
     if (E.h_tokpos) cudaFreeHost(E.h_tokpos);
     if (E.ev0) cudaEventDestroy(E.ev0);
@@ -113,6 +120,22 @@ int upload_matrix(uint8_t *dst, const void *src_host, int wtype, int src_rows, i
     CK(cudaStreamSynchronize(E.st));
     return 0;
 }
+
+// point the kernel parameters at every rank's shared buffer (own rank: local allocation)
+void bind_peers()
+{
+    StreamParams &p = E.sp;
+    for (int k = 0; k < E.cfg.tp_size; k++) {
+        uint8_t *b = E.peer[k] ? E.peer[k] : E.d_shared;  // not yet connected: harmless placeholder
+        p.part1[k] = reinterpret_cast<unsigned long long *>(b + E.sh_part1);
+        p.part2[k] = reinterpret_cast<unsigned long long *>(b + E.sh_part2);
+        p.amax[k] = reinterpret_cast<unsigned long long *>(b + E.sh_amax);
+        p.done[k] = reinterpret_cast<unsigned long long *>(b + E.sh_done);
+        p.logits[k] = reinterpret_cast<float *>(b + E.sh_logits);
+    }
+}
+
+float *logits_dev() { return reinterpret_cast<float *>(E.d_shared + E.sh_logits); }
 
 int n_splits_for(int pos)
 {
@@ -158,7 +181,7 @@ int enqueue_granular(bool count)
         CK(launch_matvec(E.d_w2 + (size_t)l * emb * rs_h, wt, emb, hid, E.d_hb, E.d_x, E.d_x, E.st)); k++;
     }
     CK(launch_rmsnorm(E.d_x, E.d_rms_final, E.d_xb, emb, E.st)); k++;
-    CK(launch_matvec(E.d_wcls, wt, c.vocab_size, emb, E.d_xb, nullptr, E.d_logits, E.st)); k++;
+    CK(launch_matvec(E.d_wcls, wt, c.vocab_size, emb, E.d_xb, nullptr, logits_dev(), E.st)); k++;
     if (count) E.graph_kernels = k;
     return 0;
 }
@@ -218,7 +241,7 @@ int enqueue_forward(int token, int pos, bool device_loop, const int *forced, int
         CK(cudaGraphLaunch(E.graph, E.st));
         E.launches += E.graph_kernels;
         if (device_loop) {
-            CK(launch_argmax(E.d_logits, E.cfg.vocab_size, E.d_amax, E.st));
+            CK(launch_argmax(logits_dev(), E.cfg.vocab_size, E.d_amax, E.st));
             advance_kernel<<<1, 1, 0, E.st>>>(E.d_tokpos, E.d_amax, forced, out_tokens);
             CK(cudaGetLastError());
             E.launches += 2;
@@ -308,8 +331,17 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     const int colmul = c.wtype == WT_Q4_0 ? 32 : (c.wtype == WT_F16 ? 8 : 4);
     if (c.emb_dim % colmul || c.hidden_dim % colmul)
         return fail("config: emb_dim/hidden_dim must be multiples of %d for this wtype", colmul);
-    if (c.tp_size != 1 && c.tp_size != 0)
-        return fail("tensor parallel init must go through llmf90_b200_tp_connect (tp_size=%d)", c.tp_size);
+    const int tp = c.tp_size <= 0 ? 1 : c.tp_size, rank = tp == 1 ? 0 : c.tp_rank;
+    if (tp != 1 && tp != 2 && tp != 4 && tp != 8) return fail("config: tp_size %d not in {1,2,4,8}", tp);
+    if (rank < 0 || rank >= tp) return fail("config: tp_rank %d out of range", rank);
+    if (tp > 1) {
+        if (c.flags & LLMF90_FLAG_GRANULAR) return fail("the granular forward is single-GPU only");
+        if (c.n_heads % tp || c.n_kv_heads % tp)
+            return fail("config: n_heads %d and n_kv_heads %d must be multiples of tp_size %d", c.n_heads,
+                        c.n_kv_heads, tp);
+        if (c.hidden_dim % (tp * colmul) || (c.emb_dim / tp) % colmul || c.vocab_size % tp)
+            return fail("config: hidden_dim / emb_dim / vocab_size do not split %d ways for this wtype", tp);
+    }
     if (!tok_emb || !rms_att || !wqkv || !wo || !rms_ffn || !w13 || !w2 || !rms_final || !wcls)
         return fail("null weight pointer");
     if (ensure_device(c.device)) return 1;
@@ -320,57 +352,69 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
                     prop.major, prop.minor);
 
     E.cfg = c;
-    E.cfg.tp_size = 1; E.cfg.tp_rank = 0;
-    E.hs = hs; E.kv = c.n_kv_heads * hs; E.nqkv = c.emb_dim + 2 * E.kv; E.kv_mul = c.n_heads / c.n_kv_heads;
+    E.cfg.tp_size = tp; E.cfg.tp_rank = rank;
+    E.hs = hs; E.kv_mul = c.n_heads / c.n_kv_heads;
     E.n_sms = prop.multiProcessorCount;
     E.use_stream = !(c.flags & LLMF90_FLAG_GRANULAR);
-    const int emb = c.emb_dim, hid = c.hidden_dim, L = c.n_layers, V = c.vocab_size, wt = c.wtype;
-    const size_t rs_e = row_stride_bytes(wt, emb), rs_h = row_stride_bytes(wt, hid);
+    const int emb = c.emb_dim, L = c.n_layers, V = c.vocab_size, wt = c.wtype;
+    const int hid_full = c.hidden_dim, kv_full = c.n_kv_heads * hs;
+    // this rank's share: heads and their KV heads, FFN rows, vocabulary rows
+    const int Hl = c.n_heads / tp, KVHl = c.n_kv_heads / tp;
+    const int att = Hl * hs, kvl = KVHl * hs, nqkv = att + 2 * kvl, hid = hid_full / tp, Vl = V / tp;
+    E.kv = kvl; E.nqkv = nqkv; E.hid_l = hid; E.att_dim = att; E.v_l = Vl;
+    const size_t rs_e = row_stride_bytes(wt, emb), rs_a = row_stride_bytes(wt, att), rs_h = row_stride_bytes(wt, hid);
 
     CK(cudaStreamCreateWithFlags(&E.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&E.ev0)); CK(cudaEventCreate(&E.ev1)); CK(cudaEventCreate(&E.ev2));
 
-    // ---- weights
+    // ---- weights (device row format), this rank's shard
     CK(dalloc(&E.d_emb, (size_t)V * rs_e));
-    CK(dalloc(&E.d_wqkv, (size_t)L * E.nqkv * rs_e));
-    CK(dalloc(&E.d_wo, (size_t)L * emb * rs_e));
+    CK(dalloc(&E.d_wqkv, (size_t)L * nqkv * rs_e));
+    CK(dalloc(&E.d_wo, (size_t)L * emb * rs_a));
     CK(dalloc(&E.d_w13, (size_t)L * 2 * hid * rs_e));
     CK(dalloc(&E.d_w2, (size_t)L * emb * rs_h));
-    CK(dalloc(&E.d_wcls, (size_t)V * rs_e));
+    CK(dalloc(&E.d_wcls, (size_t)Vl * rs_e));
     CK(dalloc(&E.d_rms_att, (size_t)L * emb));
     CK(dalloc(&E.d_rms_ffn, (size_t)L * emb));
     CK(dalloc(&E.d_rms_final, (size_t)emb));
-    E.weight_bytes = (size_t)V * rs_e * 2 + (size_t)L * (E.nqkv * rs_e + emb * rs_e + 2 * hid * rs_e + emb * rs_h) +
+    E.weight_bytes = (size_t)V * rs_e + (size_t)Vl * rs_e +
+                     (size_t)L * ((size_t)nqkv * rs_e + (size_t)emb * rs_a + (size_t)2 * hid * rs_e + (size_t)emb * rs_h) +
                      (size_t)(2 * L + 1) * emb * 4;
-    // algorithmic bytes per token, host row sizes
+    // algorithmic bytes per token on this GPU, host row sizes
+    const size_t hb_e = host_row_bytes(wt, emb), hb_hf = host_row_bytes(wt, hid_full);
+    E.active_bytes = (size_t)L * ((size_t)(nqkv + 2 * hid) * hb_e + (size_t)emb * host_row_bytes(wt, att) +
+                                  (size_t)emb * host_row_bytes(wt, hid) + 2 * (size_t)emb * 4) +
+                     (size_t)Vl * hb_e + (size_t)emb * 4 + hb_e;
     {
-        const size_t hb_e = host_row_bytes(wt, emb), hb_h = host_row_bytes(wt, hid);
-        E.active_bytes = (size_t)L * ((size_t)(E.nqkv + emb + 2 * hid) * hb_e + (size_t)emb * hb_h + 2 * emb * 4) +
-                         (size_t)V * hb_e + emb * 4 + hb_e;
-    }
-    {
-        const size_t hb_e = host_row_bytes(wt, emb), hb_h = host_row_bytes(wt, hid);
-        size_t stage_bytes = std::max({(size_t)V * hb_e, (size_t)2 * hid * hb_e, (size_t)emb * hb_h,
-                                       (size_t)E.nqkv * hb_e});
+        const int nqkv_full = emb + 2 * kv_full;
+        size_t stage_bytes = std::max({(size_t)V * hb_e, (size_t)2 * hid_full * hb_e, (size_t)emb * hb_hf,
+                                       (size_t)nqkv_full * hb_e});
         uint8_t *stage = nullptr;
         CK(dalloc(&stage, stage_bytes));
         int rc = 0;
         rc |= upload_matrix(E.d_emb, tok_emb, wt, V, emb, V, 0, emb, 0, 0, 0, stage, stage_bytes);
-        rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, V, 0, emb, 0, 0, 0, stage, stage_bytes);
+        rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, Vl, 0, emb, 0, rank * Vl, 0, stage, stage_bytes);
         for (int l = 0; l < L && !rc; l++) {
-            const uint8_t *s_qkv = (const uint8_t *)wqkv + (size_t)l * E.nqkv * hb_e;
+            const uint8_t *s_qkv = (const uint8_t *)wqkv + (size_t)l * nqkv_full * hb_e;
             const uint8_t *s_wo = (const uint8_t *)wo + (size_t)l * emb * hb_e;
-            const uint8_t *s_w13 = (const uint8_t *)w13 + (size_t)l * 2 * hid * hb_e;
-            const uint8_t *s_w2 = (const uint8_t *)w2 + (size_t)l * emb * hb_h;
-            rc |= upload_matrix(E.d_wqkv + (size_t)l * E.nqkv * rs_e, s_qkv, wt, E.nqkv, emb, E.nqkv, 0,
-                                emb, 0, 0, 0, stage, stage_bytes);
-            rc |= upload_matrix(E.d_wo + (size_t)l * emb * rs_e, s_wo, wt, emb, emb, emb, 0, emb, 0, 0, 0,
+            const uint8_t *s_w13 = (const uint8_t *)w13 + (size_t)l * 2 * hid_full * hb_e;
+            const uint8_t *s_w2 = (const uint8_t *)w2 + (size_t)l * emb * hb_hf;
+            uint8_t *d_qkv = E.d_wqkv + (size_t)l * nqkv * rs_e;
+            // Wq rows of this rank's heads | Wk rows | Wv rows of its KV heads (read_ggml.f90:272,286,300)
+            rc |= upload_matrix(d_qkv, s_qkv, wt, nqkv_full, emb, att, 0, emb, 0, rank * att, 0, stage, stage_bytes);
+            rc |= upload_matrix(d_qkv + (size_t)att * rs_e, s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
+                                emb + rank * kvl, 0, stage, stage_bytes);
+            rc |= upload_matrix(d_qkv + (size_t)(att + kvl) * rs_e, s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
+                                emb + kv_full + rank * kvl, 0, stage, stage_bytes);
+            // Wo: all rows, the input columns of this rank's heads
+            rc |= upload_matrix(E.d_wo + (size_t)l * emb * rs_a, s_wo, wt, emb, emb, emb, rank * att, att, 0, 0, 0,
                                 stage, stage_bytes);
-            // gate/up rows interleaved so that row 2i = W1 row i, row 2i+1 = W3 row i
-            rc |= upload_matrix(E.d_w13 + (size_t)l * 2 * hid * rs_e, s_w13, wt, 2 * hid, emb, 2 * hid, 0,
-                                emb, 1, 0, hid, stage, stage_bytes);
-            rc |= upload_matrix(E.d_w2 + (size_t)l * emb * rs_h, s_w2, wt, emb, hid, emb, 0, hid, 0, 0, 0,
-                                stage, stage_bytes);
+            // gate/up rows of this rank's FFN slice, interleaved: row 2i = W1 row i, row 2i+1 = W3 row i
+            rc |= upload_matrix(E.d_w13 + (size_t)l * 2 * hid * rs_e, s_w13, wt, 2 * hid_full, emb, 2 * hid, 0,
+                                emb, 1, rank * hid, hid_full, stage, stage_bytes);
+            // W2: all rows, the input columns of this rank's FFN slice
+            rc |= upload_matrix(E.d_w2 + (size_t)l * emb * rs_h, s_w2, wt, emb, hid_full, emb, rank * hid, hid, 0, 0,
+                                0, stage, stage_bytes);
         }
         cudaFree(stage);
         if (rc) { release_all(); return 1; }
@@ -380,16 +424,15 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     CK(cudaMemcpy(E.d_rms_final, rms_final, (size_t)emb * 4, cudaMemcpyHostToDevice));
 
     // ---- RunState, activations
-    const size_t cache = (size_t)L * c.seq_len * E.kv;
+    const size_t cache = (size_t)L * c.seq_len * kvl;
     CK(dalloc(&E.d_kc, cache)); CK(dalloc(&E.d_vc, cache));
     CK(cudaMemsetAsync(E.d_kc, 0, cache * 4, E.st)); CK(cudaMemsetAsync(E.d_vc, 0, cache * 4, E.st));
     CK(dalloc(&E.d_rope, (size_t)c.seq_len * (hs / 2)));
     CK(launch_rope_table(E.d_rope, c.seq_len, hs, E.st));
-    CK(dalloc(&E.d_x, (size_t)emb)); CK(dalloc(&E.d_xb, (size_t)emb)); CK(dalloc(&E.d_qkv, (size_t)E.nqkv));
+    CK(dalloc(&E.d_x, (size_t)emb)); CK(dalloc(&E.d_xb, (size_t)emb)); CK(dalloc(&E.d_qkv, (size_t)nqkv));
     CK(dalloc(&E.d_att, (size_t)emb));
-    CK(dalloc(&E.d_att_part, (size_t)c.n_heads * MAX_SPLITS * (hs + 4)));
     CK(dalloc(&E.d_h13, (size_t)2 * hid)); CK(dalloc(&E.d_hb, (size_t)hid));
-    CK(dalloc(&E.d_logits, (size_t)V)); CK(dalloc(&E.d_times, (size_t)(PH_COUNT + 2)));
+    CK(dalloc(&E.d_times, (size_t)(PH_COUNT + 2)));
     CK(cudaMemsetAsync(E.d_times, 0, (PH_COUNT + 2) * 8, E.st));
     CK(dalloc(&E.d_tokpos, (size_t)2)); CK(dalloc(&E.d_forced, (size_t)c.seq_len));
     CK(dalloc(&E.d_out_tokens, (size_t)c.seq_len)); CK(dalloc(&E.d_amax, (size_t)2 * 1024));
@@ -404,8 +447,9 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         if (!coop) { release_all(); return fail("device does not support cooperative launch"); }
         StreamParams &p = E.sp;
         p = StreamParams{};
-        p.emb = emb; p.hid = hid; p.L = L; p.H = c.n_heads; p.KVH = c.n_kv_heads; p.V = V;
-        p.seq = c.seq_len; p.hs = hs; p.kv = E.kv; p.kv_mul = E.kv_mul; p.nqkv = E.nqkv; p.wtype = wt;
+        p.emb = emb; p.hid = hid; p.L = L; p.H = Hl; p.KVH = KVHl; p.V = Vl;
+        p.seq = c.seq_len; p.hs = hs; p.kv = kvl; p.kv_mul = E.kv_mul; p.nqkv = nqkv; p.wtype = wt;
+        p.att_dim = att; p.tp = tp; p.rank = rank; p.v_off = rank * Vl; p.v_total = V;
         auto mk = [&](const uint8_t *base, int rows, int cols, int unit) {
             PhaseW w{};
             w.base = base; w.rows = rows; w.cols = cols; w.unit = unit;
@@ -413,54 +457,68 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             w.layer_stride = (unsigned long long)rows * w.rs;
             return w;
         };
-        p.ph[0] = mk(E.d_wqkv, E.nqkv, emb, 2);
-        p.ph[1] = mk(E.d_wo, emb, emb, 1);
+        p.ph[0] = mk(E.d_wqkv, nqkv, emb, 2);
+        p.ph[1] = mk(E.d_wo, emb, att, 1);
         p.ph[2] = mk(E.d_w13, 2 * hid, emb, 2);
         p.ph[3] = mk(E.d_w2, emb, hid, 1);
-        p.ph[4] = mk(E.d_wcls, V, emb, 1);
-        int target_slot = 24576, max_slots = (wt == WT_Q4_0) ? 7 : 7;
+        p.ph[4] = mk(E.d_wcls, Vl, emb, 1);
+        int target_slot = 24576, max_slots = 7;
         if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
         if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
         if (plan_stream(p, E.n_sms, smem_optin - 1024 /* static smem */, target_slot, max_slots, &E.plan)) {
             release_all();
             return fail("model rows do not fit the shared-memory ring (row stride too large)");
         }
+        // every CTA must own W13 rows (the LL hand-over's no-overwrite argument, stream.cu): tiny models
+        // run on fewer CTAs
+        E.plan.grid = std::min(E.plan.grid, hid);
         p.pf_stages = 0;
         if (const char *s = getenv("LLMF90_PF_STAGES")) p.pf_stages = std::max(0, atoi(s));
         p.pace = 38;  // ~1.15x the per-SM fair share of the measured HBM bandwidth (23 B/cycle)
         if (const char *s = getenv("LLMF90_PACE")) p.pace = std::max(0, atoi(s));
-        if (const char *s = getenv("LLMF90_WPS")) {
-            int w = atoi(s);
-            if (w >= 1 && w * E.plan.n_slots <= 15) { E.plan.wps = w; E.plan.threads = (E.plan.n_slots * w + 1) * 32; }
-        }
         for (int i = 0; i < 5; i++) p.ph[i].rps = std::max(1, E.plan.slot_bytes / (int)p.ph[i].rs);
         p.emb_table = E.d_emb;
         p.rms_att = E.d_rms_att; p.rms_ffn = E.d_rms_ffn; p.rms_final = E.d_rms_final;
         p.rope_tab = E.d_rope;
         {
-            // LL buffers (64-bit words), zero-filled: epoch 0 is never expected
-            const size_t n_part = (size_t)c.n_heads * MAX_SPLITS * (hs + 4);
-            const size_t words = 4 * (size_t)emb + hid + 2 * (size_t)E.kv + n_part + 2 * (size_t)E.n_sms + 64;
+            // rank-private LL buffers (64-bit words), zero-filled: epoch 0 is never expected
+            const size_t n_part = (size_t)Hl * MAX_SPLITS * (hs + 4);
+            const size_t words = 2 * (size_t)att + ((hid + 1) & ~1) + 2 * (size_t)kvl + n_part + 64;
             CK(dalloc(&E.d_ll, words));
             CK(cudaMemsetAsync(E.d_ll, 0, words * 8, E.st));
             unsigned long long *w = E.d_ll;
-            p.ll_x1 = w; w += emb;
-            p.ll_x2 = w; w += emb;
-            p.ll_q = w; w += emb;
-            p.ll_att = w; w += emb;
+            p.ll_q = w; w += att;
+            p.ll_att = w; w += att;
             p.ll_hb = w; w += (hid + 1) & ~1;
-            p.ll_kv = w; w += 2 * E.kv;
-            p.ll_part = w; w += n_part;
-            p.ll_amax = w;
+            p.ll_kv = w; w += 2 * kvl;
+            p.ll_part = w;
         }
-        p.logits = E.d_logits;
+        {
+            // buffers the other ranks write into (one allocation, exported over CUDA IPC when tp > 1):
+            // Wo / W2 partials, argmax records, "logits stored" flags, the all-gathered logits
+            const size_t G = (size_t)E.plan.grid;
+            E.sh_part1 = 0;
+            E.sh_part2 = E.sh_part1 + (size_t)tp * emb * 8;
+            E.sh_amax = E.sh_part2 + (size_t)tp * emb * 8;
+            E.sh_done = E.sh_amax + (size_t)tp * G * 2 * 8;
+            E.sh_logits = E.sh_done + (((size_t)tp * G * 8 + 15) & ~(size_t)15);
+            E.sh_bytes = E.sh_logits + (size_t)V * 4;
+            CK(cudaMalloc((void **)&E.d_shared, E.sh_bytes));
+            CK(cudaMemsetAsync(E.d_shared, 0, E.sh_bytes, E.st));
+            for (int k = 0; k < MAX_TP; k++) E.peer[k] = nullptr;
+            E.peer[rank] = E.d_shared;
+            E.peers_ready = (tp == 1);
+            bind_peers();
+        }
         p.kc = E.d_kc; p.vc = E.d_vc;
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.wps = E.plan.wps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
-        if (E.plan.grid > 1024) { release_all(); return fail("grid larger than argmax scratch"); }
         CK(prepare_stream_kernel(wt, E.plan.threads, E.plan.smem_bytes));
     } else {
+        CK(dalloc(&E.d_att_part, (size_t)c.n_heads * MAX_SPLITS * (hs + 4)));
+        CK(cudaMalloc((void **)&E.d_shared, (size_t)V * 4));
+        E.sh_logits = 0;
         if (build_granular_graph()) { release_all(); return 1; }
     }
     CK(cudaStreamSynchronize(E.st));
@@ -471,13 +529,14 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
 int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
 {
     if (!E.ready) return fail("llmf90_b200_transformer: engine not initialised");
+    if (!E.peers_ready) return fail("tensor-parallel engine: call llmf90_b200_tp_connect first");
     if (token < 1 || token > E.cfg.vocab_size) return fail("token %d out of range 1..%d", token, E.cfg.vocab_size);
     if (pos < 1 || pos > E.cfg.seq_len) return fail("pos %d out of range 1..%d", pos, E.cfg.seq_len);
     if (!logits) return fail("logits is null");
     CK(cudaEventRecord(E.ev0, E.st));
     if (enqueue_forward(token, pos, false, nullptr, nullptr)) return 1;
     CK(cudaEventRecord(E.ev1, E.st));
-    CK(cudaMemcpyAsync(E.h_logits, E.d_logits, (size_t)E.cfg.vocab_size * 4, cudaMemcpyDeviceToHost, E.st));
+    CK(cudaMemcpyAsync(E.h_logits, logits_dev(), (size_t)E.cfg.vocab_size * 4, cudaMemcpyDeviceToHost, E.st));
     CK(cudaStreamSynchronize(E.st));
     memcpy(logits, E.h_logits, (size_t)E.cfg.vocab_size * 4);
     CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
@@ -660,10 +719,32 @@ int llmf90_b200_rope(float *q, float *k, int32_t emb, int32_t kv, int32_t head_s
     return 0;
 }
 
-int llmf90_b200_tp_unique_id(void *) { return fail("tensor parallelism is not built in this revision"); }
-int llmf90_b200_tp_connect(const void *, int32_t, int32_t, int32_t)
+int llmf90_b200_tp_export(void *handle64)
 {
-    return fail("tensor parallelism is not built in this revision");
+    if (!E.ready || !E.use_stream) return fail("tp_export: engine not initialised");
+    if (!handle64) return fail("tp_export: null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, E.d_shared));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int llmf90_b200_tp_connect(const void *handles, int32_t n)
+{
+    if (!E.ready || !E.use_stream) return fail("tp_connect: engine not initialised");
+    if (!handles || n != E.cfg.tp_size) return fail("tp_connect: expected %d handles", E.cfg.tp_size);
+    for (int k = 0; k < n; k++) {
+        if (k == E.cfg.tp_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t *)handles + (size_t)k * 64, 64);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        E.peer[k] = (uint8_t *)ptr;
+    }
+    bind_peers();
+    E.peers_ready = true;
+    return 0;
 }
 
 }  // extern "C"

@@ -58,8 +58,15 @@ struct PhaseW {
     int rps;                 // rows per ring stage
 };
 
+constexpr int MAX_TP = 8;
+
+// All dimensions are THIS GPU's share under tensor parallelism (tp ranks): H / KVH / kv / hid / V /
+// nqkv / att_dim are local, emb is the full residual width (the residual stream is replicated).
 struct StreamParams {
     int emb, hid, L, H, KVH, V, seq, hs, kv, kv_mul, nqkv, wtype;
+    int att_dim;             // H * hs: rows of Wq and contraction length of Wo on this rank
+    int tp, rank;            // tensor-parallel size and rank (1, 0 on a single GPU)
+    int v_off, v_total;      // this rank's first vocabulary row and the full vocabulary size
     PhaseW ph[5];            // 0 QKV, 1 WO, 2 W13 (interleaved), 3 W2, 4 CLS
     const uint8_t *emb_table;  // [V][rs_emb] device row format
     const float *rms_att, *rms_ffn, *rms_final;
@@ -67,16 +74,21 @@ struct StreamParams {
     // Activations between phases travel in "LL" buffers: every float is one 64-bit word
     // {value, epoch} written and read atomically, so a reader that sees the expected epoch has
     // the value -- no grid barrier, no fence (see stream.cu).  Sizes in 64-bit words.
-    unsigned long long *ll_x1;    // [emb]   residual stream after Wo
-    unsigned long long *ll_x2;    // [emb]   residual stream after W2 (input of the next layer)
+    // Wo / W2 outputs are PARTIAL sums over this rank's share of the contraction: each rank stores
+    // its partial vector into every rank's buffer (peer stores over NVLink for the others) and
+    // every CTA of every rank adds the tp partials to its copy of the residual stream -- the
+    // all-reduce after Wo and after W2 is fused into the hand-over, one NVLink hop, no NCCL call.
+    unsigned long long *part1[MAX_TP];  // rank k's [tp][emb] buffer of Wo partials (k = rank: local)
+    unsigned long long *part2[MAX_TP];  // same for W2
     unsigned long long *ll_hb;    // [hid]   SwiGLU output
     unsigned long long *ll_q;     // [emb]   rotated query
     unsigned long long *ll_kv;    // [2 kv]  this position's rotated key and value rows
     unsigned long long *ll_att;   // [emb]   attention output (n_splits == 1)
     unsigned long long *ll_part;  // [H][MAX_SPLITS][hs + 4] split partials {m, l, -, -, acc[hs]}
-    unsigned long long *ll_amax;  // [grid][2] per-CTA {max logit bits, index}
+    unsigned long long *amax[MAX_TP];   // rank k's [tp][grid][2] per-CTA {max logit bits, index}
+    unsigned long long *done[MAX_TP];   // rank k's [tp][grid] "logits rows stored" flags (tp > 1)
+    float *logits[MAX_TP];              // rank k's full [v_total] logits buffer (all-gathered)
     unsigned int ep_base;         // epoch of layer l of this launch = ep_base + l + 1
-    float *logits;
     float *kc, *vc;          // [L][seq][kv]
     unsigned long long *phase_cycles;  // [PH_COUNT + 2] SM-cycle accumulators (+ total cycles, total ns)
     const int *tokpos;       // device {token, pos} (1-based); used when token < 0
@@ -91,7 +103,7 @@ struct StreamParams {
     int *out_tokens;         // optional device array: out_tokens[pos-1] = chosen token
     // ring geometry
     int n_slots, slot_bytes, wps;  // wps = consumer warps per slot
-    int xs_floats, res_floats;
+    int xs_floats, res_floats;  // + emb floats of residual stream after the two res planes
 };
 
 struct StreamPlan {

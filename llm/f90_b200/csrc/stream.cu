@@ -43,7 +43,7 @@ constexpr int CONS_BAR = 1;         // named barrier id used by the consumer war
 
 struct SmemView {
     uint8_t *ring;
-    float *xs, *res, *red;
+    float *xs, *res, *xres, *red;  // xres: this CTA's copy of the residual stream x (llama2.f90:520,605,620)
     uint64_t *full, *empty;
 };
 
@@ -63,6 +63,8 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
     off += (size_t)P.xs_floats * 4;
     v.res = reinterpret_cast<float *>(smem + off);
     off += (size_t)P.res_floats * 4 * 2;
+    v.xres = reinterpret_cast<float *>(smem + off);
+    off += (size_t)P.emb * 4;
     v.red = reinterpret_cast<float *>(smem + off);
     off += 64 * 4;
     v.full = reinterpret_cast<uint64_t *>(smem + off);
@@ -70,9 +72,9 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
     return v;
 }
 
-static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats)
+static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats, int emb)
 {
-    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 * 2 + 64 * 4 +
+    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 * 2 + (size_t)emb * 4 + 64 * 4 +
            2 * MAX_SLOTS * 8;
 }
 
@@ -303,14 +305,20 @@ __device__ __forceinline__ void ll_store(unsigned long long *buf, int i, float v
     const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)ep << 32);
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(buf + i), "l"(w) : "memory");
 }
+// system-scope variant: the target may be a peer GPU's buffer mapped over NVLink
+__device__ __forceinline__ void ll_store_sys(unsigned long long *buf, int i, float v, uint32_t ep)
+{
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)ep << 32);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(buf + i), "l"(w) : "memory");
+}
 __device__ __forceinline__ void ll_load2(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
 {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ unsigned long long ll_load1(const unsigned long long *p)
 {
     unsigned long long a;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
     return a;
 }
 __device__ __forceinline__ float ll_val(unsigned long long w) { return __uint_as_float((uint32_t)w); }
@@ -433,46 +441,82 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
                        row_elem(row, wtype, cols, 4 * j4 + 2), row_elem(row, wtype, cols, 4 * j4 + 3));
 }
 
-// xs = rmsnorm(x) * w   (llama2.f90:450-457).  x is polled from an LL buffer or, for layer 0,
-// taken from the embedding row in a ring slot; w comes from a ring slot.  With an embedding row the
-// CTA also publishes its own residual slice x[wr0..wr1) (llama2.f90:520) for its Wo epilogue.
-template <int WT, int PRO_V>
-__device__ __forceinline__ void load_x_norm(const unsigned long long *src, uint32_t ep, const uint8_t *emb_row,
-                                            const float *wn /* shared */, const StreamParams &P,
-                                            const SmemView &sv, const Cons &c, int wr0, int wr1)
+// x += sum over the tp ranks of their partial Wo / W2 outputs (the fused all-reduce), then
+// xs = rmsnorm(x) * w (llama2.f90:450-457).  x is this CTA's copy of the residual stream in shared
+// memory; for the very first phase it is the embedding row from a ring slot (llama2.f90:520) and
+// there is nothing to add.  `part` = this rank's [tp][emb] buffer of partials; w from a ring slot.
+// Up to 8 (float4 position, rank) requests are in flight per thread per polling round.
+template <int WT, int TP>
+__device__ __forceinline__ void load_x_norm_t(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
+                                              const float *wn /* shared */, const StreamParams &P,
+                                              const SmemView &sv, const Cons &c)
 {
+    constexpr int PPB = TP >= 4 ? 1 : 4 / TP;  // float4 positions per polling batch (4-8 requests in flight)
     const int n = P.emb, n4 = n >> 2;
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
+    float4 *xr4 = reinterpret_cast<float4 *>(sv.xres);
     float ss = 0.f;
-    for (int base = 0; base < n4; base += PRO_V * c.nt) {
-        float4 v[PRO_V];
+    for (int base = c.tid; base < n4; base += PPB * c.nt) {
+        float4 x[PPB];
         if (emb_row) {
 #pragma unroll
-            for (int k = 0; k < PRO_V; k++) {
-                const int j = base + c.tid + k * c.nt;
-                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pi = 0; pi < PPB; pi++) {
+                const int j = base + pi * c.nt;
+                x[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < n4) x[pi] = emb_row4(emb_row, P.wtype, n, j);
+            }
+        } else {
+            unsigned long long w[PPB][TP][4];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int pi = 0; pi < PPB; pi++) {
+                    const int j = base + pi * c.nt;
+                    if (j < n4) {
+#pragma unroll
+                        for (int r = 0; r < TP; r++) {
+                            const unsigned long long *src = part + (size_t)r * n + 4 * j;
+                            ll_load2(src, w[pi][r][0], w[pi][r][1]);
+                            ll_load2(src + 2, w[pi][r][2], w[pi][r][3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int pi = 0; pi < PPB; pi++) {
+                    const int j = base + pi * c.nt;
+                    if (j < n4) {
+#pragma unroll
+                        for (int r = 0; r < TP; r++)
+                            ok = ok && ll_ok(w[pi][r][0], ep) && ll_ok(w[pi][r][1], ep) && ll_ok(w[pi][r][2], ep) &&
+                                 ll_ok(w[pi][r][3], ep);
+                    }
+                }
+            } while (!ok);
+#pragma unroll
+            for (int pi = 0; pi < PPB; pi++) {
+                const int j = base + pi * c.nt;
+                x[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < n4) {
-                    v[k] = emb_row4(emb_row, P.wtype, n, j);
-                    const int e = 4 * j;
-                    if (e + 3 >= wr0 && e < wr1) {
-                        if (e >= wr0 && e < wr1) ll_store(P.ll_x2, e, v[k].x, 0u);
-                        if (e + 1 >= wr0 && e + 1 < wr1) ll_store(P.ll_x2, e + 1, v[k].y, 0u);
-                        if (e + 2 >= wr0 && e + 2 < wr1) ll_store(P.ll_x2, e + 2, v[k].z, 0u);
-                        if (e + 3 >= wr0 && e + 3 < wr1) ll_store(P.ll_x2, e + 3, v[k].w, 0u);
+                    x[pi] = xr4[j];
+                    // ranks are added in rank order on every GPU: the replicated stream stays bit-identical
+#pragma unroll
+                    for (int r = 0; r < TP; r++) {
+                        x[pi].x += ll_val(w[pi][r][0]); x[pi].y += ll_val(w[pi][r][1]);
+                        x[pi].z += ll_val(w[pi][r][2]); x[pi].w += ll_val(w[pi][r][3]);
                     }
                 }
             }
-        } else {
-            ll_gather<PRO_V>(src, n4, base, ep, c, v);
         }
 #pragma unroll
-        for (int k = 0; k < PRO_V; k++) {
-            const int j = base + c.tid + k * c.nt;
-            ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss);
-            ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+        for (int pi = 0; pi < PPB; pi++) {
+            const int j = base + pi * c.nt;
             if (j < n4) {
+                const float4 v = x[pi];
+                xr4[j] = v;
+                ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
                 const float4 w = wn4[j];
-                store_x4<WT>(sv.xs, j, make_float4(v[k].x * w.x, v[k].y * w.y, v[k].z * w.z, v[k].w * w.w));
+                store_x4<WT>(sv.xs, j, make_float4(v.x * w.x, v.y * w.y, v.z * w.z, v.w * w.w));
             }
         }
     }
@@ -487,6 +531,17 @@ __device__ __forceinline__ void load_x_norm(const unsigned long long *src, uint3
         reinterpret_cast<float4 *>(sv.xs)[idx] = t;
     }
     cons_sync(c);
+}
+
+template <int WT>
+__device__ __forceinline__ void load_x_norm(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
+                                            const float *wn, const StreamParams &P, const SmemView &sv,
+                                            const Cons &c)
+{
+    if (P.tp == 1) load_x_norm_t<WT, 1>(part, ep, emb_row, wn, P, sv, c);
+    else if (P.tp == 2) load_x_norm_t<WT, 2>(part, ep, emb_row, wn, P, sv, c);
+    else if (P.tp == 4) load_x_norm_t<WT, 4>(part, ep, emb_row, wn, P, sv, c);
+    else load_x_norm_t<WT, 8>(part, ep, emb_row, wn, P, sv, c);
 }
 
 template <int WT, int PRO_V>
@@ -676,7 +731,7 @@ template <int WT, int PRO_V>
 __device__ __forceinline__ void load_x_attn(const StreamParams &P, uint32_t ep, const SmemView &sv, const Cons &c)
 {
     const int S = P.n_splits;
-    const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.emb >> 2;
+    const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.att_dim >> 2;
     const int hs_shift = hs == 64 ? 6 : (hs == 128 ? 7 : 5);
     for (int j = c.tid; j < n4; j += c.nt) {
         const int h = (4 * j) >> hs_shift, d = (4 * j) & (hs - 1);
@@ -785,7 +840,6 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     // phase results: one plane per warp of a slot when the columns are split (f32 / f16)
     const int res_planes = (WT != WT_Q4_0) ? P.wps : 1;
     auto resv = [&](int i) -> float { return res_planes == 2 ? sv.res[i] + sv.res[P.res_floats + i] : sv.res[i]; };
-    const int wr0 = cp.r0[1], wr1 = cp.r1[1];  // this CTA's Wo rows = its residual slice
     const int half_mask = (P.hs >> 1) - 1;
     const uint32_t ns = (uint32_t)P.n_slots;
     float best = -INFINITY;  // running maxloc of this thread's logits (classifier epilogue)
@@ -811,21 +865,18 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 ring_advance(at, 1u, ns);
             }
             const float *wn = reinterpret_cast<const float *>(vec_stage_wait(P, sv, at));
-            // input: the residual stream after the previous layer's W2 (epoch of that layer)
-            load_x_norm<WT, PRO_V>(ph == 2 ? P.ll_x1 : P.ll_x2, ph == 2 ? ep : ep - 1u, emb_row, wn, P, sv, c, wr0, wr1);
+            // add the tp partial outputs of the phase before (Wo of this layer / W2 of the previous one)
+            load_x_norm<WT>(ph == 2 ? P.part1[P.rank] : P.part2[P.rank], ph == 2 ? ep : ep - 1u, emb_row, wn, P, sv, c);
             if (q == 0) vec_stage_release(P, sv, c, cs);
             vec_stage_release(P, sv, c, cs);
         }
-        // residual phases: request the old value of this thread's output rows now (own earlier
-        // writes), so the epilogue does not pay an L2 round trip (rows per CTA <= threads)
-        unsigned long long x_old = 0ull;
-        if ((ph == 1 || ph == 3) && c.tid < cp.r1[ph] - cp.r0[ph])
-            x_old = ll_load1((ph == 1 ? P.ll_x2 : P.ll_x1) + cp.r0[ph] + c.tid);
-        if (ph == 0 || ph == 2 || ph == 4) {
+        // (a CTA without rows in a Wo / W2 phase does not need its input vector: skipping the poll
+        // also keeps it from ever lagging behind on a buffer nobody waits for it to have read)
+        if (ph == 0 || ph == 2 || ph == 4 || cp.r1[ph] == cp.r0[ph]) {
         } else if (ph == 1 && P.n_splits > 1) {
             load_x_attn<WT, PRO_V>(P, ep, sv, c);
         } else {
-            load_x_plain<WT, PRO_V>(ph == 1 ? P.ll_att : P.ll_hb, ep, ph == 1 ? P.emb : P.hid, sv, c);
+            load_x_plain<WT, PRO_V>(ph == 1 ? P.ll_att : P.ll_hb, ep, ph == 1 ? P.att_dim : P.hid, sv, c);
         }
         lap(tb);
         stamp(l, ph == 0 ? 1 : 3 + 3 * ph);
@@ -846,13 +897,13 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             for (int i = 2 * c.tid; i < nr; i += 2 * c.nt) {
                 const int r = r0 + i;
                 const float a = resv(i), b = resv(i + 1);
-                if (r < P.emb) {
+                if (r < P.att_dim) {
                     const float2 cs2 = rope[(r >> 1) & half_mask];
                     ll_store(P.ll_q, r, a * cs2.x - b * cs2.y, ep);
                     ll_store(P.ll_q, r + 1, a * cs2.y + b * cs2.x, ep);
-                } else if (r < P.emb + P.kv) {
+                } else if (r < P.att_dim + P.kv) {
                     // the cache row serves later launches, the LL copy this launch's attention
-                    const int rk = r - P.emb;
+                    const int rk = r - P.att_dim;
                     const float2 cs2 = rope[(rk >> 1) & half_mask];
                     const float k0 = a * cs2.x - b * cs2.y, k1 = a * cs2.y + b * cs2.x;
                     kc[rk] = k0;
@@ -860,7 +911,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                     ll_store(P.ll_kv, rk, k0, ep);
                     ll_store(P.ll_kv, rk + 1, k1, ep);
                 } else {
-                    const int rv = r - P.emb - P.kv;
+                    const int rv = r - P.att_dim - P.kv;
                     vc[rv] = a;
                     vc[rv + 1] = b;
                     ll_store(P.ll_kv, P.kv + rv, a, ep);
@@ -874,19 +925,20 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 ll_store(P.ll_hb, (r0 + i) >> 1, (g * (1.0f / (1.0f + expf(-g)))) * u, ep);
             }
         } else if (ph == 4) {
+            // logits rows of this rank go to every rank's full logits buffer (all-gather)
             for (int i = c.tid; i < nr; i += c.nt) {
                 const float v = resv(i);
-                P.logits[r0 + i] = v;
-                if (v > best) { best = v; bidx = r0 + i; }
+                const int gi = P.v_off + r0 + i;
+                for (int k = 0; k < P.tp; k++) P.logits[k][gi] = v;
+                if (v > best) { best = v; bidx = gi; }
             }
         } else {
-            // residual add after Wo / W2 (llama2.f90:603-605, :618-620).  The old value of the
-            // slice is this thread's own earlier write (Wo and W2 have the same row partition).
-            unsigned long long *from = ph == 1 ? P.ll_x2 : P.ll_x1, *to = ph == 1 ? P.ll_x1 : P.ll_x2;
-            for (int i = c.tid; i < nr; i += c.nt) {
-                const int r = r0 + i;
-                const float old = i == c.tid ? ll_val(x_old) : ll_peek(from, r);
-                ll_store(to, r, old + resv(i), ep);
+            // Wo / W2 (llama2.f90:603-605, :618-620): publish this rank's partial sums to every
+            // rank; the residual add happens in the next norm prologue, on every CTA's copy of x
+            for (int i = c.tid; i < nr * P.tp; i += c.nt) {
+                const int k = i / nr, ii = i - k * nr;  // destination rank, row within this CTA's range
+                unsigned long long *dst = (ph == 1 ? P.part1[k] : P.part2[k]) + (size_t)P.rank * P.emb;
+                ll_store_sys(dst, r0 + ii, resv(ii), ep);
             }
         }
         if (ph == 4) break;
@@ -905,6 +957,24 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     }
     lap(PH_CLS_MV);
 
+    const uint32_t epl = P.ep_base + (uint32_t)P.L + 1u;
+    const int G = (int)gridDim.x;
+    if (P.tp > 1) {
+        // the all-gathered logits must have landed on every rank before any rank's kernel ends:
+        // each CTA flags every rank once its rows are stored, CTA 0 of every rank collects the flags
+        cons_sync(c);
+        if (c.tid == 0) {
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (int k = 0; k < P.tp; k++) ll_store_sys(P.done[k], P.rank * G + (int)blockIdx.x, 0.f, epl);
+        }
+        if (blockIdx.x == 0) {
+            for (int i = c.tid; i < P.tp * G; i += c.nt) {
+                float t[1];
+                ll_waitv<1>(P.done[P.rank], i, epl, t);
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+        }
+    }
     if (P.do_argmax) {
         // maxloc(logits) (llama2.f90:388): first maximum wins at every reduction level
 #pragma unroll
@@ -915,20 +985,23 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         }
         float *rv = sv.red;
         int *ri = reinterpret_cast<int *>(sv.red + 32);
-        const uint32_t epl = P.ep_base + (uint32_t)P.L + 1u;
         if (c.lane == 0) { rv[c.warp] = best; ri[c.warp] = bidx; }
         cons_sync(c);
         if (c.tid == 0) {
             for (int w = 1; w < c.nw; w++)
                 if (rv[w] > best || (rv[w] == best && ri[w] < bidx)) { best = rv[w]; bidx = ri[w]; }
-            ll_store(P.ll_amax, 2 * blockIdx.x, best, epl);
-            ll_store(P.ll_amax, 2 * blockIdx.x + 1, __int_as_float(bidx), epl);
+            for (int k = 0; k < P.tp; k++) {
+                unsigned long long *dst = P.amax[k] + (size_t)(P.rank * G + (int)blockIdx.x) * 2;
+                ll_store_sys(dst, 0, best, epl);
+                ll_store_sys(dst, 1, __int_as_float(bidx), epl);
+            }
         }
         if (blockIdx.x == 0 && c.warp == 0) {
+            // every rank reduces the same tp * grid records in the same order -> the same token
             best = -INFINITY; bidx = 0x7fffffff;
-            for (int i = c.lane; i < (int)gridDim.x; i += 32) {
+            for (int i = c.lane; i < P.tp * G; i += 32) {
                 float rec[2];
-                ll_waitv<2>(P.ll_amax, 2 * i, epl, rec);
+                ll_waitv<2>(P.amax[P.rank], 2 * i, epl, rec);
                 const float v = rec[0];
                 const int ix = __float_as_int(rec[1]);
                 if (v > best || (v == best && ix < bidx)) { best = v; bidx = ix; }
@@ -981,14 +1054,14 @@ int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target
     if (max_slots > MAX_CONS_WARPS) max_slots = MAX_CONS_WARPS;
     int n_slots = max_slots;
     while (n_slots > 0 &&
-           smem_bytes_for(n_slots, slot, xs_floats, res_floats) > (size_t)max_smem_optin)
+           smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb) > (size_t)max_smem_optin)
         n_slots--;
     if (n_slots < 2) return 1;
     out->n_slots = n_slots;
     out->slot_bytes = slot;
     out->wps = (2 * n_slots <= MAX_CONS_WARPS) ? 2 : 1;
     out->threads = (n_slots * out->wps + 1) * 32;
-    out->smem_bytes = (int)smem_bytes_for(n_slots, slot, xs_floats, res_floats);
+    out->smem_bytes = (int)smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb);
     out->grid = n_sms;
     out->xs_floats = xs_floats;
     out->res_floats = res_floats;
