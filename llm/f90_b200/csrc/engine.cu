@@ -519,6 +519,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         CK(dalloc(&E.d_att_part, (size_t)c.n_heads * MAX_SPLITS * (hs + 4)));
         CK(cudaMalloc((void **)&E.d_shared, (size_t)V * 4));
         E.sh_logits = 0;
+        E.peers_ready = true;
         if (build_granular_graph()) { release_all(); return 1; }
     }
     CK(cudaStreamSynchronize(E.st));
