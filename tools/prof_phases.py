@@ -4,7 +4,7 @@ from llm.f90_b200 import capi, fixtures as fx
 from llm.f90_b200.layout import Config, TINYLLAMA, LLAMA2_7B, WTYPE_BY_NAME
 model, wt = sys.argv[1], sys.argv[2]
 cfg = Config(**(TINYLLAMA if model == 'tinyllama' else LLAMA2_7B), wtype=WTYPE_BY_NAME[wt])
-w = fx.synth_weights_fast(cfg, 0)
+w = fx.synth_weights_tiled(cfg, 0)
 eng = capi.Engine(w)
 prompt = [5, 6, 7, 8, 9, 10, 11, 12, 13]
 for _ in range(2): eng.generate_greedy(prompt, 128)

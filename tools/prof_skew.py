@@ -7,7 +7,7 @@ from llm.f90_b200 import capi, fixtures as fx
 from llm.f90_b200.layout import Config, TINYLLAMA, LLAMA2_7B, WTYPE_BY_NAME
 model, wt = sys.argv[1], sys.argv[2]
 cfg = Config(**(TINYLLAMA if model == 'tinyllama' else LLAMA2_7B), wtype=WTYPE_BY_NAME[wt])
-w = fx.synth_weights_fast(cfg, 0)
+w = fx.synth_weights_tiled(cfg, 0)
 eng = capi.Engine(w)
 toks, _ = eng.generate_greedy([5, 6, 7], 64)
 ends = []

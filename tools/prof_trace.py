@@ -9,7 +9,7 @@ model, wt = sys.argv[1], sys.argv[2]
 layer = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 npos = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 cfg = Config(**(TINYLLAMA if model == 'tinyllama' else LLAMA2_7B), wtype=WTYPE_BY_NAME[wt])
-w = fx.synth_weights_fast(cfg, 0)
+w = fx.synth_weights_tiled(cfg, 0)
 eng = capi.Engine(w)
 toks, _ = eng.generate_greedy([5, 6, 7], npos)
 tr = eng.debug_trace(int(toks[-1]), npos + 1, layer).astype(np.int64)
