@@ -191,3 +191,28 @@ def test_linearity_of_classifier_property():
     with capi.Engine(w) as eng:
         b = eng.transformer(2, 1)
     assert np.allclose(b, 2 * a, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("wt", [F32, Q4_0], ids=["f32", "q4_0"])
+def test_cli_end_to_end(tmp_path, wt):
+    """`./llm -m <gguf> -n N -p prompt` (llama2.f90:87-410 mirrored in C++): GGUF loader -> tokenizer ->
+    C ABI -> printed tokens, against the oracle driven by the same file and prompt."""
+    import subprocess
+    from llm.f90_b200 import hostapi
+    cfg = Config(**SMALL, wtype=wt)
+    p = str(tmp_path / "m.gguf")
+    w = fx.write_synth_gguf(p, cfg, seed=12)
+    m = hostapi.HostModel(p)
+    vocab, _ = m.vocab()
+    prompt = "the cat sat"
+    ptoks = m.encode(prompt)
+    m.close()
+    n = 24
+    ref_toks, _, _ = oc.Oracle(w).generate(ptoks, n)
+    want = b"".join(vocab[t - 1] for t in ref_toks)
+    r = subprocess.run([hostapi.LLM_BIN, "-m", p, "-n", str(n), "-p", prompt, "-t", "0"], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    out = r.stdout
+    assert b"data offset" in out and b"tokens/second" in out and b"Timings" in out
+    text = out.split(b"\n Inference time:")[0].split(b"\n", 1)[1]  # after the loader's "data offset" line
+    assert text == want
