@@ -17,7 +17,8 @@ typedef struct llmf90_host_config {
     int32_t emb_dim, hidden_dim, n_layers, n_heads, n_kv_heads, vocab_size, seq_len, wtype;
 } llmf90_host_config;
 
-/* NULL on failure; llmf90_host_last_error() says why */
+/* NULL on failure; llmf90_host_last_error() says why.  verbose: 1 = the reference's -v listing,
+ * 0 = only the unconditional "data offset" line (read_ggml.f90:196), -1 = silent */
 llmf90_host_model *llmf90_host_load(const char *gguf_path, int32_t verbose);
 void llmf90_host_free(llmf90_host_model *m);
 const char *llmf90_host_last_error(void);

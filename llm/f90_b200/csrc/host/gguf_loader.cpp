@@ -82,7 +82,7 @@ int Vocab::lookup(const std::string &s) const
     return it == index.end() ? -1 : it->second;
 }
 
-Model load_gguf(const std::string &path, bool verbose)
+Model load_gguf(const std::string &path, bool verbose, bool print_offset)
 {
     Reader r(path);
     Model m;
@@ -158,7 +158,8 @@ Model load_gguf(const std::string &path, bool verbose)
     // tensor data starts at the next multiple of the alignment (read_ggml.f90:176-196)
     uint64_t pos = r.tell();
     m.data_offset = (pos + alignment - 1) / alignment * alignment;
-    printf(" data offset %llu\n", (unsigned long long)m.data_offset);  // the reference prints this unconditionally (:196)
+    // the reference prints this unconditionally (:196); library callers may silence it
+    if (print_offset) printf(" data offset %llu\n", (unsigned long long)m.data_offset);
 
     auto need = [&](const std::string &name) -> const TensorInfo & {
         auto it = tensors.find(name);

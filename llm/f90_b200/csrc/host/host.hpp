@@ -48,7 +48,7 @@ size_t row_bytes(int wtype, int n);
 // load_ggml (read_ggml.f90:53-511) extended per SURVEY.md 8f: tensor types 0/1/2, every GGUF KV
 // value type, dimensions from the llama.* keys.  Throws std::runtime_error with the reference's
 // style of message ("key not found", "GGUF magic", ...).
-Model load_gguf(const std::string &path, bool verbose);
+Model load_gguf(const std::string &path, bool verbose, bool print_offset = true);
 // legacy `-s tokenizer.bin` (llama2.f90:321-356): i32 max_len, then per token f32 score, i32 len, bytes
 void load_tokenizer_bin(const std::string &path, int vocab_size, Vocab &out);
 

@@ -21,7 +21,7 @@ llmf90_host_model *llmf90_host_load(const char *path, int32_t verbose)
 {
     try {
         auto *h = new llmf90_host_model;
-        h->m = llmhost::load_gguf(path ? path : "", verbose != 0);
+        h->m = llmhost::load_gguf(path ? path : "", verbose > 0, verbose >= 0);
         return h;
     } catch (const std::exception &e) {
         g_err = e.what();

@@ -58,9 +58,9 @@ def load() -> C.CDLL:
 class HostModel:
     """What `load_ggml` (read_ggml.f90:53) returns: weights in the fused layout, vocabulary, scores."""
 
-    def __init__(self, path: str, verbose: bool = False):
+    def __init__(self, path: str, verbose: bool = False, quiet: bool = True):
         self.L = load()
-        self.h = self.L.llmf90_host_load(path.encode(), int(verbose))
+        self.h = self.L.llmf90_host_load(path.encode(), 1 if verbose else (-1 if quiet else 0))
         if not self.h:
             raise HostError(self.L.llmf90_host_last_error().decode())
         cc = CHostConfig()
