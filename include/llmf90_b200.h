@@ -96,8 +96,11 @@ int llmf90_b200_times(float t[5]);
 int llmf90_b200_phase_times(float *ms, int32_t n);
 
 /* profiling aid: run one forward and record, for every CTA of the fused kernel, globaltimer stamps
- * (ns) at the 15 phase edges of `layer` (entries 0..14) and the cycles warp 0 waited for ring data
- * in the four mat-vec phases (entries 16..19); out is [n_ctas][32]. */
+ * (ns) at the 15 phase edges of `layer` (entries 0..14), the cycles warp 0 waited for ring data /
+ * computed and its stage count in the four mat-vec phases (entries 16..27), and the producer's and
+ * the consumers' ring cursors (stages issued / consumed) at every edge (entries 32..46, 48..62);
+ * entries 64..95: eight SM-clock stamps around the consumption of each of the four phases;
+ * out is [n_ctas][128]. */
 int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t *out, int32_t n_ctas);
 
 /* zero the KV cache and the timers (the state llama2.f90:316-319 initialises) */

@@ -50,7 +50,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps = _abs(CUDA_SRCS) + _abs(CUDA_HDRS)
     if force or _newer(CUDA_LIB, deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB] + _abs(CUDA_SRCS)
+        extra = ["-DLLMF90_WATCHDOG"] if os.environ.get("LLMF90_BUILD_WATCHDOG") else []  # debug builds only
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB] + _abs(CUDA_SRCS)
         subprocess.run(cmd, check=True, cwd=CSRC)
     return CUDA_LIB
 

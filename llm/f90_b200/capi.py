@@ -162,7 +162,7 @@ class Engine:
 
     def debug_trace(self, token: int, pos: int, layer: int) -> np.ndarray:
         n = self.stats()["n_sms"]
-        out = np.zeros((n, 32), np.uint64)
+        out = np.zeros((n, 128), np.uint64)
         _check(self.L.llmf90_b200_debug_trace(token, pos, layer, out.ctypes.data_as(C.POINTER(C.c_uint64)), n))
         return out
 

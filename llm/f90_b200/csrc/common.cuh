@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define WT_F32 0
 #define WT_F16 1
@@ -62,6 +63,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// non-blocking test of a phase (profiling aid)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -74,9 +88,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// Debug watchdog (compile with -DLLMF90_WATCHDOG): a wait that spins for ~1 s prints where it is
+// stuck and gives up, so that a protocol bug ends in a diagnosable wrong answer instead of a hang.
+#ifdef LLMF90_WATCHDOG
+#define LLMF90_WD_DECL long long wd_t0_ = clock64(); bool wd_fired_ = false
+#define LLMF90_WD_CHECK(code, a, b)                                                                   \
+    if (!wd_fired_ && clock64() - wd_t0_ > 2000000000ll) {                                            \
+        wd_fired_ = true;                                                                             \
+        printf("WATCHDOG cta %d tid %d code %d a %d b %d\n", (int)blockIdx.x, (int)threadIdx.x, (code), (int)(a), (int)(b)); \
+        break;                                                                                        \
+    }
+#else
+#define LLMF90_WD_DECL
+#define LLMF90_WD_CHECK(code, a, b)
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int code = 0)
 {
+    LLMF90_WD_DECL;
     while (!mbar_try_wait(bar, parity)) {
+        LLMF90_WD_CHECK(code, (smem_u32(bar) >> 3) & 31, parity)
     }
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first()

@@ -462,21 +462,21 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.ph[2] = mk(E.d_w13, 2 * hid, emb, 2);
         p.ph[3] = mk(E.d_w2, emb, hid, 1);
         p.ph[4] = mk(E.d_wcls, Vl, emb, 1);
-        int target_slot = 24576, max_slots = 7;
+        int target_slot = 24576, max_slots = 16, cons_warps = 12;
         if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
         if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
-        if (plan_stream(p, E.n_sms, smem_optin - 1024 /* static smem */, target_slot, max_slots, &E.plan)) {
+        if (const char *s = getenv("LLMF90_CONS_WARPS")) cons_warps = atoi(s);
+        // every CTA must own W13 rows (the LL hand-over's no-overwrite argument, stream.cu): tiny models
+        // run on fewer CTAs
+        if (plan_stream(p, std::min(E.n_sms, hid), smem_optin - 2048 /* static smem */, target_slot, max_slots,
+                        cons_warps, &E.plan)) {
             release_all();
             return fail("model rows do not fit the shared-memory ring (row stride too large)");
         }
-        // every CTA must own W13 rows (the LL hand-over's no-overwrite argument, stream.cu): tiny models
-        // run on fewer CTAs
-        E.plan.grid = std::min(E.plan.grid, hid);
         p.pf_stages = 0;
         if (const char *s = getenv("LLMF90_PF_STAGES")) p.pf_stages = std::max(0, atoi(s));
         p.pace = 38;  // ~1.15x the per-SM fair share of the measured HBM bandwidth (23 B/cycle)
         if (const char *s = getenv("LLMF90_PACE")) p.pace = std::max(0, atoi(s));
-        for (int i = 0; i < 5; i++) p.ph[i].rps = std::max(1, E.plan.slot_bytes / (int)p.ph[i].rs);
         p.emb_table = E.d_emb;
         p.rms_att = E.d_rms_att; p.rms_ffn = E.d_rms_ffn; p.rms_final = E.d_rms_final;
         p.rope_tab = E.d_rope;
@@ -512,7 +512,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         }
         p.kc = E.d_kc; p.vc = E.d_vc;
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
-        p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.wps = E.plan.wps;
+        p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.n_cons_warps = E.plan.n_cons_warps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
         CK(prepare_stream_kernel(wt, E.plan.threads, E.plan.smem_bytes));
     } else {
@@ -548,16 +548,16 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
 int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t *out, int32_t n_ctas)
 {
     if (!E.ready || !E.use_stream) return fail("debug_trace: needs the fused streaming engine");
-    if (!out || n_ctas < E.plan.grid) return fail("debug_trace: buffer must hold %d x 32 entries", E.plan.grid);
+    if (!out || n_ctas < E.plan.grid) return fail("debug_trace: buffer must hold %d x 128 entries", E.plan.grid);
     unsigned long long *d = nullptr;
-    CK(cudaMalloc((void **)&d, (size_t)E.plan.grid * 32 * 8));
-    CK(cudaMemset(d, 0, (size_t)E.plan.grid * 32 * 8));
+    CK(cudaMalloc((void **)&d, (size_t)E.plan.grid * 128 * 8));
+    CK(cudaMemset(d, 0, (size_t)E.plan.grid * 128 * 8));
     E.sp.trace = d; E.sp.trace_layer = layer;
     int rc = enqueue_forward(token, pos, false, nullptr, nullptr);
     E.sp.trace = nullptr;
     if (!rc) {
         cudaError_t e = cudaStreamSynchronize(E.st);
-        if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)E.plan.grid * 32 * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)E.plan.grid * 128 * 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail("debug_trace: %s", cudaGetErrorString(e));
     }
     cudaFree(d);

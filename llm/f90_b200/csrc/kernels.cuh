@@ -56,6 +56,8 @@ struct PhaseW {
     int rows, cols;
     int unit;                // rows are assigned to CTAs in multiples of `unit`
     int rps;                 // rows per ring stage
+    int ku;                  // f32 / f16: 128-bit load units per lane per row when a group of warps shares a row
+    int rows_cap;            // max rows of any CTA in this phase = stride of the partial-result planes
 };
 
 constexpr int MAX_TP = 8;
@@ -102,18 +104,19 @@ struct StreamParams {
     const int *forced;       // optional device array of forced next tokens (prompt), or null
     int *out_tokens;         // optional device array: out_tokens[pos-1] = chosen token
     // ring geometry
-    int n_slots, slot_bytes, wps;  // wps = consumer warps per slot
+    int n_slots, slot_bytes, n_cons_warps;
     int xs_floats, res_floats;  // + emb floats of residual stream after the two res planes
 };
 
 struct StreamPlan {
-    int n_slots, slot_bytes, wps, threads, smem_bytes, grid;
+    int n_slots, slot_bytes, n_cons_warps, threads, smem_bytes, grid;
     int xs_floats, res_floats;
 };
 
-// Decide ring geometry for a model on this device; returns non-zero if it cannot fit.
-int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target_slot_bytes,
-                int max_slots, StreamPlan *out);
+// Decide ring geometry for a model on `grid` CTAs (fills p.ph[i].rps / nchunks / cw / rows_cap);
+// returns non-zero if it cannot fit.
+int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots,
+                int cons_warps, StreamPlan *out);
 cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes);
 cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st);
 

@@ -38,8 +38,10 @@
 namespace llmf90 {
 
 constexpr int MAX_SLOTS = 16;
-constexpr int MAX_CONS_WARPS = 15;  // + 1 producer warp = 512 threads -> 128 registers/thread
+constexpr int MAX_CONS_WARPS = 12;  // + 1 producer warp = 416 threads -> 152 registers/thread
 constexpr int CONS_BAR = 1;         // named barrier id used by the consumer warps
+constexpr int GW = 4;               // consumer warps per group: a group of GW warps consumes one ring stage
+constexpr int NG = MAX_CONS_WARPS / GW;  // groups; group g owns the stages whose schedule index is g (mod NG)
 
 struct SmemView {
     uint8_t *ring;
@@ -62,7 +64,7 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
     v.xs = reinterpret_cast<float *>(smem + off);
     off += (size_t)P.xs_floats * 4;
     v.res = reinterpret_cast<float *>(smem + off);
-    off += (size_t)P.res_floats * 4 * 2;
+    off += (size_t)P.res_floats * 4;
     v.xres = reinterpret_cast<float *>(smem + off);
     off += (size_t)P.emb * 4;
     v.red = reinterpret_cast<float *>(smem + off);
@@ -74,7 +76,7 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
 
 static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats, int emb)
 {
-    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 * 2 + (size_t)emb * 4 + 64 * 4 +
+    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 + (size_t)emb * 4 + 64 * 4 +
            2 * MAX_SLOTS * 8;
 }
 
@@ -160,7 +162,7 @@ struct StageIter {
 // sit in a phase hand-over or in attention and every shared-memory slot is full, the requests
 // already queued for L2 keep the HBM channels busy, and the ring later refills at L2 latency.
 __device__ __forceinline__ void producer_loop(const StreamParams &P, const SmemView &sv, const CtaPlan *cp,
-                                              int token)
+                                              int token, volatile int *issued)
 {
     const uint64_t pol = l2_policy_evict_first();
     StageIter it, ip;
@@ -176,7 +178,7 @@ __device__ __forceinline__ void producer_loop(const StreamParams &P, const SmemV
     // traffic of the phase hand-overs; a paced producer keeps the queues short.
     long long next_ok = clock64();
     while (it.next(P, src, bytes)) {
-        mbar_wait(&sv.empty[slot], (k & 1u) ^ 1u);
+        mbar_wait(&sv.empty[slot], (k & 1u) ^ 1u, 1);
         if (P.pace > 0) {
             long long now = clock64();
             while (now < next_ok) now = clock64();
@@ -186,6 +188,7 @@ __device__ __forceinline__ void producer_loop(const StreamParams &P, const SmemV
         bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, src, bytes, &sv.full[slot], pol);
         if (++slot == ns) { slot = 0; k++; }
         s++;
+        *issued = (int)s;  // progress of the copy cursor, for the per-CTA trace
         while (pf < s + depth) {
             const uint8_t *psrc;
             uint32_t pbytes;
@@ -199,28 +202,21 @@ __device__ __forceinline__ void producer_loop(const StreamParams &P, const SmemV
 // ------------------------------------------------------------------ consumer helpers
 struct Cons {
     int tid, warp, lane, nt, nw;  // within the consumer group
-    int slot, sub;                // ring slot this warp serves, sub-warp index within the slot
 };
 
-// ring cursor of the consumer side: `pos` = next stage of the schedule, `my_div` = how many times
-// this warp's slot has been consumed (so its next stage is my_div * n_slots + slot)
+// ring cursor of the consumer side: the next stage of the schedule.  Every consumer warp visits
+// every stage (wait full -> its share of the rows -> arrive empty), so one cursor serves them all.
 struct CState {
     RingPos pos;
-    uint32_t my_div;
+    uint32_t gmod;  // schedule index of the next stage, mod NG (-> the group that owns it)
 };
+__device__ __forceinline__ void cons_advance(CState &cs, uint32_t n, uint32_t ns)
+{
+    ring_advance(cs.pos, n, ns);
+    cs.gmod = (cs.gmod + n) % (uint32_t)NG;
+}
 
 __device__ __forceinline__ void cons_sync(const Cons &c) { named_bar_sync(CONS_BAR, c.nt); }
-
-__device__ __forceinline__ float cons_sum(float v, const Cons &c, float *red)
-{
-    v = warp_sum(v);
-    if (c.lane == 0) red[c.warp] = v;
-    cons_sync(c);
-    float t = 0.f;
-    for (int i = 0; i < c.nw; i++) t += red[i];
-    cons_sync(c);
-    return t;
-}
 
 template <int WT, int NR>
 __device__ __forceinline__ void rows_to_res(const uint8_t *sp, size_t rs, const float *xs, int cols,
@@ -237,61 +233,230 @@ __device__ __forceinline__ void rows_to_res(const uint8_t *sp, size_t rs, const 
     }
 }
 
-// consume the `nst` stages of one weight phase: res[i] = dot(row r0 + i, xs)
-template <int WT>
-__device__ __forceinline__ void consume_phase(const PhaseW *ph, int nrows, int nst, const StreamParams &P,
-                                              const SmemView &sv, const Cons &c, CState &cs,
-                                              long long *wait_cycles)
-{
-    const int ns = P.n_slots, rps = ph->rps, cols = ph->cols;
-    const size_t rs = ph->rs;
-    const uint8_t *slot_ptr = sv.ring + (size_t)c.slot * P.slot_bytes;
-    // offset of this warp's next stage from the start of the phase
-    int off = ((int)cs.my_div - (int)cs.pos.div) * ns + (c.slot - (int)cs.pos.mod);
-    for (; off < nst; off += ns) {
-        if (wait_cycles) {
-            const long long w0 = clock64();
-            mbar_wait(&sv.full[c.slot], cs.my_div & 1u);
-            wait_cycles[0] += clock64() - w0;
-        } else {
-            mbar_wait(&sv.full[c.slot], cs.my_div & 1u);
-        }
-        const long long tc0 = wait_cycles ? clock64() : 0ll;
-        const int rbase = off * rps;
-        const int n = min(rps, nrows - rbase);
-        if constexpr (WT != WT_Q4_0) {
-            // two warps per slot split the COLUMNS: each writes its own plane of partial results
-            const int nunits = cols >> (WT == WT_F32 ? 2 : 3);
-            int ub = 0, nu = nunits;
-            if (P.wps == 2) {
-                const int h = min(nunits, ((nunits + 63) >> 6) << 5);  // first half, a multiple of 32 units
-                ub = c.sub * h;
-                nu = c.sub ? nunits - h : h;
-            }
-            stage_rows<WT>(slot_ptr, rs, n, sv.xs, ub, nu, c.lane, sv.res + c.sub * P.res_floats + rbase);
-        } else {
-            // q4_0: the wps warps that share the slot split the ROWS
-            int i = 0, iend = n;
-            if (P.wps == 2) {
-                const int h = (n + 1) >> 1;
-                i = c.sub * h;
-                iend = min(n, i + h);
-            }
-            for (; i + 4 <= iend; i += 4)
-                rows_to_res<WT, 4>(slot_ptr + (size_t)i * rs, rs, sv.xs, cols, c.lane, sv.res + rbase + i);
-            if (i + 2 <= iend) {
-                rows_to_res<WT, 2>(slot_ptr + (size_t)i * rs, rs, sv.xs, cols, c.lane, sv.res + rbase + i);
-                i += 2;
-            }
-            if (i < iend)
-                rows_to_res<WT, 1>(slot_ptr + (size_t)i * rs, rs, sv.xs, cols, c.lane, sv.res + rbase + i);
-        }
-        __syncwarp();
-        if (wait_cycles) { wait_cycles[4] += clock64() - tc0; wait_cycles[8] += 1; }
-        if (c.lane == 0) mbar_arrive(&sv.empty[c.slot]);
-        cs.my_div++;
+// Consume the `nst` stages of one weight phase.  The consumer warps form NG groups of GW warps;
+// group g owns the stages whose schedule index is g (mod NG) and touches no barrier of the others,
+// so a stage costs GW full-waits + GW empty-arrives, consecutive stages are in flight in different
+// groups, and slots are handed back one after the other in ring order (the producer refills
+// progressively, the phase tail is one stage of one group).
+//   f32 / f16: warp cl of a group takes the 128-bit units u = 128 k + 32 cl + lane of every row of
+//     the stage and keeps those units of the activation vector in registers for the whole phase
+//     (KUT units per lane; rows wider than the register budget stream x from shared memory).
+//     Lanes past the end of a row read a clamped (valid) unit against x = 0: no predication.
+//     Lane-partial sums of four rows are reduced together (6 shuffles instead of 20) and the slot
+//     is released as soon as its weights are in registers; partial sums go to plane cl of `res`,
+//     the epilogue adds the GW planes in a fixed order.
+//   q4_0: groups of 4 rows of a stage go round-robin over the group's warps (lane <-> block).
+// Not inlined on purpose: the function gets its own register allocation (x stays in registers)
+// and one copy serves all five weight phases.
+struct ConsumeArgs {
+    const PhaseW *ph;      // shared memory
+    uint8_t *ring;
+    const float *xs;
+    float *res;
+    uint64_t *full, *empty;
+    long long *wait_cycles;  // optional trace accumulators (or null); warp-uniform
+    long long *stamps;       // optional 8 clock stamps of this call (trace), or null
+    int nrows, nst, slot_bytes, n_slots, slot0, par0, gmod0, warp, lane, no_wide;
+};
+
+// four pending lane-partial sums -> four row results (see consume_phase)
+struct Pending {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    int d0 = 0, d1 = 0, d2 = 0, d3 = 0, np = 0;
+    __device__ __forceinline__ void flush(float *res, int lane)
+    {
+        const bool hi16 = lane & 16, hi8 = lane & 8;
+        float k0 = hi16 ? p2 : p0, k1 = hi16 ? p3 : p1;
+        k0 += __shfl_xor_sync(0xffffffffu, hi16 ? p0 : p2, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, hi16 ? p1 : p3, 16);
+        float k = hi8 ? k1 : k0;
+        k += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        const int r = (lane >> 3) & 3;  // which of the four pending results this lane group holds
+        const int d = r == 0 ? d0 : (r == 1 ? d1 : (r == 2 ? d2 : d3));
+        if ((lane & 7) == 0 && r < np) res[d] = k;
+        np = 0;
     }
-    ring_advance(cs.pos, (uint32_t)nst, (uint32_t)ns);
+    __device__ __forceinline__ void push(float v, int dst, float *res, int lane)
+    {
+        p3 = p2; p2 = p1; p1 = p0; p0 = v;
+        d3 = d2; d2 = d1; d1 = d0; d0 = dst;
+        if (++np == 4) flush(res, lane);
+    }
+};
+
+// ring walk of one group through a phase: owned stages are NG apart
+struct StageWalk {
+    const ConsumeArgs &a;
+    uint32_t slot, par;
+    int s;  // phase-relative index of the group's next stage
+    long long tc0 = 0;
+    int nwaits = 0;
+    __device__ __forceinline__ void stampc(int i) const
+    {
+        if (a.stamps && a.lane == 0) a.stamps[i] = clock64();
+    }
+    __device__ __forceinline__ StageWalk(const ConsumeArgs &a_) : a(a_)
+    {
+        stampc(1);
+        int first = (a.warp / GW) - a.gmod0;
+        if (first < 0) first += NG;
+        s = first;
+        slot = (uint32_t)a.slot0 + (uint32_t)first;
+        par = (uint32_t)a.par0;
+        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; par ^= 1u; }
+    }
+    __device__ __forceinline__ bool more() const { return s < a.nst; }
+    __device__ __forceinline__ const uint8_t *wait()
+    {
+        if (a.wait_cycles) {
+            const long long w0 = clock64();
+            mbar_wait(&a.full[slot], par, 2);
+            tc0 = clock64();
+            if (a.lane == 0) a.wait_cycles[0] += tc0 - w0;
+        } else {
+            mbar_wait(&a.full[slot], par, 2);
+        }
+        if (nwaits++ == 0) stampc(2);
+        return a.ring + (size_t)slot * a.slot_bytes;
+    }
+    __device__ __forceinline__ void release()
+    {
+        __syncwarp();
+        if (a.wait_cycles && a.lane == 0) { a.wait_cycles[4] += clock64() - tc0; a.wait_cycles[8] += 1; }
+        if (a.lane == 0) mbar_arrive(&a.empty[slot]);
+        if (nwaits == 1) stampc(3);
+        s += NG;
+        slot += NG;
+        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; par ^= 1u; }
+    }
+};
+
+template <int WT, int KUT>
+__device__ __forceinline__ void consume_xreg(const ConsumeArgs &a)
+{
+    const PhaseW *ph = a.ph;
+    const int nunits = ph->cols >> (WT == WT_F32 ? 2 : 3), rps = ph->rps, lane = a.lane, cl = a.warp % GW;
+    const uint32_t rs = ph->rs;
+    const float4 *x4 = reinterpret_cast<const float4 *>(a.xs);
+    float *res = a.res + (size_t)cl * ph->rows_cap;
+    XRegs<WT, KUT> x;
+    uint32_t off[KUT];  // byte offsets of this lane's units inside a row (clamped to the row)
+#pragma unroll
+    for (int k = 0; k < KUT; k++) {
+        const int u = k * (32 * GW) + cl * 32 + lane;
+        const bool ok = u < nunits;
+        off[k] = (uint32_t)min(u, nunits - 1) * 16u;
+        if (WT == WT_F16) {
+            x.v[2 * k] = ok ? x4[2 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+            x.v[2 * k + 1] = ok ? x4[2 * u + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            x.v[k] = ok ? x4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    Pending pd;
+    StageWalk w(a);
+    while (w.more()) {
+        const uint8_t *sp = w.wait();
+        const int base = w.s * rps, n = min(rps, a.nrows - base);
+        for (int r = 0; r < n; r++) {
+            const uint8_t *row = sp + (uint32_t)r * rs;
+            uint4 wv[KUT];
+#pragma unroll
+            for (int k = 0; k < KUT; k++) wv[k] = *reinterpret_cast<const uint4 *>(row + off[k]);
+            pd.push(dot_units<WT, KUT>(wv, x), base + r, res, lane);
+        }
+        w.release();
+    }
+    if (pd.np) pd.flush(res, lane);
+}
+
+// rows wider than the register budget: the activation units come from shared memory
+template <int WT>
+__device__ __forceinline__ void consume_xsmem(const ConsumeArgs &a)
+{
+    constexpr int KB = 4;
+    const PhaseW *ph = a.ph;
+    const int nunits = ph->cols >> (WT == WT_F32 ? 2 : 3), rps = ph->rps, lane = a.lane, cl = a.warp % GW;
+    const uint32_t rs = ph->rs;
+    const float4 *x4 = reinterpret_cast<const float4 *>(a.xs);
+    float *res = a.res + (size_t)cl * ph->rows_cap;
+    Pending pd;
+    StageWalk w(a);
+    while (w.more()) {
+        const uint8_t *sp = w.wait();
+        const int base = w.s * rps, n = min(rps, a.nrows - base);
+        for (int r = 0; r < n; r++) {
+            const uint8_t *row = sp + (uint32_t)r * rs;
+            float acc = 0.f;
+            for (int u0 = cl * 32 + lane; u0 < nunits; u0 += KB * 32 * GW) {
+                XRegs<WT, KB> x;
+                uint4 wv[KB];
+#pragma unroll
+                for (int k = 0; k < KB; k++) {
+                    const int u = u0 + k * (32 * GW);
+                    const bool ok = u < nunits;
+                    wv[k] = *reinterpret_cast<const uint4 *>(row + (uint32_t)min(u, nunits - 1) * 16u);
+                    if (WT == WT_F16) {
+                        x.v[2 * k] = ok ? x4[2 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x.v[2 * k + 1] = ok ? x4[2 * u + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+                        x.v[k] = ok ? x4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                acc += dot_units<WT, KB>(wv, x);
+            }
+            pd.push(acc, base + r, res, lane);
+        }
+        w.release();
+    }
+    if (pd.np) pd.flush(res, lane);
+}
+
+template <int WT>
+__device__ __noinline__ void consume_phase(const ConsumeArgs a)
+{
+    if (a.stamps && a.lane == 0) a.stamps[0] = clock64();
+    if constexpr (WT != WT_Q4_0) {
+        // units per lane per row, rounded up to an instantiated register budget
+        const int ku = a.ph->ku;
+        if (ku <= 1) consume_xreg<WT, 1>(a);
+        else if (ku <= 2) consume_xreg<WT, 2>(a);
+        else if (ku <= 4) consume_xreg<WT, 4>(a);
+        else if (ku <= 6) consume_xreg<WT, 6>(a);
+        else if (WT == WT_F32 && ku <= 8 && !a.no_wide) consume_xreg<WT, WT == WT_F32 ? 8 : 1>(a);
+        else if (WT == WT_F32 && ku <= 12 && !a.no_wide) consume_xreg<WT, WT == WT_F32 ? 12 : 1>(a);
+        else consume_xsmem<WT>(a);
+    } else {
+        const PhaseW *ph = a.ph;
+        const int rps = ph->rps, lane = a.lane, cl = a.warp % GW, cols = ph->cols;
+        const uint32_t rs = ph->rs;
+        StageWalk w(a);
+        int rot = 0;
+        while (w.more()) {
+            const uint8_t *sp = w.wait();
+            const int base = w.s * rps, n = min(rps, a.nrows - base), ngroups = (n + 3) >> 2;
+            int g = cl - rot;
+            if (g < 0) g += GW;
+            for (; g < ngroups; g += GW) {
+                int i = 4 * g;
+                const int iend = min(n, i + 4);
+                if (iend - i == 4) {
+                    rows_to_res<WT, 4>(sp + (size_t)i * rs, rs, a.xs, cols, lane, a.res + base + i);
+                } else {
+                    if (iend - i >= 2) {
+                        rows_to_res<WT, 2>(sp + (size_t)i * rs, rs, a.xs, cols, lane, a.res + base + i);
+                        i += 2;
+                    }
+                    if (i < iend) rows_to_res<WT, 1>(sp + (size_t)i * rs, rs, a.xs, cols, lane, a.res + base + i);
+                }
+            }
+            rot = (rot + ngroups) % GW;
+            w.release();
+        }
+    }
 }
 
 // ------------------------------------------------------------------ LL buffers
@@ -329,9 +494,11 @@ __device__ __forceinline__ float ll_peek(const unsigned long long *buf, int i) {
 __device__ __forceinline__ float4 ll_wait4(const unsigned long long *buf, int i, uint32_t ep)
 {
     unsigned long long a, b, c, d;
+    LLMF90_WD_DECL;
     do {
         ll_load2(buf + i, a, b);
         ll_load2(buf + i + 2, c, d);
+        LLMF90_WD_CHECK(101, i, ep)
     } while (!(ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep)));
     return make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
 }
@@ -341,7 +508,9 @@ __device__ __forceinline__ void ll_wait4n(const unsigned long long *buf, int i, 
 {
     unsigned long long w[N][4];
     bool ok;
+    LLMF90_WD_DECL;
     do {
+        LLMF90_WD_CHECK(102, i, ep)
 #pragma unroll
         for (int k = 0; k < N; k++) {
             ll_load2(buf + i + 4 * k, w[k][0], w[k][1]);
@@ -364,11 +533,13 @@ __device__ __forceinline__ void ll_waitv(const unsigned long long *buf, int i, u
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
     } else if (NV == 2) {
         unsigned long long a, b;
-        do { ll_load2(buf + i, a, b); } while (!(ll_ok(a, ep) && ll_ok(b, ep)));
+        LLMF90_WD_DECL;
+        do { ll_load2(buf + i, a, b); LLMF90_WD_CHECK(103, i, ep) } while (!(ll_ok(a, ep) && ll_ok(b, ep)));
         o[0] = ll_val(a); o[1] = ll_val(b);
     } else {
         unsigned long long a;
-        do { a = ll_load1(buf + i); } while (!ll_ok(a, ep));
+        LLMF90_WD_DECL;
+        do { a = ll_load1(buf + i); LLMF90_WD_CHECK(104, i, ep) } while (!ll_ok(a, ep));
         o[0] = ll_val(a);
     }
 }
@@ -380,7 +551,9 @@ __device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4,
 {
     unsigned long long w[PRO_V][4];
     bool ok;
+    LLMF90_WD_DECL;
     do {
+        LLMF90_WD_CHECK(105, base, ep)
 #pragma unroll
         for (int k = 0; k < PRO_V; k++) {
             const int j = base + c.tid + k * c.nt;
@@ -405,22 +578,19 @@ __device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4,
 }
 
 // ---- vector stages: every consumer thread waits for the stage and reads what it needs; after
-// the consumer-wide barrier that ends the prologue the warps that own the slot hand it back
+// the consumer-wide barrier that ends the prologue the warps of the group that owns it hand it back
 __device__ __forceinline__ const uint8_t *vec_stage_wait(const StreamParams &P, const SmemView &sv,
                                                          const RingPos &at)
 {
-    mbar_wait(&sv.full[at.mod], at.div & 1u);
+    mbar_wait(&sv.full[at.mod], at.div & 1u, 3);
     return sv.ring + (size_t)at.mod * P.slot_bytes;
 }
 // call in stage order, after a cons_sync that follows the last read of the stage
 __device__ __forceinline__ void vec_stage_release(const StreamParams &P, const SmemView &sv, const Cons &c,
                                                   CState &cs)
 {
-    if ((uint32_t)c.slot == cs.pos.mod) {
-        if (c.lane == 0) mbar_arrive(&sv.empty[cs.pos.mod]);
-        cs.my_div++;
-    }
-    ring_advance(cs.pos, 1u, (uint32_t)P.n_slots);
+    if (c.lane == 0 && (uint32_t)(c.warp / GW) == cs.gmod) mbar_arrive(&sv.empty[cs.pos.mod]);
+    cons_advance(cs, 1u, (uint32_t)P.n_slots);
 }
 
 // ---- activation-vector prologues.  Every CTA needs the whole vector; it is 8-44 KB and was
@@ -447,7 +617,7 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
 // there is nothing to add.  `part` = this rank's [tp][emb] buffer of partials; w from a ring slot.
 // Up to 8 (float4 position, rank) requests are in flight per thread per polling round.
 template <int WT, int TP>
-__device__ __forceinline__ void load_x_norm_t(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
+__device__ __forceinline__ float load_x_norm_t(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
                                               const float *wn /* shared */, const StreamParams &P,
                                               const SmemView &sv, const Cons &c)
 {
@@ -468,7 +638,9 @@ __device__ __forceinline__ void load_x_norm_t(const unsigned long long *part, ui
         } else {
             unsigned long long w[PPB][TP][4];
             bool ok;
+            LLMF90_WD_DECL;
             do {
+                LLMF90_WD_CHECK(106, base, ep)
                 ok = true;
 #pragma unroll
                 for (int pi = 0; pi < PPB; pi++) {
@@ -520,28 +692,25 @@ __device__ __forceinline__ void load_x_norm_t(const unsigned long long *part, ui
             }
         }
     }
-    const float tot = cons_sum(ss, c, sv.red);
-    const float inv = 1.0f / sqrtf(tot / (float)n + 1e-5f);
-    // second pass over this thread's own elements: scale by 1 / rms
-    for (int j = c.tid; j < n4; j += c.nt) {
-        int idx = j;
-        if (WT == WT_Q4_0) idx = (j & ~7) | ((j & 7) ^ ((j >> 3) & 7));
-        float4 t = reinterpret_cast<float4 *>(sv.xs)[idx];
-        t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
-        reinterpret_cast<float4 *>(sv.xs)[idx] = t;
-    }
+    // xs holds x * w; the common factor 1 / rms multiplies the phase's results in the epilogue
+    // (the mat-vec is linear), so there is no second pass over xs and only one barrier here
+    ss = warp_sum(ss);
+    if (c.lane == 0) sv.red[c.warp] = ss;
     cons_sync(c);
+    float tot = 0.f;
+    for (int i = 0; i < c.nw; i++) tot += sv.red[i];
+    return 1.0f / sqrtf(tot / (float)n + 1e-5f);
 }
 
 template <int WT>
-__device__ __forceinline__ void load_x_norm(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
-                                            const float *wn, const StreamParams &P, const SmemView &sv,
-                                            const Cons &c)
+__device__ __forceinline__ float load_x_norm(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
+                                             const float *wn, const StreamParams &P, const SmemView &sv,
+                                             const Cons &c)
 {
-    if (P.tp == 1) load_x_norm_t<WT, 1>(part, ep, emb_row, wn, P, sv, c);
-    else if (P.tp == 2) load_x_norm_t<WT, 2>(part, ep, emb_row, wn, P, sv, c);
-    else if (P.tp == 4) load_x_norm_t<WT, 4>(part, ep, emb_row, wn, P, sv, c);
-    else load_x_norm_t<WT, 8>(part, ep, emb_row, wn, P, sv, c);
+    if (P.tp == 1) return load_x_norm_t<WT, 1>(part, ep, emb_row, wn, P, sv, c);
+    if (P.tp == 2) return load_x_norm_t<WT, 2>(part, ep, emb_row, wn, P, sv, c);
+    if (P.tp == 4) return load_x_norm_t<WT, 4>(part, ep, emb_row, wn, P, sv, c);
+    return load_x_norm_t<WT, 8>(part, ep, emb_row, wn, P, sv, c);
 }
 
 template <int WT, int PRO_V>
@@ -763,9 +932,9 @@ __device__ __forceinline__ void load_x_attn(const StreamParams &P, uint32_t ep, 
 }
 
 // ------------------------------------------------------------------ the kernel
-// MAXT = 512: up to 15 consumer warps + the producer warp, 128 registers per thread.  Two warps
-// share a ring slot (f32 / f16: column halves, q4_0: row halves): the shared-memory load->FMA
-// latency is hidden by thread-level parallelism rather than by deep per-thread unrolling.
+// MAXT = 416: 12 consumer warps + the producer warp, 152 registers per thread.  All consumer
+// warps work on every ring stage (consume_phase): the shared-memory load->FMA latency is hidden
+// by thread-level parallelism rather than by deep per-thread unrolling.
 template <int WT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 stream_decode_kernel(const __grid_constant__ StreamParams P)
@@ -773,12 +942,14 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     constexpr int PRO_V = MAXT <= 256 ? 8 : 4;
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemView sv = carve(smem, P);
-    const int n_cons_warps = P.n_slots * P.wps;
+    const int n_cons_warps = P.n_cons_warps;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     __shared__ CtaPlan cp;
     __shared__ float2 rope[64];
     __shared__ long long tacc[PH_COUNT];  // phase timers, touched by the timer thread only
+    __shared__ volatile int prod_issued;  // stages issued by the producer so far
+    if (threadIdx.x == 0) prod_issued = 0;
     if (threadIdx.x < 5) {
         const int i = threadIdx.x;
         cp.ph[i] = P.ph[i];
@@ -790,7 +961,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     if (threadIdx.x == 32) {
         for (int i = 0; i < P.n_slots; i++) {
             mbar_init(&sv.full[i], 1);
-            mbar_init(&sv.empty[i], (uint32_t)P.wps);
+            mbar_init(&sv.empty[i], (uint32_t)GW);
         }
         fence_mbar_init();
     }
@@ -802,7 +973,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
 
     if (warp == n_cons_warps) {
         // ===================== producer warp =====================
-        if (lane == 0) producer_loop(P, sv, &cp, token);
+        if (lane == 0) producer_loop(P, sv, &cp, token, &prod_issued);
         return;
     }
 
@@ -810,10 +981,8 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     Cons c;
     c.tid = threadIdx.x; c.warp = warp; c.lane = lane;
     c.nw = n_cons_warps; c.nt = n_cons_warps * 32;
-    c.slot = P.wps == 2 ? warp >> 1 : warp;
-    c.sub = P.wps == 2 ? warp & 1 : 0;
     CState cs;
-    cs.pos.mod = 0; cs.pos.div = 0; cs.my_div = 0;
+    cs.pos.mod = 0; cs.pos.div = 0; cs.gmod = 0;
     // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh
     const bool timer = (blockIdx.x == 0 && c.tid == 0);
     long long tmark = timer ? clock64() : 0ll;
@@ -824,11 +993,25 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     // optional per-CTA trace of one layer (debug/profiling): globaltimer stamps at every phase edge
     // + per mat-vec phase the cycles warp 0 waited for ring data / computed, and its stage count
     const bool tracer = (P.trace != nullptr && c.tid == 0);
-    __shared__ long long twait[12];
+    const bool tracer_warp = (P.trace != nullptr && c.warp == 0);  // warp-uniform
+    __shared__ long long twait[12 + 32];  // 12 accumulators + 8 clock stamps for each of the 4 layer phases
     if (tracer)
-        for (int i = 0; i < 12; i++) twait[i] = 0;
+        for (int i = 0; i < 44; i++) twait[i] = 0;
     auto stamp = [&](int l, int k) {
-        if (tracer && l == P.trace_layer) P.trace[(size_t)blockIdx.x * 32 + k] = globaltimer_ns();
+        if (tracer && l == P.trace_layer) {
+            unsigned long long *row = P.trace + (size_t)blockIdx.x * 128;
+            row[k] = globaltimer_ns();
+            row[32 + k] = (unsigned long long)prod_issued;                             // producer cursor
+            row[48 + k] = (unsigned long long)(cs.pos.div * (uint32_t)P.n_slots + cs.pos.mod);  // consumer cursor
+            // how many of the next n_slots stages have already landed in the ring
+            RingPos at = cs.pos;
+            int landed = 0;
+            for (int i = 0; i < P.n_slots; i++) {
+                landed += mbar_test(&sv.full[at.mod], at.div & 1u) ? 1 : 0;
+                ring_advance(at, 1u, (uint32_t)P.n_slots);
+            }
+            row[48 + k] |= (unsigned long long)landed << 32;
+        }
     };
     auto lap = [&](int bucket) {
         if (timer) {
@@ -837,9 +1020,15 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             tmark = now;
         }
     };
-    // phase results: one plane per warp of a slot when the columns are split (f32 / f16)
-    const int res_planes = (WT != WT_Q4_0) ? P.wps : 1;
-    auto resv = [&](int i) -> float { return res_planes == 2 ? sv.res[i] + sv.res[P.res_floats + i] : sv.res[i]; };
+    // phase results: the chunk lanes' planes of partial sums are added in a fixed order, times the
+    // 1 / rms factor of the phase's rmsnorm (1 for Wo / W2)
+    int res_planes = 1, res_cap = 0;
+    float rscale = 1.f;
+    auto resv = [&](int i) -> float {
+        float t = sv.res[i];
+        for (int p = 1; p < res_planes; p++) t += sv.res[p * res_cap + i];
+        return t * rscale;
+    };
     const int half_mask = (P.hs >> 1) - 1;
     const uint32_t ns = (uint32_t)P.n_slots;
     float best = -INFINITY;  // running maxloc of this thread's logits (classifier epilogue)
@@ -866,27 +1055,46 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             }
             const float *wn = reinterpret_cast<const float *>(vec_stage_wait(P, sv, at));
             // add the tp partial outputs of the phase before (Wo of this layer / W2 of the previous one)
-            load_x_norm<WT>(ph == 2 ? P.part1[P.rank] : P.part2[P.rank], ph == 2 ? ep : ep - 1u, emb_row, wn, P, sv, c);
+            rscale = load_x_norm<WT>(ph == 2 ? P.part1[P.rank] : P.part2[P.rank], ph == 2 ? ep : ep - 1u, emb_row, wn,
+                                     P, sv, c);
             if (q == 0) vec_stage_release(P, sv, c, cs);
             vec_stage_release(P, sv, c, cs);
         }
         // (a CTA without rows in a Wo / W2 phase does not need its input vector: skipping the poll
         // also keeps it from ever lagging behind on a buffer nobody waits for it to have read)
-        if (ph == 0 || ph == 2 || ph == 4 || cp.r1[ph] == cp.r0[ph]) {
-        } else if (ph == 1 && P.n_splits > 1) {
-            load_x_attn<WT, PRO_V>(P, ep, sv, c);
-        } else {
-            load_x_plain<WT, PRO_V>(ph == 1 ? P.ll_att : P.ll_hb, ep, ph == 1 ? P.att_dim : P.hid, sv, c);
+        if (ph == 1 || ph == 3) {
+            rscale = 1.f;
+            if (cp.r1[ph] == cp.r0[ph]) {
+            } else if (ph == 1 && P.n_splits > 1) {
+                load_x_attn<WT, PRO_V>(P, ep, sv, c);
+            } else {
+                load_x_plain<WT, PRO_V>(ph == 1 ? P.ll_att : P.ll_hb, ep, ph == 1 ? P.att_dim : P.hid, sv, c);
+            }
         }
         lap(tb);
         stamp(l, ph == 0 ? 1 : 3 + 3 * ph);
 
         // ---- the mat-vec: consume this CTA's stages of the phase from the ring
         const int r0 = cp.r0[ph], nr = cp.r1[ph] - cp.r0[ph];
-        consume_phase<WT>(&cp.ph[ph], nr, cp.nst[ph], P, sv, c, cs,
-                          (tracer && l == P.trace_layer && ph < 4) ? &twait[ph] : nullptr);
+        res_planes = (WT != WT_Q4_0) ? GW : 1;
+        res_cap = cp.ph[ph].rows_cap;
+        {
+            ConsumeArgs ca;
+            ca.ph = &cp.ph[ph]; ca.ring = sv.ring; ca.xs = sv.xs; ca.res = sv.res;
+            ca.full = sv.full; ca.empty = sv.empty;
+            ca.wait_cycles = (tracer_warp && l == P.trace_layer && ph < 4) ? &twait[ph] : nullptr;
+            ca.nrows = nr; ca.nst = cp.nst[ph]; ca.slot_bytes = P.slot_bytes; ca.n_slots = P.n_slots;
+            ca.slot0 = (int)cs.pos.mod; ca.par0 = (int)(cs.pos.div & 1u); ca.gmod0 = (int)cs.gmod;
+            ca.warp = c.warp; ca.lane = c.lane; ca.no_wide = 0;
+            ca.stamps = ca.wait_cycles ? &twait[12 + 8 * ph] : nullptr;
+            if (ca.stamps && c.lane == 0) ca.stamps[7] = clock64();  // before the call
+            consume_phase<WT>(ca);
+            if (ca.stamps && c.lane == 0) ca.stamps[4] = clock64();  // after the return
+            cons_advance(cs, (uint32_t)cp.nst[ph], ns);
+        }
         stamp(l, ph == 0 ? 2 : 4 + 3 * ph);
         cons_sync(c);
+        if (tracer && l == P.trace_layer && ph < 4) twait[12 + 8 * ph + 5] = clock64();  // after the barrier
         lap(tb + 1);
 
         // ---- epilogue
@@ -953,7 +1161,9 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             stamp(l, 5);
         }
         if (ph == 3 && tracer && l == P.trace_layer)
-            for (int i = 0; i < 12; i++) P.trace[(size_t)blockIdx.x * 32 + 16 + i] = (unsigned long long)twait[i];
+            for (int i = 0; i < 12; i++) P.trace[(size_t)blockIdx.x * 128 + 16 + i] = (unsigned long long)twait[i];
+        if (ph == 3 && tracer && l == P.trace_layer)
+            for (int i = 0; i < 32; i++) P.trace[(size_t)blockIdx.x * 128 + 64 + i] = (unsigned long long)twait[12 + i];
     }
     lap(PH_CLS_MV);
 
@@ -1031,16 +1241,21 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
 }
 
 // ------------------------------------------------------------------ host side
-int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target_slot_bytes,
-                int max_slots, StreamPlan *out)
+int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots,
+                int cons_warps, StreamPlan *out)
 {
+    cons_warps = MAX_CONS_WARPS;  // NG groups of GW warps
     unsigned int rs_max = 0;
-    int max_rows = 0;
+    int res_floats = 0;
     for (int i = 0; i < 5; i++) {
-        if (p.ph[i].rs > rs_max) rs_max = p.ph[i].rs;
-        const int U = p.ph[i].rows / p.ph[i].unit;
-        const int per = ((U + n_sms - 1) / n_sms + 1) * p.ph[i].unit;
-        if (per > max_rows) max_rows = per;
+        PhaseW &w = p.ph[i];
+        if (w.rs > rs_max) rs_max = w.rs;
+        const int U = w.rows / w.unit;
+        w.rows_cap = ((U + grid - 1) / grid) * w.unit;
+        const int nunits = w.cols >> (p.wtype == WT_F32 ? 2 : 3);
+        w.ku = p.wtype == WT_Q4_0 ? 0 : (nunits + 32 * GW - 1) / (32 * GW);
+        const int planes = p.wtype == WT_Q4_0 ? 1 : GW;
+        if (planes * w.rows_cap > res_floats) res_floats = planes * w.rows_cap;
     }
     if ((unsigned)p.emb * 4u > rs_max) rs_max = (unsigned)p.emb * 4u;  // f32 vector stages
     int slot = target_slot_bytes > (int)rs_max ? target_slot_bytes : (int)rs_max;
@@ -1050,21 +1265,22 @@ int plan_stream(const StreamParams &p, int n_sms, int max_smem_optin, int target
     const int att_scratch = MAX_SLOTS * (p.hs + 4);
     if (att_scratch > xs_floats) xs_floats = att_scratch;
     xs_floats = (xs_floats + 31) & ~31;
-    const int res_floats = (max_rows + 31) & ~31;
-    if (max_slots > MAX_CONS_WARPS) max_slots = MAX_CONS_WARPS;
+    res_floats = (res_floats + 31) & ~31;
+    if (max_slots > MAX_SLOTS) max_slots = MAX_SLOTS;
     int n_slots = max_slots;
     while (n_slots > 0 &&
            smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb) > (size_t)max_smem_optin)
         n_slots--;
-    if (n_slots < 2) return 1;
+    if (n_slots < NG) return 1;
     out->n_slots = n_slots;
     out->slot_bytes = slot;
-    out->wps = (2 * n_slots <= MAX_CONS_WARPS) ? 2 : 1;
-    out->threads = (n_slots * out->wps + 1) * 32;
+    out->n_cons_warps = cons_warps;
+    out->threads = (cons_warps + 1) * 32;
     out->smem_bytes = (int)smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb);
-    out->grid = n_sms;
+    out->grid = grid;
     out->xs_floats = xs_floats;
     out->res_floats = res_floats;
+    for (int i = 0; i < 5; i++) p.ph[i].rps = slot / (int)p.ph[i].rs > 0 ? slot / (int)p.ph[i].rs : 1;
     return 0;
 }
 
@@ -1072,7 +1288,7 @@ template <int WT>
 static const void *kernel_for(int threads)
 {
     (void)threads;
-    return (const void *)stream_decode_kernel<WT, 512>;
+    return (const void *)stream_decode_kernel<WT, 416>;
 }
 
 static const void *kernel_for(int wtype, int threads)

@@ -28,4 +28,18 @@ wait = tr[:, 16:20]
 print("warp-0 wait cycles in mv phases (qkv, wo, w13, w2): p50", np.median(wait, axis=0), "max", wait.max(axis=0))
 print("warp-0 compute cycles: p50", np.median(tr[:, 20:24], axis=0), "max", tr[:, 20:24].max(axis=0))
 print("warp-0 stages: p50", np.median(tr[:, 24:28], axis=0), "max", tr[:, 24:28].max(axis=0))
+landed = (tr[:, 48:63] >> 32).astype(np.int64)
+tr[:, 48:63] &= 0xffffffff
+lead = tr[:, 32:47] - tr[:, 48:63]
+print("stages already landed in the ring at each edge: min p50 max")
+for k, nme in enumerate(names):
+    print(f"{k:2d} {nme:8s} {landed[:, k].min():4d} {int(np.median(landed[:, k])):4d} {landed[:, k].max():4d}")
+print("producer lead (stages issued - stages consumed) at each edge: min p50 max")
+for k, nme in enumerate(names):
+    print(f"{k:2d} {nme:8s} {lead[:, k].min():4d} {int(np.median(lead[:, k])):4d} {lead[:, k].max():4d}   issued p50 {int(np.median(tr[:, 32 + k]))} consumed p50 {int(np.median(tr[:, 48 + k]))}")
+st = tr[:, 64:96].reshape(-1, 4, 8).astype(np.int64)
+print("warp-0 consume stamps (cycles since 'before call', p50 over CTAs): entry, walk-ctor, 1st wait done, 1st stage released, returned, after cons_sync")
+for phi, nme in enumerate(["qkv", "wo", "w13", "w2"]):
+    b = st[:, phi, 7]
+    print(f"   {nme:4s}", [int(np.median(st[:, phi, i] - b)) for i in (0, 1, 2, 3, 4, 5)])
 np.save("gpurun_out/trace.npy", tr)
