@@ -63,6 +63,7 @@ struct Engine {
     unsigned long long *d_times = nullptr;  // [PH_COUNT + 2]
     int *d_tokpos = nullptr, *d_forced = nullptr, *d_out_tokens = nullptr, *d_amax = nullptr;
     unsigned long long *d_ll = nullptr;  // all LL buffers of the fused kernel, one allocation
+    SchedStage *d_sched = nullptr;       // per-CTA stage lists of the producer warps
     unsigned int launch_seq = 0;
     float *h_logits = nullptr;  // pinned
     int *h_tokpos = nullptr;    // pinned
@@ -92,7 +93,7 @@ void release_all()
     void *ptrs[] = {E.d_emb, E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls, E.d_rms_att, E.d_rms_ffn,
                     E.d_rms_final, E.d_rope, E.d_kc, E.d_vc, E.d_x, E.d_xb, E.d_qkv, E.d_att,
                     E.d_att_part, E.d_h13, E.d_hb, (void *)E.d_times, E.d_tokpos, E.d_forced,
-                    E.d_out_tokens, E.d_amax, E.d_ll};
+                    E.d_out_tokens, E.d_amax, E.d_ll, E.d_sched};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int k = 0; k < MAX_TP; k++)
@@ -139,8 +140,10 @@ float *logits_dev() { return reinterpret_cast<float *>(E.d_shared + E.sh_logits)
 
 int n_splits_for(int pos)
 {
-    int s = (pos + 255) / 256;
-    return std::max(1, std::min(MAX_SPLITS, s));
+    // a power of two (the kernel splits items with shifts): runs of <= 256 positions up to 2048
+    int s = 1;
+    while (s < MAX_SPLITS && s * 256 < pos) s *= 2;
+    return s;
 }
 
 int ensure_device(int dev)
@@ -482,15 +485,18 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.rope_tab = E.d_rope;
         {
             // rank-private LL buffers (64-bit words), zero-filled: epoch 0 is never expected
+            int rep = 4;
+            if (const char *s = getenv("LLMF90_LL_REP")) rep = std::max(1, std::min(16, atoi(s)));
+            p.ll_rep = rep;
             const size_t n_part = (size_t)Hl * MAX_SPLITS * (hs + 4);
-            const size_t words = 2 * (size_t)att + ((hid + 1) & ~1) + 2 * (size_t)kvl + n_part + 64;
+            const size_t words = (size_t)rep * (2 * (size_t)att + ((hid + 1) & ~1) + 2 * (size_t)kvl) + n_part + 64;
             CK(dalloc(&E.d_ll, words));
             CK(cudaMemsetAsync(E.d_ll, 0, words * 8, E.st));
             unsigned long long *w = E.d_ll;
-            p.ll_q = w; w += att;
-            p.ll_att = w; w += att;
-            p.ll_hb = w; w += (hid + 1) & ~1;
-            p.ll_kv = w; w += 2 * kvl;
+            p.ll_q = w; w += (size_t)rep * att;
+            p.ll_att = w; w += (size_t)rep * att;
+            p.ll_hb = w; w += (size_t)rep * ((hid + 1) & ~1);
+            p.ll_kv = w; w += (size_t)rep * 2 * kvl;
             p.ll_part = w;
         }
         {
@@ -498,8 +504,8 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             // Wo / W2 partials, argmax records, "logits stored" flags, the all-gathered logits
             const size_t G = (size_t)E.plan.grid;
             E.sh_part1 = 0;
-            E.sh_part2 = E.sh_part1 + (size_t)tp * emb * 8;
-            E.sh_amax = E.sh_part2 + (size_t)tp * emb * 8;
+            E.sh_part2 = E.sh_part1 + (size_t)p.ll_rep * tp * emb * 8;
+            E.sh_amax = E.sh_part2 + (size_t)p.ll_rep * tp * emb * 8;
             E.sh_done = E.sh_amax + (size_t)tp * G * 2 * 8;
             E.sh_logits = E.sh_done + (((size_t)tp * G * 8 + 15) & ~(size_t)15);
             E.sh_bytes = E.sh_logits + (size_t)V * 4;
@@ -514,6 +520,16 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.n_cons_warps = E.plan.n_cons_warps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
+        {
+            SchedStage *h = nullptr;
+            build_schedule(p, E.plan.grid, &h);
+            const size_t bytes = (size_t)E.plan.grid * p.sched_stride * sizeof(SchedStage);
+            cudaError_t e = cudaMalloc((void **)&E.d_sched, bytes);
+            if (e == cudaSuccess) e = cudaMemcpy(E.d_sched, h, bytes, cudaMemcpyHostToDevice);
+            free(h);
+            CK(e);
+            p.sched = E.d_sched;
+        }
         CK(prepare_stream_kernel(wt, E.plan.threads, E.plan.smem_bytes));
     } else {
         CK(dalloc(&E.d_att_part, (size_t)c.n_heads * MAX_SPLITS * (hs + 4)));

@@ -62,6 +62,16 @@ struct PhaseW {
 
 constexpr int MAX_TP = 8;
 
+// One ring stage of a CTA's static weight-streaming schedule (built on the host once per engine,
+// copied to shared memory at kernel start): the producer warp just walks its CTA's list
+//   [embedding row][the stages of ONE layer][final norm vector + classifier stages],
+// repeating the layer section L times with src + layer * (stride16 << 4).
+struct SchedStage {
+    unsigned long long src;  // device address (layer 0)
+    unsigned int bytes;
+    unsigned int stride16;   // bytes between layers / 16
+};
+
 // All dimensions are THIS GPU's share under tensor parallelism (tp ranks): H / KVH / kv / hid / V /
 // nqkv / att_dim are local, emb is the full residual width (the residual stream is replicated).
 struct StreamParams {
@@ -90,6 +100,11 @@ struct StreamParams {
     unsigned long long *amax[MAX_TP];   // rank k's [tp][grid][2] per-CTA {max logit bits, index}
     unsigned long long *done[MAX_TP];   // rank k's [tp][grid] "logits rows stored" flags (tp > 1)
     float *logits[MAX_TP];              // rank k's full [v_total] logits buffer (all-gathered)
+    // Every CTA polls every LL vector, i.e. 148 CTAs hammer the same few L2 lines: each vector is kept
+    // in ll_rep replicas (producers store to all of them, CTA b polls replica b % ll_rep) to spread
+    // the hot spot.  Replica strides in 64-bit words: q / att: att_dim, hb: hid rounded up to even,
+    // kv: 2 kv, part1 / part2: tp * emb.
+    int ll_rep;
     unsigned int ep_base;         // epoch of layer l of this launch = ep_base + l + 1
     float *kc, *vc;          // [L][seq][kv]
     unsigned long long *phase_cycles;  // [PH_COUNT + 2] SM-cycle accumulators (+ total cycles, total ns)
@@ -98,7 +113,9 @@ struct StreamParams {
     int n_splits;            // attention position splits
     unsigned long long *trace;  // optional [grid][32] debug trace of layer `trace_layer` (or null)
     int trace_layer;
-    int pf_stages;           // L2 prefetch distance beyond the shared-memory ring, in stages
+    const SchedStage *sched; // [grid][sched_stride] per-CTA stage lists (entry 0 = embedding row 0: + (token-1) * bytes)
+    int sched_stride;        // entries per CTA (padded)
+    int pf_stages;           // L2 prefetch distance beyond the ring, in stages (0 = off); used only while HBM would idle
     int pace;                // producer pacing: SM cycles per KB issued (0 = unpaced)
     int do_argmax;           // fuse maxloc after the classifier and write tokpos = {argmax, pos+1}
     const int *forced;       // optional device array of forced next tokens (prompt), or null
@@ -117,6 +134,8 @@ struct StreamPlan {
 // returns non-zero if it cannot fit.
 int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots,
                 int cons_warps, StreamPlan *out);
+// the per-CTA stage lists for `grid` CTAs: out has grid * (*stride) entries (call after plan_stream)
+void build_schedule(StreamParams &p, int grid, SchedStage **out);  // fills p.sched_stride
 cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes);
 cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st);
 

@@ -11,13 +11,12 @@
 //     rms_ffn vector, its rows of W13 (gate/up rows interleaved at upload) and W2, finally the
 //     rms_final vector and its rows of Wcls -- and streams it with 1-D TMA bulk copies
 //     (cp.async.bulk, mbarrier complete_tx) into a ring of shared-memory slots.  Nothing in the
-//     schedule depends on activations, so the producer never waits for a grid barrier: while
-//     the consumers finish a phase, synchronise the grid and rebuild the activation vector, the
-//     ring keeps filling.
-//   * CONSUMER warps each own one ring slot: wait on its `full` mbarrier, do the dot products
-//     of the rows in the slot against the activation vector (registers / shared memory; f16 and
-//     q4_0 dequantisation fused into the load, f32 accumulation, warp-shuffle reduction),
-//     release the slot with an `empty` mbarrier arrive.
+//     schedule depends on activations, so the producer never waits for a hand-over: while the
+//     consumers finish a phase and rebuild the activation vector, the ring keeps filling.
+//   * 12 CONSUMER warps in NG groups of GW; a group owns every NG-th stage of the ring: wait on
+//     its `full` mbarrier, dot the rows in the slot with the activation vector (kept in
+//     registers for the phase; f16 / q4_0 dequantisation fused into the load, f32 accumulation,
+//     batched warp-shuffle reduction), release the slot with an `empty` mbarrier arrive.
 //   * Between phases the consumers run the tiny epilogues in place -- RoPE + KV-cache append,
 //     SwiGLU, residual add -- and publish their slice as {value, epoch} 64-bit words ("LL"
 //     buffers, the protocol NCCL uses for small messages): the next phase's prologue polls the
@@ -27,32 +26,47 @@
 //   * Attention (scores, softmax, value gather) is a phase of the same kernel: (head, split)
 //     items over the CTAs, online softmax, merged in the Wo prologue when there are splits.
 //
-// All ring bookkeeping is incremental (no integer division on the hot path), the big pieces
-// are deliberately NOT inlined (one copy of the mat-vec code serves all five weight phases: the
-// whole kernel stays within the instruction cache), and the per-CTA row ranges are computed
-// once per launch into shared memory.
+// CODE SIZE IS A FIRST-CLASS CONSTRAINT.  Every piece of this kernel runs once per phase, i.e. its
+// instructions are cold each time unless one layer's worth of code fits the 32 KB L1.5
+// instruction cache; a cold 128-byte line (8 instructions) costs ~300 cycles (measured: a
+// 228 KB build of this kernel spent most of every hand-over fetching instructions).  Hence: one
+// generic prologue / consume / epilogue for all phases (data-driven, not specialised), modest
+// unrolling, profiling hooks out of line, cold paths (position splits, tensor-parallel tails)
+// in non-inlined functions.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
 namespace llmf90 {
 
 constexpr int MAX_SLOTS = 16;
-constexpr int MAX_CONS_WARPS = 12;  // + 1 producer warp = 416 threads -> 152 registers/thread
+constexpr int MAX_CONS_WARPS = 12;  // + 1 producer warp = 416 threads -> 128 registers/thread
 constexpr int CONS_BAR = 1;         // named barrier id used by the consumer warps
 constexpr int GW = 4;               // consumer warps per group: a group of GW warps consumes one ring stage
 constexpr int NG = MAX_CONS_WARPS / GW;  // groups; group g owns the stages whose schedule index is g (mod NG)
+// The ring has a multiple of NG slots, so a slot always belongs to the same group: a group sees
+// the uses of its slots in order and the one-bit mbarrier phase parity can never alias.
 
 struct SmemView {
     uint8_t *ring;
     float *xs, *res, *xres, *red;  // xres: this CTA's copy of the residual stream x (llama2.f90:520,605,620)
     uint64_t *full, *empty;
+    const SchedStage *sched;  // this CTA's stage list (copied from global memory at kernel start)
 };
 
 // per-launch constants of this CTA, computed once into shared memory
 struct CtaPlan {
     PhaseW ph[5];
     int r0[5], r1[5], nst[5];
+};
+
+// profiling state of a CTA (shared memory): phase timers of the timer thread, trace scratch
+struct Prof {
+    long long tacc[PH_COUNT];
+    long long tmark;
+    long long twait[12 + 32];  // 12 accumulators + 8 clock stamps for each of the 4 layer phases
+    volatile int prod_issued;  // stages issued by the producer so far
 };
 
 __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
@@ -71,13 +85,15 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
     off += 64 * 4;
     v.full = reinterpret_cast<uint64_t *>(smem + off);
     v.empty = v.full + MAX_SLOTS;
+    off += 2 * MAX_SLOTS * 8;
+    v.sched = reinterpret_cast<const SchedStage *>(smem + off);
     return v;
 }
 
-static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats, int emb)
+static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats, int emb, int sched_entries)
 {
     return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 + (size_t)emb * 4 + 64 * 4 +
-           2 * MAX_SLOTS * 8;
+           2 * MAX_SLOTS * 8 + (size_t)sched_entries * sizeof(SchedStage);
 }
 
 __host__ __device__ inline void cta_rows(const PhaseW &ph, int cta, int G, int &r0, int &r1)
@@ -98,104 +114,73 @@ __device__ __forceinline__ void ring_advance(RingPos &p, uint32_t n, uint32_t ns
 }
 
 // ------------------------------------------------------------------ producer
-// Segment order (linear index q): 0 = embedding row of the token; per layer l, base 1 + 6l:
-// +0 rms_att vector, +1 QKV, +2 WO, +3 rms_ffn vector, +4 W13, +5 W2; then rms_final vector, CLS.
+// Segment order of a CTA's schedule: the embedding row of the token; per layer: rms_att vector,
+// its rows of QKV, of WO, rms_ffn vector, its rows of W13, of W2; then rms_final vector, CLS.
 // The small f32 vectors and the embedding row travel through the ring like weights ("vector
 // stages", one stage each, read by all consumer warps in the prologue) so that no prologue waits
-// for a demand miss queued behind megabytes of in-flight weight requests.
-struct StageIter {
-    int q, q_end, k6, layer;  // k6 = position inside the layer's six segments
-    int r, nrows, rps;
-    unsigned int rs;
-    const uint8_t *src;
-    const CtaPlan *cp;
-    int token;
-
-    __device__ __forceinline__ void vec(const void *p, unsigned int bytes)
-    {
-        r = 0; nrows = 1; rps = 1; rs = bytes;
-        src = reinterpret_cast<const uint8_t *>(p);
-    }
-    __device__ __forceinline__ bool rows(int ph, int l)
-    {
-        const int n = cp->r1[ph] - cp->r0[ph];
-        if (n <= 0) return false;
-        const PhaseW &w = cp->ph[ph];
-        r = 0; nrows = n; rps = w.rps; rs = w.rs;
-        src = w.base + (size_t)l * w.layer_stride + (size_t)cp->r0[ph] * w.rs;
-        return true;
-    }
-    // position on the next non-empty segment at or after q
-    __device__ __forceinline__ void settle(const StreamParams &P)
-    {
-        const int qf = 1 + 6 * P.L;
-        for (; q < q_end; q++, k6++) {
-            if (k6 == 6) { k6 = 0; layer++; }
-            if (q == 0) { vec(P.emb_table + (size_t)(token - 1) * cp->ph[0].rs, cp->ph[0].rs); return; }
-            if (q == qf) { vec(P.rms_final, (unsigned)P.emb * 4u); return; }
-            if (q > qf) { if (rows(4, 0)) return; continue; }
-            if (k6 == 0) { vec(P.rms_att + (size_t)layer * P.emb, (unsigned)P.emb * 4u); return; }
-            if (k6 == 3) { vec(P.rms_ffn + (size_t)layer * P.emb, (unsigned)P.emb * 4u); return; }
-            if (rows(k6 < 3 ? k6 - 1 : k6 - 2, layer)) return;
-        }
-    }
-    __device__ __forceinline__ void init(const StreamParams &P, const CtaPlan *plan, int tok)
-    {
-        cp = plan; token = tok; q = 0; q_end = 3 + 6 * P.L; k6 = -1; layer = 0;
-        settle(P);
-    }
-    __device__ __forceinline__ bool next(const StreamParams &P, const uint8_t *&p, uint32_t &bytes)
-    {
-        if (q >= q_end) return false;
-        const int n = min(rps, nrows - r);
-        p = src + (size_t)r * rs;
-        bytes = (uint32_t)n * rs;
-        r += n;
-        if (r >= nrows) { q++; k6++; settle(P); }
-        return true;
-    }
-};
-
-// Two cursors walk the schedule: the copy cursor (TMA bulk copies into the ring) and, pf_stages
-// stages ahead of it, the L2-prefetch cursor (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2).  The
-// second cursor turns part of the 126 MB L2 into a deeper level of the ring: when the consumers
-// sit in a phase hand-over or in attention and every shared-memory slot is full, the requests
-// already queued for L2 keep the HBM channels busy, and the ring later refills at L2 latency.
-__device__ __forceinline__ void producer_loop(const StreamParams &P, const SmemView &sv, const CtaPlan *cp,
-                                              int token, volatile int *issued)
+// for a demand miss queued behind megabytes of in-flight weight requests.  The list is static
+// (nothing in it depends on activations): the host builds it once (build_schedule), the
+// producer warp walks it -- a handful of instructions per stage.
+__device__ __noinline__ void producer_loop(const StreamParams &P, const SmemView sv, const CtaPlan *cp, int token,
+                                           volatile int *issued)
 {
     const uint64_t pol = l2_policy_evict_first();
-    StageIter it, ip;
-    it.init(P, cp, token);
-    ip = it;
+    const uint4 *tab = reinterpret_cast<const uint4 *>(sv.sched);
     const uint32_t ns = (uint32_t)P.n_slots;
-    const uint32_t depth = ns + (uint32_t)P.pf_stages;
-    uint32_t slot = 0, k = 0, s = 0, pf = P.pf_stages > 0 ? 0u : 0xffffffffu;
-    const uint8_t *src;
-    uint32_t bytes;
+    // this CTA's section sizes follow from its row ranges (the host list was built from the same cta_rows)
+    const int n_layer = 2 + cp->nst[0] + cp->nst[1] + cp->nst[2] + cp->nst[3];
+    const int e_layer_end = 1 + n_layer, total = 1 + P.L * n_layer + 1 + cp->nst[4];
+    uint32_t slot = 0, par = 1;
+    int e = 0, l = 0;
+    // L2 prefetch cursor (pf_stages > 0): while the ring is full AND everything issued has landed --
+    // the consumers sit in a hand-over and HBM would idle -- the stages beyond the ring are pulled
+    // into L2, so that the ring later refills at L2 speed.
+    int ps = 0, pe = 0, pl = 0;
+    uint32_t last_slot = 0, last_par = 0;
     // pacing: issue at most one KB per `pace` SM cycles (0 = unpaced).  Every byte in flight
     // beyond bandwidth x latency only adds queueing delay in front of the latency-critical LL
     // traffic of the phase hand-overs; a paced producer keeps the queues short.
     long long next_ok = clock64();
-    while (it.next(P, src, bytes)) {
-        mbar_wait(&sv.empty[slot], (k & 1u) ^ 1u, 1);
+    auto stage_addr = [&](int ee, int ll, int ss, uint32_t &bytes) {
+        const uint4 st = tab[ee];
+        bytes = st.z;
+        unsigned long long src = ((unsigned long long)st.y << 32 | st.x) + ((unsigned long long)st.w << 4) * (unsigned)ll;
+        if (ss == 0) src += (unsigned long long)(token - 1) * bytes;  // the token's embedding row
+        return src;
+    };
+#pragma unroll 1
+    for (int s = 0; s < total; s++) {
+        uint32_t bytes;
+        const unsigned long long src = stage_addr(e, l, s, bytes);
+        if (ps <= s) { ps = s + 1; pe = e; pl = l; if (++pe == e_layer_end && pl + 1 < P.L) { pe = 1; pl++; } }
+        if (++e == e_layer_end && l + 1 < P.L) { e = 1; l++; }
+        if (P.pf_stages > 0) {
+            while (!mbar_test(&sv.empty[slot], par)) {
+                if (ps < total && ps < s + (int)ns + P.pf_stages && s > 0 && mbar_test(&sv.full[last_slot], last_par)) {
+                    long long now = clock64();
+                    if (now >= next_ok) {
+                        uint32_t pb;
+                        const unsigned long long pa = stage_addr(pe, pl, ps, pb);
+                        bulk_prefetch_l2(reinterpret_cast<const void *>(pa), pb);
+                        next_ok = now + (((long long)pb * P.pace) >> 10);
+                        ps++;
+                        if (++pe == e_layer_end && pl + 1 < P.L) { pe = 1; pl++; }
+                    }
+                }
+            }
+        } else {
+            mbar_wait(&sv.empty[slot], par, 1);
+        }
         if (P.pace > 0) {
             long long now = clock64();
             while (now < next_ok) now = clock64();
             next_ok = now + (((long long)bytes * P.pace) >> 10);
         }
         mbar_arrive_expect_tx(&sv.full[slot], bytes);
-        bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, src, bytes, &sv.full[slot], pol);
-        if (++slot == ns) { slot = 0; k++; }
-        s++;
-        *issued = (int)s;  // progress of the copy cursor, for the per-CTA trace
-        while (pf < s + depth) {
-            const uint8_t *psrc;
-            uint32_t pbytes;
-            if (!ip.next(P, psrc, pbytes)) { pf = 0xffffffffu; break; }
-            if (pf >= s + ns - 1) bulk_prefetch_l2(psrc, pbytes);  // nearer stages go straight to the ring
-            pf++;
-        }
+        bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, reinterpret_cast<const void *>(src), bytes, &sv.full[slot], pol);
+        last_slot = slot; last_par = par ^ 1u;  // parity of the use just issued
+        if (++slot == ns) { slot = 0; par ^= 1u; }
+        *issued = s + 1;  // progress of the copy cursor, for the per-CTA trace
     }
 }
 
@@ -204,8 +189,7 @@ struct Cons {
     int tid, warp, lane, nt, nw;  // within the consumer group
 };
 
-// ring cursor of the consumer side: the next stage of the schedule.  Every consumer warp visits
-// every stage (wait full -> its share of the rows -> arrive empty), so one cursor serves them all.
+// ring cursor of the consumer side: the next stage of the schedule
 struct CState {
     RingPos pos;
     uint32_t gmod;  // schedule index of the next stage, mod NG (-> the group that owns it)
@@ -240,14 +224,13 @@ __device__ __forceinline__ void rows_to_res(const uint8_t *sp, size_t rs, const 
 // progressively, the phase tail is one stage of one group).
 //   f32 / f16: warp cl of a group takes the 128-bit units u = 128 k + 32 cl + lane of every row of
 //     the stage and keeps those units of the activation vector in registers for the whole phase
-//     (KUT units per lane; rows wider than the register budget stream x from shared memory).
+//     (KUT <= 4 units per lane; wider rows stream x from shared memory).
 //     Lanes past the end of a row read a clamped (valid) unit against x = 0: no predication.
 //     Lane-partial sums of four rows are reduced together (6 shuffles instead of 20) and the slot
 //     is released as soon as its weights are in registers; partial sums go to plane cl of `res`,
 //     the epilogue adds the GW planes in a fixed order.
 //   q4_0: groups of 4 rows of a stage go round-robin over the group's warps (lane <-> block).
-// Not inlined on purpose: the function gets its own register allocation (x stays in registers)
-// and one copy serves all five weight phases.
+// Not inlined on purpose: own register allocation (x stays in registers), one copy for all phases.
 struct ConsumeArgs {
     const PhaseW *ph;      // shared memory
     uint8_t *ring;
@@ -256,7 +239,7 @@ struct ConsumeArgs {
     uint64_t *full, *empty;
     long long *wait_cycles;  // optional trace accumulators (or null); warp-uniform
     long long *stamps;       // optional 8 clock stamps of this call (trace), or null
-    int nrows, nst, slot_bytes, n_slots, slot0, par0, gmod0, warp, lane, no_wide;
+    int nrows, nst, slot_bytes, n_slots, slot0, par0, gmod0, warp, lane;
 };
 
 // four pending lane-partial sums -> four row results (see consume_phase)
@@ -316,10 +299,10 @@ struct StageWalk {
             mbar_wait(&a.full[slot], par, 2);
             tc0 = clock64();
             if (a.lane == 0) a.wait_cycles[0] += tc0 - w0;
+            if (nwaits++ == 0) stampc(2);
         } else {
             mbar_wait(&a.full[slot], par, 2);
         }
-        if (nwaits++ == 0) stampc(2);
         return a.ring + (size_t)slot * a.slot_bytes;
     }
     __device__ __forceinline__ void release()
@@ -327,7 +310,7 @@ struct StageWalk {
         __syncwarp();
         if (a.wait_cycles && a.lane == 0) { a.wait_cycles[4] += clock64() - tc0; a.wait_cycles[8] += 1; }
         if (a.lane == 0) mbar_arrive(&a.empty[slot]);
-        if (nwaits == 1) stampc(3);
+        if (a.wait_cycles && nwaits == 1) stampc(3);
         s += NG;
         slot += NG;
         if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; par ^= 1u; }
@@ -361,12 +344,40 @@ __device__ __forceinline__ void consume_xreg(const ConsumeArgs &a)
     while (w.more()) {
         const uint8_t *sp = w.wait();
         const int base = w.s * rps, n = min(rps, a.nrows - base);
+#pragma unroll 1
         for (int r = 0; r < n; r++) {
             const uint8_t *row = sp + (uint32_t)r * rs;
-            uint4 wv[KUT];
+            // units in batches of four: four independent accumulator chains, <= 4 loads in flight
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int k = 0; k < KUT; k++) wv[k] = *reinterpret_cast<const uint4 *>(row + off[k]);
-            pd.push(dot_units<WT, KUT>(wv, x), base + r, res, lane);
+            for (int kb = 0; kb < KUT; kb += 4) {
+                uint4 wv[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (kb + k < KUT) wv[k] = *reinterpret_cast<const uint4 *>(row + off[kb + k]);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (kb + k < KUT) {
+                        if (WT == WT_F16) {
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].x));
+                            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].y));
+                            const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].z));
+                            const float2 f3 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].w));
+                            const float4 xa = x.v[2 * (kb + k)], xb = x.v[2 * (kb + k) + 1];
+                            a0 = fmaf(f0.x, xa.x, a0); a1 = fmaf(f0.y, xa.y, a1);
+                            a2 = fmaf(f1.x, xa.z, a2); a3 = fmaf(f1.y, xa.w, a3);
+                            a0 = fmaf(f2.x, xb.x, a0); a1 = fmaf(f2.y, xb.y, a1);
+                            a2 = fmaf(f3.x, xb.z, a2); a3 = fmaf(f3.y, xb.w, a3);
+                        } else {
+                            const float4 xa = x.v[kb + k];
+                            a0 = fmaf(__uint_as_float(wv[k].x), xa.x, a0);
+                            a1 = fmaf(__uint_as_float(wv[k].y), xa.y, a1);
+                            a2 = fmaf(__uint_as_float(wv[k].z), xa.z, a2);
+                            a3 = fmaf(__uint_as_float(wv[k].w), xa.w, a3);
+                        }
+                    }
+            }
+            pd.push((a0 + a1) + (a2 + a3), base + r, res, lane);
         }
         w.release();
     }
@@ -388,9 +399,11 @@ __device__ __forceinline__ void consume_xsmem(const ConsumeArgs &a)
     while (w.more()) {
         const uint8_t *sp = w.wait();
         const int base = w.s * rps, n = min(rps, a.nrows - base);
+#pragma unroll 1
         for (int r = 0; r < n; r++) {
             const uint8_t *row = sp + (uint32_t)r * rs;
             float acc = 0.f;
+#pragma unroll 1
             for (int u0 = cl * 32 + lane; u0 < nunits; u0 += KB * 32 * GW) {
                 XRegs<WT, KB> x;
                 uint4 wv[KB];
@@ -398,12 +411,13 @@ __device__ __forceinline__ void consume_xsmem(const ConsumeArgs &a)
                 for (int k = 0; k < KB; k++) {
                     const int u = u0 + k * (32 * GW);
                     const bool ok = u < nunits;
-                    wv[k] = *reinterpret_cast<const uint4 *>(row + (uint32_t)min(u, nunits - 1) * 16u);
+                    const int uc = min(u, nunits - 1);
+                    wv[k] = *reinterpret_cast<const uint4 *>(row + (uint32_t)uc * 16u);
                     if (WT == WT_F16) {
-                        x.v[2 * k] = ok ? x4[2 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        x.v[2 * k + 1] = ok ? x4[2 * u + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x.v[2 * k] = ok ? x4[2 * uc] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x.v[2 * k + 1] = ok ? x4[2 * uc + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
                     } else {
-                        x.v[k] = ok ? x4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x.v[k] = ok ? x4[uc] : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
                 acc += dot_units<WT, KB>(wv, x);
@@ -422,12 +436,10 @@ __device__ __noinline__ void consume_phase(const ConsumeArgs a)
     if constexpr (WT != WT_Q4_0) {
         // units per lane per row, rounded up to an instantiated register budget
         const int ku = a.ph->ku;
-        if (ku <= 1) consume_xreg<WT, 1>(a);
-        else if (ku <= 2) consume_xreg<WT, 2>(a);
+        if (ku <= 2) consume_xreg<WT, 2>(a);
         else if (ku <= 4) consume_xreg<WT, 4>(a);
-        else if (ku <= 6) consume_xreg<WT, 6>(a);
-        else if (WT == WT_F32 && ku <= 8 && !a.no_wide) consume_xreg<WT, WT == WT_F32 ? 8 : 1>(a);
-        else if (WT == WT_F32 && ku <= 12 && !a.no_wide) consume_xreg<WT, WT == WT_F32 ? 12 : 1>(a);
+        else if (WT == WT_F16 && ku <= 6) consume_xreg<WT, WT == WT_F16 ? 6 : 2>(a);
+        else if (WT == WT_F32 && ku <= 12) consume_xreg<WT, WT == WT_F32 ? 12 : 2>(a);
         else consume_xsmem<WT>(a);
     } else {
         const PhaseW *ph = a.ph;
@@ -476,6 +488,25 @@ __device__ __forceinline__ void ll_store_sys(unsigned long long *buf, int i, flo
     const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)ep << 32);
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(buf + i), "l"(w) : "memory");
 }
+// two consecutive words (i even) with one 16-byte store; each 8-byte half is still self-validating
+__device__ __forceinline__ void ll_store2(unsigned long long *buf, int i, float v0, float v1, uint32_t ep)
+{
+    const unsigned long long e = (unsigned long long)ep << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(buf + i), "l"(e | __float_as_uint(v0)),
+                 "l"(e | __float_as_uint(v1))
+                 : "memory");
+}
+// store to every replica of an LL vector (replicas are `stride` words apart, see StreamParams::ll_rep)
+__device__ __forceinline__ void ll_store_rep(unsigned long long *buf, int stride, int nrep, int i, float v, uint32_t ep)
+{
+#pragma unroll 1
+    for (int r = 0; r < nrep; r++) ll_store(buf + (size_t)r * stride, i, v, ep);
+}
+__device__ __forceinline__ void ll_store_sys_rep(unsigned long long *buf, int stride, int nrep, int i, float v, uint32_t ep)
+{
+#pragma unroll 1
+    for (int r = 0; r < nrep; r++) ll_store_sys(buf + (size_t)r * stride, i, v, ep);
+}
 __device__ __forceinline__ void ll_load2(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
 {
     asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
@@ -488,8 +519,6 @@ __device__ __forceinline__ unsigned long long ll_load1(const unsigned long long 
 }
 __device__ __forceinline__ float ll_val(unsigned long long w) { return __uint_as_float((uint32_t)w); }
 __device__ __forceinline__ bool ll_ok(unsigned long long w, uint32_t ep) { return (uint32_t)(w >> 32) == ep; }
-// value only (own earlier write, no polling)
-__device__ __forceinline__ float ll_peek(const unsigned long long *buf, int i) { return ll_val(ll_load1(buf + i)); }
 // poll four consecutive floats (i % 4 == 0)
 __device__ __forceinline__ float4 ll_wait4(const unsigned long long *buf, int i, uint32_t ep)
 {
@@ -543,38 +572,36 @@ __device__ __forceinline__ void ll_waitv(const unsigned long long *buf, int i, u
         o[0] = ll_val(a);
     }
 }
-// a thread's batch of up to PRO_V float4: all requests of a polling round are issued before the
-// first check (one L2 round trip per round)
-template <int PRO_V>
+// A thread's batch of PV float4 positions j = base + tid + k * nt of an LL vector: all requests of
+// a polling round are issued before the first check (one L2 round trip per round).  Positions
+// past the end are clamped to the last one (a harmless duplicate request).
+template <int PV>
 __device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4, int base, uint32_t ep,
-                                          const Cons &c, float4 (&v)[PRO_V])
+                                          const Cons &c, float4 (&v)[PV])
 {
-    unsigned long long w[PRO_V][4];
+    unsigned long long w[PV][4];
+    int jj[PV];
+#pragma unroll
+    for (int k = 0; k < PV; k++) {
+        const int j = base + c.tid + k * c.nt;
+        jj[k] = min(j, n4 - 1);
+    }
     bool ok;
     LLMF90_WD_DECL;
     do {
         LLMF90_WD_CHECK(105, base, ep)
 #pragma unroll
-        for (int k = 0; k < PRO_V; k++) {
-            const int j = base + c.tid + k * c.nt;
-            if (j < n4) {
-                ll_load2(buf + 4 * j, w[k][0], w[k][1]);
-                ll_load2(buf + 4 * j + 2, w[k][2], w[k][3]);
-            }
+        for (int k = 0; k < PV; k++) {
+            ll_load2(buf + 4 * jj[k], w[k][0], w[k][1]);
+            ll_load2(buf + 4 * jj[k] + 2, w[k][2], w[k][3]);
         }
         ok = true;
 #pragma unroll
-        for (int k = 0; k < PRO_V; k++) {
-            const int j = base + c.tid + k * c.nt;
-            if (j < n4) ok = ok && ll_ok(w[k][0], ep) && ll_ok(w[k][1], ep) && ll_ok(w[k][2], ep) && ll_ok(w[k][3], ep);
-        }
+        for (int k = 0; k < PV; k++)
+            ok = ok && ll_ok(w[k][0], ep) && ll_ok(w[k][1], ep) && ll_ok(w[k][2], ep) && ll_ok(w[k][3], ep);
     } while (!ok);
 #pragma unroll
-    for (int k = 0; k < PRO_V; k++) {
-        const int j = base + c.tid + k * c.nt;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < n4) v[k] = make_float4(ll_val(w[k][0]), ll_val(w[k][1]), ll_val(w[k][2]), ll_val(w[k][3]));
-    }
+    for (int k = 0; k < PV; k++) v[k] = make_float4(ll_val(w[k][0]), ll_val(w[k][1]), ll_val(w[k][2]), ll_val(w[k][3]));
 }
 
 // ---- vector stages: every consumer thread waits for the stage and reads what it needs; after
@@ -593,10 +620,15 @@ __device__ __forceinline__ void vec_stage_release(const StreamParams &P, const S
     cons_advance(cs, 1u, (uint32_t)P.n_slots);
 }
 
-// ---- activation-vector prologues.  Every CTA needs the whole vector; it is 8-44 KB and was
-// just written by the other CTAs, so it comes from L2.  All loads of a thread are issued
-// before the first use (PRO_V independent 128-bit requests in flight per thread): one L2 round
-// trip per prologue instead of one per element.
+// ---- activation-vector prologue, one routine for all phases.  Every CTA needs the whole vector;
+// it is 8-44 KB and was just written by the other CTAs, so it comes from L2 (LL words).
+//   Wo / W2 (norm == false):  xs = the attention output / the SwiGLU output.
+//   QKV / W13 / classifier:   x += sum over the tp ranks of their partial Wo / W2 outputs (the
+//     fused all-reduce; ranks are added in rank order on every GPU, so the replicated stream stays
+//     bit-identical), xs = x * w.  The common rmsnorm factor 1 / sqrt(mean(x^2) + 1e-5)
+//     (llama2.f90:450-457) is returned and multiplies the phase's results in the epilogue (the
+//     mat-vec is linear): no second pass over xs.  x is this CTA's copy of the residual stream in
+//     shared memory; for the very first phase it is the embedding row from a ring slot (:520).
 template <int WT>
 __device__ __forceinline__ void store_x4(float *xs, int j4, const float4 v)
 {
@@ -611,123 +643,68 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
                        row_elem(row, wtype, cols, 4 * j4 + 2), row_elem(row, wtype, cols, 4 * j4 + 3));
 }
 
-// x += sum over the tp ranks of their partial Wo / W2 outputs (the fused all-reduce), then
-// xs = rmsnorm(x) * w (llama2.f90:450-457).  x is this CTA's copy of the residual stream in shared
-// memory; for the very first phase it is the embedding row from a ring slot (llama2.f90:520) and
-// there is nothing to add.  `part` = this rank's [tp][emb] buffer of partials; w from a ring slot.
-// Up to 8 (float4 position, rank) requests are in flight per thread per polling round.
-template <int WT, int TP>
-__device__ __forceinline__ float load_x_norm_t(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
-                                              const float *wn /* shared */, const StreamParams &P,
-                                              const SmemView &sv, const Cons &c)
+template <int WT>
+__device__ __forceinline__ float gather_x(const unsigned long long *src, int nsrc, uint32_t ep, int n, bool norm,
+                                          const uint8_t *emb_row, const float *wn /* shared */,
+                                          const StreamParams &P, const SmemView &sv, const Cons &c)
 {
-    constexpr int PPB = TP >= 4 ? 1 : 4 / TP;  // float4 positions per polling batch (4-8 requests in flight)
-    const int n = P.emb, n4 = n >> 2;
+    constexpr int PV = 2;
+    const int n4 = n >> 2;
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
     float4 *xr4 = reinterpret_cast<float4 *>(sv.xres);
     float ss = 0.f;
-    for (int base = c.tid; base < n4; base += PPB * c.nt) {
-        float4 x[PPB];
+#pragma unroll 1
+    for (int base = 0; base < n4; base += PV * c.nt) {
+        float4 v[PV];
         if (emb_row) {
 #pragma unroll
-            for (int pi = 0; pi < PPB; pi++) {
-                const int j = base + pi * c.nt;
-                x[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < n4) x[pi] = emb_row4(emb_row, P.wtype, n, j);
+            for (int k = 0; k < PV; k++) {
+                const int j = base + c.tid + k * c.nt;
+                v[k] = emb_row4(emb_row, P.wtype, n, min(j, n4 - 1));
             }
         } else {
-            unsigned long long w[PPB][TP][4];
-            bool ok;
-            LLMF90_WD_DECL;
-            do {
-                LLMF90_WD_CHECK(106, base, ep)
-                ok = true;
+            ll_gather<PV>(src, n4, base, ep, c, v);
+            if (norm) {
 #pragma unroll
-                for (int pi = 0; pi < PPB; pi++) {
-                    const int j = base + pi * c.nt;
-                    if (j < n4) {
-#pragma unroll
-                        for (int r = 0; r < TP; r++) {
-                            const unsigned long long *src = part + (size_t)r * n + 4 * j;
-                            ll_load2(src, w[pi][r][0], w[pi][r][1]);
-                            ll_load2(src + 2, w[pi][r][2], w[pi][r][3]);
-                        }
-                    }
+                for (int k = 0; k < PV; k++) {
+                    const int j = base + c.tid + k * c.nt;
+                    const float4 x = xr4[min(j, n4 - 1)];
+                    v[k].x += x.x; v[k].y += x.y; v[k].z += x.z; v[k].w += x.w;
                 }
+#pragma unroll 1
+                for (int r = 1; r < nsrc; r++) {
+                    float4 t[PV];
+                    ll_gather<PV>(src + (size_t)r * n, n4, base, ep, c, t);
 #pragma unroll
-                for (int pi = 0; pi < PPB; pi++) {
-                    const int j = base + pi * c.nt;
-                    if (j < n4) {
-#pragma unroll
-                        for (int r = 0; r < TP; r++)
-                            ok = ok && ll_ok(w[pi][r][0], ep) && ll_ok(w[pi][r][1], ep) && ll_ok(w[pi][r][2], ep) &&
-                                 ll_ok(w[pi][r][3], ep);
-                    }
-                }
-            } while (!ok);
-#pragma unroll
-            for (int pi = 0; pi < PPB; pi++) {
-                const int j = base + pi * c.nt;
-                x[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < n4) {
-                    x[pi] = xr4[j];
-                    // ranks are added in rank order on every GPU: the replicated stream stays bit-identical
-#pragma unroll
-                    for (int r = 0; r < TP; r++) {
-                        x[pi].x += ll_val(w[pi][r][0]); x[pi].y += ll_val(w[pi][r][1]);
-                        x[pi].z += ll_val(w[pi][r][2]); x[pi].w += ll_val(w[pi][r][3]);
-                    }
+                    for (int k = 0; k < PV; k++) { v[k].x += t[k].x; v[k].y += t[k].y; v[k].z += t[k].z; v[k].w += t[k].w; }
                 }
             }
         }
 #pragma unroll
-        for (int pi = 0; pi < PPB; pi++) {
-            const int j = base + pi * c.nt;
+        for (int k = 0; k < PV; k++) {
+            const int j = base + c.tid + k * c.nt;
             if (j < n4) {
-                const float4 v = x[pi];
-                xr4[j] = v;
-                ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-                const float4 w = wn4[j];
-                store_x4<WT>(sv.xs, j, make_float4(v.x * w.x, v.y * w.y, v.z * w.z, v.w * w.w));
+                float4 t = v[k];
+                if (norm) {
+                    xr4[j] = t;
+                    ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+                    const float4 w = wn4[j];
+                    t.x *= w.x; t.y *= w.y; t.z *= w.z; t.w *= w.w;
+                }
+                store_x4<WT>(sv.xs, j, t);
             }
         }
     }
-    // xs holds x * w; the common factor 1 / rms multiplies the phase's results in the epilogue
-    // (the mat-vec is linear), so there is no second pass over xs and only one barrier here
+    if (!norm) {
+        cons_sync(c);
+        return 1.f;
+    }
     ss = warp_sum(ss);
     if (c.lane == 0) sv.red[c.warp] = ss;
     cons_sync(c);
     float tot = 0.f;
     for (int i = 0; i < c.nw; i++) tot += sv.red[i];
     return 1.0f / sqrtf(tot / (float)n + 1e-5f);
-}
-
-template <int WT>
-__device__ __forceinline__ float load_x_norm(const unsigned long long *part, uint32_t ep, const uint8_t *emb_row,
-                                             const float *wn, const StreamParams &P, const SmemView &sv,
-                                             const Cons &c)
-{
-    if (P.tp == 1) return load_x_norm_t<WT, 1>(part, ep, emb_row, wn, P, sv, c);
-    if (P.tp == 2) return load_x_norm_t<WT, 2>(part, ep, emb_row, wn, P, sv, c);
-    if (P.tp == 4) return load_x_norm_t<WT, 4>(part, ep, emb_row, wn, P, sv, c);
-    return load_x_norm_t<WT, 8>(part, ep, emb_row, wn, P, sv, c);
-}
-
-template <int WT, int PRO_V>
-__device__ __forceinline__ void load_x_plain(const unsigned long long *src, uint32_t ep, int n, const SmemView &sv,
-                                             const Cons &c)
-{
-    const int n4 = n >> 2;
-    for (int base = 0; base < n4; base += PRO_V * c.nt) {
-        float4 v[PRO_V];
-        ll_gather<PRO_V>(src, n4, base, ep, c, v);
-#pragma unroll
-        for (int k = 0; k < PRO_V; k++) {
-            const int j = base + c.tid + k * c.nt;
-            if (j < n4) store_x4<WT>(sv.xs, j, v[k]);
-        }
-    }
-    cons_sync(c);
 }
 
 // ------------------------------------------------------------------ attention phase
@@ -738,6 +715,7 @@ __device__ __forceinline__ void load_x_plain(const unsigned long long *src, uint
 //            are all issued up front: ONE L2 round trip per group), two shuffles finish the dot
 //   softmax: online (running max / sum) over the 8 positions, three shuffles each
 //   values : lane <-> head dimension (hs/32 consecutive dims), p_t broadcast by shuffle
+// Positions past the end of a group read a clamped (valid) row with probability 0.
 // Warp partials merge through shared memory.  With one split the normalised head output goes
 // straight to P.att; otherwise {m, l, acc} partials go to P.att_part and the Wo prologue merges.
 constexpr int ATT_PSTRIDE_PAD = 4;  // partial record = {m, l, -, -, acc[hs]}
@@ -757,23 +735,30 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 }
 
 template <int HS>
-__device__ __forceinline__ void attention_phase_t(const StreamParams &P, const SmemView &sv, const Cons &c,
-                                                  int layer, int pos, uint32_t ep)
+__device__ __noinline__ void attention_phase_t(const StreamParams &P, const SmemView sv, const Cons c, int layer,
+                                               int pos, uint32_t ep)
 {
     constexpr int hs = HS, vec = HS >> 5;  // HS in {32, 64, 128}
     constexpr int q4n = HS >> 4;           // float4 per lane of a quarter head: 2, 4, 8
     const int S = P.n_splits;
     const int items = P.H * S;
     const int npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches)
-    const int chunk = (((npast + S - 1) / S) + 7) & ~7;
+    const int s_shift = 31 - __clz(S), kvm_shift = 31 - __clz(P.kv_mul);
+    const bool kvm_pow2 = (P.kv_mul & (P.kv_mul - 1)) == 0;
+    const int chunk = (((npast + S - 1) >> s_shift) + 7) & ~7;
     const int pstride = hs + ATT_PSTRIDE_PAD;
-    const float scale = sqrtf((float)hs);
+    const float rscale = 1.0f / sqrtf((float)hs);
     float *sc = sv.xs;  // [nw][pstride]  (xs is dead between weight phases)
     const float *kc = P.kc + (size_t)layer * P.seq * P.kv;
     const float *vc = P.vc + (size_t)layer * P.seq * P.kv;
     const int pl = c.lane >> 2, dq = c.lane & 3;
+    const int rep = (int)blockIdx.x % P.ll_rep;  // the replica of the LL vectors this CTA polls
+    const unsigned long long *ll_q = P.ll_q + (size_t)rep * P.att_dim, *ll_kv = P.ll_kv + (size_t)rep * 2 * P.kv;
+#pragma unroll 1
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int h = item / S, sp = item - h * S, g = h / P.kv_mul;
+        // (S is a power of two; kv_mul is one in every common model: shifts, the division is a cold path)
+        const int h = item >> s_shift, sp = item & (S - 1);
+        const int g = kvm_pow2 ? h >> kvm_shift : h / P.kv_mul;
         const int t0 = sp * chunk, t1 = min(npast, t0 + chunk);
         float m = -INFINITY, l = 0.f, acc[vec];
 #pragma unroll
@@ -782,26 +767,21 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
         // polled after the first group's K / V requests are in flight
         float4 qq[q4n];
         bool have_q = false;
+#pragma unroll 1
         for (int tb = t0 + 8 * c.warp; tb < t1; tb += 8 * c.nw) {
             const int t = tb + pl;
             const bool valid = t < t1;
-            const int cnt = min(8, t1 - tb);
             const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)min(t, t1 - 1) * P.kv + (size_t)g * hs +
                                                                 dq * (hs >> 2));
-            const float *vb = vc + (size_t)tb * P.kv + (size_t)g * hs + c.lane * vec;
+            const float *vb = vc + (size_t)g * hs + c.lane * vec;
             float4 kk[q4n];
             float vv[8][vec];
 #pragma unroll
             for (int i = 0; i < q4n; i++) kk[i] = __ldcg(kr + i);
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if (u < cnt) load_vec<vec>(vb + (size_t)u * P.kv, vv[u]);
-                else
-#pragma unroll
-                    for (int i = 0; i < vec; i++) vv[u][i] = 0.f;
-            }
+            for (int u = 0; u < 8; u++) load_vec<vec>(vb + (size_t)min(tb + u, t1 - 1) * P.kv, vv[u]);
             if (!have_q) {
-                ll_wait4n<q4n>(P.ll_q, h * hs + dq * (hs >> 2), ep, qq);
+                ll_wait4n<q4n>(ll_q, h * hs + dq * (hs >> 2), ep, qq);
                 have_q = true;
             }
             float sdot = 0.f;
@@ -812,7 +792,7 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
             }
             sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
             sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-            sdot = valid ? sdot / scale : -INFINITY;  // dot_product(q_t,k_t)/sqrt(head_size), :582
+            sdot = valid ? sdot * rscale : -INFINITY;  // dot_product(q_t,k_t)/sqrt(head_size), :582
             float bm = sdot;
             bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
             bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
@@ -839,9 +819,9 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
             // the current position: its key / value rows were produced in this launch (LL buffer)
             float4 kk[q4n];
             float vv[vec];
-            if (!have_q) ll_wait4n<q4n>(P.ll_q, h * hs + dq * (hs >> 2), ep, qq);
-            ll_wait4n<q4n>(P.ll_kv, g * hs + dq * (hs >> 2), ep, kk);
-            ll_waitv<vec>(P.ll_kv, P.kv + g * hs + c.lane * vec, ep, vv);
+            if (!have_q) ll_wait4n<q4n>(ll_q, h * hs + dq * (hs >> 2), ep, qq);
+            ll_wait4n<q4n>(ll_kv, g * hs + dq * (hs >> 2), ep, kk);
+            ll_waitv<vec>(ll_kv, P.kv + g * hs + c.lane * vec, ep, vv);
             float sdot = 0.f;
 #pragma unroll
             for (int i = 0; i < q4n; i++) {
@@ -850,7 +830,7 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
             }
             sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
             sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-            sdot = sdot / scale;  // identical in every lane (all lanes hold the same position)
+            sdot = sdot * rscale;  // identical in every lane (all lanes hold the same position)
             const float mn = fmaxf(m, sdot);
             const float corr = expf(m - mn), p = expf(sdot - mn);
             l = fmaf(l, corr, p);
@@ -863,20 +843,24 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
 #pragma unroll
         for (int i = 0; i < vec; i++) mine[ATT_PSTRIDE_PAD + c.lane * vec + i] = acc[i];
         cons_sync(c);
-        for (int d = c.tid; d < hs; d += c.nt) {
+        // thread = (head dimension d, LL replica): every thread publishes one word
+        for (int w = c.tid; w < hs * (S == 1 ? P.ll_rep : 1); w += c.nt) {
+            const int d = w & (hs - 1), rr = w / hs;
             float M = -INFINITY;
-            for (int w = 0; w < c.nw; w++) M = fmaxf(M, sc[(size_t)w * pstride]);
+#pragma unroll 1
+            for (int w = 0; w < c.nw; w++) M = fmaxf(M, sc[w * pstride]);
             float L = 0.f, A = 0.f;
+#pragma unroll 1
             for (int w = 0; w < c.nw; w++) {
-                const float mw = sc[(size_t)w * pstride];
+                const float mw = sc[w * pstride];
                 if (mw > -INFINITY) {
-                    const float e = expf(mw - M);
-                    L = fmaf(sc[(size_t)w * pstride + 1], e, L);
-                    A = fmaf(sc[(size_t)w * pstride + ATT_PSTRIDE_PAD + d], e, A);
+                    const float e = __expf(mw - M);
+                    L = fmaf(sc[w * pstride + 1], e, L);
+                    A = fmaf(sc[w * pstride + ATT_PSTRIDE_PAD + d], e, A);
                 }
             }
             if (S == 1) {
-                ll_store(P.ll_att, h * hs + d, A / L, ep);
+                ll_store(P.ll_att + (size_t)rr * P.att_dim, h * hs + d, A / L, ep);
             } else {
                 unsigned long long *out = P.ll_part + (size_t)(h * S + sp) * pstride;
                 ll_store(out, ATT_PSTRIDE_PAD + d, A, ep);
@@ -887,17 +871,9 @@ __device__ __forceinline__ void attention_phase_t(const StreamParams &P, const S
     }
 }
 
-__device__ __forceinline__ void attention_phase(const StreamParams &P, const SmemView &sv, const Cons &c,
-                                                int layer, int pos, uint32_t ep)
-{
-    if (P.hs == 64) attention_phase_t<64>(P, sv, c, layer, pos, ep);
-    else if (P.hs == 128) attention_phase_t<128>(P, sv, c, layer, pos, ep);
-    else attention_phase_t<32>(P, sv, c, layer, pos, ep);
-}
-
-// xs = attention output (all heads), merging the position splits (n_splits > 1)
-template <int WT, int PRO_V>
-__device__ __forceinline__ void load_x_attn(const StreamParams &P, uint32_t ep, const SmemView &sv, const Cons &c)
+// xs = attention output (all heads), merging the position splits (n_splits > 1; long contexts only)
+template <int WT>
+__device__ __noinline__ void load_x_attn(const StreamParams &P, uint32_t ep, const SmemView sv, const Cons c)
 {
     const int S = P.n_splits;
     const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.att_dim >> 2;
@@ -931,15 +907,104 @@ __device__ __forceinline__ void load_x_attn(const StreamParams &P, uint32_t ep, 
     cons_sync(c);
 }
 
+// ------------------------------------------------------------------ profiling hooks (out of line)
+__device__ __noinline__ void prof_lap(Prof *pf, int bucket)
+{
+    const long long now = clock64();
+    pf->tacc[bucket] += now - pf->tmark;
+    pf->tmark = now;
+}
+// per-CTA trace of one layer: globaltimer stamp, producer / consumer ring cursors and the number
+// of landed stages at phase edge k
+__device__ __noinline__ void prof_stamp(const StreamParams &P, const SmemView sv, const CState cs, Prof *pf, int k)
+{
+    unsigned long long *row = P.trace + (size_t)blockIdx.x * 128;
+    row[k] = globaltimer_ns();
+    row[32 + k] = (unsigned long long)pf->prod_issued;
+    RingPos at = cs.pos;
+    int landed = 0;
+    for (int i = 0; i < P.n_slots; i++) {
+        landed += mbar_test(&sv.full[at.mod], at.div & 1u) ? 1 : 0;
+        ring_advance(at, 1u, (uint32_t)P.n_slots);
+    }
+    row[48 + k] = (unsigned long long)(cs.pos.div * (uint32_t)P.n_slots + cs.pos.mod) | ((unsigned long long)landed << 32);
+}
+
+// ------------------------------------------------------------------ token tail (once per launch)
+// all-gathered logits must have landed on every rank before any rank's kernel ends (tp > 1), then
+// maxloc(logits) (llama2.f90:388): first maximum wins at every reduction level
+__device__ __noinline__ void token_tail(const StreamParams &P, const SmemView sv, const Cons c, float best, int bidx,
+                                        int pos)
+{
+    const uint32_t epl = P.ep_base + (uint32_t)P.L + 1u;
+    const int G = (int)gridDim.x;
+    if (P.tp > 1) {
+        // each CTA flags every rank once its rows are stored, CTA 0 of every rank collects the flags
+        cons_sync(c);
+        if (c.tid == 0) {
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (int k = 0; k < P.tp; k++) ll_store_sys(P.done[k], P.rank * G + (int)blockIdx.x, 0.f, epl);
+        }
+        if (blockIdx.x == 0) {
+            for (int i = c.tid; i < P.tp * G; i += c.nt) {
+                float t[1];
+                ll_waitv<1>(P.done[P.rank], i, epl, t);
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+        }
+    }
+    if (!P.do_argmax) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    float *rv = sv.red;
+    int *ri = reinterpret_cast<int *>(sv.red + 32);
+    if (c.lane == 0) { rv[c.warp] = best; ri[c.warp] = bidx; }
+    cons_sync(c);
+    if (c.tid == 0) {
+        for (int w = 1; w < c.nw; w++)
+            if (rv[w] > best || (rv[w] == best && ri[w] < bidx)) { best = rv[w]; bidx = ri[w]; }
+        for (int k = 0; k < P.tp; k++) {
+            unsigned long long *dst = P.amax[k] + (size_t)(P.rank * G + (int)blockIdx.x) * 2;
+            ll_store_sys(dst, 0, best, epl);
+            ll_store_sys(dst, 1, __int_as_float(bidx), epl);
+        }
+    }
+    if (blockIdx.x == 0 && c.warp == 0) {
+        // every rank reduces the same tp * grid records in the same order -> the same token
+        best = -INFINITY; bidx = 0x7fffffff;
+        for (int i = c.lane; i < P.tp * G; i += 32) {
+            float rec[2];
+            ll_waitv<2>(P.amax[P.rank], 2 * i, epl, rec);
+            const float v = rec[0];
+            const int ix = __float_as_int(rec[1]);
+            if (v > best || (v == best && ix < bidx)) { best = v; bidx = ix; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if (c.lane == 0) {
+            int next = bidx + 1;
+            if (P.forced && P.forced[pos - 1] > 0) next = P.forced[pos - 1];
+            if (P.out_tokens) P.out_tokens[pos - 1] = next;
+            int *tp = const_cast<int *>(P.tokpos);
+            tp[0] = next;
+            tp[1] = pos + 1;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
-// MAXT = 416: 12 consumer warps + the producer warp, 152 registers per thread.  All consumer
-// warps work on every ring stage (consume_phase): the shared-memory load->FMA latency is hidden
-// by thread-level parallelism rather than by deep per-thread unrolling.
 template <int WT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 stream_decode_kernel(const __grid_constant__ StreamParams P)
 {
-    constexpr int PRO_V = MAXT <= 256 ? 8 : 4;
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemView sv = carve(smem, P);
     const int n_cons_warps = P.n_cons_warps;
@@ -947,9 +1012,8 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
 
     __shared__ CtaPlan cp;
     __shared__ float2 rope[64];
-    __shared__ long long tacc[PH_COUNT];  // phase timers, touched by the timer thread only
-    __shared__ volatile int prod_issued;  // stages issued by the producer so far
-    if (threadIdx.x == 0) prod_issued = 0;
+    __shared__ Prof pf;
+    if (threadIdx.x == 0) pf.prod_issued = 0;
     if (threadIdx.x < 5) {
         const int i = threadIdx.x;
         cp.ph[i] = P.ph[i];
@@ -957,6 +1021,11 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         cta_rows(P.ph[i], blockIdx.x, gridDim.x, r0, r1);
         cp.r0[i] = r0; cp.r1[i] = r1;
         cp.nst[i] = (r1 - r0 + P.ph[i].rps - 1) / P.ph[i].rps;
+    }
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(P.sched + (size_t)blockIdx.x * P.sched_stride);
+        uint4 *d = reinterpret_cast<uint4 *>(const_cast<SchedStage *>(sv.sched));
+        for (int i = threadIdx.x; i < P.sched_stride; i += blockDim.x) d[i] = __ldg(g + i);
     }
     if (threadIdx.x == 32) {
         for (int i = 0; i < P.n_slots; i++) {
@@ -973,7 +1042,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
 
     if (warp == n_cons_warps) {
         // ===================== producer warp =====================
-        if (lane == 0) producer_loop(P, sv, &cp, token, &prod_issued);
+        if (lane == 0) producer_loop(P, sv, &cp, token, &pf.prod_issued);
         return;
     }
 
@@ -983,70 +1052,46 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     c.nw = n_cons_warps; c.nt = n_cons_warps * 32;
     CState cs;
     cs.pos.mod = 0; cs.pos.div = 0; cs.gmod = 0;
-    // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh
+    // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh;
+    // optional per-CTA trace of one layer (debug/profiling)
     const bool timer = (blockIdx.x == 0 && c.tid == 0);
-    long long tmark = timer ? clock64() : 0ll;
+    const bool tracing = P.trace != nullptr;
     const unsigned long long t_ns0 = timer ? globaltimer_ns() : 0ull;
-    const long long t_c0 = tmark;
-    if (timer)
-        for (int i = 0; i < PH_COUNT; i++) tacc[i] = 0;
-    // optional per-CTA trace of one layer (debug/profiling): globaltimer stamps at every phase edge
-    // + per mat-vec phase the cycles warp 0 waited for ring data / computed, and its stage count
-    const bool tracer = (P.trace != nullptr && c.tid == 0);
-    const bool tracer_warp = (P.trace != nullptr && c.warp == 0);  // warp-uniform
-    __shared__ long long twait[12 + 32];  // 12 accumulators + 8 clock stamps for each of the 4 layer phases
-    if (tracer)
-        for (int i = 0; i < 44; i++) twait[i] = 0;
-    auto stamp = [&](int l, int k) {
-        if (tracer && l == P.trace_layer) {
-            unsigned long long *row = P.trace + (size_t)blockIdx.x * 128;
-            row[k] = globaltimer_ns();
-            row[32 + k] = (unsigned long long)prod_issued;                             // producer cursor
-            row[48 + k] = (unsigned long long)(cs.pos.div * (uint32_t)P.n_slots + cs.pos.mod);  // consumer cursor
-            // how many of the next n_slots stages have already landed in the ring
-            RingPos at = cs.pos;
-            int landed = 0;
-            for (int i = 0; i < P.n_slots; i++) {
-                landed += mbar_test(&sv.full[at.mod], at.div & 1u) ? 1 : 0;
-                ring_advance(at, 1u, (uint32_t)P.n_slots);
-            }
-            row[48 + k] |= (unsigned long long)landed << 32;
-        }
-    };
-    auto lap = [&](int bucket) {
-        if (timer) {
-            const long long now = clock64();
-            tacc[bucket] += now - tmark;
-            tmark = now;
-        }
-    };
-    // phase results: the chunk lanes' planes of partial sums are added in a fixed order, times the
-    // 1 / rms factor of the phase's rmsnorm (1 for Wo / W2)
-    int res_planes = 1, res_cap = 0;
-    float rscale = 1.f;
-    auto resv = [&](int i) -> float {
-        float t = sv.res[i];
-        for (int p = 1; p < res_planes; p++) t += sv.res[p * res_cap + i];
-        return t * rscale;
-    };
+    const long long t_c0 = timer ? clock64() : 0ll;
+    if (timer) {
+        for (int i = 0; i < PH_COUNT; i++) pf.tacc[i] = 0;
+        pf.tmark = t_c0;
+    }
+    if (tracing && c.tid == 0)
+        for (int i = 0; i < 44; i++) pf.twait[i] = 0;
+#define LAP(b) do { if (timer) prof_lap(&pf, (b)); } while (0)
+#define STAMP(l_, k_) do { if (tracing && c.tid == 0 && (l_) == P.trace_layer) prof_stamp(P, sv, cs, &pf, (k_)); } while (0)
     const int half_mask = (P.hs >> 1) - 1;
     const uint32_t ns = (uint32_t)P.n_slots;
+    const int nrep = P.ll_rep, rep = (int)blockIdx.x % nrep;  // LL vector replicas; the one this CTA polls
+    const int hb_stride = (P.hid + 1) & ~1;
+    constexpr int planes = (WT != WT_Q4_0) ? GW : 1;
     float best = -INFINITY;  // running maxloc of this thread's logits (classifier epilogue)
     int bidx = 0x7fffffff;
 
     // One loop over the 4 L + 1 weight phases (q = 4 l + {0 QKV, 1 WO, 2 W13, 3 W2}; q = 4 L is the
-    // classifier): prologue -> ring consumption -> epilogue -> grid barrier.  A single inlined
-    // copy of every piece serves all phases, so the hot code is small and call-free.
+    // classifier): prologue -> ring consumption -> epilogue (-> attention).  A single copy of
+    // every piece serves all phases.
     const int nq = 4 * P.L + 1;
+#pragma unroll 1
     for (int q = 0; q < nq; q++) {
         const int ph = q < 4 * P.L ? (q & 3) : 4, l = q >> 2;
         const uint32_t ep = P.ep_base + (uint32_t)l + 1u;  // epoch of everything layer l publishes
         const int tb = ph == 0 ? 0 : 2 + 3 * ph;  // timer bucket / trace stamp base of this phase
-        if (ph == 0) stamp(l, 0);
+        const bool norm = !(ph & 1);
+        const int r0 = cp.r0[ph], nr = cp.r1[ph] - cp.r0[ph];
+        if (ph == 0) STAMP(l, 0);
 
         // ---- prologue: the activation vector of this phase, in shared memory
-        if (ph == 0 || ph == 2 || ph == 4) {
-            // rmsnorm (llama2.f90:527, :608, :627); layer 0 starts from the embedding row (:520)
+        float rscale = 1.f;
+        if (norm) {
+            // rmsnorm (llama2.f90:527, :608, :627); layer 0 starts from the embedding row (:520);
+            // adds the tp partial outputs of the phase before (Wo of this layer / W2 of the previous one)
             const uint8_t *emb_row = nullptr;
             RingPos at = cs.pos;
             if (q == 0) {
@@ -1054,193 +1099,139 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 ring_advance(at, 1u, ns);
             }
             const float *wn = reinterpret_cast<const float *>(vec_stage_wait(P, sv, at));
-            // add the tp partial outputs of the phase before (Wo of this layer / W2 of the previous one)
-            rscale = load_x_norm<WT>(ph == 2 ? P.part1[P.rank] : P.part2[P.rank], ph == 2 ? ep : ep - 1u, emb_row, wn,
-                                     P, sv, c);
+            rscale = gather_x<WT>((ph == 2 ? P.part1[P.rank] : P.part2[P.rank]) + (size_t)rep * P.tp * P.emb, P.tp,
+                                  ph == 2 ? ep : ep - 1u, P.emb, true, emb_row, wn, P, sv, c);
             if (q == 0) vec_stage_release(P, sv, c, cs);
             vec_stage_release(P, sv, c, cs);
+        } else if (nr > 0) {
+            // (a CTA without rows in a Wo / W2 phase does not need its input vector: skipping the poll
+            // also keeps it from ever lagging behind on a buffer nobody waits for it to have read)
+            if (ph == 1 && P.n_splits > 1) load_x_attn<WT>(P, ep, sv, c);
+            else gather_x<WT>(ph == 1 ? P.ll_att + (size_t)rep * P.att_dim : P.ll_hb + (size_t)rep * hb_stride, 1, ep,
+                              ph == 1 ? P.att_dim : P.hid, false, nullptr, nullptr, P, sv, c);
         }
-        // (a CTA without rows in a Wo / W2 phase does not need its input vector: skipping the poll
-        // also keeps it from ever lagging behind on a buffer nobody waits for it to have read)
-        if (ph == 1 || ph == 3) {
-            rscale = 1.f;
-            if (cp.r1[ph] == cp.r0[ph]) {
-            } else if (ph == 1 && P.n_splits > 1) {
-                load_x_attn<WT, PRO_V>(P, ep, sv, c);
-            } else {
-                load_x_plain<WT, PRO_V>(ph == 1 ? P.ll_att : P.ll_hb, ep, ph == 1 ? P.att_dim : P.hid, sv, c);
-            }
-        }
-        lap(tb);
-        stamp(l, ph == 0 ? 1 : 3 + 3 * ph);
+        LAP(tb);
+        STAMP(l, ph == 0 ? 1 : 3 + 3 * ph);
 
         // ---- the mat-vec: consume this CTA's stages of the phase from the ring
-        const int r0 = cp.r0[ph], nr = cp.r1[ph] - cp.r0[ph];
-        res_planes = (WT != WT_Q4_0) ? GW : 1;
-        res_cap = cp.ph[ph].rows_cap;
         {
             ConsumeArgs ca;
             ca.ph = &cp.ph[ph]; ca.ring = sv.ring; ca.xs = sv.xs; ca.res = sv.res;
             ca.full = sv.full; ca.empty = sv.empty;
-            ca.wait_cycles = (tracer_warp && l == P.trace_layer && ph < 4) ? &twait[ph] : nullptr;
+            ca.wait_cycles = (tracing && c.warp == 0 && l == P.trace_layer && ph < 4) ? &pf.twait[ph] : nullptr;
+            ca.stamps = ca.wait_cycles ? &pf.twait[12 + 8 * ph] : nullptr;
             ca.nrows = nr; ca.nst = cp.nst[ph]; ca.slot_bytes = P.slot_bytes; ca.n_slots = P.n_slots;
             ca.slot0 = (int)cs.pos.mod; ca.par0 = (int)(cs.pos.div & 1u); ca.gmod0 = (int)cs.gmod;
-            ca.warp = c.warp; ca.lane = c.lane; ca.no_wide = 0;
-            ca.stamps = ca.wait_cycles ? &twait[12 + 8 * ph] : nullptr;
+            ca.warp = c.warp; ca.lane = c.lane;
             if (ca.stamps && c.lane == 0) ca.stamps[7] = clock64();  // before the call
             consume_phase<WT>(ca);
             if (ca.stamps && c.lane == 0) ca.stamps[4] = clock64();  // after the return
             cons_advance(cs, (uint32_t)cp.nst[ph], ns);
         }
-        stamp(l, ph == 0 ? 2 : 4 + 3 * ph);
+        STAMP(l, ph == 0 ? 2 : 4 + 3 * ph);
         cons_sync(c);
-        if (tracer && l == P.trace_layer && ph < 4) twait[12 + 8 * ph + 5] = clock64();  // after the barrier
-        lap(tb + 1);
+        if (tracing && c.tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 5] = clock64();
+        LAP(tb + 1);
 
-        // ---- epilogue
-        if (ph == 0) {
-            // RoPE on q and k (reference quirks Q1/Q2 are in the table), KV append (llama2.f90:543-565)
-            float *kc = P.kc + ((size_t)l * P.seq + (pos - 1)) * P.kv;
-            float *vc = P.vc + ((size_t)l * P.seq + (pos - 1)) * P.kv;
-            for (int i = 2 * c.tid; i < nr; i += 2 * c.nt) {
+        // ---- epilogue.  A work item is (row pair, LL replica [, destination rank]): the planes of
+        // partial sums are added in a fixed order, times the 1 / rms factor of the phase's rmsnorm,
+        // and every thread publishes ONE 16-byte LL record -- relaxed gpu-scope stores are slow one
+        // after the other from one thread, so they are spread over the threads instead.
+        {
+            const int cap = cp.ph[ph].rows_cap;
+            const int nsub = ph == 4 ? 1 : ((ph & 1) ? nrep * P.tp : nrep), npairs = (nr + 1) >> 1;
+#pragma unroll 1
+            for (int w = c.tid; w < npairs * nsub; w += c.nt) {
+                const int pair = w / nsub, sub = w - pair * nsub, i = 2 * pair;
+                const bool two = i + 1 < nr;
+                float a = sv.res[i], b = two ? sv.res[i + 1] : 0.f;
+#pragma unroll
+                for (int p = 1; p < planes; p++) {
+                    a += sv.res[p * cap + i];
+                    b += two ? sv.res[p * cap + i + 1] : 0.f;
+                }
+                a *= rscale; b *= rscale;
                 const int r = r0 + i;
-                const float a = resv(i), b = resv(i + 1);
-                if (r < P.att_dim) {
-                    const float2 cs2 = rope[(r >> 1) & half_mask];
-                    ll_store(P.ll_q, r, a * cs2.x - b * cs2.y, ep);
-                    ll_store(P.ll_q, r + 1, a * cs2.y + b * cs2.x, ep);
-                } else if (r < P.att_dim + P.kv) {
-                    // the cache row serves later launches, the LL copy this launch's attention
-                    const int rk = r - P.att_dim;
-                    const float2 cs2 = rope[(rk >> 1) & half_mask];
-                    const float k0 = a * cs2.x - b * cs2.y, k1 = a * cs2.y + b * cs2.x;
-                    kc[rk] = k0;
-                    kc[rk + 1] = k1;
-                    ll_store(P.ll_kv, rk, k0, ep);
-                    ll_store(P.ll_kv, rk + 1, k1, ep);
+                if (ph == 0) {
+                    // RoPE on q and k (reference quirks Q1/Q2 are in the table), KV append (llama2.f90:543-565)
+                    const bool isq = r < P.att_dim, isv = r >= P.att_dim + P.kv;
+                    const int rk = isq ? r : (isv ? r - P.att_dim - P.kv : r - P.att_dim);
+                    const float2 cs2 = isv ? make_float2(1.f, 0.f) : rope[(rk >> 1) & half_mask];
+                    const float o0 = a * cs2.x - b * cs2.y, o1 = a * cs2.y + b * cs2.x;
+                    if (!isq && sub == 0) {
+                        // the cache row serves later launches, the LL copy this launch's attention
+                        float *cache = (isv ? P.vc : P.kc) + ((size_t)l * P.seq + (pos - 1)) * P.kv;
+                        *reinterpret_cast<float2 *>(cache + rk) = make_float2(o0, o1);
+                    }
+                    unsigned long long *dst = isq ? P.ll_q + (size_t)sub * P.att_dim
+                                                  : P.ll_kv + (size_t)sub * 2 * P.kv + (isv ? P.kv : 0);
+                    ll_store2(dst, rk, o0, o1, ep);
+                } else if (ph == 2) {
+                    // SwiGLU on the interleaved gate/up rows (llama2.f90:613-616)
+                    ll_store(P.ll_hb + (size_t)sub * hb_stride, r >> 1, (a * (1.0f / (1.0f + expf(-a)))) * b, ep);
+                } else if (ph == 4) {
+                    // logits rows of this rank go to every rank's full logits buffer (all-gather)
+                    const int gi = P.v_off + r;
+                    for (int k = 0; k < P.tp; k++) {
+                        P.logits[k][gi] = a;
+                        if (two) P.logits[k][gi + 1] = b;
+                    }
+                    if (a > best) { best = a; bidx = gi; }
+                    if (two && b > best) { best = b; bidx = gi + 1; }
                 } else {
-                    const int rv = r - P.att_dim - P.kv;
-                    vc[rv] = a;
-                    vc[rv + 1] = b;
-                    ll_store(P.ll_kv, P.kv + rv, a, ep);
-                    ll_store(P.ll_kv, P.kv + rv + 1, b, ep);
+                    // Wo / W2 (llama2.f90:603-605, :618-620): publish this rank's partial sums to every
+                    // rank; the residual add happens in the next norm prologue, on every CTA's copy of x
+                    const int k = sub / nrep, rr = sub - k * nrep;  // destination rank, replica
+                    unsigned long long *dst = (ph == 1 ? P.part1[k] : P.part2[k]) + ((size_t)rr * P.tp + P.rank) * P.emb;
+                    ll_store_sys(dst, r, a, ep);  // (r may be odd here: no 16-byte store)
+                    if (two) ll_store_sys(dst, r + 1, b, ep);
                 }
             }
-        } else if (ph == 2) {
-            // SwiGLU on the interleaved gate/up rows (llama2.f90:613-616)
-            for (int i = 2 * c.tid; i < nr; i += 2 * c.nt) {
-                const float g = resv(i), u = resv(i + 1);
-                ll_store(P.ll_hb, (r0 + i) >> 1, (g * (1.0f / (1.0f + expf(-g)))) * u, ep);
-            }
-        } else if (ph == 4) {
-            // logits rows of this rank go to every rank's full logits buffer (all-gather)
-            for (int i = c.tid; i < nr; i += c.nt) {
-                const float v = resv(i);
-                const int gi = P.v_off + r0 + i;
-                for (int k = 0; k < P.tp; k++) P.logits[k][gi] = v;
-                if (v > best) { best = v; bidx = gi; }
-            }
-        } else {
-            // Wo / W2 (llama2.f90:603-605, :618-620): publish this rank's partial sums to every
-            // rank; the residual add happens in the next norm prologue, on every CTA's copy of x
-            for (int i = c.tid; i < nr * P.tp; i += c.nt) {
-                const int k = i / nr, ii = i - k * nr;  // destination rank, row within this CTA's range
-                unsigned long long *dst = (ph == 1 ? P.part1[k] : P.part2[k]) + (size_t)P.rank * P.emb;
-                ll_store_sys(dst, r0 + ii, resv(ii), ep);
-            }
         }
+        if (tracing && c.tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 6] = clock64();
         if (ph == 4) break;
-        lap(tb + 2);
-        stamp(l, ph == 0 ? 3 : 5 + 3 * ph);
+        LAP(tb + 2);
+        STAMP(l, ph == 0 ? 3 : 5 + 3 * ph);
 
         if (ph == 0) {
             // ---- attention (llama2.f90:574-598)
-            attention_phase(P, sv, c, l, pos, ep);
-            lap(PH_ATT);
-            stamp(l, 4);
-            stamp(l, 5);
+            if (P.hs == 64) attention_phase_t<64>(P, sv, c, l, pos, ep);
+            else if (P.hs == 128) attention_phase_t<128>(P, sv, c, l, pos, ep);
+            else attention_phase_t<32>(P, sv, c, l, pos, ep);
+            LAP(PH_ATT);
+            STAMP(l, 4);
+            STAMP(l, 5);
         }
-        if (ph == 3 && tracer && l == P.trace_layer)
-            for (int i = 0; i < 12; i++) P.trace[(size_t)blockIdx.x * 128 + 16 + i] = (unsigned long long)twait[i];
-        if (ph == 3 && tracer && l == P.trace_layer)
-            for (int i = 0; i < 32; i++) P.trace[(size_t)blockIdx.x * 128 + 64 + i] = (unsigned long long)twait[12 + i];
+        if (ph == 3 && tracing && c.tid == 0 && l == P.trace_layer)
+            for (int i = 0; i < 44; i++)
+                P.trace[(size_t)blockIdx.x * 128 + (i < 12 ? 16 + i : 64 + i - 12)] = (unsigned long long)pf.twait[i];
     }
-    lap(PH_CLS_MV);
+    LAP(PH_CLS_MV);
 
-    const uint32_t epl = P.ep_base + (uint32_t)P.L + 1u;
-    const int G = (int)gridDim.x;
-    if (P.tp > 1) {
-        // the all-gathered logits must have landed on every rank before any rank's kernel ends:
-        // each CTA flags every rank once its rows are stored, CTA 0 of every rank collects the flags
-        cons_sync(c);
-        if (c.tid == 0) {
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
-            for (int k = 0; k < P.tp; k++) ll_store_sys(P.done[k], P.rank * G + (int)blockIdx.x, 0.f, epl);
-        }
-        if (blockIdx.x == 0) {
-            for (int i = c.tid; i < P.tp * G; i += c.nt) {
-                float t[1];
-                ll_waitv<1>(P.done[P.rank], i, epl, t);
-            }
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
-        }
-    }
-    if (P.do_argmax) {
-        // maxloc(logits) (llama2.f90:388): first maximum wins at every reduction level
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-        }
-        float *rv = sv.red;
-        int *ri = reinterpret_cast<int *>(sv.red + 32);
-        if (c.lane == 0) { rv[c.warp] = best; ri[c.warp] = bidx; }
-        cons_sync(c);
-        if (c.tid == 0) {
-            for (int w = 1; w < c.nw; w++)
-                if (rv[w] > best || (rv[w] == best && ri[w] < bidx)) { best = rv[w]; bidx = ri[w]; }
-            for (int k = 0; k < P.tp; k++) {
-                unsigned long long *dst = P.amax[k] + (size_t)(P.rank * G + (int)blockIdx.x) * 2;
-                ll_store_sys(dst, 0, best, epl);
-                ll_store_sys(dst, 1, __int_as_float(bidx), epl);
-            }
-        }
-        if (blockIdx.x == 0 && c.warp == 0) {
-            // every rank reduces the same tp * grid records in the same order -> the same token
-            best = -INFINITY; bidx = 0x7fffffff;
-            for (int i = c.lane; i < P.tp * G; i += 32) {
-                float rec[2];
-                ll_waitv<2>(P.amax[P.rank], 2 * i, epl, rec);
-                const float v = rec[0];
-                const int ix = __float_as_int(rec[1]);
-                if (v > best || (v == best && ix < bidx)) { best = v; bidx = ix; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-                if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-            }
-            if (c.lane == 0) {
-                int next = bidx + 1;
-                if (P.forced && P.forced[pos - 1] > 0) next = P.forced[pos - 1];
-                if (P.out_tokens) P.out_tokens[pos - 1] = next;
-                int *tp = const_cast<int *>(P.tokpos);
-                tp[0] = next;
-                tp[1] = pos + 1;
-            }
-        }
-    }
+    token_tail(P, sv, c, best, bidx, pos);
     if (timer) {
-        lap(PH_ARGMAX);
-        for (int i = 0; i < PH_COUNT; i++) P.phase_cycles[i] += (unsigned long long)tacc[i];
+        prof_lap(&pf, PH_ARGMAX);
+        for (int i = 0; i < PH_COUNT; i++) P.phase_cycles[i] += (unsigned long long)pf.tacc[i];
         P.phase_cycles[PH_COUNT] += (unsigned long long)(clock64() - t_c0);
         P.phase_cycles[PH_COUNT + 1] += globaltimer_ns() - t_ns0;
     }
+#undef LAP
+#undef STAMP
 }
 
 // ------------------------------------------------------------------ host side
+// stages a CTA can have in the layer section / after it (upper bounds over all CTAs)
+static void sched_caps(const StreamParams &p, int *layer, int *post)
+{
+    int per_layer = 2, cls = 0;
+    for (int i = 0; i < 5; i++) {
+        const int st = (p.ph[i].rows_cap + p.ph[i].rps - 1) / p.ph[i].rps;
+        if (i < 4) per_layer += st; else cls = st;
+    }
+    *layer = per_layer;
+    *post = 1 + cls;
+}
+
 int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots,
                 int cons_warps, StreamPlan *out)
 {
@@ -1267,21 +1258,62 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
     xs_floats = (xs_floats + 31) & ~31;
     res_floats = (res_floats + 31) & ~31;
     if (max_slots > MAX_SLOTS) max_slots = MAX_SLOTS;
+    for (int i = 0; i < 5; i++) p.ph[i].rps = slot / (int)p.ph[i].rs > 0 ? slot / (int)p.ph[i].rs : 1;
+    int cap_layer, cap_post;
+    sched_caps(p, &cap_layer, &cap_post);
+    const int sched_entries = 1 + cap_layer + cap_post + 1;
     int n_slots = max_slots;
     while (n_slots > 0 &&
-           smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb) > (size_t)max_smem_optin)
+           smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb, sched_entries) > (size_t)max_smem_optin)
         n_slots--;
+    n_slots = n_slots / NG * NG;  // a slot always belongs to the same group (see NG)
     if (n_slots < NG) return 1;
     out->n_slots = n_slots;
     out->slot_bytes = slot;
     out->n_cons_warps = cons_warps;
     out->threads = (cons_warps + 1) * 32;
-    out->smem_bytes = (int)smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb);
+    out->smem_bytes = (int)smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb, sched_entries);
     out->grid = grid;
     out->xs_floats = xs_floats;
     out->res_floats = res_floats;
-    for (int i = 0; i < 5; i++) p.ph[i].rps = slot / (int)p.ph[i].rs > 0 ? slot / (int)p.ph[i].rs : 1;
     return 0;
+}
+
+void build_schedule(StreamParams &p, int grid, SchedStage **out)
+{
+    // section sizes are per CTA (they follow from its row ranges: the kernel derives them from the same
+    // cta_rows()); only the padded stride is shared
+    int cap_layer, cap_post;
+    sched_caps(p, &cap_layer, &cap_post);
+    const int cap = 1 + cap_layer + cap_post + 1;
+    SchedStage *tab = (SchedStage *)calloc((size_t)grid * cap, sizeof(SchedStage));
+    for (int cta = 0; cta < grid; cta++) {
+        SchedStage *t = tab + (size_t)cta * cap;
+        int n = 0;
+        auto vec = [&](const void *ptr, unsigned bytes, size_t layer_stride) {
+            t[n].src = (unsigned long long)ptr; t[n].bytes = bytes; t[n].stride16 = (unsigned)(layer_stride >> 4); n++;
+        };
+        auto rows = [&](int ph) {
+            int r0, r1;
+            cta_rows(p.ph[ph], cta, grid, r0, r1);
+            const PhaseW &w = p.ph[ph];
+            for (int r = r0; r < r1; r += w.rps) {
+                const int k = r1 - r < w.rps ? r1 - r : w.rps;
+                vec(w.base + (size_t)r * w.rs, (unsigned)k * w.rs, ph < 4 ? (size_t)w.layer_stride : 0);
+            }
+        };
+        vec(p.emb_table, p.ph[0].rs, 0);  // row 0; the kernel adds (token - 1) rows
+        vec(p.rms_att, (unsigned)p.emb * 4u, (size_t)p.emb * 4u);
+        rows(0);
+        rows(1);
+        vec(p.rms_ffn, (unsigned)p.emb * 4u, (size_t)p.emb * 4u);
+        rows(2);
+        rows(3);
+        vec(p.rms_final, (unsigned)p.emb * 4u, 0);
+        rows(4);
+    }
+    p.sched_stride = cap;
+    *out = tab;
 }
 
 template <int WT>

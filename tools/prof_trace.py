@@ -38,8 +38,8 @@ print("producer lead (stages issued - stages consumed) at each edge: min p50 max
 for k, nme in enumerate(names):
     print(f"{k:2d} {nme:8s} {lead[:, k].min():4d} {int(np.median(lead[:, k])):4d} {lead[:, k].max():4d}   issued p50 {int(np.median(tr[:, 32 + k]))} consumed p50 {int(np.median(tr[:, 48 + k]))}")
 st = tr[:, 64:96].reshape(-1, 4, 8).astype(np.int64)
-print("warp-0 consume stamps (cycles since 'before call', p50 over CTAs): entry, walk-ctor, 1st wait done, 1st stage released, returned, after cons_sync")
+print("warp-0 consume stamps (cycles since 'before call', p50 over CTAs): entry, walk-ctor, 1st wait done, 1st stage released, returned, after cons_sync, after epilogue")
 for phi, nme in enumerate(["qkv", "wo", "w13", "w2"]):
     b = st[:, phi, 7]
-    print(f"   {nme:4s}", [int(np.median(st[:, phi, i] - b)) for i in (0, 1, 2, 3, 4, 5)])
+    print(f"   {nme:4s}", [int(np.median(st[:, phi, i] - b)) for i in (0, 1, 2, 3, 4, 5, 6)])
 np.save("gpurun_out/trace.npy", tr)
