@@ -38,6 +38,22 @@ __host__ __device__ inline size_t host_row_bytes(int wtype, int cols)
     return ((size_t)cols / 32) * 18;
 }
 
+// q4_0 matrices of the fused streaming kernel use a TILED device format made for mma.sync
+// (m16n8k16): 16 rows x 8 blocks (256 columns) form a "group" of 2304 bytes laid out in the order
+// the 32 lanes of a warp fetch it (lane = 4 g + t; g = row within 8, t = 32-bit word of a block):
+//   chunk 0 (512 B): lane -> 16 B = word t of blocks 0..3 of row g
+//   chunk 1        : word t of blocks 4..7 of row g
+//   chunk 2, 3     : the same for row g + 8
+//   scales (256 B) : lane -> 4 halves d[g][2t], d[g][2t+1], d[g+8][2t], d[g+8][2t+1]
+// A row group (16 rows) is its ceil(blocks / 8) groups back to back; rows and blocks past the
+// matrix are zero (scale 0).  Same bytes as ggml's 18-byte blocks, only permuted.
+constexpr int Q4T_GROUP_BYTES = 2304;
+__host__ __device__ inline int q4t_groups(int cols) { return ((cols >> 5) + 7) >> 3; }
+__host__ __device__ inline size_t q4t_matrix_bytes(int rows, int cols)
+{
+    return (size_t)((rows + 15) >> 4) * (size_t)q4t_groups(cols) * Q4T_GROUP_BYTES;
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ small PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -112,12 +112,15 @@ void release_all()
 // `dst` (device row format): dst row r = src row map(r), columns [col0, col0+ncols).
 int upload_matrix(uint8_t *dst, const void *src_host, int wtype, int src_rows, int src_cols,
                   int dst_rows, int col0, int ncols, int map_kind, int row0, int half,
-                  uint8_t *stage, size_t stage_bytes)
+                  uint8_t *stage, size_t stage_bytes, bool tiled = false)
 {
     const size_t src_bytes = (size_t)src_rows * host_row_bytes(wtype, src_cols);
     if (src_bytes > stage_bytes) return fail("internal: staging buffer too small");
     CK(cudaMemcpyAsync(stage, src_host, src_bytes, cudaMemcpyHostToDevice, E.st));
-    CK(launch_repack(stage, wtype, src_cols, dst, dst_rows, col0, ncols, map_kind, row0, half, E.st));
+    if (tiled)  // q4_0 matrices of the fused kernel: tiled mma format (common.cuh)
+        CK(launch_repack_q4_tiled(stage, src_cols, dst, dst_rows, col0, ncols, map_kind, row0, half, E.st));
+    else
+        CK(launch_repack(stage, wtype, src_cols, dst, dst_rows, col0, ncols, map_kind, row0, half, E.st));
     CK(cudaStreamSynchronize(E.st));
     return 0;
 }
@@ -140,9 +143,13 @@ float *logits_dev() { return reinterpret_cast<float *>(E.d_shared + E.sh_logits)
 
 int n_splits_for(int pos)
 {
-    // a power of two (the kernel splits items with shifts): runs of <= 256 positions up to 2048
+    // a power of two (the kernel splits items with shifts): runs of <= 256 positions up to 2048, and
+    // enough (head, split) items to occupy the SMs (only H CTAs work otherwise) while a split keeps
+    // at least 16 positions
     int s = 1;
     while (s < MAX_SPLITS && s * 256 < pos) s *= 2;
+    static const int min_items = getenv("LLMF90_ATT_ITEMS") ? atoi(getenv("LLMF90_ATT_ITEMS")) : 0;
+    while (s < MAX_SPLITS && E.sp.H * s * 2 <= min_items && (pos - 1) / (2 * s) >= 16) s *= 2;
     return s;
 }
 
@@ -366,17 +373,23 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     const int att = Hl * hs, kvl = KVHl * hs, nqkv = att + 2 * kvl, hid = hid_full / tp, Vl = V / tp;
     E.kv = kvl; E.nqkv = nqkv; E.hid_l = hid; E.att_dim = att; E.v_l = Vl;
     const size_t rs_e = row_stride_bytes(wt, emb), rs_a = row_stride_bytes(wt, att), rs_h = row_stride_bytes(wt, hid);
+    // the five streamed matrices of a q4_0 model use the tiled mma format in the fused kernel (the
+    // embedding table and the granular path keep plain rows)
+    const bool tiled = E.use_stream && wt == WT_Q4_0;
+    auto mbytes = [&](int rows, int cols) -> size_t {
+        return tiled ? q4t_matrix_bytes(rows, cols) : (size_t)rows * row_stride_bytes(wt, cols);
+    };
 
     CK(cudaStreamCreateWithFlags(&E.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&E.ev0)); CK(cudaEventCreate(&E.ev1)); CK(cudaEventCreate(&E.ev2));
 
     // ---- weights (device row format), this rank's shard
     CK(dalloc(&E.d_emb, (size_t)V * rs_e));
-    CK(dalloc(&E.d_wqkv, (size_t)L * nqkv * rs_e));
-    CK(dalloc(&E.d_wo, (size_t)L * emb * rs_a));
-    CK(dalloc(&E.d_w13, (size_t)L * 2 * hid * rs_e));
-    CK(dalloc(&E.d_w2, (size_t)L * emb * rs_h));
-    CK(dalloc(&E.d_wcls, (size_t)Vl * rs_e));
+    CK(dalloc(&E.d_wqkv, (size_t)L * mbytes(nqkv, emb)));
+    CK(dalloc(&E.d_wo, (size_t)L * mbytes(emb, att)));
+    CK(dalloc(&E.d_w13, (size_t)L * mbytes(2 * hid, emb)));
+    CK(dalloc(&E.d_w2, (size_t)L * mbytes(emb, hid)));
+    CK(dalloc(&E.d_wcls, mbytes(Vl, emb)));
     CK(dalloc(&E.d_rms_att, (size_t)L * emb));
     CK(dalloc(&E.d_rms_ffn, (size_t)L * emb));
     CK(dalloc(&E.d_rms_final, (size_t)emb));
@@ -396,28 +409,29 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         CK(dalloc(&stage, stage_bytes));
         int rc = 0;
         rc |= upload_matrix(E.d_emb, tok_emb, wt, V, emb, V, 0, emb, 0, 0, 0, stage, stage_bytes);
-        rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, Vl, 0, emb, 0, rank * Vl, 0, stage, stage_bytes);
+        rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, Vl, 0, emb, 0, rank * Vl, 0, stage, stage_bytes, tiled);
         for (int l = 0; l < L && !rc; l++) {
             const uint8_t *s_qkv = (const uint8_t *)wqkv + (size_t)l * nqkv_full * hb_e;
             const uint8_t *s_wo = (const uint8_t *)wo + (size_t)l * emb * hb_e;
             const uint8_t *s_w13 = (const uint8_t *)w13 + (size_t)l * 2 * hid_full * hb_e;
             const uint8_t *s_w2 = (const uint8_t *)w2 + (size_t)l * emb * hb_hf;
-            uint8_t *d_qkv = E.d_wqkv + (size_t)l * nqkv * rs_e;
+            uint8_t *d_qkv = E.d_wqkv + (size_t)l * mbytes(nqkv, emb);
             // Wq rows of this rank's heads | Wk rows | Wv rows of its KV heads (read_ggml.f90:272,286,300)
-            rc |= upload_matrix(d_qkv, s_qkv, wt, nqkv_full, emb, att, 0, emb, 0, rank * att, 0, stage, stage_bytes);
-            rc |= upload_matrix(d_qkv + (size_t)att * rs_e, s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
-                                emb + rank * kvl, 0, stage, stage_bytes);
-            rc |= upload_matrix(d_qkv + (size_t)(att + kvl) * rs_e, s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
-                                emb + kv_full + rank * kvl, 0, stage, stage_bytes);
+            // (att and kvl are multiples of 32, so the three pieces start on tile boundaries)
+            rc |= upload_matrix(d_qkv, s_qkv, wt, nqkv_full, emb, att, 0, emb, 0, rank * att, 0, stage, stage_bytes, tiled);
+            rc |= upload_matrix(d_qkv + mbytes(att, emb), s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
+                                emb + rank * kvl, 0, stage, stage_bytes, tiled);
+            rc |= upload_matrix(d_qkv + mbytes(att + kvl, emb), s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
+                                emb + kv_full + rank * kvl, 0, stage, stage_bytes, tiled);
             // Wo: all rows, the input columns of this rank's heads
-            rc |= upload_matrix(E.d_wo + (size_t)l * emb * rs_a, s_wo, wt, emb, emb, emb, rank * att, att, 0, 0, 0,
-                                stage, stage_bytes);
+            rc |= upload_matrix(E.d_wo + (size_t)l * mbytes(emb, att), s_wo, wt, emb, emb, emb, rank * att, att, 0, 0, 0,
+                                stage, stage_bytes, tiled);
             // gate/up rows of this rank's FFN slice, interleaved: row 2i = W1 row i, row 2i+1 = W3 row i
-            rc |= upload_matrix(E.d_w13 + (size_t)l * 2 * hid * rs_e, s_w13, wt, 2 * hid_full, emb, 2 * hid, 0,
-                                emb, 1, rank * hid, hid_full, stage, stage_bytes);
+            rc |= upload_matrix(E.d_w13 + (size_t)l * mbytes(2 * hid, emb), s_w13, wt, 2 * hid_full, emb, 2 * hid, 0,
+                                emb, 1, rank * hid, hid_full, stage, stage_bytes, tiled);
             // W2: all rows, the input columns of this rank's FFN slice
-            rc |= upload_matrix(E.d_w2 + (size_t)l * emb * rs_h, s_w2, wt, emb, hid_full, emb, rank * hid, hid, 0, 0,
-                                0, stage, stage_bytes);
+            rc |= upload_matrix(E.d_w2 + (size_t)l * mbytes(emb, hid), s_w2, wt, emb, hid_full, emb, rank * hid, hid, 0, 0,
+                                0, stage, stage_bytes, tiled);
         }
         cudaFree(stage);
         if (rc) { release_all(); return 1; }
@@ -455,9 +469,16 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.att_dim = att; p.tp = tp; p.rank = rank; p.v_off = rank * Vl; p.v_total = V;
         auto mk = [&](const uint8_t *base, int rows, int cols, int unit) {
             PhaseW w{};
-            w.base = base; w.rows = rows; w.cols = cols; w.unit = unit;
+            w.base = base; w.rows = rows; w.rows_real = rows; w.cols = cols; w.unit = unit;
             w.rs = (unsigned)row_stride_bytes(wt, cols);
             w.layer_stride = (unsigned long long)rows * w.rs;
+            if (tiled) {
+                // tiled q4_0: rows go to CTAs in row groups of 16; rs = bytes of one row group
+                w.rows = (rows + 15) & ~15; w.unit = 16;
+                w.ngrp = q4t_groups(cols);
+                w.rs = (unsigned)(w.ngrp * Q4T_GROUP_BYTES);
+                w.layer_stride = (unsigned long long)q4t_matrix_bytes(rows, cols);
+            }
             return w;
         };
         p.ph[0] = mk(E.d_wqkv, nqkv, emb, 2);
@@ -471,7 +492,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         if (const char *s = getenv("LLMF90_CONS_WARPS")) cons_warps = atoi(s);
         // every CTA must own W13 rows (the LL hand-over's no-overwrite argument, stream.cu): tiny models
         // run on fewer CTAs
-        if (plan_stream(p, std::min(E.n_sms, hid), smem_optin - 2048 /* static smem */, target_slot, max_slots,
+        if (plan_stream(p, std::min(E.n_sms, tiled ? (2 * hid + 15) / 16 : hid), smem_optin - 2048 /* static smem */, target_slot, max_slots,
                         cons_warps, &E.plan)) {
             release_all();
             return fail("model rows do not fit the shared-memory ring (row stride too large)");

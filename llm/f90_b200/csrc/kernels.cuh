@@ -40,6 +40,10 @@ cudaError_t launch_argmax(const float *v, int n, int *out_token, cudaStream_t st
 cudaError_t launch_repack(const uint8_t *src, int wtype, int src_cols, uint8_t *dst, int dst_rows,
                           int col0, int ncols, int map_kind, int row0, int half, cudaStream_t st);
 
+// same for q4_0 into the tiled mma format of the fused kernel (common.cuh, Q4T_GROUP_BYTES)
+cudaError_t launch_repack_q4_tiled(const uint8_t *src, int src_cols, uint8_t *dst, int dst_rows, int col0,
+                                   int ncols, int map_kind, int row0, int half, cudaStream_t st);
+
 // ---------------------------------------------------------------- fused streaming kernel (stream.cu)
 // fine-grained phase timers of the streaming kernel (CTA 0); _PRO = prologue (activation
 // vector load / rmsnorm / attention merge), _MV = ring consumption, _BAR = epilogue + grid barrier
@@ -56,6 +60,8 @@ struct PhaseW {
     int rows, cols;
     int unit;                // rows are assigned to CTAs in multiples of `unit`
     int rps;                 // rows per ring stage
+    int rows_real;           // rows of the matrix (rows is padded to a multiple of 16 for q4_0)
+    int ngrp, spg;           // q4_0 (tiled format): 8-block groups per row group, ring stages per row group
     int ku;                  // f32 / f16: 128-bit load units per lane per row when a group of warps shares a row
     int rows_cap;            // max rows of any CTA in this phase = stride of the partial-result planes
 };

@@ -413,6 +413,40 @@ __global__ void repack_q4_kernel(const uint8_t *__restrict__ src, int src_cols,
     }
 }
 
+// q4_0 -> tiled mma format (common.cuh): one thread per (row, block)
+__global__ void repack_q4_tiled_kernel(const uint8_t *__restrict__ src, int src_cols,
+                                       uint8_t *__restrict__ dst, int dst_rows, int col0, int ncols,
+                                       int map_kind, int row0, int half)
+{
+    const int nb = ncols >> 5, src_nb = src_cols >> 5, b0 = col0 >> 5, ngrp = q4t_groups(ncols);
+    const size_t n = (size_t)dst_rows * nb;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / nb), j = (int)(i % nb);
+        const uint8_t *s = src + ((size_t)map_row(r, map_kind, row0, half) * src_nb + b0 + j) * 18;
+        uint8_t *grp = dst + ((size_t)(r >> 4) * ngrp + (j >> 3)) * Q4T_GROUP_BYTES;
+        const int g = r & 7, hi_row = (r >> 3) & 1, jb = j & 7;
+        const int chunk = 2 * hi_row + (jb >> 2);
+        for (int t = 0; t < 4; t++) {
+            uint8_t *d = grp + chunk * 512 + (g * 4 + t) * 16 + (jb & 3) * 4;
+            for (int k = 0; k < 4; k++) d[k] = s[2 + 4 * t + k];
+        }
+        uint8_t *sc = grp + 2048 + (g * 4 + (jb >> 1)) * 8 + (2 * hi_row + (jb & 1)) * 2;
+        sc[0] = s[0];
+        sc[1] = s[1];
+    }
+}
+
+cudaError_t launch_repack_q4_tiled(const uint8_t *src, int src_cols, uint8_t *dst, int dst_rows, int col0,
+                                   int ncols, int map_kind, int row0, int half, cudaStream_t st)
+{
+    if (dst_rows == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(dst, 0, q4t_matrix_bytes(dst_rows, ncols), st);
+    if (e != cudaSuccess) return e;
+    repack_q4_tiled_kernel<<<148 * 8, 256, 0, st>>>(src, src_cols, dst, dst_rows, col0, ncols, map_kind, row0, half);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_repack(const uint8_t *src, int wtype, int src_cols, uint8_t *dst, int dst_rows,
                           int col0, int ncols, int map_kind, int row0, int half, cudaStream_t st)
 {

@@ -103,6 +103,13 @@ __host__ __device__ inline void cta_rows(const PhaseW &ph, int cta, int G, int &
     r1 = (int)((long long)(cta + 1) * U / G) * ph.unit;
 }
 
+// ring stages that n (a multiple of the phase's unit) rows of a phase take
+__host__ __device__ inline int phase_stages(const PhaseW &ph, int n)
+{
+    if (ph.spg > 0) return (n >> 4) * ph.spg;  // tiled q4_0: spg stages per row group of 16
+    return (n + ph.rps - 1) / ph.rps;
+}
+
 // stage index = div * n_slots + mod, advanced without division
 struct RingPos {
     uint32_t mod, div;
@@ -202,21 +209,6 @@ __device__ __forceinline__ void cons_advance(CState &cs, uint32_t n, uint32_t ns
 
 __device__ __forceinline__ void cons_sync(const Cons &c) { named_bar_sync(CONS_BAR, c.nt); }
 
-template <int WT, int NR>
-__device__ __forceinline__ void rows_to_res(const uint8_t *sp, size_t rs, const float *xs, int cols,
-                                            int lane, float *res)
-{
-    float acc[NR];
-#pragma unroll
-    for (int i = 0; i < NR; i++) acc[i] = 0.f;
-    dot_rows<WT, NR>(sp, rs, xs, cols, lane, acc);
-#pragma unroll
-    for (int i = 0; i < NR; i++) {
-        const float v = warp_sum(acc[i]);
-        if (lane == 0) res[i] = v;
-    }
-}
-
 // Consume the `nst` stages of one weight phase.  The consumer warps form NG groups of GW warps;
 // group g owns the stages whose schedule index is g (mod NG) and touches no barrier of the others,
 // so a stage costs GW full-waits + GW empty-arrives, consecutive stages are in flight in different
@@ -229,7 +221,7 @@ __device__ __forceinline__ void rows_to_res(const uint8_t *sp, size_t rs, const 
 //     Lane-partial sums of four rows are reduced together (6 shuffles instead of 20) and the slot
 //     is released as soon as its weights are in registers; partial sums go to plane cl of `res`,
 //     the epilogue adds the GW planes in a fixed order.
-//   q4_0: groups of 4 rows of a stage go round-robin over the group's warps (lane <-> block).
+//   q4_0: tensor cores, see consume_q4.
 // Not inlined on purpose: own register allocation (x stays in registers), one copy for all phases.
 struct ConsumeArgs {
     const PhaseW *ph;      // shared memory
@@ -429,6 +421,89 @@ __device__ __forceinline__ void consume_xsmem(const ConsumeArgs &a)
     if (pd.np) pd.flush(res, lane);
 }
 
+// q4_0 on the tensor cores (legacy mma.sync m16n8k16, f16 x f16 -> f32): the dequantisation is the
+// instruction bottleneck of a q4_0 mat-vec at B200's HBM rate, and on CUDA cores it costs >= 2
+// instructions per weight.  Here a nibble pair becomes a half2 {1024 + q} with ONE lop3 (the 0x6400
+// exponent trick; high nibbles give 1024 + 16 q and meet activations pre-scaled by 1/16, exact),
+// the products run on the tensor pipe, and the offsets are removed per block with the pre-computed
+// C[b] = 1032 sum(x over the low nibbles) + 72 sum(x over the high nibbles).  The block scale
+// cannot be applied inside the mma, so the n dimension separates blocks: the B operand
+// (activations) of the mma pair of block b is non-zero only in columns b and 4 + b, and D[row][b],
+// D[row][4 + b] end up holding the unscaled sums of block b against the two f16 halves x = hi + lo
+// of the activations (f16 alone would cost 3 digits: greedy tokens flip at near ties).
+// Tiled weight format: common.cuh.  A stage holds the groups [g0, g1) of one row group of 16 rows;
+// the warps of the consumer group take them round-robin and write per-warp partial sums to plane
+// (stage within the row group) * GW + warp.
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t uint4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+__device__ __forceinline__ void consume_q4(const ConsumeArgs &a)
+{
+    const PhaseW *ph = a.ph;
+    const int ngrp = ph->ngrp, spg = ph->spg, lane = a.lane, g = lane >> 2, t = lane & 3, cl = a.warp % GW;
+    // activations as f16 pairs x = hi + lo in B-fragment order, [half group of 4 blocks][hi | lo][block][t],
+    // then the per-block offset corrections [hi | lo][block] (store_x4)
+    const uint4 *xh4 = reinterpret_cast<const uint4 *>(a.xs);
+    const float *C = a.xs + (size_t)ngrp * 256 + (size_t)(t >> 1) * ngrp * 8;
+    StageWalk w(a);
+    while (w.more()) {
+        const uint8_t *sp = w.wait();
+        const int rgl = w.s / spg, si = w.s - rgl * spg;
+        const int g0 = si * ngrp / spg, g1 = (si + 1) * ngrp / spg;
+        float acc0 = 0.f, acc1 = 0.f;  // rows g and g + 8 of the row group
+#pragma unroll 1
+        for (int gi = g0 + cl; gi < g1; gi += GW) {
+            const uint8_t *gp = sp + (size_t)(gi - g0) * Q4T_GROUP_BYTES;
+            uint4 cg[2], c8[2];
+            cg[0] = *reinterpret_cast<const uint4 *>(gp + lane * 16);
+            cg[1] = *reinterpret_cast<const uint4 *>(gp + 512 + lane * 16);
+            c8[0] = *reinterpret_cast<const uint4 *>(gp + 1024 + lane * 16);
+            c8[1] = *reinterpret_cast<const uint4 *>(gp + 1536 + lane * 16);
+#pragma unroll
+            for (int hb = 0; hb < 2; hb++) {
+                // four blocks per accumulation: column n = 4 p + b of D holds block b times the hi (p = 0) /
+                // lo (p = 1) part of x; this lane's B column is n = g, its D columns are 2t, 2t + 1
+                const uint4 xb = xh4[((gi * 2 + hb) * 8 + g) * 4 + t];
+                const uint2 sc = *reinterpret_cast<const uint2 *>(gp + 2048 + (g * 4 + 2 * hb + (t & 1)) * 8);
+                const float2 cc = *reinterpret_cast<const float2 *>(C + gi * 8 + 4 * hb + 2 * (t & 1));
+                // two accumulators (low / high nibbles): two independent mma chains of four
+                float d[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t wg = uint4_word(cg[hb], j), w8 = uint4_word(c8[hb], j);
+                    const uint32_t m = ((g & 3) == j) ? 0xffffffffu : 0u;
+                    const uint32_t wgs = wg >> 8, w8s = w8 >> 8;
+                    mma16816(d, (wg & 0x000f000fu) | 0x64006400u, (w8 & 0x000f000fu) | 0x64006400u,
+                             (wgs & 0x000f000fu) | 0x64006400u, (w8s & 0x000f000fu) | 0x64006400u, xb.x & m, xb.y & m);
+                    mma16816(e, (wg & 0x00f000f0u) | 0x64006400u, (w8 & 0x00f000f0u) | 0x64006400u,
+                             (wgs & 0x00f000f0u) | 0x64006400u, (w8s & 0x00f000f0u) | 0x64006400u, xb.z & m, xb.w & m);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) d[k] += e[k];
+                const float2 s01 = __half22float2(*reinterpret_cast<const __half2 *>(&sc.x));
+                const float2 s23 = __half22float2(*reinterpret_cast<const __half2 *>(&sc.y));
+                acc0 = fmaf(s01.x, d[0] - cc.x, acc0); acc0 = fmaf(s01.y, d[1] - cc.y, acc0);
+                acc1 = fmaf(s23.x, d[2] - cc.x, acc1); acc1 = fmaf(s23.y, d[3] - cc.y, acc1);
+            }
+        }
+        // sum over t: blocks 0,1 | 2,3 and the hi | lo parts
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+        if (t == 0) {
+            float *res = a.res + (size_t)(si * GW + cl) * ph->rows_cap + rgl * 16 + g;
+            res[0] = acc0;
+            res[8] = acc1;
+        }
+        w.release();
+    }
+}
+
 template <int WT>
 __device__ __noinline__ void consume_phase(const ConsumeArgs a)
 {
@@ -442,32 +517,7 @@ __device__ __noinline__ void consume_phase(const ConsumeArgs a)
         else if (WT == WT_F32 && ku <= 12) consume_xreg<WT, WT == WT_F32 ? 12 : 2>(a);
         else consume_xsmem<WT>(a);
     } else {
-        const PhaseW *ph = a.ph;
-        const int rps = ph->rps, lane = a.lane, cl = a.warp % GW, cols = ph->cols;
-        const uint32_t rs = ph->rs;
-        StageWalk w(a);
-        int rot = 0;
-        while (w.more()) {
-            const uint8_t *sp = w.wait();
-            const int base = w.s * rps, n = min(rps, a.nrows - base), ngroups = (n + 3) >> 2;
-            int g = cl - rot;
-            if (g < 0) g += GW;
-            for (; g < ngroups; g += GW) {
-                int i = 4 * g;
-                const int iend = min(n, i + 4);
-                if (iend - i == 4) {
-                    rows_to_res<WT, 4>(sp + (size_t)i * rs, rs, a.xs, cols, lane, a.res + base + i);
-                } else {
-                    if (iend - i >= 2) {
-                        rows_to_res<WT, 2>(sp + (size_t)i * rs, rs, a.xs, cols, lane, a.res + base + i);
-                        i += 2;
-                    }
-                    if (i < iend) rows_to_res<WT, 1>(sp + (size_t)i * rs, rs, a.xs, cols, lane, a.res + base + i);
-                }
-            }
-            rot = (rot + ngroups) % GW;
-            w.release();
-        }
+        consume_q4(a);
     }
 }
 
@@ -629,12 +679,60 @@ __device__ __forceinline__ void vec_stage_release(const StreamParams &P, const S
 //     (llama2.f90:450-457) is returned and multiplies the phase's results in the epilogue (the
 //     mat-vec is linear): no second pass over xs.  x is this CTA's copy of the residual stream in
 //     shared memory; for the very first phase it is the embedding row from a ring slot (:520).
+// f32 / f16: xs is the plain float vector.  q4_0 (consume_q4): xs holds the activations as f16
+// pairs x = hi + lo in mma B-fragment order -- for every half group of 4 blocks, [hi | lo][block][t]
+// records of 16 bytes: {x[4t], x[4t+2]}, {x[4t+1], x[4t+3]} of the low 16 elements of the block,
+// then the same of the high 16 elements pre-scaled by 1/16 -- followed by the float corrections
+// C[hi | lo][block] = 1032 sum(low elements) + 72 sum(high elements) (sums of the ROUNDED values, so
+// that the offset 1024 + q -> q - 8 cancels exactly).  All 32 lanes call it together: an aligned
+// group of 8 lanes holds the 8 float4 of one block.
 template <int WT>
-__device__ __forceinline__ void store_x4(float *xs, int j4, const float4 v)
+__device__ __forceinline__ void store_x4(float *xs, int n, int j4, const float4 v, bool valid)
 {
-    int idx = j4;
-    if (WT == WT_Q4_0) idx = (j4 & ~7) | ((j4 & 7) ^ ((j4 >> 3) & 7));  // == xs_index<WT> per float4
-    reinterpret_cast<float4 *>(xs)[idx] = v;
+    if constexpr (WT != WT_Q4_0) {
+        if (valid) reinterpret_cast<float4 *>(xs)[j4] = v;
+    } else {
+        const int B = j4 >> 3, i = j4 & 7, t = i & 3, ngrp = q4t_groups(n);
+        const bool hi_nib = i >= 4;
+        const float sc = hi_nib ? 0.0625f : 1.f, cf = hi_nib ? 72.f * 16.f : 1032.f;
+        const float x0 = v.x * sc, x1 = v.z * sc, x2 = v.y * sc, x3 = v.w * sc;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        const float2 g01 = __half22float2(l01), g23 = __half22float2(l23);
+        float ch = valid ? ((f01.x + f01.y) + (f23.x + f23.y)) * cf : 0.f;
+        float cl = valid ? ((g01.x + g01.y) + (g23.x + g23.y)) * cf : 0.f;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            ch += __shfl_xor_sync(0xffffffffu, ch, o);
+            cl += __shfl_xor_sync(0xffffffffu, cl, o);
+        }
+        if (valid) {
+            uint8_t *rec = reinterpret_cast<uint8_t *>(xs) + ((size_t)((B >> 2) * 8 + (B & 3)) * 4 + t) * 16 + (hi_nib ? 8 : 0);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t *>(&h01); o.y = *reinterpret_cast<const uint32_t *>(&h23);
+            *reinterpret_cast<uint2 *>(rec) = o;                  // p = 0: hi part
+            o.x = *reinterpret_cast<const uint32_t *>(&l01); o.y = *reinterpret_cast<const uint32_t *>(&l23);
+            *reinterpret_cast<uint2 *>(rec + 4 * 4 * 16) = o;     // p = 1: lo part, 4 blocks x 4 t further
+            if (i == 0) {
+                xs[(size_t)ngrp * 256 + B] = ch;
+                xs[(size_t)ngrp * 256 + ngrp * 8 + B] = cl;
+            }
+        }
+    }
+}
+// q4_0: blocks past the end of the vector (the last group of 8 may be partial) read as zero
+__device__ __forceinline__ void q4_zero_tail(float *xs, int n, int tid, int nt)
+{
+    const int nblk = n >> 5, ngrp = q4t_groups(n);
+    for (int b = nblk + tid; b < ngrp * 8; b += nt) {
+        uint8_t *rec = reinterpret_cast<uint8_t *>(xs) + (size_t)((b >> 2) * 8 + (b & 3)) * 64;
+        uint4 *p = reinterpret_cast<uint4 *>(rec), *q = reinterpret_cast<uint4 *>(rec + 256);
+        p[0] = p[1] = p[2] = p[3] = make_uint4(0u, 0u, 0u, 0u);
+        q[0] = q[1] = q[2] = q[3] = make_uint4(0u, 0u, 0u, 0u);
+        xs[(size_t)ngrp * 256 + b] = 0.f;
+        xs[(size_t)ngrp * 256 + ngrp * 8 + b] = 0.f;
+    }
 }
 
 __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int cols, int j4)
@@ -648,7 +746,7 @@ __device__ __forceinline__ float gather_x(const unsigned long long *src, int nsr
                                           const uint8_t *emb_row, const float *wn /* shared */,
                                           const StreamParams &P, const SmemView &sv, const Cons &c)
 {
-    constexpr int PV = 2;
+    constexpr int PV = 4;
     const int n4 = n >> 2;
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
     float4 *xr4 = reinterpret_cast<float4 *>(sv.xres);
@@ -683,18 +781,18 @@ __device__ __forceinline__ float gather_x(const unsigned long long *src, int nsr
 #pragma unroll
         for (int k = 0; k < PV; k++) {
             const int j = base + c.tid + k * c.nt;
-            if (j < n4) {
-                float4 t = v[k];
-                if (norm) {
-                    xr4[j] = t;
-                    ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
-                    const float4 w = wn4[j];
-                    t.x *= w.x; t.y *= w.y; t.z *= w.z; t.w *= w.w;
-                }
-                store_x4<WT>(sv.xs, j, t);
+            const bool valid = j < n4;
+            float4 t = v[k];
+            if (valid && norm) {
+                xr4[j] = t;
+                ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+                const float4 w = wn4[j];
+                t.x *= w.x; t.y *= w.y; t.z *= w.z; t.w *= w.w;
             }
+            store_x4<WT>(sv.xs, n, j, t, valid);
         }
     }
+    if (WT == WT_Q4_0) q4_zero_tail(sv.xs, n, c.tid, c.nt);
     if (!norm) {
         cons_sync(c);
         return 1.f;
@@ -878,7 +976,9 @@ __device__ __noinline__ void load_x_attn(const StreamParams &P, uint32_t ep, con
     const int S = P.n_splits;
     const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.att_dim >> 2;
     const int hs_shift = hs == 64 ? 6 : (hs == 128 ? 7 : 5);
-    for (int j = c.tid; j < n4; j += c.nt) {
+    for (int jj = c.tid; jj < ((n4 + 31) & ~31); jj += c.nt) {
+        const bool valid = jj < n4;
+        const int j = valid ? jj : n4 - 1;
         const int h = (4 * j) >> hs_shift, d = (4 * j) & (hs - 1);
         const unsigned long long *part = P.ll_part + (size_t)h * S * pstride;
         float M = -INFINITY, ms[8], ls[8];
@@ -902,8 +1002,9 @@ __device__ __noinline__ void load_x_attn(const StreamParams &P, uint32_t ep, con
                 num.x = fmaf(av[s].x, w, num.x); num.y = fmaf(av[s].y, w, num.y);
                 num.z = fmaf(av[s].z, w, num.z); num.w = fmaf(av[s].w, w, num.w);
             }
-        store_x4<WT>(sv.xs, j, make_float4(num.x / den, num.y / den, num.z / den, num.w / den));
+        store_x4<WT>(sv.xs, P.att_dim, jj, make_float4(num.x / den, num.y / den, num.z / den, num.w / den), valid);
     }
+    if (WT == WT_Q4_0) q4_zero_tail(sv.xs, P.att_dim, c.tid, c.nt);
     cons_sync(c);
 }
 
@@ -1020,7 +1121,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         int r0, r1;
         cta_rows(P.ph[i], blockIdx.x, gridDim.x, r0, r1);
         cp.r0[i] = r0; cp.r1[i] = r1;
-        cp.nst[i] = (r1 - r0 + P.ph[i].rps - 1) / P.ph[i].rps;
+        cp.nst[i] = phase_stages(P.ph[i], r1 - r0);
     }
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(P.sched + (size_t)blockIdx.x * P.sched_stride);
@@ -1070,7 +1171,6 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     const uint32_t ns = (uint32_t)P.n_slots;
     const int nrep = P.ll_rep, rep = (int)blockIdx.x % nrep;  // LL vector replicas; the one this CTA polls
     const int hb_stride = (P.hid + 1) & ~1;
-    constexpr int planes = (WT != WT_Q4_0) ? GW : 1;
     float best = -INFINITY;  // running maxloc of this thread's logits (classifier epilogue)
     int bidx = 0x7fffffff;
 
@@ -1138,14 +1238,16 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         // and every thread publishes ONE 16-byte LL record -- relaxed gpu-scope stores are slow one
         // after the other from one thread, so they are spread over the threads instead.
         {
-            const int cap = cp.ph[ph].rows_cap;
+            const int cap = cp.ph[ph].rows_cap, rows_real = cp.ph[ph].rows_real;
+            const int planes = (WT == WT_Q4_0) ? cp.ph[ph].spg * GW : GW;
             const int nsub = ph == 4 ? 1 : ((ph & 1) ? nrep * P.tp : nrep), npairs = (nr + 1) >> 1;
 #pragma unroll 1
             for (int w = c.tid; w < npairs * nsub; w += c.nt) {
                 const int pair = w / nsub, sub = w - pair * nsub, i = 2 * pair;
-                const bool two = i + 1 < nr;
+                if (r0 + i >= rows_real) continue;  // padding rows of a tiled q4_0 matrix
+                const bool two = i + 1 < nr && r0 + i + 1 < rows_real;
                 float a = sv.res[i], b = two ? sv.res[i + 1] : 0.f;
-#pragma unroll
+#pragma unroll 4
                 for (int p = 1; p < planes; p++) {
                     a += sv.res[p * cap + i];
                     b += two ? sv.res[p * cap + i + 1] : 0.f;
@@ -1225,7 +1327,7 @@ static void sched_caps(const StreamParams &p, int *layer, int *post)
 {
     int per_layer = 2, cls = 0;
     for (int i = 0; i < 5; i++) {
-        const int st = (p.ph[i].rows_cap + p.ph[i].rps - 1) / p.ph[i].rps;
+        const int st = phase_stages(p.ph[i], p.ph[i].rows_cap);
         if (i < 4) per_layer += st; else cls = st;
     }
     *layer = per_layer;
@@ -1236,29 +1338,43 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
                 int cons_warps, StreamPlan *out)
 {
     cons_warps = MAX_CONS_WARPS;  // NG groups of GW warps
-    unsigned int rs_max = 0;
+    const bool tiled = p.ph[0].ngrp > 0;  // q4_0 in the tiled mma format
+    unsigned int rs_max = (unsigned)p.emb * 4u;  // f32 vector stages
+    if ((unsigned)row_stride_bytes(p.wtype, p.emb) > rs_max) rs_max = (unsigned)row_stride_bytes(p.wtype, p.emb);
+    for (int i = 0; i < 5; i++) {
+        PhaseW &w = p.ph[i];
+        if (tiled) {
+            // split a row group into stages of whole 8-block groups that fit the target slot
+            w.spg = (int)((w.rs + (unsigned)target_slot_bytes - 1) / (unsigned)target_slot_bytes);
+            const unsigned stage = (unsigned)((w.ngrp + w.spg - 1) / w.spg) * Q4T_GROUP_BYTES;
+            if (stage > rs_max) rs_max = stage;
+        } else {
+            w.spg = 0;
+            if (w.rs > rs_max) rs_max = w.rs;
+        }
+    }
+    int slot = (!tiled && target_slot_bytes > (int)rs_max) ? target_slot_bytes : (int)rs_max;
+    slot = (slot + 127) & ~127;
     int res_floats = 0;
     for (int i = 0; i < 5; i++) {
         PhaseW &w = p.ph[i];
-        if (w.rs > rs_max) rs_max = w.rs;
         const int U = w.rows / w.unit;
         w.rows_cap = ((U + grid - 1) / grid) * w.unit;
         const int nunits = w.cols >> (p.wtype == WT_F32 ? 2 : 3);
-        w.ku = p.wtype == WT_Q4_0 ? 0 : (nunits + 32 * GW - 1) / (32 * GW);
-        const int planes = p.wtype == WT_Q4_0 ? 1 : GW;
+        w.ku = tiled ? 0 : (nunits + 32 * GW - 1) / (32 * GW);
+        const int planes = tiled ? w.spg * GW : GW;
         if (planes * w.rows_cap > res_floats) res_floats = planes * w.rows_cap;
     }
-    if ((unsigned)p.emb * 4u > rs_max) rs_max = (unsigned)p.emb * 4u;  // f32 vector stages
-    int slot = target_slot_bytes > (int)rs_max ? target_slot_bytes : (int)rs_max;
-    slot = (slot + 127) & ~127;
     int xs_floats = p.emb > p.hid ? p.emb : p.hid;
+    if (tiled)  // f16 hi + lo activations in fragment order + two corrections per block (store_x4)
+        for (int i = 0; i < 5; i++) xs_floats = xs_floats > p.ph[i].ngrp * 272 ? xs_floats : p.ph[i].ngrp * 272;
     // attention scratch ([consumer warps][hs+4] partials) also lives in xs
     const int att_scratch = MAX_SLOTS * (p.hs + 4);
     if (att_scratch > xs_floats) xs_floats = att_scratch;
     xs_floats = (xs_floats + 31) & ~31;
     res_floats = (res_floats + 31) & ~31;
     if (max_slots > MAX_SLOTS) max_slots = MAX_SLOTS;
-    for (int i = 0; i < 5; i++) p.ph[i].rps = slot / (int)p.ph[i].rs > 0 ? slot / (int)p.ph[i].rs : 1;
+    for (int i = 0; i < 5; i++) p.ph[i].rps = (!tiled && slot / (int)p.ph[i].rs > 0) ? slot / (int)p.ph[i].rs : 1;
     int cap_layer, cap_post;
     sched_caps(p, &cap_layer, &cap_post);
     const int sched_entries = 1 + cap_layer + cap_post + 1;
@@ -1297,12 +1413,22 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
             int r0, r1;
             cta_rows(p.ph[ph], cta, grid, r0, r1);
             const PhaseW &w = p.ph[ph];
+            const size_t ls = ph < 4 ? (size_t)w.layer_stride : 0;
+            if (w.spg > 0) {
+                // tiled q4_0: spg stages per row group of 16, stage i = groups [i ngrp / spg, (i + 1) ngrp / spg)
+                for (int rg = r0 >> 4; rg < (r1 >> 4); rg++)
+                    for (int i = 0; i < w.spg; i++) {
+                        const int g0 = i * w.ngrp / w.spg, g1 = (i + 1) * w.ngrp / w.spg;
+                        vec(w.base + ((size_t)rg * w.ngrp + g0) * Q4T_GROUP_BYTES, (unsigned)(g1 - g0) * Q4T_GROUP_BYTES, ls);
+                    }
+                return;
+            }
             for (int r = r0; r < r1; r += w.rps) {
                 const int k = r1 - r < w.rps ? r1 - r : w.rps;
-                vec(w.base + (size_t)r * w.rs, (unsigned)k * w.rs, ph < 4 ? (size_t)w.layer_stride : 0);
+                vec(w.base + (size_t)r * w.rs, (unsigned)k * w.rs, ls);
             }
         };
-        vec(p.emb_table, p.ph[0].rs, 0);  // row 0; the kernel adds (token - 1) rows
+        vec(p.emb_table, (unsigned)row_stride_bytes(p.wtype, p.emb), 0);  // row 0; the kernel adds (token - 1) rows
         vec(p.rms_att, (unsigned)p.emb * 4u, (size_t)p.emb * 4u);
         rows(0);
         rows(1);
