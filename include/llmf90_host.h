@@ -20,6 +20,9 @@ typedef struct llmf90_host_config {
 /* NULL on failure; llmf90_host_last_error() says why.  verbose: 1 = the reference's -v listing,
  * 0 = only the unconditional "data offset" line (read_ggml.f90:196), -1 = silent */
 llmf90_host_model *llmf90_host_load(const char *gguf_path, int32_t verbose);
+/* the legacy `--ak` packed f32 model file (llama2.f90:158-294); no vocabulary: add one with
+ * llmf90_host_load_tokenizer (the reference's -s) */
+llmf90_host_model *llmf90_host_load_ak(const char *path, int32_t verbose);
 void llmf90_host_free(llmf90_host_model *m);
 const char *llmf90_host_last_error(void);
 int llmf90_host_get_config(const llmf90_host_model *m, llmf90_host_config *out);

@@ -23,7 +23,7 @@ CUDA_SRCS = ["ops.cu", "stream.cu", "engine.cu"]
 CUDA_HDRS = ["common.cuh", "kernels.cuh", os.path.join(ROOT, "include", "llmf90_b200.h")]
 CUDA_LIB = os.path.join(HERE, "libllmf90_b200.so")
 HOST_LIB = os.path.join(HERE, "libllmf90_host.so")
-HOST_SRCS = ["host/gguf_loader.cpp", "host/tokenizer.cpp", "host/host_api.cpp"]
+HOST_SRCS = ["host/gguf_loader.cpp", "host/ak_loader.cpp", "host/tokenizer.cpp", "host/host_api.cpp"]
 HOST_HDRS = ["host/host.hpp", os.path.join(ROOT, "include", "llmf90_host.h")]
 LLM_BIN = os.path.join(HERE, "bin", "llm")
 

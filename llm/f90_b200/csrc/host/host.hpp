@@ -49,6 +49,8 @@ size_t row_bytes(int wtype, int n);
 // value type, dimensions from the llama.* keys.  Throws std::runtime_error with the reference's
 // style of message ("key not found", "GGUF magic", ...).
 Model load_gguf(const std::string &path, bool verbose, bool print_offset = true);
+// legacy `--ak` packed f32 model file (llama2.f90:158-294; ak_loader.cpp); carries no vocabulary
+Model load_ak(const std::string &path, bool verbose);
 // legacy `-s tokenizer.bin` (llama2.f90:321-356): i32 max_len, then per token f32 score, i32 len, bytes
 void load_tokenizer_bin(const std::string &path, int vocab_size, Vocab &out);
 

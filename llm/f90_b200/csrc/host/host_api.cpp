@@ -29,6 +29,18 @@ llmf90_host_model *llmf90_host_load(const char *path, int32_t verbose)
     }
 }
 
+llmf90_host_model *llmf90_host_load_ak(const char *path, int32_t verbose)
+{
+    try {
+        auto *h = new llmf90_host_model;
+        h->m = llmhost::load_ak(path ? path : "", verbose > 0);
+        return h;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
 void llmf90_host_free(llmf90_host_model *m) { delete m; }
 
 int llmf90_host_get_config(const llmf90_host_model *m, llmf90_host_config *out)

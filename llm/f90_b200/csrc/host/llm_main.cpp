@@ -54,11 +54,11 @@ Args parse_args(int argc, char **argv)
 int main(int argc, char **argv)
 {
     const Args a = parse_args(argc, argv);
-    if (a.ak) die("--ak (packed llama2.c-style f32 file) is not supported by this build; convert to GGUF");
+    if (a.ak && a.tokenizer.empty()) die("--ak model files carry no vocabulary: pass -s tokenizer.bin");
 
     llmhost::Model m;
     try {
-        m = llmhost::load_gguf(a.model_file, a.verbose);
+        m = a.ak ? llmhost::load_ak(a.model_file, a.verbose) : llmhost::load_gguf(a.model_file, a.verbose);
         if (!a.tokenizer.empty()) llmhost::load_tokenizer_bin(a.tokenizer, m.cfg.vocab_size, m.vocab);
     } catch (const std::exception &e) {
         die(e.what());

@@ -127,6 +127,40 @@ def fuse_tensors(cfg: Config, t: dict[str, np.ndarray]) -> Weights:
     )
 
 
+def write_ak(path: str, cfg: Config, t: dict[str, np.ndarray]) -> None:
+    """The reference's legacy ``--ak`` packed f32 model file (llama2.f90:158-294): 7 x int32 header,
+    then the tensors in the llama2.c order without RoPE tables (all Wq, all Wk, all Wv, all Wo,
+    ..., W1, W2, W3 grouped by kind over the layers)."""
+    L = cfg.n_layers
+    with open(path, "wb") as f:
+        f.write(np.array([cfg.emb_dim, cfg.hidden_dim, L, cfg.n_heads, cfg.n_kv_heads, cfg.vocab_size, cfg.seq_len],
+                         np.int32).tobytes())
+        put = lambda a: f.write(np.ascontiguousarray(a, np.float32).tobytes())
+        put(t["token_embd.weight"])
+        for l in range(L):
+            put(t[f"blk.{l}.attn_norm.weight"])
+        for n in ("attn_q", "attn_k", "attn_v", "attn_output"):
+            for l in range(L):
+                put(t[f"blk.{l}.{n}.weight"])
+        for l in range(L):
+            put(t[f"blk.{l}.ffn_norm.weight"])
+        for n in ("ffn_gate", "ffn_down", "ffn_up"):
+            for l in range(L):
+                put(t[f"blk.{l}.{n}.weight"])
+        put(t["output_norm.weight"])
+        put(t["output.weight"])
+
+
+def write_tokenizer_bin(path: str, tokens: list[bytes], scores) -> None:
+    """The reference's ``-s tokenizer.bin`` (llama2.f90:321-356): int32 max_len, then per token
+    f32 score, int32 length, bytes."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", max(len(s) for s in tokens)))
+        for s, sc in zip(tokens, scores):
+            f.write(struct.pack("<fi", float(sc), len(s)) + s)
+
+
 def synth_weights(cfg: Config, seed: int = 0) -> Weights:
     return fuse_tensors(cfg, synth_tensors(cfg, seed))
 

@@ -35,6 +35,8 @@ def load() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         L.llmf90_host_load.restype = C.c_void_p
         L.llmf90_host_load.argtypes = [C.c_char_p, C.c_int32]
+        L.llmf90_host_load_ak.restype = C.c_void_p
+        L.llmf90_host_load_ak.argtypes = [C.c_char_p, C.c_int32]
         L.llmf90_host_free.argtypes = [C.c_void_p]
         L.llmf90_host_last_error.restype = C.c_char_p
         L.llmf90_host_get_config.argtypes = [C.c_void_p, C.POINTER(CHostConfig)]
@@ -58,9 +60,12 @@ def load() -> C.CDLL:
 class HostModel:
     """What `load_ggml` (read_ggml.f90:53) returns: weights in the fused layout, vocabulary, scores."""
 
-    def __init__(self, path: str, verbose: bool = False, quiet: bool = True):
+    def __init__(self, path: str, verbose: bool = False, quiet: bool = True, ak: bool = False):
         self.L = load()
-        self.h = self.L.llmf90_host_load(path.encode(), 1 if verbose else (-1 if quiet else 0))
+        if ak:  # the legacy packed f32 file (llama2.f90:158-294)
+            self.h = self.L.llmf90_host_load_ak(path.encode(), 1 if verbose else 0)
+        else:
+            self.h = self.L.llmf90_host_load(path.encode(), 1 if verbose else (-1 if quiet else 0))
         if not self.h:
             raise HostError(self.L.llmf90_host_last_error().decode())
         cc = CHostConfig()

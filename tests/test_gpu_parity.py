@@ -216,3 +216,32 @@ def test_cli_end_to_end(tmp_path, wt):
     assert b"data offset" in out and b"tokens/second" in out and b"Timings" in out
     text = out.split(b"\n Inference time:")[0].split(b"\n", 1)[1]  # after the loader's "data offset" line
     assert text == want
+
+
+def test_cli_ak_packed_model(tmp_path):
+    """`./llm --ak -m model.bin -s tokenizer.bin` (llama2.f90:158-294, :321-356): the legacy packed f32 file
+    and the separate tokenizer file drive the same forward pass as the GGUF of the same weights."""
+    import subprocess
+    from llm.f90_b200 import hostapi
+    cfg = Config(**SMALL, wtype=F32)
+    t = fx.synth_tensors(cfg, seed=12)
+    w = fx.fuse_tensors(cfg, t)
+    p, tb = str(tmp_path / "m.bin"), str(tmp_path / "tok.bin")
+    fx.write_ak(p, cfg, t)
+    vocab, scores = fx.synth_vocab(cfg.vocab_size)
+    fx.write_tokenizer_bin(tb, vocab, scores)
+    m = hostapi.HostModel(p, ak=True)
+    m.load_tokenizer(tb)
+    prompt = "the cat sat"
+    ptoks = m.encode(prompt)
+    m.close()
+    n = 20
+    ref_toks, _, _ = oc.Oracle(w).generate(ptoks, n)
+    want = b"".join(vocab[t - 1] for t in ref_toks)
+    r = subprocess.run([hostapi.LLM_BIN, "--ak", "-m", p, "-s", tb, "-n", str(n), "-p", prompt, "-t", "0"],
+                       capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    assert r.stdout.split(b"\n Inference time:")[0] == want
+    # without -s there is no vocabulary: refuse like the reference's other fatal conditions (print + stop)
+    r = subprocess.run([hostapi.LLM_BIN, "--ak", "-m", p, "-n", "4"], capture_output=True, timeout=60)
+    assert r.returncode != 0 and b"tokenizer" in r.stdout

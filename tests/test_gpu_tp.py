@@ -31,6 +31,8 @@ def free_port():
 def test_tp_matches_oracle(tmp_path, built, wt, shape, world):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    if shape["n_kv_heads"] % world:
+        pytest.skip("KV heads do not split this many ways (the engine rejects the configuration)")
     import torch.multiprocessing as mp
     from tp_worker import gpu_tp_generate
     cfg = Config(**shape, wtype=wt)

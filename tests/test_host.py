@@ -147,6 +147,30 @@ def test_tokenizer_bin_override(tmp_path):
     m.close()
 
 
+def test_ak_packed_file_loads_into_the_fused_layout(tmp_path):
+    """--ak (llama2.f90:158-294): same TransformerWeights as the GGUF path; vocabulary from -s."""
+    cfg = Config(**TINY)
+    t = fx.synth_tensors(cfg, seed=4)
+    p = str(tmp_path / "m.bin")
+    fx.write_ak(p, cfg, t)
+    m = hostapi.HostModel(p, ak=True)
+    assert m.cfg == cfg
+    got, ref = m.weights(), fx.fuse_tensors(cfg, t)
+    for f in ref.FIELDS:
+        assert np.array_equal(getattr(got, f).reshape(-1), getattr(ref, f).reshape(-1)), f
+    toks, scores = fx.synth_vocab(cfg.vocab_size)
+    tb = str(tmp_path / "tok.bin")
+    fx.write_tokenizer_bin(tb, toks, scores)
+    m.load_tokenizer(tb)
+    assert m.vocab()[0] == toks
+    m.close()
+    # truncated file: the reference would hit end-of-file in a stream read; we say so
+    with open(p, "r+b") as f:
+        f.truncate(1000)
+    with pytest.raises(hostapi.HostError, match="end of file"):
+        hostapi.HostModel(p, ak=True)
+
+
 def test_argmax_and_sampler():
     lg = np.array([0.5, 3.0, 3.0, -1.0], np.float32)
     assert hostapi.argmax(lg) == 2  # first maximum, 1-based

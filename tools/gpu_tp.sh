@@ -1,0 +1,8 @@
+#!/bin/bash
+# multi-GPU visit: TP parity tests + the TP bench line (N = number of GPUs of this box)
+N=${1:-2}
+mkdir -p gpurun_out
+timeout 200 python -m pytest tests/test_gpu_tp.py -m gpu -x -q 2>&1 | tail -5
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_tp$N.json 2> gpurun_out/bench_tp$N.err
+tail -2 gpurun_out/bench_tp$N.json | cut -c1-1500
+tail -3 gpurun_out/bench_tp$N.err
