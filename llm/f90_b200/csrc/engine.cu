@@ -508,6 +508,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             // rank-private LL buffers (64-bit words), zero-filled: epoch 0 is never expected
             int rep = 4;
             if (const char *s = getenv("LLMF90_LL_REP")) rep = std::max(1, std::min(16, atoi(s)));
+            while (rep & (rep - 1)) rep &= rep - 1;  // a power of two (the kernel splits work items with shifts)
             p.ll_rep = rep;
             const size_t n_part = (size_t)Hl * MAX_SPLITS * (hs + 4);
             const size_t words = (size_t)rep * (2 * (size_t)att + ((hid + 1) & ~1) + 2 * (size_t)kvl) + n_part + 64;

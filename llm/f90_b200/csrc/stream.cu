@@ -746,7 +746,7 @@ __device__ __forceinline__ float gather_x(const unsigned long long *src, int nsr
                                           const uint8_t *emb_row, const float *wn /* shared */,
                                           const StreamParams &P, const SmemView &sv, const Cons &c)
 {
-    constexpr int PV = 4;
+    constexpr int PV = 2;
     const int n4 = n >> 2;
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
     float4 *xr4 = reinterpret_cast<float4 *>(sv.xres);
@@ -1240,10 +1240,12 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         {
             const int cap = cp.ph[ph].rows_cap, rows_real = cp.ph[ph].rows_real;
             const int planes = (WT == WT_Q4_0) ? cp.ph[ph].spg * GW : GW;
+            // (replica and rank counts are powers of two: shifts)
             const int nsub = ph == 4 ? 1 : ((ph & 1) ? nrep * P.tp : nrep), npairs = (nr + 1) >> 1;
+            const int sub_shift = 31 - __clz(nsub);
 #pragma unroll 1
             for (int w = c.tid; w < npairs * nsub; w += c.nt) {
-                const int pair = w / nsub, sub = w - pair * nsub, i = 2 * pair;
+                const int pair = w >> sub_shift, sub = w & (nsub - 1), i = 2 * pair;
                 if (r0 + i >= rows_real) continue;  // padding rows of a tiled q4_0 matrix
                 const bool two = i + 1 < nr && r0 + i + 1 < rows_real;
                 float a = sv.res[i], b = two ? sv.res[i + 1] : 0.f;
@@ -1283,7 +1285,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 } else {
                     // Wo / W2 (llama2.f90:603-605, :618-620): publish this rank's partial sums to every
                     // rank; the residual add happens in the next norm prologue, on every CTA's copy of x
-                    const int k = sub / nrep, rr = sub - k * nrep;  // destination rank, replica
+                    const int k = sub >> (31 - __clz(nrep)), rr = sub & (nrep - 1);  // destination rank, replica
                     unsigned long long *dst = (ph == 1 ? P.part1[k] : P.part2[k]) + ((size_t)rr * P.tp + P.rank) * P.emb;
                     ll_store_sys(dst, r, a, ep);  // (r may be odd here: no 16-byte store)
                     if (two) ll_store_sys(dst, r + 1, b, ep);

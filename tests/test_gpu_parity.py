@@ -229,6 +229,9 @@ def test_cli_ak_packed_model(tmp_path):
     p, tb = str(tmp_path / "m.bin"), str(tmp_path / "tok.bin")
     fx.write_ak(p, cfg, t)
     vocab, scores = fx.synth_vocab(cfg.vocab_size)
+    # tokenizer.bin entries are used as they are (llama2.f90:321-356): write them the way load_ggml leaves
+    # GGUF tokens, with a leading U+2581 already turned into a space (read_ggml.f90:483-503)
+    vocab = [b" " + t[3:] if t.startswith(b"\xe2\x96\x81") else t for t in vocab]
     fx.write_tokenizer_bin(tb, vocab, scores)
     m = hostapi.HostModel(p, ak=True)
     m.load_tokenizer(tb)
