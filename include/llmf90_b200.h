@@ -50,6 +50,10 @@ extern "C" {
 /* flags */
 #define LLMF90_FLAG_GRANULAR 1u  /* run the forward as separate kernels (rmsnorm, matvec, rope,
                                     attention ...) instead of the fused weight-streaming kernel */
+#define LLMF90_FLAG_PROFILE  2u  /* fused kernel with per-phase timers (llmf90_b200_phase_times, the five
+                                    reference buckets of llmf90_b200_times); costs 5-8 % of the token
+                                    time, so it is off by default: all forward time then goes to bucket 4.
+                                    Also switched on by the environment variable LLMF90_PROFILE=1 */
 
 /* mirror of `type Config` (weight_module.f90:28-31) + dtype and placement */
 typedef struct llmf90_b200_config {

@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libllmf90_b200.so")
 
 FLAG_GRANULAR = 1
+FLAG_PROFILE = 2  # fused kernel with per-phase timers (slower; phase_times / debug_trace tools)
 
 EXPORTS = [
     "llmf90_b200_init", "llmf90_b200_transformer", "llmf90_b200_times", "llmf90_b200_reset",
@@ -100,13 +101,14 @@ class Engine:
     """The process-wide engine singleton behind the C ABI."""
 
     def __init__(self, weights: Weights, device: int = 0, granular: bool = False, tp_rank: int = 0,
-                 tp_size: int = 1):
+                 tp_size: int = 1, profile: bool = False):
         self.L = load()
         c = weights.cfg
         self.cfg = c
         self.tp_rank, self.tp_size = tp_rank, tp_size
         cc = CConfig(c.emb_dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads, c.vocab_size,
-                     c.seq_len, c.wtype, device, tp_rank, tp_size, FLAG_GRANULAR if granular else 0)
+                     c.seq_len, c.wtype, device, tp_rank, tp_size,
+                     (FLAG_GRANULAR if granular else 0) | (FLAG_PROFILE if profile else 0))
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
         _check(self.L.llmf90_b200_init(C.byref(cc), ptr(weights.token_embedding_table),
                                        ptr(weights.rms_att_weight), ptr(weights.wqkv), ptr(weights.wo),

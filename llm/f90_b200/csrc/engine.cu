@@ -69,6 +69,7 @@ struct Engine {
     int *h_tokpos = nullptr;    // pinned
     // drivers
     bool use_stream = true;
+    bool prof = false;  // instrumented fused kernel (LLMF90_FLAG_PROFILE / LLMF90_PROFILE=1)
     StreamParams sp{};
     StreamPlan plan{};
     cudaGraphExec_t graph = nullptr;
@@ -241,7 +242,7 @@ int enqueue_forward(int token, int pos, bool device_loop, const int *forced, int
         p.out_tokens = out_tokens;
         E.launch_seq++;
         p.ep_base = E.launch_seq * (unsigned)(E.cfg.n_layers + 1);
-        CK(launch_stream(p, E.plan, E.st));
+        CK(launch_stream(p, E.plan, E.prof || p.trace != nullptr, E.st));
         E.launches += 1;
     } else {
         if (!device_loop) {
@@ -366,6 +367,8 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     E.hs = hs; E.kv_mul = c.n_heads / c.n_kv_heads;
     E.n_sms = prop.multiProcessorCount;
     E.use_stream = !(c.flags & LLMF90_FLAG_GRANULAR);
+    E.prof = (c.flags & LLMF90_FLAG_PROFILE) != 0;
+    if (const char *s = getenv("LLMF90_PROFILE")) E.prof = E.prof || atoi(s) != 0;
     const int emb = c.emb_dim, L = c.n_layers, V = c.vocab_size, wt = c.wtype;
     const int hid_full = c.hidden_dim, kv_full = c.n_kv_heads * hs;
     // this rank's share: heads and their KV heads, FFN rows, vocabulary rows
@@ -579,7 +582,7 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
     CK(cudaStreamSynchronize(E.st));
     memcpy(logits, E.h_logits, (size_t)E.cfg.vocab_size * 4);
     CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
-    if (!E.use_stream) E.host_times[3] += E.last_ms;  // granular path: whole forward in bucket 4
+    if (!E.use_stream || !E.prof) E.host_times[3] += E.last_ms;  // no per-phase timers: whole forward in bucket 4
     return 0;
 }
 

@@ -143,6 +143,7 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
 // the per-CTA stage lists for `grid` CTAs: out has grid * (*stride) entries (call after plan_stream)
 void build_schedule(StreamParams &p, int grid, SchedStage **out);  // fills p.sched_stride
 cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes);
-cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st);
+// prof: the instrumented kernel (phase timers of CTA 0, optional per-CTA trace) instead of the production one
+cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, bool prof, cudaStream_t st);
 
 }  // namespace llmf90

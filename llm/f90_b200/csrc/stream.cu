@@ -262,7 +262,8 @@ struct Pending {
     }
 };
 
-// ring walk of one group through a phase: owned stages are NG apart
+// ring walk of one group through a phase: owned stages are NG apart (PROF: trace instrumentation)
+template <bool PROF>
 struct StageWalk {
     const ConsumeArgs &a;
     uint32_t slot, par;
@@ -271,7 +272,8 @@ struct StageWalk {
     int nwaits = 0;
     __device__ __forceinline__ void stampc(int i) const
     {
-        if (a.stamps && a.lane == 0) a.stamps[i] = clock64();
+        if constexpr (PROF)
+            if (a.stamps && a.lane == 0) a.stamps[i] = clock64();
     }
     __device__ __forceinline__ StageWalk(const ConsumeArgs &a_) : a(a_)
     {
@@ -286,7 +288,7 @@ struct StageWalk {
     __device__ __forceinline__ bool more() const { return s < a.nst; }
     __device__ __forceinline__ const uint8_t *wait()
     {
-        if (a.wait_cycles) {
+        if (PROF && a.wait_cycles) {
             const long long w0 = clock64();
             mbar_wait(&a.full[slot], par, 2);
             tc0 = clock64();
@@ -300,16 +302,16 @@ struct StageWalk {
     __device__ __forceinline__ void release()
     {
         __syncwarp();
-        if (a.wait_cycles && a.lane == 0) { a.wait_cycles[4] += clock64() - tc0; a.wait_cycles[8] += 1; }
+        if (PROF && a.wait_cycles && a.lane == 0) { a.wait_cycles[4] += clock64() - tc0; a.wait_cycles[8] += 1; }
         if (a.lane == 0) mbar_arrive(&a.empty[slot]);
-        if (a.wait_cycles && nwaits == 1) stampc(3);
+        if (PROF && a.wait_cycles && nwaits == 1) stampc(3);
         s += NG;
         slot += NG;
         if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; par ^= 1u; }
     }
 };
 
-template <int WT, int KUT>
+template <int WT, int KUT, bool PROF>
 __device__ __forceinline__ void consume_xreg(const ConsumeArgs &a)
 {
     const PhaseW *ph = a.ph;
@@ -332,7 +334,7 @@ __device__ __forceinline__ void consume_xreg(const ConsumeArgs &a)
         }
     }
     Pending pd;
-    StageWalk w(a);
+    StageWalk<PROF> w(a);
     while (w.more()) {
         const uint8_t *sp = w.wait();
         const int base = w.s * rps, n = min(rps, a.nrows - base);
@@ -377,7 +379,7 @@ __device__ __forceinline__ void consume_xreg(const ConsumeArgs &a)
 }
 
 // rows wider than the register budget: the activation units come from shared memory
-template <int WT>
+template <int WT, bool PROF>
 __device__ __forceinline__ void consume_xsmem(const ConsumeArgs &a)
 {
     constexpr int KB = 4;
@@ -387,7 +389,7 @@ __device__ __forceinline__ void consume_xsmem(const ConsumeArgs &a)
     const float4 *x4 = reinterpret_cast<const float4 *>(a.xs);
     float *res = a.res + (size_t)cl * ph->rows_cap;
     Pending pd;
-    StageWalk w(a);
+    StageWalk<PROF> w(a);
     while (w.more()) {
         const uint8_t *sp = w.wait();
         const int base = w.s * rps, n = min(rps, a.nrows - base);
@@ -443,6 +445,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 }
 __device__ __forceinline__ uint32_t uint4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
+template <bool PROF>
 __device__ __forceinline__ void consume_q4(const ConsumeArgs &a)
 {
     const PhaseW *ph = a.ph;
@@ -451,7 +454,7 @@ __device__ __forceinline__ void consume_q4(const ConsumeArgs &a)
     // then the per-block offset corrections [hi | lo][block] (store_x4)
     const uint4 *xh4 = reinterpret_cast<const uint4 *>(a.xs);
     const float *C = a.xs + (size_t)ngrp * 256 + (size_t)(t >> 1) * ngrp * 8;
-    StageWalk w(a);
+    StageWalk<PROF> w(a);
     while (w.more()) {
         const uint8_t *sp = w.wait();
         const int rgl = w.s / spg, si = w.s - rgl * spg;
@@ -504,20 +507,20 @@ __device__ __forceinline__ void consume_q4(const ConsumeArgs &a)
     }
 }
 
-template <int WT>
+template <int WT, bool PROF>
 __device__ __noinline__ void consume_phase(const ConsumeArgs a)
 {
-    if (a.stamps && a.lane == 0) a.stamps[0] = clock64();
+    if (PROF && a.stamps && a.lane == 0) a.stamps[0] = clock64();
     if constexpr (WT != WT_Q4_0) {
         // units per lane per row, rounded up to an instantiated register budget
         const int ku = a.ph->ku;
-        if (ku <= 2) consume_xreg<WT, 2>(a);
-        else if (ku <= 4) consume_xreg<WT, 4>(a);
-        else if (WT == WT_F16 && ku <= 6) consume_xreg<WT, WT == WT_F16 ? 6 : 2>(a);
-        else if (WT == WT_F32 && ku <= 12) consume_xreg<WT, WT == WT_F32 ? 12 : 2>(a);
-        else consume_xsmem<WT>(a);
+        if (ku <= 2) consume_xreg<WT, 2, PROF>(a);
+        else if (ku <= 4) consume_xreg<WT, 4, PROF>(a);
+        else if (WT == WT_F16 && ku <= 6) consume_xreg<WT, WT == WT_F16 ? 6 : 2, PROF>(a);
+        else if (WT == WT_F32 && ku <= 12) consume_xreg<WT, WT == WT_F32 ? 12 : 2, PROF>(a);
+        else consume_xsmem<WT, PROF>(a);
     } else {
-        consume_q4(a);
+        consume_q4<PROF>(a);
     }
 }
 
@@ -1102,8 +1105,10 @@ __device__ __noinline__ void token_tail(const StreamParams &P, const SmemView sv
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int WT, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1)
+// PROF = false is the production kernel; PROF = true adds the phase timers of CTA 0 and the optional
+// per-CTA trace (the instrumentation alone costs 5-8 % of the token time: measured).
+template <int WT, bool PROF>
+__global__ void __launch_bounds__(416, 1)
 stream_decode_kernel(const __grid_constant__ StreamParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1155,8 +1160,8 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     cs.pos.mod = 0; cs.pos.div = 0; cs.gmod = 0;
     // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh;
     // optional per-CTA trace of one layer (debug/profiling)
-    const bool timer = (blockIdx.x == 0 && c.tid == 0);
-    const bool tracing = P.trace != nullptr;
+    const bool timer = PROF && (blockIdx.x == 0 && c.tid == 0);
+    const bool tracing = PROF && P.trace != nullptr;
     const unsigned long long t_ns0 = timer ? globaltimer_ns() : 0ull;
     const long long t_c0 = timer ? clock64() : 0ll;
     if (timer) {
@@ -1165,8 +1170,8 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     }
     if (tracing && c.tid == 0)
         for (int i = 0; i < 44; i++) pf.twait[i] = 0;
-#define LAP(b) do { if (timer) prof_lap(&pf, (b)); } while (0)
-#define STAMP(l_, k_) do { if (tracing && c.tid == 0 && (l_) == P.trace_layer) prof_stamp(P, sv, cs, &pf, (k_)); } while (0)
+#define LAP(b) do { if constexpr (PROF) { if (timer) prof_lap(&pf, (b)); } } while (0)
+#define STAMP(l_, k_) do { if constexpr (PROF) { if (tracing && c.tid == 0 && (l_) == P.trace_layer) prof_stamp(P, sv, cs, &pf, (k_)); } } while (0)
     const int half_mask = (P.hs >> 1) - 1;
     const uint32_t ns = (uint32_t)P.n_slots;
     const int nrep = P.ll_rep, rep = (int)blockIdx.x % nrep;  // LL vector replicas; the one this CTA polls
@@ -1224,7 +1229,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             ca.slot0 = (int)cs.pos.mod; ca.par0 = (int)(cs.pos.div & 1u); ca.gmod0 = (int)cs.gmod;
             ca.warp = c.warp; ca.lane = c.lane;
             if (ca.stamps && c.lane == 0) ca.stamps[7] = clock64();  // before the call
-            consume_phase<WT>(ca);
+            consume_phase<WT, PROF>(ca);
             if (ca.stamps && c.lane == 0) ca.stamps[4] = clock64();  // after the return
             cons_advance(cs, (uint32_t)cp.nst[ph], ns);
         }
@@ -1444,35 +1449,33 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
     *out = tab;
 }
 
-template <int WT>
-static const void *kernel_for(int threads)
+static const void *kernel_for(int wtype, bool prof)
 {
-    (void)threads;
-    return (const void *)stream_decode_kernel<WT, 416>;
-}
-
-static const void *kernel_for(int wtype, int threads)
-{
-    if (wtype == WT_F32) return kernel_for<WT_F32>(threads);
-    if (wtype == WT_F16) return kernel_for<WT_F16>(threads);
-    if (wtype == WT_Q4_0) return kernel_for<WT_Q4_0>(threads);
+    if (wtype == WT_F32) return prof ? (const void *)stream_decode_kernel<WT_F32, true> : (const void *)stream_decode_kernel<WT_F32, false>;
+    if (wtype == WT_F16) return prof ? (const void *)stream_decode_kernel<WT_F16, true> : (const void *)stream_decode_kernel<WT_F16, false>;
+    if (wtype == WT_Q4_0) return prof ? (const void *)stream_decode_kernel<WT_Q4_0, true> : (const void *)stream_decode_kernel<WT_Q4_0, false>;
     return nullptr;
 }
 
 cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes)
 {
-    const void *fn = kernel_for(wtype, threads);
-    if (!fn) return cudaErrorInvalidValue;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    (void)threads;
+    for (int prof = 0; prof < 2; prof++) {
+        const void *fn = kernel_for(wtype, prof != 0);
+        if (!fn) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
-cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, cudaStream_t st)
+cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, bool prof, cudaStream_t st)
 {
     StreamParams q = p;
     void *args[] = {(void *)&q};
-    const void *fn = kernel_for(p.wtype, plan.threads);
+    const void *fn = kernel_for(p.wtype, prof);
     if (!fn) return cudaErrorInvalidValue;
-    // cooperative launch: guarantees all CTAs are co-resident (the grid barrier needs it)
+    // cooperative launch: guarantees all CTAs are co-resident (the LL hand-over polls across CTAs)
     return cudaLaunchCooperativeKernel(fn, dim3(plan.grid), dim3(plan.threads), args,
                                        (size_t)plan.smem_bytes, st);
 }

@@ -248,3 +248,22 @@ def test_cli_ak_packed_model(tmp_path):
     # without -s there is no vocabulary: refuse like the reference's other fatal conditions (print + stop)
     r = subprocess.run([hostapi.LLM_BIN, "--ak", "-m", p, "-n", "4"], capture_output=True, timeout=60)
     assert r.returncode != 0 and b"tokenizer" in r.stdout
+
+
+def test_profile_flag_selects_the_instrumented_kernel():
+    """LLMF90_FLAG_PROFILE: same logits bit for bit, per-phase timers filled; without it every forward goes
+    to the reference's bucket 4 (llama2.f90:407-410 prints five buckets)."""
+    cfg = Config(**SMALL, wtype=F16)
+    w = fx.synth_weights(cfg, 9)
+    with capi.Engine(w) as eng:
+        a = [eng.transformer(5 + i, 1 + i).copy() for i in range(6)]
+        assert sum(eng.phase_times().values()) == 0.0
+        t = eng.times()
+        assert t[3] > 0 and t[0] == 0 and t[4] == 0
+    with capi.Engine(w, profile=True) as eng:
+        b = [eng.transformer(5 + i, 1 + i).copy() for i in range(6)]
+        ph = eng.phase_times()
+        assert ph["w13_mv"] > 0 and ph["qkv_pro"] > 0 and ph["cls_mv"] > 0
+        t = eng.times()
+        assert (t > 0).all()
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

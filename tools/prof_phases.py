@@ -5,7 +5,7 @@ from llm.f90_b200.layout import Config, TINYLLAMA, LLAMA2_7B, WTYPE_BY_NAME
 model, wt = sys.argv[1], sys.argv[2]
 cfg = Config(**(TINYLLAMA if model == 'tinyllama' else LLAMA2_7B), wtype=WTYPE_BY_NAME[wt])
 w = fx.synth_weights_tiled(cfg, 0)
-eng = capi.Engine(w)
+eng = capi.Engine(w, profile='--noprof' not in sys.argv)
 prompt = [5, 6, 7, 8, 9, 10, 11, 12, 13]
 for _ in range(2): eng.generate_greedy(prompt, 128)
 eng.reset()
