@@ -489,7 +489,8 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.ph[2] = mk(E.d_w13, 2 * hid, emb, 2);
         p.ph[3] = mk(E.d_w2, emb, hid, 1);
         p.ph[4] = mk(E.d_wcls, Vl, emb, 1);
-        int target_slot = 24576, max_slots = 16, cons_warps = 12;
+        int target_slot = 24576, max_slots = 5, cons_warps = 12;  // 5 slots: measured optimum (a deeper ring
+        // prefetches more but its queued bulk loads delay the hand-over traffic: 4: 1.039, 5: 1.010, 6: 1.033, 7: 1.10 ms)
         if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
         if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
         if (const char *s = getenv("LLMF90_CONS_WARPS")) cons_warps = atoi(s);
@@ -500,6 +501,8 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             release_all();
             return fail("model rows do not fit the shared-memory ring (row stride too large)");
         }
+        p.lookahead = 0;
+        if (const char *s = getenv("LLMF90_LOOKAHEAD")) p.lookahead = std::max(0, atoi(s));
         p.pf_stages = 0;
         if (const char *s = getenv("LLMF90_PF_STAGES")) p.pf_stages = std::max(0, atoi(s));
         p.pace = 38;  // ~1.15x the per-SM fair share of the measured HBM bandwidth (23 B/cycle)
@@ -543,6 +546,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         }
         p.kc = E.d_kc; p.vc = E.d_vc;
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
+        p.lookahead = std::min(p.lookahead, E.plan.n_slots - 1);
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.n_cons_warps = E.plan.n_cons_warps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
         {

@@ -75,8 +75,9 @@ constexpr int MAX_TP = 8;
 struct SchedStage {
     unsigned long long src;  // device address (layer 0)
     unsigned int bytes;
-    unsigned int stride16;   // bytes between layers / 16
+    unsigned int stride16;   // bytes between layers / 16; bit 31: first stage of a phase (SCHED_PHASE_START)
 };
+constexpr unsigned int SCHED_PHASE_START = 0x80000000u;
 
 // All dimensions are THIS GPU's share under tensor parallelism (tp ranks): H / KVH / kv / hid / V /
 // nqkv / att_dim are local, emb is the full residual width (the residual stream is replicated).
@@ -121,6 +122,8 @@ struct StreamParams {
     int trace_layer;
     const SchedStage *sched; // [grid][sched_stride] per-CTA stage lists (entry 0 = embedding row 0: + (token-1) * bytes)
     int sched_stride;        // entries per CTA (padded)
+    int lookahead;           // stages of the NEXT phase the producer may issue while the consumers are still in
+                             // the current one (0 = no limit): queued bulk loads delay the hand-over traffic
     int pf_stages;           // L2 prefetch distance beyond the ring, in stages (0 = off); used only while HBM would idle
     int pace;                // producer pacing: SM cycles per KB issued (0 = unpaced)
     int do_argmax;           // fuse maxloc after the classifier and write tokpos = {argmax, pos+1}

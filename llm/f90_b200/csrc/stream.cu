@@ -45,8 +45,13 @@ constexpr int MAX_CONS_WARPS = 12;  // + 1 producer warp = 416 threads -> 128 re
 constexpr int CONS_BAR = 1;         // named barrier id used by the consumer warps
 constexpr int GW = 4;               // consumer warps per group: a group of GW warps consumes one ring stage
 constexpr int NG = MAX_CONS_WARPS / GW;  // groups; group g owns the stages whose schedule index is g (mod NG)
-// The ring has a multiple of NG slots, so a slot always belongs to the same group: a group sees
-// the uses of its slots in order and the one-bit mbarrier phase parity can never alias.
+// Successive uses of a slot may belong to different groups, and a group may start waiting for use
+// k + 1 of a slot before use k has landed: with ONE full barrier per slot the one-bit mbarrier phase
+// parity would alias (a wait on the parity of use k + 1 returns at once while use k is in flight).
+// Every slot therefore has TWO full barriers, for its even and its odd uses: a waiter for use k + 1
+// can only be confused with use k - 1, which was consumed before use k could even be issued.
+// Use k of a slot: barrier (k & 1), parity ((k >> 1) & 1).  (The empty barriers have one waiter,
+// the producer, that sees the uses of a slot in order.)
 
 struct SmemView {
     uint8_t *ring;
@@ -83,9 +88,9 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
     off += (size_t)P.emb * 4;
     v.red = reinterpret_cast<float *>(smem + off);
     off += 64 * 4;
-    v.full = reinterpret_cast<uint64_t *>(smem + off);
-    v.empty = v.full + MAX_SLOTS;
-    off += 2 * MAX_SLOTS * 8;
+    v.full = reinterpret_cast<uint64_t *>(smem + off);  // [2][MAX_SLOTS]: even / odd uses of a slot
+    v.empty = v.full + 2 * MAX_SLOTS;
+    off += 3 * MAX_SLOTS * 8;
     v.sched = reinterpret_cast<const SchedStage *>(smem + off);
     return v;
 }
@@ -93,7 +98,7 @@ __device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
 static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats, int emb, int sched_entries)
 {
     return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 + (size_t)emb * 4 + 64 * 4 +
-           2 * MAX_SLOTS * 8 + (size_t)sched_entries * sizeof(SchedStage);
+           3 * MAX_SLOTS * 8 + (size_t)sched_entries * sizeof(SchedStage);
 }
 
 __host__ __device__ inline void cta_rows(const PhaseW &ph, int cta, int G, int &r0, int &r1)
@@ -120,6 +125,9 @@ __device__ __forceinline__ void ring_advance(RingPos &p, uint32_t n, uint32_t ns
     while (p.mod >= ns) { p.mod -= ns; p.div++; }
 }
 
+__device__ __forceinline__ uint64_t *full_bar(uint64_t *full, uint32_t slot, uint32_t use) { return full + (use & 1u) * MAX_SLOTS + slot; }
+__device__ __forceinline__ uint32_t full_par(uint32_t use) { return (use >> 1) & 1u; }
+
 // ------------------------------------------------------------------ producer
 // Segment order of a CTA's schedule: the embedding row of the token; per layer: rms_att vector,
 // its rows of QKV, of WO, rms_ffn vector, its rows of W13, of W2; then rms_final vector, CLS.
@@ -137,13 +145,15 @@ __device__ __noinline__ void producer_loop(const StreamParams &P, const SmemView
     // this CTA's section sizes follow from its row ranges (the host list was built from the same cta_rows)
     const int n_layer = 2 + cp->nst[0] + cp->nst[1] + cp->nst[2] + cp->nst[3];
     const int e_layer_end = 1 + n_layer, total = 1 + P.L * n_layer + 1 + cp->nst[4];
-    uint32_t slot = 0, par = 1;
+    uint32_t slot = 0, par = 1, use = 0;  // par: parity of the empty barrier to wait for; use: use count of the slots
     int e = 0, l = 0;
     // L2 prefetch cursor (pf_stages > 0): while the ring is full AND everything issued has landed --
     // the consumers sit in a hand-over and HBM would idle -- the stages beyond the ring are pulled
     // into L2, so that the ring later refills at L2 speed.
     int ps = 0, pe = 0, pl = 0;
-    uint32_t last_slot = 0, last_par = 0;
+    uint32_t last_slot = 0, last_use = 0;
+    uint32_t bslot = 0xffffffffu, bpar = 0, par_of_last = 0;  // empty barrier (slot, parity) of the last stage of the previous phase
+    int ahead = 0;
     // pacing: issue at most one KB per `pace` SM cycles (0 = unpaced).  Every byte in flight
     // beyond bandwidth x latency only adds queueing delay in front of the latency-critical LL
     // traffic of the phase hand-overs; a paced producer keeps the queues short.
@@ -151,7 +161,8 @@ __device__ __noinline__ void producer_loop(const StreamParams &P, const SmemView
     auto stage_addr = [&](int ee, int ll, int ss, uint32_t &bytes) {
         const uint4 st = tab[ee];
         bytes = st.z;
-        unsigned long long src = ((unsigned long long)st.y << 32 | st.x) + ((unsigned long long)st.w << 4) * (unsigned)ll;
+        unsigned long long src = ((unsigned long long)st.y << 32 | st.x) +
+                                 ((unsigned long long)(st.w & ~SCHED_PHASE_START) << 4) * (unsigned)ll;
         if (ss == 0) src += (unsigned long long)(token - 1) * bytes;  // the token's embedding row
         return src;
     };
@@ -159,11 +170,20 @@ __device__ __noinline__ void producer_loop(const StreamParams &P, const SmemView
     for (int s = 0; s < total; s++) {
         uint32_t bytes;
         const unsigned long long src = stage_addr(e, l, s, bytes);
+        // hand-over protection: at most `lookahead` stages of the next phase are issued before the last
+        // stage of the current phase has been released by the consumers
+        if (P.lookahead > 0 && s > 0) {
+            if (tab[e].w & SCHED_PHASE_START) { ahead = 0; bslot = last_slot; bpar = par_of_last; }
+            if (++ahead > P.lookahead && bslot != 0xffffffffu) {
+                while (!mbar_test(&sv.empty[bslot], bpar)) { }
+                bslot = 0xffffffffu;
+            }
+        }
         if (ps <= s) { ps = s + 1; pe = e; pl = l; if (++pe == e_layer_end && pl + 1 < P.L) { pe = 1; pl++; } }
         if (++e == e_layer_end && l + 1 < P.L) { e = 1; l++; }
         if (P.pf_stages > 0) {
             while (!mbar_test(&sv.empty[slot], par)) {
-                if (ps < total && ps < s + (int)ns + P.pf_stages && s > 0 && mbar_test(&sv.full[last_slot], last_par)) {
+                if (ps < total && ps < s + (int)ns + P.pf_stages && s > 0 && mbar_test(full_bar(sv.full, last_slot, last_use), full_par(last_use))) {
                     long long now = clock64();
                     if (now >= next_ok) {
                         uint32_t pb;
@@ -183,10 +203,11 @@ __device__ __noinline__ void producer_loop(const StreamParams &P, const SmemView
             while (now < next_ok) now = clock64();
             next_ok = now + (((long long)bytes * P.pace) >> 10);
         }
-        mbar_arrive_expect_tx(&sv.full[slot], bytes);
-        bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, reinterpret_cast<const void *>(src), bytes, &sv.full[slot], pol);
-        last_slot = slot; last_par = par ^ 1u;  // parity of the use just issued
-        if (++slot == ns) { slot = 0; par ^= 1u; }
+        uint64_t *fb = full_bar(sv.full, slot, use);
+        mbar_arrive_expect_tx(fb, bytes);
+        bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, reinterpret_cast<const void *>(src), bytes, fb, pol);
+        last_slot = slot; last_use = use; par_of_last = par ^ 1u;  // its release completes the empty phase of parity (use & 1)
+        if (++slot == ns) { slot = 0; par ^= 1u; use++; }
         *issued = s + 1;  // progress of the copy cursor, for the per-CTA trace
     }
 }
@@ -231,7 +252,7 @@ struct ConsumeArgs {
     uint64_t *full, *empty;
     long long *wait_cycles;  // optional trace accumulators (or null); warp-uniform
     long long *stamps;       // optional 8 clock stamps of this call (trace), or null
-    int nrows, nst, slot_bytes, n_slots, slot0, par0, gmod0, warp, lane;
+    int nrows, nst, slot_bytes, n_slots, slot0, use0, gmod0, warp, lane;  // use0: use count of slot0 (mod 4)
 };
 
 // four pending lane-partial sums -> four row results (see consume_phase)
@@ -266,7 +287,7 @@ struct Pending {
 template <bool PROF>
 struct StageWalk {
     const ConsumeArgs &a;
-    uint32_t slot, par;
+    uint32_t slot, use;
     int s;  // phase-relative index of the group's next stage
     long long tc0 = 0;
     int nwaits = 0;
@@ -282,20 +303,20 @@ struct StageWalk {
         if (first < 0) first += NG;
         s = first;
         slot = (uint32_t)a.slot0 + (uint32_t)first;
-        par = (uint32_t)a.par0;
-        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; par ^= 1u; }
+        use = (uint32_t)a.use0;
+        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; use++; }
     }
     __device__ __forceinline__ bool more() const { return s < a.nst; }
     __device__ __forceinline__ const uint8_t *wait()
     {
         if (PROF && a.wait_cycles) {
             const long long w0 = clock64();
-            mbar_wait(&a.full[slot], par, 2);
+            mbar_wait(full_bar(a.full, slot, use), full_par(use), 2);
             tc0 = clock64();
             if (a.lane == 0) a.wait_cycles[0] += tc0 - w0;
             if (nwaits++ == 0) stampc(2);
         } else {
-            mbar_wait(&a.full[slot], par, 2);
+            mbar_wait(full_bar(a.full, slot, use), full_par(use), 2);
         }
         return a.ring + (size_t)slot * a.slot_bytes;
     }
@@ -307,7 +328,7 @@ struct StageWalk {
         if (PROF && a.wait_cycles && nwaits == 1) stampc(3);
         s += NG;
         slot += NG;
-        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; par ^= 1u; }
+        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; use++; }
     }
 };
 
@@ -662,7 +683,7 @@ __device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4,
 __device__ __forceinline__ const uint8_t *vec_stage_wait(const StreamParams &P, const SmemView &sv,
                                                          const RingPos &at)
 {
-    mbar_wait(&sv.full[at.mod], at.div & 1u, 3);
+    mbar_wait(full_bar(sv.full, at.mod, at.div), full_par(at.div), 3);
     return sv.ring + (size_t)at.mod * P.slot_bytes;
 }
 // call in stage order, after a cons_sync that follows the last read of the stage
@@ -972,7 +993,9 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const Smem
     }
 }
 
-// xs = attention output (all heads), merging the position splits (n_splits > 1; long contexts only)
+// xs = attention output (all heads), merging the position splits (n_splits > 1).  A thread owns one
+// float4 of the output; the {m, l} pair and the float4 of all S partial records are requested
+// together (one L2 round trip per polling round).
 template <int WT>
 __device__ __noinline__ void load_x_attn(const StreamParams &P, uint32_t ep, const SmemView sv, const Cons c)
 {
@@ -984,26 +1007,39 @@ __device__ __noinline__ void load_x_attn(const StreamParams &P, uint32_t ep, con
         const int j = valid ? jj : n4 - 1;
         const int h = (4 * j) >> hs_shift, d = (4 * j) & (hs - 1);
         const unsigned long long *part = P.ll_part + (size_t)h * S * pstride;
-        float M = -INFINITY, ms[8], ls[8];
-        float4 av[8];
+        unsigned long long ml[8][2], av[8][4];
+        bool ok;
+        LLMF90_WD_DECL;
+        do {
+            LLMF90_WD_CHECK(107, j, ep)
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                if (s < S) {
+                    const unsigned long long *rec = part + (size_t)s * pstride;
+                    ll_load2(rec, ml[s][0], ml[s][1]);
+                    ll_load2(rec + ATT_PSTRIDE_PAD + d, av[s][0], av[s][1]);
+                    ll_load2(rec + ATT_PSTRIDE_PAD + d + 2, av[s][2], av[s][3]);
+                }
+            ok = true;
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                if (s < S)
+                    ok = ok && ll_ok(ml[s][0], ep) && ll_ok(ml[s][1], ep) && ll_ok(av[s][0], ep) && ll_ok(av[s][1], ep) &&
+                         ll_ok(av[s][2], ep) && ll_ok(av[s][3], ep);
+        } while (!ok);
+        float M = -INFINITY;
 #pragma unroll
         for (int s = 0; s < 8; s++)
-            if (s < S) {
-                float ml[2];
-                ll_waitv<2>(part + (size_t)s * pstride, 0, ep, ml);
-                ms[s] = ml[0]; ls[s] = ml[1];
-                av[s] = ll_wait4(part + (size_t)s * pstride, ATT_PSTRIDE_PAD + d, ep);
-                M = fmaxf(M, ms[s]);
-            }
+            if (s < S) M = fmaxf(M, ll_val(ml[s][0]));
         float den = 0.f;
         float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int s = 0; s < 8; s++)
-            if (s < S && ms[s] > -INFINITY) {
-                const float w = expf(ms[s] - M);
-                den = fmaf(ls[s], w, den);
-                num.x = fmaf(av[s].x, w, num.x); num.y = fmaf(av[s].y, w, num.y);
-                num.z = fmaf(av[s].z, w, num.z); num.w = fmaf(av[s].w, w, num.w);
+            if (s < S && ll_val(ml[s][0]) > -INFINITY) {
+                const float w = expf(ll_val(ml[s][0]) - M);
+                den = fmaf(ll_val(ml[s][1]), w, den);
+                num.x = fmaf(ll_val(av[s][0]), w, num.x); num.y = fmaf(ll_val(av[s][1]), w, num.y);
+                num.z = fmaf(ll_val(av[s][2]), w, num.z); num.w = fmaf(ll_val(av[s][3]), w, num.w);
             }
         store_x4<WT>(sv.xs, P.att_dim, jj, make_float4(num.x / den, num.y / den, num.z / den, num.w / den), valid);
     }
@@ -1028,7 +1064,7 @@ __device__ __noinline__ void prof_stamp(const StreamParams &P, const SmemView sv
     RingPos at = cs.pos;
     int landed = 0;
     for (int i = 0; i < P.n_slots; i++) {
-        landed += mbar_test(&sv.full[at.mod], at.div & 1u) ? 1 : 0;
+        landed += mbar_test(full_bar(sv.full, at.mod, at.div), full_par(at.div)) ? 1 : 0;
         ring_advance(at, 1u, (uint32_t)P.n_slots);
     }
     row[48 + k] = (unsigned long long)(cs.pos.div * (uint32_t)P.n_slots + cs.pos.mod) | ((unsigned long long)landed << 32);
@@ -1136,6 +1172,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     if (threadIdx.x == 32) {
         for (int i = 0; i < P.n_slots; i++) {
             mbar_init(&sv.full[i], 1);
+            mbar_init(&sv.full[MAX_SLOTS + i], 1);
             mbar_init(&sv.empty[i], (uint32_t)GW);
         }
         fence_mbar_init();
@@ -1226,7 +1263,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             ca.wait_cycles = (tracing && c.warp == 0 && l == P.trace_layer && ph < 4) ? &pf.twait[ph] : nullptr;
             ca.stamps = ca.wait_cycles ? &pf.twait[12 + 8 * ph] : nullptr;
             ca.nrows = nr; ca.nst = cp.nst[ph]; ca.slot_bytes = P.slot_bytes; ca.n_slots = P.n_slots;
-            ca.slot0 = (int)cs.pos.mod; ca.par0 = (int)(cs.pos.div & 1u); ca.gmod0 = (int)cs.gmod;
+            ca.slot0 = (int)cs.pos.mod; ca.use0 = (int)(cs.pos.div & 3u); ca.gmod0 = (int)cs.gmod;
             ca.warp = c.warp; ca.lane = c.lane;
             if (ca.stamps && c.lane == 0) ca.stamps[7] = clock64();  // before the call
             consume_phase<WT, PROF>(ca);
@@ -1389,7 +1426,6 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
     while (n_slots > 0 &&
            smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb, sched_entries) > (size_t)max_smem_optin)
         n_slots--;
-    n_slots = n_slots / NG * NG;  // a slot always belongs to the same group (see NG)
     if (n_slots < NG) return 1;
     out->n_slots = n_slots;
     out->slot_bytes = slot;
@@ -1413,14 +1449,19 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
     for (int cta = 0; cta < grid; cta++) {
         SchedStage *t = tab + (size_t)cta * cap;
         int n = 0;
+        bool start = true;  // the next stage pushed is the first of a phase (its vector stage, if it has one)
         auto vec = [&](const void *ptr, unsigned bytes, size_t layer_stride) {
-            t[n].src = (unsigned long long)ptr; t[n].bytes = bytes; t[n].stride16 = (unsigned)(layer_stride >> 4); n++;
+            t[n].src = (unsigned long long)ptr; t[n].bytes = bytes;
+            t[n].stride16 = (unsigned)(layer_stride >> 4) | (start ? SCHED_PHASE_START : 0u);
+            start = false;
+            n++;
         };
         auto rows = [&](int ph) {
             int r0, r1;
             cta_rows(p.ph[ph], cta, grid, r0, r1);
             const PhaseW &w = p.ph[ph];
             const size_t ls = ph < 4 ? (size_t)w.layer_stride : 0;
+            if (ph == 1 || ph == 3) start = true;  // Wo / W2 have no vector stage: the phase starts with its rows
             if (w.spg > 0) {
                 // tiled q4_0: spg stages per row group of 16, stage i = groups [i ngrp / spg, (i + 1) ngrp / spg)
                 for (int rg = r0 >> 4; rg < (r1 >> 4); rg++)
@@ -1436,12 +1477,15 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
             }
         };
         vec(p.emb_table, (unsigned)row_stride_bytes(p.wtype, p.emb), 0);  // row 0; the kernel adds (token - 1) rows
+        start = true;
         vec(p.rms_att, (unsigned)p.emb * 4u, (size_t)p.emb * 4u);
         rows(0);
         rows(1);
+        start = true;
         vec(p.rms_ffn, (unsigned)p.emb * 4u, (size_t)p.emb * 4u);
         rows(2);
         rows(3);
+        start = true;
         vec(p.rms_final, (unsigned)p.emb * 4u, 0);
         rows(4);
     }
