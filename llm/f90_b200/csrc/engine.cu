@@ -546,6 +546,8 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         }
         p.kc = E.d_kc; p.vc = E.d_vc;
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
+        if (const char *s = getenv("LLMF90_SMEM_PAD"))  // experiment: unused shared memory (shrinks L1)
+            E.plan.smem_bytes = std::min(E.plan.smem_bytes + atoi(s), smem_optin - 2048);
         p.lookahead = std::min(p.lookahead, E.plan.n_slots - 1);
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.n_cons_warps = E.plan.n_cons_warps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;

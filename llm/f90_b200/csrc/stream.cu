@@ -64,6 +64,9 @@ struct SmemView {
 struct CtaPlan {
     PhaseW ph[5];
     int r0[5], r1[5], nst[5];
+    // shared-memory geometry for the out-of-line pieces (they take this plan instead of a stack copy of
+    // SmemView: local memory goes through what little L1 the ring leaves)
+    int off_xs, off_res, off_xres, off_red, off_full, slot_bytes, n_slots, n_cons_warps;
 };
 
 // profiling state of a CTA (shared memory): phase timers of the timer thread, trace scratch
@@ -528,9 +531,22 @@ __device__ __forceinline__ void consume_q4(const ConsumeArgs &a)
     }
 }
 
+// Scalar parameters only (they travel in registers): a by-value struct would be written to and read
+// back from local memory by every thread, four times per layer.
 template <int WT, bool PROF>
-__device__ __noinline__ void consume_phase(const ConsumeArgs a)
+__device__ __noinline__ void consume_phase(const CtaPlan *cp, Prof *pf, int ph, uint32_t cursor /* slot0 | use0 << 8 | gmod0 << 16 | trace << 24 */)
 {
+    extern __shared__ __align__(128) uint8_t smem[];
+    ConsumeArgs a;
+    a.ph = &cp->ph[ph]; a.ring = smem;
+    a.xs = reinterpret_cast<const float *>(smem + cp->off_xs);
+    a.res = reinterpret_cast<float *>(smem + cp->off_res);
+    a.full = reinterpret_cast<uint64_t *>(smem + cp->off_full); a.empty = a.full + 2 * MAX_SLOTS;
+    a.nrows = cp->r1[ph] - cp->r0[ph]; a.nst = cp->nst[ph]; a.slot_bytes = cp->slot_bytes; a.n_slots = cp->n_slots;
+    a.slot0 = (int)(cursor & 255u); a.use0 = (int)((cursor >> 8) & 255u); a.gmod0 = (int)((cursor >> 16) & 255u);
+    a.warp = (int)(threadIdx.x >> 5); a.lane = (int)(threadIdx.x & 31);
+    a.wait_cycles = (PROF && (cursor >> 24)) ? &pf->twait[ph] : nullptr;
+    a.stamps = a.wait_cycles ? &pf->twait[12 + 8 * ph] : nullptr;
     if (PROF && a.stamps && a.lane == 0) a.stamps[0] = clock64();
     if constexpr (WT != WT_Q4_0) {
         // units per lane per row, rounded up to an instantiated register budget
@@ -605,27 +621,25 @@ __device__ __forceinline__ float4 ll_wait4(const unsigned long long *buf, int i,
     } while (!(ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep)));
     return make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
 }
-// poll N consecutive float4 (i % 4 == 0): all requests of a round in flight together
+// poll N consecutive float4 (i % 4 == 0); values are unpacked as they are checked, so that the raw
+// {value, epoch} words do not all stay live (register pressure of the attention phase)
 template <int N>
 __device__ __forceinline__ void ll_wait4n(const unsigned long long *buf, int i, uint32_t ep, float4 (&o)[N])
 {
-    unsigned long long w[N][4];
     bool ok;
     LLMF90_WD_DECL;
     do {
         LLMF90_WD_CHECK(102, i, ep)
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            ll_load2(buf + i + 4 * k, w[k][0], w[k][1]);
-            ll_load2(buf + i + 4 * k + 2, w[k][2], w[k][3]);
-        }
         ok = true;
 #pragma unroll
-        for (int k = 0; k < N; k++)
-            ok = ok && ll_ok(w[k][0], ep) && ll_ok(w[k][1], ep) && ll_ok(w[k][2], ep) && ll_ok(w[k][3], ep);
+        for (int k = 0; k < N; k++) {
+            unsigned long long a, b, c, d;
+            ll_load2(buf + i + 4 * k, a, b);
+            ll_load2(buf + i + 4 * k + 2, c, d);
+            ok = ok && ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep);
+            o[k] = make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
+        }
     } while (!ok);
-#pragma unroll
-    for (int k = 0; k < N; k++) o[k] = make_float4(ll_val(w[k][0]), ll_val(w[k][1]), ll_val(w[k][2]), ll_val(w[k][3]));
 }
 // poll NV (<= 4) consecutive floats (i % NV == 0)
 template <int NV>
@@ -680,18 +694,32 @@ __device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4,
 
 // ---- vector stages: every consumer thread waits for the stage and reads what it needs; after
 // the consumer-wide barrier that ends the prologue the warps of the group that owns it hand it back
-__device__ __forceinline__ const uint8_t *vec_stage_wait(const StreamParams &P, const SmemView &sv,
-                                                         const RingPos &at)
+// (the out-of-line pieces and the phase loop address shared memory through the plan's offsets instead
+// of keeping a SmemView alive: whatever is live across a call is spilled around it)
+__device__ __forceinline__ uint8_t *smem_base()
 {
-    mbar_wait(full_bar(sv.full, at.mod, at.div), full_par(at.div), 3);
-    return sv.ring + (size_t)at.mod * P.slot_bytes;
+    extern __shared__ __align__(128) uint8_t smem[];
+    return smem;
+}
+__device__ __forceinline__ uint64_t *plan_full(const CtaPlan *cp) { return reinterpret_cast<uint64_t *>(smem_base() + cp->off_full); }
+__device__ __forceinline__ uint64_t *plan_empty(const CtaPlan *cp) { return plan_full(cp) + 2 * MAX_SLOTS; }
+__device__ __forceinline__ Cons plan_cons(const CtaPlan *cp)
+{
+    Cons c;
+    c.tid = (int)threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
+    c.nw = cp->n_cons_warps; c.nt = c.nw * 32;
+    return c;
+}
+__device__ __forceinline__ const uint8_t *vec_stage_wait(const CtaPlan *cp, const RingPos &at)
+{
+    mbar_wait(full_bar(plan_full(cp), at.mod, at.div), full_par(at.div), 3);
+    return smem_base() + (size_t)at.mod * cp->slot_bytes;
 }
 // call in stage order, after a cons_sync that follows the last read of the stage
-__device__ __forceinline__ void vec_stage_release(const StreamParams &P, const SmemView &sv, const Cons &c,
-                                                  CState &cs)
+__device__ __forceinline__ void vec_stage_release(const CtaPlan *cp, CState &cs)
 {
-    if (c.lane == 0 && (uint32_t)(c.warp / GW) == cs.gmod) mbar_arrive(&sv.empty[cs.pos.mod]);
-    cons_advance(cs, 1u, (uint32_t)P.n_slots);
+    if ((threadIdx.x & 31) == 0 && (uint32_t)(threadIdx.x >> 5) / GW == cs.gmod) mbar_arrive(&plan_empty(cp)[cs.pos.mod]);
+    cons_advance(cs, 1u, (uint32_t)cp->n_slots);
 }
 
 // ---- activation-vector prologue, one routine for all phases.  Every CTA needs the whole vector;
@@ -765,11 +793,19 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
                        row_elem(row, wtype, cols, 4 * j4 + 2), row_elem(row, wtype, cols, 4 * j4 + 3));
 }
 
+// (out of line with scalar parameters: its registers do not add to the pressure of the phase loop)
 template <int WT>
-__device__ __forceinline__ float gather_x(const unsigned long long *src, int nsrc, uint32_t ep, int n, bool norm,
-                                          const uint8_t *emb_row, const float *wn /* shared */,
-                                          const StreamParams &P, const SmemView &sv, const Cons &c)
+__device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long long *src, int nsrc, uint32_t ep, int n,
+                                       int norm, int wtype, const uint8_t *emb_row, const float *wn /* shared */)
 {
+    extern __shared__ __align__(128) uint8_t smem[];
+    SmemView sv;
+    sv.xs = reinterpret_cast<float *>(smem + cp->off_xs);
+    sv.xres = reinterpret_cast<float *>(smem + cp->off_xres);
+    sv.red = reinterpret_cast<float *>(smem + cp->off_red);
+    Cons c;
+    c.tid = (int)threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
+    c.nw = cp->n_cons_warps; c.nt = c.nw * 32;
     constexpr int PV = 2;
     const int n4 = n >> 2;
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
@@ -782,7 +818,7 @@ __device__ __forceinline__ float gather_x(const unsigned long long *src, int nsr
 #pragma unroll
             for (int k = 0; k < PV; k++) {
                 const int j = base + c.tid + k * c.nt;
-                v[k] = emb_row4(emb_row, P.wtype, n, min(j, n4 - 1));
+                v[k] = emb_row4(emb_row, wtype, n, min(j, n4 - 1));
             }
         } else {
             ll_gather<PV>(src, n4, base, ep, c, v);
@@ -857,9 +893,14 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 }
 
 template <int HS>
-__device__ __noinline__ void attention_phase_t(const StreamParams &P, const SmemView sv, const Cons c, int layer,
-                                               int pos, uint32_t ep)
+__device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaPlan *cp, int layer, int pos, uint32_t ep)
 {
+    extern __shared__ __align__(128) uint8_t smem[];
+    SmemView sv;
+    sv.xs = reinterpret_cast<float *>(smem + cp->off_xs);
+    Cons c;
+    c.tid = (int)threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
+    c.nw = cp->n_cons_warps; c.nt = c.nw * 32;
     constexpr int hs = HS, vec = HS >> 5;  // HS in {32, 64, 128}
     constexpr int q4n = HS >> 4;           // float4 per lane of a quarter head: 2, 4, 8
     const int S = P.n_splits;
@@ -997,8 +1038,11 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const Smem
 // float4 of the output; the {m, l} pair and the float4 of all S partial records are requested
 // together (one L2 round trip per polling round).
 template <int WT>
-__device__ __noinline__ void load_x_attn(const StreamParams &P, uint32_t ep, const SmemView sv, const Cons c)
+__device__ __noinline__ void load_x_attn(const StreamParams &P, const CtaPlan *cp, uint32_t ep)
 {
+    SmemView sv;
+    sv.xs = reinterpret_cast<float *>(smem_base() + cp->off_xs);
+    const Cons c = plan_cons(cp);
     const int S = P.n_splits;
     const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.att_dim >> 2;
     const int hs_shift = hs == 64 ? 6 : (hs == 128 ? 7 : 5);
@@ -1056,8 +1100,12 @@ __device__ __noinline__ void prof_lap(Prof *pf, int bucket)
 }
 // per-CTA trace of one layer: globaltimer stamp, producer / consumer ring cursors and the number
 // of landed stages at phase edge k
-__device__ __noinline__ void prof_stamp(const StreamParams &P, const SmemView sv, const CState cs, Prof *pf, int k)
+__device__ __noinline__ void prof_stamp(const StreamParams &P, const CtaPlan *cp, uint32_t pos_mod, uint32_t pos_div, Prof *pf, int k)
 {
+    SmemView sv;
+    sv.full = plan_full(cp);
+    CState cs;
+    cs.pos.mod = pos_mod; cs.pos.div = pos_div;
     unsigned long long *row = P.trace + (size_t)blockIdx.x * 128;
     row[k] = globaltimer_ns();
     row[32 + k] = (unsigned long long)pf->prod_issued;
@@ -1073,9 +1121,11 @@ __device__ __noinline__ void prof_stamp(const StreamParams &P, const SmemView sv
 // ------------------------------------------------------------------ token tail (once per launch)
 // all-gathered logits must have landed on every rank before any rank's kernel ends (tp > 1), then
 // maxloc(logits) (llama2.f90:388): first maximum wins at every reduction level
-__device__ __noinline__ void token_tail(const StreamParams &P, const SmemView sv, const Cons c, float best, int bidx,
-                                        int pos)
+__device__ __noinline__ void token_tail(const StreamParams &P, const CtaPlan *cp, float best, int bidx, int pos)
 {
+    SmemView sv;
+    sv.red = reinterpret_cast<float *>(smem_base() + cp->off_red);
+    const Cons c = plan_cons(cp);
     const uint32_t epl = P.ep_base + (uint32_t)P.L + 1u;
     const int G = (int)gridDim.x;
     if (P.tp > 1) {
@@ -1156,6 +1206,14 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     __shared__ float2 rope[64];
     __shared__ Prof pf;
     if (threadIdx.x == 0) pf.prod_issued = 0;
+    if (threadIdx.x == 5) {
+        cp.off_xs = (int)(reinterpret_cast<uint8_t *>(sv.xs) - smem);
+        cp.off_res = (int)(reinterpret_cast<uint8_t *>(sv.res) - smem);
+        cp.off_xres = (int)(reinterpret_cast<uint8_t *>(sv.xres) - smem);
+        cp.off_red = (int)(reinterpret_cast<uint8_t *>(sv.red) - smem);
+        cp.off_full = (int)(reinterpret_cast<uint8_t *>(sv.full) - smem);
+        cp.slot_bytes = P.slot_bytes; cp.n_slots = P.n_slots; cp.n_cons_warps = P.n_cons_warps;
+    }
     if (threadIdx.x < 5) {
         const int i = threadIdx.x;
         cp.ph[i] = P.ph[i];
@@ -1190,14 +1248,12 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     }
 
     // ===================== consumer warps =====================
-    Cons c;
-    c.tid = threadIdx.x; c.warp = warp; c.lane = lane;
-    c.nw = n_cons_warps; c.nt = n_cons_warps * 32;
+    const int tid = (int)threadIdx.x, nt = n_cons_warps * 32;
     CState cs;
     cs.pos.mod = 0; cs.pos.div = 0; cs.gmod = 0;
     // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh;
     // optional per-CTA trace of one layer (debug/profiling)
-    const bool timer = PROF && (blockIdx.x == 0 && c.tid == 0);
+    const bool timer = PROF && (blockIdx.x == 0 && tid == 0);
     const bool tracing = PROF && P.trace != nullptr;
     const unsigned long long t_ns0 = timer ? globaltimer_ns() : 0ull;
     const long long t_c0 = timer ? clock64() : 0ll;
@@ -1205,10 +1261,10 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         for (int i = 0; i < PH_COUNT; i++) pf.tacc[i] = 0;
         pf.tmark = t_c0;
     }
-    if (tracing && c.tid == 0)
+    if (tracing && tid == 0)
         for (int i = 0; i < 44; i++) pf.twait[i] = 0;
 #define LAP(b) do { if constexpr (PROF) { if (timer) prof_lap(&pf, (b)); } } while (0)
-#define STAMP(l_, k_) do { if constexpr (PROF) { if (tracing && c.tid == 0 && (l_) == P.trace_layer) prof_stamp(P, sv, cs, &pf, (k_)); } } while (0)
+#define STAMP(l_, k_) do { if constexpr (PROF) { if (tracing && tid == 0 && (l_) == P.trace_layer) prof_stamp(P, &cp, cs.pos.mod, cs.pos.div, &pf, (k_)); } } while (0)
     const int half_mask = (P.hs >> 1) - 1;
     const uint32_t ns = (uint32_t)P.n_slots;
     const int nrep = P.ll_rep, rep = (int)blockIdx.x % nrep;  // LL vector replicas; the one this CTA polls
@@ -1237,42 +1293,36 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             const uint8_t *emb_row = nullptr;
             RingPos at = cs.pos;
             if (q == 0) {
-                emb_row = vec_stage_wait(P, sv, at);
+                emb_row = vec_stage_wait(&cp, at);
                 ring_advance(at, 1u, ns);
             }
-            const float *wn = reinterpret_cast<const float *>(vec_stage_wait(P, sv, at));
-            rscale = gather_x<WT>((ph == 2 ? P.part1[P.rank] : P.part2[P.rank]) + (size_t)rep * P.tp * P.emb, P.tp,
-                                  ph == 2 ? ep : ep - 1u, P.emb, true, emb_row, wn, P, sv, c);
-            if (q == 0) vec_stage_release(P, sv, c, cs);
-            vec_stage_release(P, sv, c, cs);
+            const float *wn = reinterpret_cast<const float *>(vec_stage_wait(&cp, at));
+            rscale = gather_x<WT>(&cp, (ph == 2 ? P.part1[P.rank] : P.part2[P.rank]) + (size_t)rep * P.tp * P.emb, P.tp,
+                                  ph == 2 ? ep : ep - 1u, P.emb, 1, P.wtype, emb_row, wn);
+            if (q == 0) vec_stage_release(&cp, cs);
+            vec_stage_release(&cp, cs);
         } else if (nr > 0) {
             // (a CTA without rows in a Wo / W2 phase does not need its input vector: skipping the poll
             // also keeps it from ever lagging behind on a buffer nobody waits for it to have read)
-            if (ph == 1 && P.n_splits > 1) load_x_attn<WT>(P, ep, sv, c);
-            else gather_x<WT>(ph == 1 ? P.ll_att + (size_t)rep * P.att_dim : P.ll_hb + (size_t)rep * hb_stride, 1, ep,
-                              ph == 1 ? P.att_dim : P.hid, false, nullptr, nullptr, P, sv, c);
+            if (ph == 1 && P.n_splits > 1) load_x_attn<WT>(P, &cp, ep);
+            else gather_x<WT>(&cp, ph == 1 ? P.ll_att + (size_t)rep * P.att_dim : P.ll_hb + (size_t)rep * hb_stride, 1, ep,
+                              ph == 1 ? P.att_dim : P.hid, 0, P.wtype, nullptr, nullptr);
         }
         LAP(tb);
         STAMP(l, ph == 0 ? 1 : 3 + 3 * ph);
 
         // ---- the mat-vec: consume this CTA's stages of the phase from the ring
         {
-            ConsumeArgs ca;
-            ca.ph = &cp.ph[ph]; ca.ring = sv.ring; ca.xs = sv.xs; ca.res = sv.res;
-            ca.full = sv.full; ca.empty = sv.empty;
-            ca.wait_cycles = (tracing && c.warp == 0 && l == P.trace_layer && ph < 4) ? &pf.twait[ph] : nullptr;
-            ca.stamps = ca.wait_cycles ? &pf.twait[12 + 8 * ph] : nullptr;
-            ca.nrows = nr; ca.nst = cp.nst[ph]; ca.slot_bytes = P.slot_bytes; ca.n_slots = P.n_slots;
-            ca.slot0 = (int)cs.pos.mod; ca.use0 = (int)(cs.pos.div & 3u); ca.gmod0 = (int)cs.gmod;
-            ca.warp = c.warp; ca.lane = c.lane;
-            if (ca.stamps && c.lane == 0) ca.stamps[7] = clock64();  // before the call
-            consume_phase<WT, PROF>(ca);
-            if (ca.stamps && c.lane == 0) ca.stamps[4] = clock64();  // after the return
+            const bool trace_me = tracing && warp == 0 && l == P.trace_layer && ph < 4;
+            const uint32_t cursor = cs.pos.mod | ((cs.pos.div & 3u) << 8) | (cs.gmod << 16) | (trace_me ? 1u << 24 : 0u);
+            if (trace_me && lane == 0) pf.twait[12 + 8 * ph + 7] = clock64();  // before the call
+            consume_phase<WT, PROF>(&cp, &pf, ph, cursor);
+            if (trace_me && lane == 0) pf.twait[12 + 8 * ph + 4] = clock64();  // after the return
             cons_advance(cs, (uint32_t)cp.nst[ph], ns);
         }
         STAMP(l, ph == 0 ? 2 : 4 + 3 * ph);
-        cons_sync(c);
-        if (tracing && c.tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 5] = clock64();
+        named_bar_sync(CONS_BAR, nt);
+        if (tracing && tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 5] = clock64();
         LAP(tb + 1);
 
         // ---- epilogue.  A work item is (row pair, LL replica [, destination rank]): the planes of
@@ -1285,16 +1335,17 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             // (replica and rank counts are powers of two: shifts)
             const int nsub = ph == 4 ? 1 : ((ph & 1) ? nrep * P.tp : nrep), npairs = (nr + 1) >> 1;
             const int sub_shift = 31 - __clz(nsub);
+            const float *res = reinterpret_cast<const float *>(smem_base() + cp.off_res);
 #pragma unroll 1
-            for (int w = c.tid; w < npairs * nsub; w += c.nt) {
+            for (int w = tid; w < npairs * nsub; w += nt) {
                 const int pair = w >> sub_shift, sub = w & (nsub - 1), i = 2 * pair;
                 if (r0 + i >= rows_real) continue;  // padding rows of a tiled q4_0 matrix
                 const bool two = i + 1 < nr && r0 + i + 1 < rows_real;
-                float a = sv.res[i], b = two ? sv.res[i + 1] : 0.f;
+                float a = res[i], b = two ? res[i + 1] : 0.f;
 #pragma unroll 4
                 for (int p = 1; p < planes; p++) {
-                    a += sv.res[p * cap + i];
-                    b += two ? sv.res[p * cap + i + 1] : 0.f;
+                    a += res[p * cap + i];
+                    b += two ? res[p * cap + i + 1] : 0.f;
                 }
                 a *= rscale; b *= rscale;
                 const int r = r0 + i;
@@ -1334,27 +1385,27 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
                 }
             }
         }
-        if (tracing && c.tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 6] = clock64();
+        if (tracing && tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 6] = clock64();
         if (ph == 4) break;
         LAP(tb + 2);
         STAMP(l, ph == 0 ? 3 : 5 + 3 * ph);
 
         if (ph == 0) {
             // ---- attention (llama2.f90:574-598)
-            if (P.hs == 64) attention_phase_t<64>(P, sv, c, l, pos, ep);
-            else if (P.hs == 128) attention_phase_t<128>(P, sv, c, l, pos, ep);
-            else attention_phase_t<32>(P, sv, c, l, pos, ep);
+            if (P.hs == 64) attention_phase_t<64>(P, &cp, l, pos, ep);
+            else if (P.hs == 128) attention_phase_t<128>(P, &cp, l, pos, ep);
+            else attention_phase_t<32>(P, &cp, l, pos, ep);
             LAP(PH_ATT);
             STAMP(l, 4);
             STAMP(l, 5);
         }
-        if (ph == 3 && tracing && c.tid == 0 && l == P.trace_layer)
+        if (ph == 3 && tracing && tid == 0 && l == P.trace_layer)
             for (int i = 0; i < 44; i++)
                 P.trace[(size_t)blockIdx.x * 128 + (i < 12 ? 16 + i : 64 + i - 12)] = (unsigned long long)pf.twait[i];
     }
     LAP(PH_CLS_MV);
 
-    token_tail(P, sv, c, best, bidx, pos);
+    token_tail(P, &cp, best, bidx, pos);
     if (timer) {
         prof_lap(&pf, PH_ARGMAX);
         for (int i = 0; i < PH_COUNT; i++) P.phase_cycles[i] += (unsigned long long)pf.tacc[i];
