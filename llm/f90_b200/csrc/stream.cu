@@ -67,6 +67,13 @@ struct CtaPlan {
     // shared-memory geometry for the out-of-line pieces (they take this plan instead of a stack copy of
     // SmemView: local memory goes through what little L1 the ring leaves)
     int off_xs, off_res, off_xres, off_red, off_full, slot_bytes, n_slots, n_cons_warps;
+    // what the attention phase needs of the kernel parameters (in a device function they would be loads
+    // through a generic pointer that the compiler hoists into registers -- and spills)
+    struct Att {
+        float *kc, *vc;
+        unsigned long long *ll_q, *ll_kv, *ll_att, *ll_part;
+        int H, seq, kv, kv_mul, att_dim, ll_rep;
+    } att;
 };
 
 // profiling state of a CTA (shared memory): phase timers of the timer thread, trace scratch
@@ -893,7 +900,7 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 }
 
 template <int HS>
-__device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaPlan *cp, int layer, int pos, uint32_t ep)
+__device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int n_splits, int layer, int pos, uint32_t ep)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     SmemView sv;
@@ -903,25 +910,26 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaP
     c.nw = cp->n_cons_warps; c.nt = c.nw * 32;
     constexpr int hs = HS, vec = HS >> 5;  // HS in {32, 64, 128}
     constexpr int q4n = HS >> 4;           // float4 per lane of a quarter head: 2, 4, 8
-    const int S = P.n_splits;
-    const int items = P.H * S;
+    const CtaPlan::Att &T = cp->att;
+    const int S = n_splits;
+    const int items = T.H * S;
     const int npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches)
-    const int s_shift = 31 - __clz(S), kvm_shift = 31 - __clz(P.kv_mul);
-    const bool kvm_pow2 = (P.kv_mul & (P.kv_mul - 1)) == 0;
+    const int s_shift = 31 - __clz(S), kvm_shift = 31 - __clz(T.kv_mul);
+    const bool kvm_pow2 = (T.kv_mul & (T.kv_mul - 1)) == 0;
     const int chunk = (((npast + S - 1) >> s_shift) + 7) & ~7;
     const int pstride = hs + ATT_PSTRIDE_PAD;
     const float rscale = 1.0f / sqrtf((float)hs);
     float *sc = sv.xs;  // [nw][pstride]  (xs is dead between weight phases)
-    const float *kc = P.kc + (size_t)layer * P.seq * P.kv;
-    const float *vc = P.vc + (size_t)layer * P.seq * P.kv;
+    const float *kc = T.kc + (size_t)layer * T.seq * T.kv;
+    const float *vc = T.vc + (size_t)layer * T.seq * T.kv;
     const int pl = c.lane >> 2, dq = c.lane & 3;
-    const int rep = (int)blockIdx.x % P.ll_rep;  // the replica of the LL vectors this CTA polls
-    const unsigned long long *ll_q = P.ll_q + (size_t)rep * P.att_dim, *ll_kv = P.ll_kv + (size_t)rep * 2 * P.kv;
+    const int rep = (int)blockIdx.x % T.ll_rep;  // the replica of the LL vectors this CTA polls
+    const unsigned long long *ll_q = T.ll_q + (size_t)rep * T.att_dim, *ll_kv = T.ll_kv + (size_t)rep * 2 * T.kv;
 #pragma unroll 1
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         // (S is a power of two; kv_mul is one in every common model: shifts, the division is a cold path)
         const int h = item >> s_shift, sp = item & (S - 1);
-        const int g = kvm_pow2 ? h >> kvm_shift : h / P.kv_mul;
+        const int g = kvm_pow2 ? h >> kvm_shift : h / T.kv_mul;
         const int t0 = sp * chunk, t1 = min(npast, t0 + chunk);
         float m = -INFINITY, l = 0.f, acc[vec];
 #pragma unroll
@@ -934,7 +942,7 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaP
         for (int tb = t0 + 8 * c.warp; tb < t1; tb += 8 * c.nw) {
             const int t = tb + pl;
             const bool valid = t < t1;
-            const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)min(t, t1 - 1) * P.kv + (size_t)g * hs +
+            const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)min(t, t1 - 1) * T.kv + (size_t)g * hs +
                                                                 dq * (hs >> 2));
             const float *vb = vc + (size_t)g * hs + c.lane * vec;
             float4 kk[q4n];
@@ -942,7 +950,7 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaP
 #pragma unroll
             for (int i = 0; i < q4n; i++) kk[i] = __ldcg(kr + i);
 #pragma unroll
-            for (int u = 0; u < 8; u++) load_vec<vec>(vb + (size_t)min(tb + u, t1 - 1) * P.kv, vv[u]);
+            for (int u = 0; u < 8; u++) load_vec<vec>(vb + (size_t)min(tb + u, t1 - 1) * T.kv, vv[u]);
             if (!have_q) {
                 ll_wait4n<q4n>(ll_q, h * hs + dq * (hs >> 2), ep, qq);
                 have_q = true;
@@ -984,7 +992,7 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaP
             float vv[vec];
             if (!have_q) ll_wait4n<q4n>(ll_q, h * hs + dq * (hs >> 2), ep, qq);
             ll_wait4n<q4n>(ll_kv, g * hs + dq * (hs >> 2), ep, kk);
-            ll_waitv<vec>(ll_kv, P.kv + g * hs + c.lane * vec, ep, vv);
+            ll_waitv<vec>(ll_kv, T.kv + g * hs + c.lane * vec, ep, vv);
             float sdot = 0.f;
 #pragma unroll
             for (int i = 0; i < q4n; i++) {
@@ -1007,7 +1015,7 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaP
         for (int i = 0; i < vec; i++) mine[ATT_PSTRIDE_PAD + c.lane * vec + i] = acc[i];
         cons_sync(c);
         // thread = (head dimension d, LL replica): every thread publishes one word
-        for (int w = c.tid; w < hs * (S == 1 ? P.ll_rep : 1); w += c.nt) {
+        for (int w = c.tid; w < hs * (S == 1 ? T.ll_rep : 1); w += c.nt) {
             const int d = w & (hs - 1), rr = w / hs;
             float M = -INFINITY;
 #pragma unroll 1
@@ -1023,9 +1031,9 @@ __device__ __noinline__ void attention_phase_t(const StreamParams &P, const CtaP
                 }
             }
             if (S == 1) {
-                ll_store(P.ll_att + (size_t)rr * P.att_dim, h * hs + d, A / L, ep);
+                ll_store(T.ll_att + (size_t)rr * T.att_dim, h * hs + d, A / L, ep);
             } else {
-                unsigned long long *out = P.ll_part + (size_t)(h * S + sp) * pstride;
+                unsigned long long *out = T.ll_part + (size_t)(h * S + sp) * pstride;
                 ll_store(out, ATT_PSTRIDE_PAD + d, A, ep);
                 if (d == 0) { ll_store(out, 0, M, ep); ll_store(out, 1, L, ep); }
             }
@@ -1213,6 +1221,9 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         cp.off_red = (int)(reinterpret_cast<uint8_t *>(sv.red) - smem);
         cp.off_full = (int)(reinterpret_cast<uint8_t *>(sv.full) - smem);
         cp.slot_bytes = P.slot_bytes; cp.n_slots = P.n_slots; cp.n_cons_warps = P.n_cons_warps;
+        cp.att.kc = P.kc; cp.att.vc = P.vc; cp.att.ll_q = P.ll_q; cp.att.ll_kv = P.ll_kv; cp.att.ll_att = P.ll_att;
+        cp.att.ll_part = P.ll_part; cp.att.H = P.H; cp.att.seq = P.seq; cp.att.kv = P.kv; cp.att.kv_mul = P.kv_mul;
+        cp.att.att_dim = P.att_dim; cp.att.ll_rep = P.ll_rep;
     }
     if (threadIdx.x < 5) {
         const int i = threadIdx.x;
@@ -1392,9 +1403,9 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
 
         if (ph == 0) {
             // ---- attention (llama2.f90:574-598)
-            if (P.hs == 64) attention_phase_t<64>(P, &cp, l, pos, ep);
-            else if (P.hs == 128) attention_phase_t<128>(P, &cp, l, pos, ep);
-            else attention_phase_t<32>(P, &cp, l, pos, ep);
+            if (P.hs == 64) attention_phase_t<64>(&cp, P.n_splits, l, pos, ep);
+            else if (P.hs == 128) attention_phase_t<128>(&cp, P.n_splits, l, pos, ep);
+            else attention_phase_t<32>(&cp, P.n_splits, l, pos, ep);
             LAP(PH_ATT);
             STAMP(l, 4);
             STAMP(l, 5);
