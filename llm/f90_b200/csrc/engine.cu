@@ -512,7 +512,9 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.rope_tab = E.d_rope;
         {
             // rank-private LL buffers (64-bit words), zero-filled: epoch 0 is never expected
-            int rep = 4;
+            // replicas multiply the peer stores of a tensor-parallel run (rows x tp x replicas over NVLink):
+            // 4 on one GPU, 2 at tp 2, 1 from tp 4 on
+            int rep = tp >= 4 ? 1 : (tp == 2 ? 2 : 4);
             if (const char *s = getenv("LLMF90_LL_REP")) rep = std::max(1, std::min(16, atoi(s)));
             while (rep & (rep - 1)) rep &= rep - 1;  // a power of two (the kernel splits work items with shifts)
             p.ll_rep = rep;
