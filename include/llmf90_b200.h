@@ -89,7 +89,9 @@ int llmf90_b200_init(const llmf90_b200_config *cfg,
 int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits);
 
 /* s%times(1:5) in milliseconds, accumulated since init/reset (llama2.f90:526-638, :407-410).
- * Bucket 2 (RoPE) is fused into bucket 1's kernel phase and reported as 0. */
+ * With LLMF90_FLAG_PROFILE (or LLMF90_PROFILE=1) the five buckets come from the kernel's phase
+ * timers; without it (the default, faster kernel) and on the granular path the whole forward pass
+ * is reported in bucket 4 and the others are 0. */
 int llmf90_b200_times(float t[5]);
 
 /* profiling aid: the fused kernel's fine-grained phase timers in ms (17 buckets per layer loop:
