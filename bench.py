@@ -167,6 +167,31 @@ def ncu_traffic(model: str, wtype: str):
         return None
 
 
+def tp1_same_workload(model: str, wtype: str, steps: int, local_rank: int, timeout_s: int = 420):
+    """tokens/s of the SAME workload on ONE GPU, measured by a child `bench.py --gpus 1` on this
+    rank's GPU while the other ranks wait: the N > 1 line runs Llama-2-7B f16 but the N = 1 default
+    is TinyLlama f32, so this is the figure tensor-parallel scaling should be read against.
+    Returns (value, note); value None when the child did not produce a line."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK",
+                        "MASTER_ADDR", "MASTER_PORT") and not k.startswith("TORCHELASTIC")}
+    vis = [d for d in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if d]
+    env["CUDA_VISIBLE_DEVICES"] = vis[local_rank] if local_rank < len(vis) else str(local_rank)
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--model", model, "--wtype", wtype,
+           "--steps", str(max(1, min(steps, 5))), "--warmup", "3", "--no-cpu-baseline", "--no-tp1"]
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s).stdout
+        for ln in reversed(out.strip().splitlines()):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                if "value" in d:
+                    return float(d["value"]), "child bench.py --gpus 1, same workload, same GPU as rank 0"
+                return None, str(d.get("error", "no value in child line"))[:200]
+        return None, "child printed no JSON line"
+    except Exception as e:  # a missing figure must not cost the tensor-parallel line itself
+        return None, f"{type(e).__name__}: {e}"[:200]
+
+
 # ------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -178,6 +203,8 @@ def main():
     ap.add_argument("--wtype", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pos", type=int, default=0, help="positions of the CPU sample (0 = auto)")
+    ap.add_argument("--no-tp1", action="store_true", help="N > 1: skip the one-GPU run of the same workload")
+    ap.add_argument("--force-tp1", action="store_true", help="N = 1: run the child measurement anyway (test hook)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -331,6 +358,9 @@ def main():
                                 "sample": f"first {n_pos} of the {N_POS} positions, 1 thread, {wall:.1f} s wall; "
                                           f"C restatement of llama2.f90 (no Fortran compiler in the image); "
                                           f"box has {host_cores()} host cores"}
+    if (world > 1 and not a.no_tp1) or a.force_tp1:
+        v1, note = tp1_same_workload(model, wtype, a.steps, local_rank)
+        line["config"]["tp1_same_workload"] = {"value": v1, "unit": "tokens/s", "how": note}
     if world > 1:
         barrier()
     eng.close()
