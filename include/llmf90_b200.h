@@ -162,6 +162,40 @@ typedef struct llmf90_b200_stats {
 } llmf90_b200_stats;
 int llmf90_b200_get_stats(llmf90_b200_stats *out);
 
+/* ---- the fused kernel's plan for a configuration, computed WITHOUT a device ----
+ * What init decides before the first launch: the grid, the shared-memory ring, and for every CTA
+ * the list of bulk copies (TMA stages) one token takes -- [embedding row][one layer: rms_att, its QKV
+ * rows, its Wo rows, rms_ffn, its W13 rows, its W2 rows][rms_final, its classifier rows]; the kernel
+ * walks the layer section n_layers times adding layer_stride16 * 16 bytes per layer.  Sources are in
+ * a virtual address space: region k starts at LLMF90_PLAN_VBASE(k), k = 0..4 the five streamed
+ * matrices (QKV, Wo, W13, W2, classifier) of this rank's shard, 5 the embedding table, 6 / 7 / 8 the
+ * rms_att / rms_ffn / rms_final vectors.  The CPU test-suite uses it to check, for full-size models
+ * and every tensor-parallel split, that the stages are 16-byte aligned, fit a ring slot and cover every
+ * matrix exactly once (tests/test_plan.py).  n_sms / smem_optin describe the device (B200: 148 SMs,
+ * 232448 bytes of opt-in shared memory per block). */
+#define LLMF90_PLAN_VBASE(k) (((uint64_t)(k) + 1u) << 40)
+typedef struct llmf90_b200_plan_info {
+    int32_t grid, threads;            /* CTAs (one per SM) and threads per CTA                     */
+    int32_t n_slots, slot_bytes;      /* the ring                                                   */
+    int32_t smem_bytes;               /* dynamic + static shared memory per CTA                     */
+    int32_t sched_stride;             /* schedule entries reserved per CTA (unused ones: bytes = 0) */
+    int32_t n_layers;
+    int32_t rows[5], cols[5];         /* this rank's share of the five matrices                     */
+    uint64_t matrix_bytes[5];         /* device bytes of one layer of each                          */
+    uint64_t vector_bytes;            /* one rmsnorm weight vector                                  */
+    uint64_t emb_row_bytes;           /* one row of the embedding table                             */
+} llmf90_b200_plan_info;
+typedef struct llmf90_b200_sched_stage {
+    uint64_t src;                     /* virtual source address of the stage (layer 0)              */
+    uint32_t bytes;                   /* 0 = unused entry                                           */
+    uint32_t layer_stride16;          /* bytes / 16 to add per layer                                */
+    uint32_t phase_start;             /* 1 on the first stage of a phase                            */
+    uint32_t reserved;
+} llmf90_b200_sched_stage;
+/* sched may be NULL (info only); otherwise it receives grid * sched_stride entries, CTA-major. */
+int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_optin,
+                     llmf90_b200_plan_info *info, llmf90_b200_sched_stage *sched, int64_t sched_entries);
+
 /* device-resident variant used for the HBM-resident measurement: runs `n_steps` forwards for
  * positions pos0..pos0+n_steps-1 feeding each one the greedy pick of the previous one, without
  * any host<->device traffic; returns the device time in ms. */

@@ -25,6 +25,7 @@ EXPORTS = [
     "llmf90_b200_matvec", "llmf90_b200_rmsnorm", "llmf90_b200_softmax", "llmf90_b200_rope",
     "llmf90_b200_tp_export", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
     "llmf90_b200_bench_device_loop", "llmf90_b200_phase_times", "llmf90_b200_debug_trace",
+    "llmf90_b200_plan",
 ]
 
 
@@ -41,6 +42,23 @@ class CStats(C.Structure):
                 ("stream_slot_bytes", C.c_int32), ("stream_smem_bytes", C.c_int32),
                 ("stream_threads", C.c_int32), ("last_loop_total_ms", C.c_float),
                 ("last_loop_after_first_ms", C.c_float)]
+
+
+class CPlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("grid", "threads", "n_slots", "slot_bytes", "smem_bytes", "sched_stride",
+                                         "n_layers")] + \
+               [("rows", C.c_int32 * 5), ("cols", C.c_int32 * 5), ("matrix_bytes", C.c_uint64 * 5),
+                ("vector_bytes", C.c_uint64), ("emb_row_bytes", C.c_uint64)]
+
+
+SCHED_DTYPE = np.dtype([("src", np.uint64), ("bytes", np.uint32), ("layer_stride16", np.uint32),
+                        ("phase_start", np.uint32), ("reserved", np.uint32)])
+B200_SMS, B200_SMEM_OPTIN = 148, 232448
+
+
+def plan_vbase(k: int) -> int:
+    """LLMF90_PLAN_VBASE(k): start of region k of the planner's virtual address space."""
+    return (k + 1) << 40
 
 
 class EngineError(RuntimeError):
@@ -75,6 +93,7 @@ def load() -> C.CDLL:
     L.llmf90_b200_tp_connect.argtypes = [vp, C.c_int32]
     L.llmf90_b200_get_stats.argtypes = [C.POINTER(CStats)]
     L.llmf90_b200_bench_device_loop.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp]
+    L.llmf90_b200_plan.argtypes = [C.POINTER(CConfig), C.c_int32, C.c_int32, C.POINTER(CPlanInfo), vp, C.c_int64]
     for name in EXPORTS:
         if name != "llmf90_b200_last_error":
             getattr(L, name).restype = C.c_int
@@ -203,6 +222,24 @@ def host_generate(engine: Engine, prompt_tokens, n: int, want_logits: bool = Fal
         token = int(prompt_tokens[pos - 1]) if pos <= len(prompt_tokens) else int(np.argmax(buf)) + 1
         toks[pos - 1] = token
     return toks, lg_all
+
+
+def plan(cfg: Config, tp_rank: int = 0, tp_size: int = 1, n_sms: int = B200_SMS,
+         smem_optin: int = B200_SMEM_OPTIN):
+    """llmf90_b200_plan: the fused kernel's grid / ring / per-CTA stage lists for a configuration,
+    computed on the host (no device needed).  Returns (info dict, stages[grid, sched_stride])."""
+    L = load()
+    cc = CConfig(cfg.emb_dim, cfg.hidden_dim, cfg.n_layers, cfg.n_heads, cfg.n_kv_heads, cfg.vocab_size,
+                 cfg.seq_len, cfg.wtype, 0, tp_rank, tp_size, 0)
+    info = CPlanInfo()
+    _check(L.llmf90_b200_plan(C.byref(cc), n_sms, smem_optin, C.byref(info), None, 0))
+    st = np.zeros((info.grid, info.sched_stride), SCHED_DTYPE)
+    _check(L.llmf90_b200_plan(C.byref(cc), n_sms, smem_optin, C.byref(info), st.ctypes.data_as(C.c_void_p), st.size))
+    d = {}
+    for n, _ in CPlanInfo._fields_:
+        v = getattr(info, n)
+        d[n] = list(v) if hasattr(v, "__len__") else v
+    return d, st
 
 
 # ---- operators

@@ -311,27 +311,9 @@ int op_buf(TmpStream &t, T **p, size_t n, const void *host)
     if (host) CK(cudaMemcpyAsync(*p, host, n * sizeof(T), cudaMemcpyHostToDevice, t.s));
     return 0;
 }
-}  // namespace
-
-// ====================================================================== C ABI
-extern "C" {
-
-const char *llmf90_b200_last_error(void) { return g_err.c_str(); }
-
-int llmf90_b200_free(void)
+// ---- what init and the dry planner share: the checks on a configuration ...
+int check_config(const llmf90_b200_config &c, int *hs_out, int *tp_out, int *rank_out)
 {
-    if (E.st) cudaStreamSynchronize(E.st);
-    release_all();
-    return 0;
-}
-
-int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const float *rms_att,
-                     const void *wqkv, const void *wo, const float *rms_ffn, const void *w13,
-                     const void *w2, const float *rms_final, const void *wcls)
-{
-    if (!cfg) return fail("config is null");
-    if (E.ready || E.st) llmf90_b200_free();
-    const llmf90_b200_config c = *cfg;
     if (c.emb_dim <= 0 || c.hidden_dim <= 0 || c.n_layers <= 0 || c.n_heads <= 0 || c.n_kv_heads <= 0 ||
         c.vocab_size <= 0 || c.seq_len <= 0)
         return fail("config: non-positive dimension");
@@ -353,6 +335,75 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         if (c.hidden_dim % (tp * colmul) || (c.emb_dim / tp) % colmul || c.vocab_size % tp)
             return fail("config: hidden_dim / emb_dim / vocab_size do not split %d ways for this wtype", tp);
     }
+    *hs_out = hs; *tp_out = tp; *rank_out = rank;
+    return 0;
+}
+
+// ... and the fused kernel's view of one rank's share of the model: dimensions and the five streamed
+// matrices (bases[] = QKV, Wo, W13, W2, classifier in device memory -- or in the planner's virtual
+// address space)
+void stream_geometry(StreamParams &p, const llmf90_b200_config &c, int hs, int tp, int rank, bool tiled,
+                     const uint8_t *const bases[5])
+{
+    const int emb = c.emb_dim, wt = c.wtype;
+    const int Hl = c.n_heads / tp, KVHl = c.n_kv_heads / tp;
+    const int att = Hl * hs, kvl = KVHl * hs, nqkv = att + 2 * kvl, hid = c.hidden_dim / tp, Vl = c.vocab_size / tp;
+    p = StreamParams{};
+    p.emb = emb; p.hid = hid; p.L = c.n_layers; p.H = Hl; p.KVH = KVHl; p.V = Vl;
+    p.seq = c.seq_len; p.hs = hs; p.kv = kvl; p.kv_mul = c.n_heads / c.n_kv_heads; p.nqkv = nqkv; p.wtype = wt;
+    p.att_dim = att; p.tp = tp; p.rank = rank; p.v_off = rank * Vl; p.v_total = c.vocab_size;
+    auto mk = [&](const uint8_t *base, int rows, int cols, int unit) {
+        PhaseW w{};
+        w.base = base; w.rows = rows; w.rows_real = rows; w.cols = cols; w.unit = unit;
+        w.rs = (unsigned)row_stride_bytes(wt, cols);
+        w.layer_stride = (unsigned long long)rows * w.rs;
+        if (tiled) {
+            // tiled q4_0: rows go to CTAs in row groups of 16; rs = bytes of one row group
+            w.rows = (rows + 15) & ~15; w.unit = 16;
+            w.ngrp = q4t_groups(cols);
+            w.rs = (unsigned)(w.ngrp * Q4T_GROUP_BYTES);
+            w.layer_stride = (unsigned long long)q4t_matrix_bytes(rows, cols);
+        }
+        return w;
+    };
+    p.ph[0] = mk(bases[0], nqkv, emb, 2);
+    p.ph[1] = mk(bases[1], emb, att, 1);
+    p.ph[2] = mk(bases[2], 2 * hid, emb, 2);
+    p.ph[3] = mk(bases[3], emb, hid, 1);
+    p.ph[4] = mk(bases[4], Vl, emb, 1);
+}
+// every CTA must own W13 rows (the LL hand-over's no-overwrite argument, stream.cu): tiny models run
+// on fewer CTAs
+int stream_grid(const StreamParams &p, int n_sms, bool tiled)
+{
+    return std::min(n_sms, tiled ? (2 * p.hid + 15) / 16 : p.hid);
+}
+constexpr int STREAM_TARGET_SLOT = 24576, STREAM_MAX_SLOTS = 5;  // measured optimum (a deeper ring prefetches
+// more but its queued bulk loads delay the hand-over traffic: 4 slots 1.039, 5: 1.010, 6: 1.033, 7: 1.10 ms)
+constexpr int STREAM_STATIC_SMEM = 2048;  // the kernel's static shared memory (plan, RoPE row, timers)
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *llmf90_b200_last_error(void) { return g_err.c_str(); }
+
+int llmf90_b200_free(void)
+{
+    if (E.st) cudaStreamSynchronize(E.st);
+    release_all();
+    return 0;
+}
+
+int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const float *rms_att,
+                     const void *wqkv, const void *wo, const float *rms_ffn, const void *w13,
+                     const void *w2, const float *rms_final, const void *wcls)
+{
+    if (!cfg) return fail("config is null");
+    if (E.ready || E.st) llmf90_b200_free();
+    const llmf90_b200_config c = *cfg;
+    int hs, tp, rank;
+    if (check_config(c, &hs, &tp, &rank)) return 1;
     if (!tok_emb || !rms_att || !wqkv || !wo || !rms_ffn || !w13 || !w2 || !rms_final || !wcls)
         return fail("null weight pointer");
     if (ensure_device(c.device)) return 1;
@@ -466,37 +517,13 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
         if (!coop) { release_all(); return fail("device does not support cooperative launch"); }
         StreamParams &p = E.sp;
-        p = StreamParams{};
-        p.emb = emb; p.hid = hid; p.L = L; p.H = Hl; p.KVH = KVHl; p.V = Vl;
-        p.seq = c.seq_len; p.hs = hs; p.kv = kvl; p.kv_mul = E.kv_mul; p.nqkv = nqkv; p.wtype = wt;
-        p.att_dim = att; p.tp = tp; p.rank = rank; p.v_off = rank * Vl; p.v_total = V;
-        auto mk = [&](const uint8_t *base, int rows, int cols, int unit) {
-            PhaseW w{};
-            w.base = base; w.rows = rows; w.rows_real = rows; w.cols = cols; w.unit = unit;
-            w.rs = (unsigned)row_stride_bytes(wt, cols);
-            w.layer_stride = (unsigned long long)rows * w.rs;
-            if (tiled) {
-                // tiled q4_0: rows go to CTAs in row groups of 16; rs = bytes of one row group
-                w.rows = (rows + 15) & ~15; w.unit = 16;
-                w.ngrp = q4t_groups(cols);
-                w.rs = (unsigned)(w.ngrp * Q4T_GROUP_BYTES);
-                w.layer_stride = (unsigned long long)q4t_matrix_bytes(rows, cols);
-            }
-            return w;
-        };
-        p.ph[0] = mk(E.d_wqkv, nqkv, emb, 2);
-        p.ph[1] = mk(E.d_wo, emb, att, 1);
-        p.ph[2] = mk(E.d_w13, 2 * hid, emb, 2);
-        p.ph[3] = mk(E.d_w2, emb, hid, 1);
-        p.ph[4] = mk(E.d_wcls, Vl, emb, 1);
-        int target_slot = 24576, max_slots = 5, cons_warps = 12;  // 5 slots: measured optimum (a deeper ring
-        // prefetches more but its queued bulk loads delay the hand-over traffic: 4: 1.039, 5: 1.010, 6: 1.033, 7: 1.10 ms)
+        const uint8_t *const bases[5] = {E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls};
+        stream_geometry(p, c, hs, tp, rank, tiled, bases);
+        int target_slot = STREAM_TARGET_SLOT, max_slots = STREAM_MAX_SLOTS, cons_warps = 12;
         if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
         if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
         if (const char *s = getenv("LLMF90_CONS_WARPS")) cons_warps = atoi(s);
-        // every CTA must own W13 rows (the LL hand-over's no-overwrite argument, stream.cu): tiny models
-        // run on fewer CTAs
-        if (plan_stream(p, std::min(E.n_sms, tiled ? (2 * hid + 15) / 16 : hid), smem_optin - 2048 /* static smem */, target_slot, max_slots,
+        if (plan_stream(p, stream_grid(p, E.n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, target_slot, max_slots,
                         cons_warps, &E.plan)) {
             release_all();
             return fail("model rows do not fit the shared-memory ring (row stride too large)");
@@ -549,7 +576,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         p.kc = E.d_kc; p.vc = E.d_vc;
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
         if (const char *s = getenv("LLMF90_SMEM_PAD"))  // experiment: unused shared memory (shrinks L1)
-            E.plan.smem_bytes = std::min(E.plan.smem_bytes + atoi(s), smem_optin - 2048);
+            E.plan.smem_bytes = std::min(E.plan.smem_bytes + atoi(s), smem_optin - STREAM_STATIC_SMEM);
         p.lookahead = std::min(p.lookahead, E.plan.n_slots - 1);
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.n_cons_warps = E.plan.n_cons_warps;
         p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
@@ -703,6 +730,56 @@ int llmf90_b200_get_stats(llmf90_b200_stats *out)
         out->stream_smem_bytes = E.plan.smem_bytes; out->stream_threads = E.plan.threads;
     }
     return 0;
+}
+
+// ---------------------------------------------------------------- the planner, without a device
+int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_optin, llmf90_b200_plan_info *info,
+                     llmf90_b200_sched_stage *sched, int64_t sched_entries)
+{
+    if (!cfg || !info) return fail("plan: null argument");
+    if (n_sms <= 0 || smem_optin <= STREAM_STATIC_SMEM) return fail("plan: bad device description");
+    int hs, tp, rank;
+    if (check_config(*cfg, &hs, &tp, &rank)) return 1;
+    if (cfg->flags & LLMF90_FLAG_GRANULAR) return fail("plan: the granular forward has no ring plan");
+    const bool tiled = cfg->wtype == WT_Q4_0;
+    const uint8_t *bases[5];
+    for (int i = 0; i < 5; i++) bases[i] = reinterpret_cast<const uint8_t *>(LLMF90_PLAN_VBASE(i));
+    StreamParams p;
+    stream_geometry(p, *cfg, hs, tp, rank, tiled, bases);
+    p.emb_table = reinterpret_cast<const uint8_t *>(LLMF90_PLAN_VBASE(5));
+    p.rms_att = reinterpret_cast<const float *>(LLMF90_PLAN_VBASE(6));
+    p.rms_ffn = reinterpret_cast<const float *>(LLMF90_PLAN_VBASE(7));
+    p.rms_final = reinterpret_cast<const float *>(LLMF90_PLAN_VBASE(8));
+    StreamPlan plan{};
+    if (plan_stream(p, stream_grid(p, n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, STREAM_TARGET_SLOT,
+                    STREAM_MAX_SLOTS, 12, &plan))
+        return fail("model rows do not fit the shared-memory ring (row stride too large)");
+    SchedStage *h = nullptr;
+    build_schedule(p, plan.grid, &h);
+    memset(info, 0, sizeof *info);
+    info->grid = plan.grid; info->threads = plan.threads; info->n_slots = plan.n_slots;
+    info->slot_bytes = plan.slot_bytes; info->smem_bytes = plan.smem_bytes + STREAM_STATIC_SMEM;
+    info->sched_stride = p.sched_stride; info->n_layers = p.L;
+    for (int i = 0; i < 5; i++) {
+        info->rows[i] = p.ph[i].rows_real; info->cols[i] = p.ph[i].cols;
+        info->matrix_bytes[i] = tiled ? (uint64_t)q4t_matrix_bytes(p.ph[i].rows_real, p.ph[i].cols)
+                                      : (uint64_t)p.ph[i].rows_real * p.ph[i].rs;
+    }
+    info->vector_bytes = (uint64_t)p.emb * 4u;
+    info->emb_row_bytes = (uint64_t)row_stride_bytes(p.wtype, p.emb);
+    const int64_t need = (int64_t)plan.grid * p.sched_stride;
+    int rc = 0;
+    if (sched) {
+        if (sched_entries < need) rc = fail("plan: schedule buffer too small (%lld entries needed)", (long long)need);
+        else
+            for (int64_t i = 0; i < need; i++) {
+                sched[i].src = h[i].src; sched[i].bytes = h[i].bytes;
+                sched[i].layer_stride16 = h[i].stride16 & ~SCHED_PHASE_START;
+                sched[i].phase_start = (h[i].stride16 & SCHED_PHASE_START) ? 1u : 0u;
+            }
+    }
+    free(h);
+    return rc;
 }
 
 // ---------------------------------------------------------------- operator wrappers

@@ -1,0 +1,105 @@
+"""The fused kernel's host-side plan (llmf90_b200_plan), checked without a GPU.
+
+init decides the grid, the shared-memory ring and, for every CTA, the list of bulk copies one token
+takes.  A wrong list does not fail loudly on the device -- a misaligned or oversized bulk copy faults,
+a row streamed twice or never gives wrong logits only for some shapes -- so the properties are pinned
+here for the full-size models of BASELINE.json and every tensor-parallel split:
+
+  * every stage is 16-byte aligned (cp.async.bulk), non-empty and fits one ring slot;
+  * the stages of all CTAs cover each of the five streamed matrices exactly once (llama2.f90:529-531,
+    :603-605, :610-612, :618-620, :634-636 read every row once per token);
+  * the per-layer stride stays inside the matrix' allocation for the last layer;
+  * the ring fits the B200's opt-in shared memory.
+"""
+import numpy as np
+import pytest
+
+from llm.f90_b200 import capi
+from llm.f90_b200.layout import F16 as WT_F16, F32 as WT_F32, Q4_0 as WT_Q4_0
+from llm.f90_b200.layout import Config, LLAMA2_7B, SMALL, TINYLLAMA
+
+# "odd": a vocabulary that is not a multiple of the 16-row q4_0 tile (the last tile is padded) and FFN
+# rows that do not divide by the grid
+ODD = {**SMALL, "vocab_size": 1003, "hidden_dim": 1376}
+MODELS = {"small": SMALL, "odd": ODD, "tinyllama": TINYLLAMA, "llama2-7b": LLAMA2_7B}
+CASES = [(m, wt, tp) for m in MODELS for wt in (WT_F32, WT_F16, WT_Q4_0) for tp in (1, 2, 4, 8)]
+
+
+def _splits(dims, wt, tp):
+    colmul = {WT_F32: 4, WT_F16: 8, WT_Q4_0: 32}[wt]
+    return (dims["n_heads"] % tp == 0 and dims["n_kv_heads"] % tp == 0 and dims["hidden_dim"] % (tp * colmul) == 0
+            and (dims["emb_dim"] // tp) % colmul == 0 and dims["vocab_size"] % tp == 0)
+
+
+def _region(src):
+    return (np.asarray(src, np.uint64) >> np.uint64(40)).astype(np.int64) - 1
+
+
+@pytest.mark.parametrize("model,wt,tp", CASES, ids=[f"{m}-{wt}-tp{tp}" for m, wt, tp in CASES])
+def test_plan_covers_every_matrix_once(model, wt, tp):
+    dims = MODELS[model]
+    if not _splits(dims, wt, tp):
+        pytest.skip("this model does not split that many ways")
+    cfg = Config(**dims, wtype=wt)
+    for rank in sorted({0, tp - 1}):
+        info, st = capi.plan(cfg, tp_rank=rank, tp_size=tp)
+        assert info["grid"] <= capi.B200_SMS and info["threads"] == 416
+        assert info["n_slots"] >= 3 and info["slot_bytes"] % 128 == 0
+        assert info["smem_bytes"] <= capi.B200_SMEM_OPTIN
+        assert info["n_layers"] == cfg.n_layers
+        used = st[st["bytes"] > 0]
+        # ---- every bulk copy: aligned, fits a slot
+        assert (used["src"] % 16 == 0).all() and (used["bytes"] % 16 == 0).all()
+        assert (used["bytes"] <= info["slot_bytes"]).all()
+        reg = _region(used["src"])
+        assert reg.min() >= 0 and reg.max() <= 8
+        # ---- the five matrices: the union of all CTAs' stages is the matrix, nothing twice
+        for k in range(5):
+            m = used[reg == k]
+            off = (m["src"] - np.uint64(capi.plan_vbase(k))).astype(np.int64)
+            order = np.argsort(off)
+            off, nb = off[order], m["bytes"][order].astype(np.int64)
+            assert off[0] == 0, f"matrix {k}: first stage starts at {off[0]}"
+            assert (off[1:] == off[:-1] + nb[:-1]).all(), f"matrix {k}: gap or overlap between stages"
+            assert off[-1] + nb[-1] == info["matrix_bytes"][k], f"matrix {k}: stages end before / after the matrix"
+            stride = m["layer_stride16"].astype(np.int64) * 16
+            if k < 4:
+                assert (stride == info["matrix_bytes"][k]).all()  # layer l = layer 0 + l * one layer's bytes
+            else:
+                assert (stride == 0).all()                         # the classifier is not per layer
+        # ---- per CTA: one embedding row, the three norm vectors, phases flagged in order
+        for cta in range(info["grid"]):
+            row = st[cta][st[cta]["bytes"] > 0]
+            r = _region(row["src"])
+            assert r[0] == 5 and row["bytes"][0] == info["emb_row_bytes"]
+            for k in (6, 7, 8):
+                v = row[r == k]
+                assert len(v) == 1 and v["bytes"][0] == info["vector_bytes"] and v["phase_start"][0] == 1
+                assert v["layer_stride16"][0] * 16 == (info["vector_bytes"] if k < 8 else 0)
+            # the order the kernel consumes: emb, rms_att, QKV, Wo, rms_ffn, W13, W2, rms_final, classifier
+            rank_of = {5: 0, 6: 1, 0: 2, 1: 3, 7: 4, 2: 5, 3: 6, 8: 7, 4: 8}
+            seq = np.array([rank_of[int(x)] for x in r])
+            assert (np.diff(seq) >= 0).all()
+            assert (r == 2).any(), "every CTA must own W13 rows (LL hand-over argument, stream.cu)"
+
+
+def test_plan_rejects_what_init_rejects():
+    bad = Config(**{**TINYLLAMA, "n_heads": 24}, wtype=WT_F32)  # head size 85.33
+    with pytest.raises(capi.EngineError):
+        capi.plan(bad)
+    with pytest.raises(capi.EngineError):
+        capi.plan(Config(**TINYLLAMA, wtype=WT_F32), tp_rank=0, tp_size=8)  # 4 KV heads
+
+
+def test_plan_balance_is_within_one_unit():
+    """Rows go to CTAs in units (1 row, 2 for the interleaved W13 / fused QKV, 16 for tiled q4_0):
+    no CTA has more than one unit more than another in any phase."""
+    for wt in (WT_F32, WT_Q4_0):
+        info, st = capi.plan(Config(**LLAMA2_7B, wtype=wt))
+        reg = np.where(st["bytes"] > 0, _region(st["src"]), -1)
+        for k in range(5):
+            per_cta = np.where(reg == k, st["bytes"], 0).sum(axis=1).astype(np.int64)
+            rows = info["rows"][k]
+            unit = 16 if wt == WT_Q4_0 else (2 if k in (0, 2) else 1)
+            per_unit = info["matrix_bytes"][k] / (((rows + unit - 1) // unit))
+            assert per_cta.max() - per_cta.min() <= per_unit + 1e-6
