@@ -378,8 +378,13 @@ int stream_grid(const StreamParams &p, int n_sms, bool tiled)
 {
     return std::min(n_sms, tiled ? (2 * p.hid + 15) / 16 : p.hid);
 }
-constexpr int STREAM_TARGET_SLOT = 24576, STREAM_MAX_SLOTS = 5;  // measured optimum (a deeper ring prefetches
-// more but its queued bulk loads delay the hand-over traffic: 4 slots 1.039, 5: 1.010, 6: 1.033, 7: 1.10 ms)
+constexpr int STREAM_MAX_SLOTS = 5;  // measured optimum (a deeper ring prefetches more but its queued bulk
+// loads delay the hand-over traffic: TinyLlama f32 4 slots 1.039, 5: 1.010, 6: 1.033, 7: 1.10 ms)
+// Stage size the planner aims for.  Tiled q4_0 splits a 16-row group into ceil(group bytes / target)
+// stages and every stage adds GW partial-sum planes to the epilogue: Llama-2-7B q4_0 measured 3.11 /
+// 2.69 / 2.56 / 2.11 / 2.06 / 2.14 ms per token at 8 / 12 / 16 / 24 / 36 / 50 KB (36 KB = one whole
+// group of a 4096-column matrix; the ring then holds 4 slots).
+inline int stream_target_slot(bool tiled) { return tiled ? 36864 : 24576; }
 constexpr int STREAM_STATIC_SMEM = 2048;  // the kernel's static shared memory (plan, RoPE row, timers)
 }  // namespace
 
@@ -519,7 +524,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         StreamParams &p = E.sp;
         const uint8_t *const bases[5] = {E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls};
         stream_geometry(p, c, hs, tp, rank, tiled, bases);
-        int target_slot = STREAM_TARGET_SLOT, max_slots = STREAM_MAX_SLOTS, cons_warps = 12;
+        int target_slot = stream_target_slot(tiled), max_slots = STREAM_MAX_SLOTS, cons_warps = 12;
         if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
         if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
         if (const char *s = getenv("LLMF90_CONS_WARPS")) cons_warps = atoi(s);
@@ -751,7 +756,7 @@ int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_
     p.rms_ffn = reinterpret_cast<const float *>(LLMF90_PLAN_VBASE(7));
     p.rms_final = reinterpret_cast<const float *>(LLMF90_PLAN_VBASE(8));
     StreamPlan plan{};
-    if (plan_stream(p, stream_grid(p, n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, STREAM_TARGET_SLOT,
+    if (plan_stream(p, stream_grid(p, n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, stream_target_slot(tiled),
                     STREAM_MAX_SLOTS, 12, &plan))
         return fail("model rows do not fit the shared-memory ring (row stride too large)");
     SchedStage *h = nullptr;
