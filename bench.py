@@ -213,7 +213,7 @@ def main():
     if a.gpus != world and world > 1:
         a.gpus = world
     # workload: configs[1] at N=1 (TinyLlama-1.1B f32, the configuration the metric is quoted on);
-    # N > 1 runs configs[4], Llama-2-7B f16 row-parallel (TinyLlama's 4 KV heads do not split 8 ways)
+    # N > 1 runs configs[4], Llama-2-7B f16 row-parallel (the configuration BASELINE.json names for 8 GPUs)
     model = a.model or ("tinyllama" if a.gpus == 1 else "llama2-7b")
     wtype = a.wtype or ("f32" if a.gpus == 1 else "f16")
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

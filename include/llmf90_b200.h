@@ -137,7 +137,9 @@ int llmf90_b200_rope(float *q, float *k, int32_t emb, int32_t kv, int32_t head_s
 /* ---- tensor parallelism plumbing (one process per GPU) ----
  * Every rank calls llmf90_b200_init with the FULL host weights and its tp_rank / tp_size: the
  * library uploads only the rank's shard (its heads' Wq rows, their KV heads' Wk / Wv rows, the
- * matching Wo columns, its FFN rows of W1 / W3 and columns of W2, its vocabulary rows).  The
+ * matching Wo columns, its FFN rows of W1 / W3 and columns of W2, its vocabulary rows).
+ * n_heads must be a multiple of tp_size; n_kv_heads a multiple, or a divisor (each KV head is then
+ * replicated on tp_size / n_kv_heads ranks: TinyLlama's 4 KV heads on 8 GPUs).  The
  * all-reduce after Wo and after W2 is fused into the decode kernel: every rank stores its partial
  * vector straight into every other rank's hand-over buffer over NVLink.  For that the ranks
  * exchange one 64-byte CUDA IPC handle each (any host transport: MPI, torch.distributed, a file):

@@ -329,9 +329,10 @@ int check_config(const llmf90_b200_config &c, int *hs_out, int *tp_out, int *ran
     if (rank < 0 || rank >= tp) return fail("config: tp_rank %d out of range", rank);
     if (tp > 1) {
         if (c.flags & LLMF90_FLAG_GRANULAR) return fail("the granular forward is single-GPU only");
-        if (c.n_heads % tp || c.n_kv_heads % tp)
-            return fail("config: n_heads %d and n_kv_heads %d must be multiples of tp_size %d", c.n_heads,
-                        c.n_kv_heads, tp);
+        // fewer KV heads than ranks: each KV head is replicated on tp / n_kv_heads ranks
+        if (c.n_heads % tp || (c.n_kv_heads % tp && tp % c.n_kv_heads))
+            return fail("config: n_heads %d must be a multiple of tp_size %d, n_kv_heads %d a multiple or a divisor",
+                        c.n_heads, tp, c.n_kv_heads);
         if (c.hidden_dim % (tp * colmul) || (c.emb_dim / tp) % colmul || c.vocab_size % tp)
             return fail("config: hidden_dim / emb_dim / vocab_size do not split %d ways for this wtype", tp);
     }
@@ -346,11 +347,11 @@ void stream_geometry(StreamParams &p, const llmf90_b200_config &c, int hs, int t
                      const uint8_t *const bases[5])
 {
     const int emb = c.emb_dim, wt = c.wtype;
-    const int Hl = c.n_heads / tp, KVHl = c.n_kv_heads / tp;
+    const int Hl = c.n_heads / tp, KVHl = std::max(1, c.n_kv_heads / tp);
     const int att = Hl * hs, kvl = KVHl * hs, nqkv = att + 2 * kvl, hid = c.hidden_dim / tp, Vl = c.vocab_size / tp;
     p = StreamParams{};
     p.emb = emb; p.hid = hid; p.L = c.n_layers; p.H = Hl; p.KVH = KVHl; p.V = Vl;
-    p.seq = c.seq_len; p.hs = hs; p.kv = kvl; p.kv_mul = c.n_heads / c.n_kv_heads; p.nqkv = nqkv; p.wtype = wt;
+    p.seq = c.seq_len; p.hs = hs; p.kv = kvl; p.kv_mul = Hl / KVHl /* local heads per local KV head */; p.nqkv = nqkv; p.wtype = wt;
     p.att_dim = att; p.tp = tp; p.rank = rank; p.v_off = rank * Vl; p.v_total = c.vocab_size;
     auto mk = [&](const uint8_t *base, int rows, int cols, int unit) {
         PhaseW w{};
@@ -428,8 +429,11 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     const int emb = c.emb_dim, L = c.n_layers, V = c.vocab_size, wt = c.wtype;
     const int hid_full = c.hidden_dim, kv_full = c.n_kv_heads * hs;
     // this rank's share: heads and their KV heads, FFN rows, vocabulary rows
-    const int Hl = c.n_heads / tp, KVHl = c.n_kv_heads / tp;
+    // (with fewer KV heads than ranks a rank's heads all map to ONE KV head, h / kv_mul, which it holds a
+    // copy of: KV head index rank * KVH / tp)
+    const int Hl = c.n_heads / tp, KVHl = std::max(1, c.n_kv_heads / tp);
     const int att = Hl * hs, kvl = KVHl * hs, nqkv = att + 2 * kvl, hid = hid_full / tp, Vl = V / tp;
+    const int kv_row0 = (rank * c.n_kv_heads / tp) * hs;  // first Wk / Wv row of this rank's KV heads
     E.kv = kvl; E.nqkv = nqkv; E.hid_l = hid; E.att_dim = att; E.v_l = Vl;
     const size_t rs_e = row_stride_bytes(wt, emb), rs_a = row_stride_bytes(wt, att), rs_h = row_stride_bytes(wt, hid);
     // the five streamed matrices of a q4_0 model use the tiled mma format in the fused kernel (the
@@ -479,9 +483,9 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             // (att and kvl are multiples of 32, so the three pieces start on tile boundaries)
             rc |= upload_matrix(d_qkv, s_qkv, wt, nqkv_full, emb, att, 0, emb, 0, rank * att, 0, stage, stage_bytes, tiled);
             rc |= upload_matrix(d_qkv + mbytes(att, emb), s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
-                                emb + rank * kvl, 0, stage, stage_bytes, tiled);
+                                emb + kv_row0, 0, stage, stage_bytes, tiled);
             rc |= upload_matrix(d_qkv + mbytes(att + kvl, emb), s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
-                                emb + kv_full + rank * kvl, 0, stage, stage_bytes, tiled);
+                                emb + kv_full + kv_row0, 0, stage, stage_bytes, tiled);
             // Wo: all rows, the input columns of this rank's heads
             rc |= upload_matrix(E.d_wo + (size_t)l * mbytes(emb, att), s_wo, wt, emb, emb, emb, rank * att, att, 0, 0, 0,
                                 stage, stage_bytes, tiled);

@@ -26,13 +26,15 @@ def free_port():
         return s.getsockname()[1]
 
 
+KV1 = dict(SMALL, n_kv_heads=1)  # fewer KV heads than ranks: the KV head is replicated
+
+
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("wt,shape", [(F32, SMALL), (F16, MID), (Q4_0, MID)], ids=["f32-small", "f16-mid", "q4-mid"])
+@pytest.mark.parametrize("wt,shape", [(F32, SMALL), (F16, MID), (Q4_0, MID), (F32, KV1)],
+                         ids=["f32-small", "f16-mid", "q4-mid", "f32-small-kv1"])
 def test_tp_matches_oracle(tmp_path, built, wt, shape, world):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    if shape["n_kv_heads"] % world:
-        pytest.skip("KV heads do not split this many ways (the engine rejects the configuration)")
     import torch.multiprocessing as mp
     from tp_worker import gpu_tp_generate
     cfg = Config(**shape, wtype=wt)

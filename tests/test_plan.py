@@ -27,7 +27,8 @@ CASES = [(m, wt, tp) for m in MODELS for wt in (WT_F32, WT_F16, WT_Q4_0) for tp 
 
 def _splits(dims, wt, tp):
     colmul = {WT_F32: 4, WT_F16: 8, WT_Q4_0: 32}[wt]
-    return (dims["n_heads"] % tp == 0 and dims["n_kv_heads"] % tp == 0 and dims["hidden_dim"] % (tp * colmul) == 0
+    kv_ok = dims["n_kv_heads"] % tp == 0 or tp % dims["n_kv_heads"] == 0  # split, or replicated on tp / KVH ranks
+    return (dims["n_heads"] % tp == 0 and kv_ok and dims["hidden_dim"] % (tp * colmul) == 0
             and (dims["emb_dim"] // tp) % colmul == 0 and dims["vocab_size"] % tp == 0)
 
 
@@ -88,7 +89,9 @@ def test_plan_rejects_what_init_rejects():
     with pytest.raises(capi.EngineError):
         capi.plan(bad)
     with pytest.raises(capi.EngineError):
-        capi.plan(Config(**TINYLLAMA, wtype=WT_F32), tp_rank=0, tp_size=8)  # 4 KV heads
+        capi.plan(Config(**TINYLLAMA, wtype=WT_F32), tp_rank=0, tp_size=3)
+    info, _ = capi.plan(Config(**TINYLLAMA, wtype=WT_F32), tp_rank=5, tp_size=8)  # 4 KV heads, each on 2 ranks
+    assert info["rows"][0] == (2048 // 8) + 2 * 64  # 4 query heads + one (replicated) KV head: K and V rows
 
 
 def test_plan_balance_is_within_one_unit():

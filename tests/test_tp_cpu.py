@@ -20,13 +20,20 @@ def free_port():
 
 
 def test_shard_ranges_cover_everything_once():
-    for shape, size in ((TINYLLAMA, 4), (LLAMA2_7B, 8), (TINY, 2)):
+    # (TINYLLAMA, 8): 4 KV heads on 8 ranks -- every KV head lives on two ranks
+    for shape, size in ((TINYLLAMA, 4), (LLAMA2_7B, 8), (TINY, 2), (TINYLLAMA, 8)):
         cfg = Config(**shape)
         sh = [tp.shard(cfg, r, size) for r in range(size)]
-        for field, total in (("heads", cfg.n_heads), ("kv_heads", cfg.n_kv_heads), ("att_cols", cfg.emb_dim),
-                             ("ffn_rows", cfg.hidden_dim), ("vocab_rows", cfg.vocab_size)):
+        copies = max(1, size // cfg.n_kv_heads)
+        for field, total, mult in (("heads", cfg.n_heads, 1), ("kv_heads", cfg.n_kv_heads, copies),
+                                   ("att_cols", cfg.emb_dim, 1), ("ffn_rows", cfg.hidden_dim, 1),
+                                   ("vocab_rows", cfg.vocab_size, 1)):
             got = sorted(i for s in sh for i in getattr(s, field))
-            assert got == list(range(total)), field
+            assert got == sorted(list(range(total)) * mult), field
+        for s in sh:  # Wk / Wv rows are the rows of exactly those KV heads
+            hs, e, kv = cfg.head_size, cfg.emb_dim, cfg.kv_head_size
+            assert list(s.k_rows) == [e + g * hs + i for g in s.kv_heads for i in range(hs)]
+            assert list(s.v_rows) == [e + kv + g * hs + i for g in s.kv_heads for i in range(hs)]
         # a rank's query heads read only its own KV heads (quirk Q3: kv head = h // kv_mul)
         kv_mul = cfg.n_heads // cfg.n_kv_heads
         for s in sh:
@@ -34,8 +41,8 @@ def test_shard_ranges_cover_everything_once():
 
 
 def test_shard_rejects_impossible_splits():
-    with pytest.raises(ValueError):
-        tp.shard(Config(**TINYLLAMA), 0, 8)  # 4 KV heads do not split 8 ways
+    with pytest.raises(ValueError):  # 3 KV heads: neither a multiple nor a divisor of 2 ranks
+        tp.shard(Config(emb_dim=768, hidden_dim=2048, n_layers=2, n_heads=24, n_kv_heads=3, vocab_size=512, seq_len=64), 0, 2)
     with pytest.raises(ValueError):
         tp.shard(Config(**TINY), 0, 3)
 
@@ -46,11 +53,13 @@ def test_active_bytes_per_rank_matches_baseline_md():
     assert tp.active_bytes_per_rank(c, 1) == 4_138_057_728
 
 
-@pytest.mark.parametrize("wt", [F32, Q4_0], ids=["f32", "q4_0"])
-def test_two_rank_gloo_forward_matches_oracle(tmp_path, wt):
+@pytest.mark.parametrize("wt,kvh", [(F32, None), (Q4_0, None), (F32, 1)], ids=["f32", "q4_0", "f32-replicated-kv"])
+def test_two_rank_gloo_forward_matches_oracle(tmp_path, wt, kvh):
     import torch.multiprocessing as mp
     from tp_worker import cpu_tp_forward
     shape = dict(SMALL, n_layers=2)
+    if kvh:  # fewer KV heads than ranks: both ranks hold a copy of the one KV head
+        shape["n_kv_heads"] = kvh
     cfg = Config(**shape, wtype=wt)
     tokens = [2, 17, 400, 33, 9]
     out = str(tmp_path / "tp_logits.npy")

@@ -28,8 +28,9 @@ def cpu_tp_forward(rank, world, port, shape, wtype, seed, tokens, out_path):
     w = fx.synth_weights(cfg, seed)
     sh = tp.shard(cfg, rank, world)
     s = {k: v.astype(np.float64) for k, v in tp.shard_f32(w, rank, world).items()}
-    hs, kv_mul = cfg.head_size, cfg.n_heads // cfg.n_kv_heads
+    hs = cfg.head_size
     hl, kvl = len(sh.heads), len(sh.kv_heads) * hs
+    kv_mul = hl // len(sh.kv_heads)  # local heads per local KV head (== the global ratio unless KV heads are replicated)
     kc = np.zeros((cfg.n_layers, cfg.seq_len, kvl))
     vc = np.zeros_like(kc)
     rms = lambda x, g: x * g / np.sqrt(x @ x / x.size + 1e-5)
