@@ -139,7 +139,7 @@ struct StreamPlan {
     int xs_floats, res_floats;
 };
 
-// Decide ring geometry for a model on `grid` CTAs (fills p.ph[i].rps / nchunks / cw / rows_cap);
+// Decide ring geometry for a model on `grid` CTAs (fills p.ph[i].spg / rps / ku / rows_cap);
 // returns non-zero if it cannot fit.
 int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots,
                 int cons_warps, StreamPlan *out);

@@ -593,17 +593,6 @@ __device__ __forceinline__ void ll_store2(unsigned long long *buf, int i, float 
                  "l"(e | __float_as_uint(v1))
                  : "memory");
 }
-// store to every replica of an LL vector (replicas are `stride` words apart, see StreamParams::ll_rep)
-__device__ __forceinline__ void ll_store_rep(unsigned long long *buf, int stride, int nrep, int i, float v, uint32_t ep)
-{
-#pragma unroll 1
-    for (int r = 0; r < nrep; r++) ll_store(buf + (size_t)r * stride, i, v, ep);
-}
-__device__ __forceinline__ void ll_store_sys_rep(unsigned long long *buf, int stride, int nrep, int i, float v, uint32_t ep)
-{
-#pragma unroll 1
-    for (int r = 0; r < nrep; r++) ll_store_sys(buf + (size_t)r * stride, i, v, ep);
-}
 __device__ __forceinline__ void ll_load2(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
 {
     asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
