@@ -103,7 +103,7 @@ def load() -> C.CDLL:
 
 def _check(rc: int) -> None:
     if rc != 0:
-        raise EngineError(load().llmf90_b200_last_error().decode())
+        raise EngineError(load().llmf90_b200_last_error().decode(errors="replace"))
 
 
 def _fp(a: np.ndarray):

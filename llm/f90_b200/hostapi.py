@@ -67,7 +67,7 @@ class HostModel:
         else:
             self.h = self.L.llmf90_host_load(path.encode(), 1 if verbose else (-1 if quiet else 0))
         if not self.h:
-            raise HostError(self.L.llmf90_host_last_error().decode())
+            raise HostError(self.L.llmf90_host_last_error().decode(errors="replace"))
         cc = CHostConfig()
         self.L.llmf90_host_get_config(self.h, C.byref(cc))
         self.cfg = Config(**{n: getattr(cc, n) for n, _ in CHostConfig._fields_})
@@ -107,7 +107,7 @@ class HostModel:
 
     def load_tokenizer(self, path: str) -> None:
         if self.L.llmf90_host_load_tokenizer(self.h, path.encode()):
-            raise HostError(self.L.llmf90_host_last_error().decode())
+            raise HostError(self.L.llmf90_host_last_error().decode(errors="replace"))
 
     def encode(self, text: bytes | str) -> list[int]:
         """bpe_encode (llama2.f90:658-724): 1-based token ids."""
@@ -116,7 +116,7 @@ class HostModel:
         out = (C.c_int32 * max(1, len(text)))()
         n = self.L.llmf90_host_encode(self.h, text, len(text), out, max(1, len(text)))
         if n < 0:
-            raise HostError(self.L.llmf90_host_last_error().decode())
+            raise HostError(self.L.llmf90_host_last_error().decode(errors="replace"))
         return list(out[:n])
 
 

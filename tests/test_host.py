@@ -190,3 +190,42 @@ def test_cli_rejects_unknown_flags_like_the_reference():
 def test_bench_prompt_tokenises():
     toks = hostapi.encode_with_synth_vocab("I stopped posting on knitting forums because", 32000)
     assert 5 < len(toks) < 44 and all(1 <= t <= 32000 for t in toks)
+
+
+_FUZZ_CHILD = r'''
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[3])
+from llm.f90_b200 import hostapi
+data = open(sys.argv[1], "rb").read()
+rng = np.random.default_rng(int(sys.argv[2]))
+head = min(len(data) - 8, 6000)  # header, metadata and tensor infos of the tiny model
+blobs = [data[:c] for c in list(range(0, 48)) + [int(c) for c in rng.integers(48, len(data), 40)]]
+for _ in range(60):                # one wrong byte
+    b = bytearray(data); b[int(rng.integers(0, head))] = int(rng.integers(0, 256)); blobs.append(bytes(b))
+for _ in range(40):                # an absurd 64-bit count / length / offset
+    b = bytearray(data); i = int(rng.integers(0, head)); b[i:i + 8] = (0xFFFFFFFFFFFFFFF0).to_bytes(8, "little")
+    blobs.append(bytes(b))
+ok = err = 0
+for blob in blobs:
+    open(sys.argv[1] + ".case", "wb").write(blob)
+    try:
+        hostapi.HostModel(sys.argv[1] + ".case").close()
+        ok += 1
+    except hostapi.HostError:
+        err += 1
+print("FUZZ", len(blobs), ok, err)
+'''
+
+
+def test_loader_survives_truncated_and_corrupted_files(tmp_path):
+    """The reference prints a message and stops on a bad file (read_ggml.f90:122-125); the mirror must
+    do the same -- an error, never a crash or an unbounded allocation -- whatever the bytes are.  Runs in
+    a child process so that a crash would show up as a failed test, not a dead test run."""
+    p = str(tmp_path / "good.gguf")
+    fx.write_synth_gguf(p, Config(**TINY, wtype=F32), 0)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([os.sys.executable, "-c", _FUZZ_CHILD, p, "7", root], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n, ok, err = (int(x) for x in r.stdout.split("FUZZ")[1].split())
+    assert ok + err == n and err >= 48  # every truncation fails cleanly; a flipped weight byte may still load
