@@ -1,11 +1,14 @@
 // llm_main.cpp -- the `./llm -m <gguf>` command (program llama2, llama2.f90:87-410) with the forward
 // pass behind the C ABI of libllmf90_b200.so.  Same flags, same token loop, same report lines.
 #include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../../../include/llmf90_b200.h"
 #include "host.hpp"
@@ -17,7 +20,11 @@ struct Args {  // type args (llama2.f90:7-14), defaults :26-32
     std::string model_file = "stories15M.bin", prompt, tokenizer;
     bool verbose = false, ak = false;
     int n = 256;
-    int device = 0, granular = 0;
+    int device = -1, granular = 0;
+    // extension: tensor parallelism, one `llm` process per GPU started with the same flags plus its
+    // --tp-rank; the ranks meet in --tp-dir (a fresh directory on a shared file system)
+    int tp_size = 1, tp_rank = 0;
+    std::string tp_dir;
 };
 
 [[noreturn]] void die(const std::string &msg)
@@ -44,9 +51,50 @@ Args parse_args(int argc, char **argv)
         else if (f == "--ak") { a.ak = true; i += 1; }
         else if (f == "--device") { a.device = atoi(val().c_str()); i += 2; }       // extension
         else if (f == "--granular") { a.granular = 1; i += 1; }                     // extension
+        else if (f == "--tp-size") { a.tp_size = atoi(val().c_str()); i += 2; }     // extension
+        else if (f == "--tp-rank") { a.tp_rank = atoi(val().c_str()); i += 2; }     // extension
+        else if (f == "--tp-dir") { a.tp_dir = val(); i += 2; }                     // extension
         else die("Unrecognized option: " + f);                                      // llama2.f90:74-75
     }
     return a;
+}
+
+// ---- tensor-parallel rendezvous through a directory: every rank publishes its 64-byte CUDA IPC handle
+// (llmf90_b200_tp_export) plus a random seed as <dir>/rank<r>.tp (written to a temporary name, then
+// renamed: a reader never sees half a file), waits for the other ranks' files and connects
+// (llmf90_b200_tp_connect).  Rank 0's seed drives every rank's sampler: all ranks must feed the same
+// token, so they must draw the same random numbers.
+constexpr size_t TP_REC = 64 + 8;
+
+std::string tp_file(const Args &a, int r) { return a.tp_dir + "/rank" + std::to_string(r) + ".tp"; }
+
+uint64_t tp_rendezvous(const Args &a, uint64_t my_seed)
+{
+    unsigned char rec[TP_REC];
+    if (llmf90_b200_tp_export(rec)) die(llmf90_b200_last_error());
+    memcpy(rec + 64, &my_seed, 8);
+    const std::string mine = tp_file(a, a.tp_rank), tmp = mine + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f || fwrite(rec, 1, TP_REC, f) != TP_REC || fclose(f) != 0 || rename(tmp.c_str(), mine.c_str()) != 0)
+        die("cannot write " + mine);
+    std::vector<unsigned char> all((size_t)a.tp_size * 64);
+    uint64_t seed0 = my_seed;
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(600);
+    for (int r = 0; r < a.tp_size; r++) {
+        unsigned char got[TP_REC];
+        for (;;) {
+            FILE *g = fopen(tp_file(a, r).c_str(), "rb");
+            const size_t n = g ? fread(got, 1, TP_REC, g) : 0;
+            if (g) fclose(g);
+            if (n == TP_REC) break;
+            if (std::chrono::steady_clock::now() > deadline) die("timed out waiting for " + tp_file(a, r));
+            std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        }
+        memcpy(all.data() + (size_t)r * 64, got, 64);
+        if (r == 0) memcpy(&seed0, got + 64, 8);
+    }
+    if (llmf90_b200_tp_connect(all.data(), a.tp_size)) die(llmf90_b200_last_error());
+    return seed0;
 }
 
 }  // namespace
@@ -55,24 +103,30 @@ int main(int argc, char **argv)
 {
     const Args a = parse_args(argc, argv);
     if (a.ak && a.tokenizer.empty()) die("--ak model files carry no vocabulary: pass -s tokenizer.bin");
+    if (a.tp_size != 1 && a.tp_size != 2 && a.tp_size != 4 && a.tp_size != 8) die("--tp-size must be 1, 2, 4 or 8");
+    if (a.tp_rank < 0 || a.tp_rank >= a.tp_size) die("--tp-rank out of range");
+    if (a.tp_size > 1 && a.tp_dir.empty()) die("--tp-size > 1 needs --tp-dir <fresh directory shared by the ranks>");
+    const bool talk = a.tp_rank == 0;  // one rank prints; all ranks compute the same tokens
 
     llmhost::Model m;
     try {
-        m = a.ak ? llmhost::load_ak(a.model_file, a.verbose) : llmhost::load_gguf(a.model_file, a.verbose);
+        m = a.ak ? llmhost::load_ak(a.model_file, a.verbose && talk)
+                 : llmhost::load_gguf(a.model_file, a.verbose && talk, /*print_offset=*/talk);
         if (!a.tokenizer.empty()) llmhost::load_tokenizer_bin(a.tokenizer, m.cfg.vocab_size, m.vocab);
     } catch (const std::exception &e) {
         die(e.what());
     }
-    if (a.verbose) printf(" Loaded weights\n");
+    if (a.verbose && talk) printf(" Loaded weights\n");
 
     int seq_len = m.cfg.seq_len;
     if (a.n <= seq_len) seq_len = a.n;  // llama2.f90:363-368
-    else printf(" %d greater than maxinum squence length\n set to %d\n", a.n, seq_len);
+    else if (talk) printf(" %d greater than maxinum squence length\n set to %d\n", a.n, seq_len);
 
     llmf90_b200_config cfg{};
     cfg.emb_dim = m.cfg.emb_dim; cfg.hidden_dim = m.cfg.hidden_dim; cfg.n_layers = m.cfg.n_layers;
     cfg.n_heads = m.cfg.n_heads; cfg.n_kv_heads = m.cfg.n_kv_heads; cfg.vocab_size = m.cfg.vocab_size;
-    cfg.seq_len = m.cfg.seq_len; cfg.wtype = m.cfg.wtype; cfg.device = a.device; cfg.tp_rank = 0; cfg.tp_size = 1;
+    cfg.seq_len = m.cfg.seq_len; cfg.wtype = m.cfg.wtype; cfg.device = a.device >= 0 ? a.device : a.tp_rank;
+    cfg.tp_rank = a.tp_rank; cfg.tp_size = a.tp_size;
     cfg.flags = a.granular ? LLMF90_FLAG_GRANULAR : 0;
     if (llmf90_b200_init(&cfg, m.w.token_embedding_table.data(), m.w.rms_att_weight.data(), m.w.wqkv.data(),
                          m.w.wo.data(), m.w.rms_ffn_weight.data(), m.w.w13.data(), m.w.w2.data(),
@@ -87,7 +141,9 @@ int main(int argc, char **argv)
     }
 
     std::vector<float> logits(m.cfg.vocab_size), scratch;
-    std::mt19937 rng(std::random_device{}());  // the reference never seeds random_number (llama2.f90:433)
+    uint64_t seed = ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();  // the reference never seeds random_number (llama2.f90:433)
+    if (a.tp_size > 1) seed = tp_rendezvous(a, seed);
+    std::mt19937_64 rng(seed);
     std::uniform_real_distribution<float> uni(0.f, 1.f);
     using clk = std::chrono::steady_clock;
     clk::time_point t_start{};
@@ -98,18 +154,23 @@ int main(int argc, char **argv)
         if (pos <= (int)prompt_tokens.size()) token = prompt_tokens[pos - 1];
         else if (a.temperature == 0.f) token = llmhost::argmax1(logits.data(), m.cfg.vocab_size);
         else token = llmhost::sample_cdf(logits.data(), m.cfg.vocab_size, a.temperature, uni(rng), scratch);
-        const std::string &piece = m.vocab.tokens[token - 1];
-        fwrite(piece.data(), 1, piece.size(), stdout);
-        fflush(stdout);
+        if (talk) {
+            const std::string &piece = m.vocab.tokens[token - 1];
+            fwrite(piece.data(), 1, piece.size(), stdout);
+            fflush(stdout);
+        }
         if (!started) { t_start = clk::now(); started = true; }  // start after the first token (:399-401)
     }
     const double ms = std::chrono::duration<double, std::milli>(clk::now() - t_start).count();
-    printf("\n Inference time:  %g  seconds\n", ms / 1000.0);
-    printf(" %g tokens/second\n", 1000.0 * (seq_len - 1) / ms);
-    printf(" Timings\n");
-    float t[5] = {0, 0, 0, 0, 0};
-    llmf90_b200_times(t);
-    for (int l = 0; l < 5; l++) printf(" %d %g\n", l + 1, t[l] / seq_len);
+    if (talk) {
+        printf("\n Inference time:  %g  seconds\n", ms / 1000.0);
+        printf(" %g tokens/second\n", 1000.0 * (seq_len - 1) / ms);
+        printf(" Timings\n");
+        float t[5] = {0, 0, 0, 0, 0};
+        llmf90_b200_times(t);
+        for (int l = 0; l < 5; l++) printf(" %d %g\n", l + 1, t[l] / seq_len);
+    }
     llmf90_b200_free();
+    if (a.tp_size > 1) remove(tp_file(a, a.tp_rank).c_str());
     return 0;
 }

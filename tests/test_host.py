@@ -187,6 +187,18 @@ def test_cli_rejects_unknown_flags_like_the_reference():
     assert r.returncode != 0 and "Unrecognized option: --bogus" in r.stdout
 
 
+def test_cli_tensor_parallel_flags_are_checked_before_anything_is_loaded():
+    """`llm --tp-size N --tp-rank r --tp-dir d` (extension: one process per GPU, rendezvous through a
+    directory); bad combinations stop with a message, like every other bad flag."""
+    run = lambda *a: subprocess.run([hostapi.LLM_BIN, *a], capture_output=True, text=True)
+    r = run("--tp-size", "3")
+    assert r.returncode != 0 and "--tp-size must be 1, 2, 4 or 8" in r.stdout
+    r = run("--tp-size", "2")
+    assert r.returncode != 0 and "needs --tp-dir" in r.stdout
+    r = run("--tp-size", "2", "--tp-rank", "2", "--tp-dir", "/tmp")
+    assert r.returncode != 0 and "--tp-rank out of range" in r.stdout
+
+
 def test_bench_prompt_tokenises():
     toks = hostapi.encode_with_synth_vocab("I stopped posting on knitting forums because", 32000)
     assert 5 < len(toks) < 44 and all(1 <= t <= 32000 for t in toks)
