@@ -1,4 +1,4 @@
-"""Generate tests/golden/hf_tiny_logits.npz -- an INDEPENDENT pin for the oracle's structure.
+"""Generate tests/golden/hf_*_logits.npz -- an INDEPENDENT pin for the oracle's structure.
 
 The reference ships no golden vectors and cannot be compiled here (no Fortran compiler), so
 the oracle is cross-checked against a third implementation instead: Hugging Face
@@ -27,6 +27,14 @@ from llm.f90_b200.layout import Config, TINY, F32  # noqa: E402
 
 SEED = 1234
 TOKENS_0BASED = [1, 17, 5, 300, 44, 9, 511, 2, 77, 130]  # fed at positions 1..10
+# head geometries pinned: TINY (kv_mul 2, head size 32); TinyLlama's grouping (8 query heads per KV
+# head -- the case the reference's slice quirk Q3 is about, llama2.f90:581,591) and Llama-2-7B's
+# (multi-head attention, head size 128)
+CASES = {
+    "tiny": TINY,
+    "gqa8": dict(emb_dim=256, hidden_dim=704, n_layers=2, n_heads=8, n_kv_heads=1, vocab_size=512, seq_len=64),
+    "mha128": dict(emb_dim=256, hidden_dim=704, n_layers=2, n_heads=2, n_kv_heads=2, vocab_size=512, seq_len=64),
+}
 
 
 def gguf_to_hf_rows(w: np.ndarray, n_head: int) -> np.ndarray:
@@ -36,10 +44,10 @@ def gguf_to_hf_rows(w: np.ndarray, n_head: int) -> np.ndarray:
     return w.reshape(n_head, hs // 2, 2, inn).swapaxes(1, 2).reshape(out, inn)
 
 
-def main():
+def make(name: str, shape: dict):
     from transformers import LlamaConfig, LlamaForCausalLM
 
-    cfg = Config(**TINY, wtype=F32)
+    cfg = Config(**shape, wtype=F32)
     t = fx.synth_tensors(cfg, SEED)
     hc = LlamaConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.emb_dim,
                      intermediate_size=cfg.hidden_dim, num_hidden_layers=cfg.n_layers,
@@ -68,11 +76,12 @@ def main():
     assert all("rotary" in k for k in missing.missing_keys), missing
     with torch.no_grad():
         out = model(torch.tensor([TOKENS_0BASED])).logits[0].double().numpy()
-    path = os.path.join(os.path.dirname(__file__), "hf_tiny_logits.npz")
+    path = os.path.join(os.path.dirname(__file__), f"hf_{name}_logits.npz")
     np.savez_compressed(path, logits=out.astype(np.float32), tokens_0based=np.array(TOKENS_0BASED),
                         seed=SEED)
     print("wrote", path, out.shape, float(np.abs(out).max()))
 
 
 if __name__ == "__main__":
-    main()
+    for name, shape in CASES.items():
+        make(name, shape)

@@ -14,13 +14,22 @@ from llm.f90_b200.layout import Config, TINY, SMALL, F32, F16, Q4_0, row_bytes, 
 from oracle import oracle_c as oc
 from oracle.oracle_np import OracleNP
 
-GOLD = os.path.join(os.path.dirname(__file__), "golden", "hf_tiny_logits.npz")
+GOLD_DIR = os.path.join(os.path.dirname(__file__), "golden")
+GOLD = os.path.join(GOLD_DIR, "hf_tiny_logits.npz")
+# the head geometries of tests/golden/make_hf_golden.py (CASES): TINY; TinyLlama's 8 query heads per KV
+# head (quirk Q3's case); Llama-2-7B's multi-head attention with head size 128
+GOLD_SHAPES = {
+    "tiny": TINY,
+    "gqa8": dict(emb_dim=256, hidden_dim=704, n_layers=2, n_heads=8, n_kv_heads=1, vocab_size=512, seq_len=64),
+    "mha128": dict(emb_dim=256, hidden_dim=704, n_layers=2, n_heads=2, n_kv_heads=2, vocab_size=512, seq_len=64),
+}
 
 
-def test_hf_golden_canonical_mode():
+@pytest.mark.parametrize("name", list(GOLD_SHAPES))
+def test_hf_golden_canonical_mode(name):
     """Structure pin: canonical-RoPE oracle == Hugging Face LlamaForCausalLM (f32) to 5e-6."""
-    g = np.load(GOLD)
-    cfg = Config(**TINY, wtype=F32)
+    g = np.load(os.path.join(GOLD_DIR, f"hf_{name}_logits.npz"))
+    cfg = Config(**GOLD_SHAPES[name], wtype=F32)
     w = fx.synth_weights(cfg, int(g["seed"]))
     o = oc.Oracle(w, canonical=True)
     n = OracleNP(w, canonical=True)
