@@ -101,12 +101,10 @@ int llmf90_b200_times(float t[5]);
 #define LLMF90_N_PHASES 17
 int llmf90_b200_phase_times(float *ms, int32_t n);
 
-/* profiling aid: run one forward and record, for every CTA of the fused kernel, globaltimer stamps
- * (ns) at the 15 phase edges of `layer` (entries 0..14), the cycles warp 0 waited for ring data /
- * computed and its stage count in the four mat-vec phases (entries 16..27), and the producer's and
- * the consumers' ring cursors (stages issued / consumed) at every edge (entries 32..46, 48..62);
- * entries 64..95: eight SM-clock stamps around the consumption of each of the four phases;
- * out is [n_ctas][128]. */
+/* profiling aid: run one forward with the instrumented kernel and record, for every CTA, globaltimer
+ * stamps (ns) taken by its thread 0 at the phase edges of `layer`: entry 0 layer start, 1 QKV prologue
+ * done, 2 QKV tiles of warp 0 done, 4 attention done, 6 / 7 the same for Wo, 9 / 10 for W13, 12 / 13 for
+ * W2 (other entries 0); out is [n_ctas][128]. */
 int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t *out, int32_t n_ctas);
 
 /* zero the KV cache and the timers (the state llama2.f90:316-319 initialises) */
@@ -166,9 +164,11 @@ int llmf90_b200_get_stats(llmf90_b200_stats *out);
 
 /* ---- the fused kernel's plan for a configuration, computed WITHOUT a device ----
  * What init decides before the first launch: the grid, the shared-memory ring, and for every CTA
- * the list of bulk copies (TMA stages) one token takes -- [embedding row][one layer: rms_att, its QKV
- * rows, its Wo rows, rms_ffn, its W13 rows, its W2 rows][rms_final, its classifier rows]; the kernel
- * walks the layer section n_layers times adding layer_stride16 * 16 bytes per layer.  Sources are in
+ * the list of bulk copies one token takes -- [embedding row][one layer: rms_att, its QKV rows, its Wo
+ * rows, rms_ffn, its W13 rows, its W2 rows][rms_final, its classifier rows]; the kernel walks the layer
+ * section n_layers times adding layer_stride16 * 16 bytes per layer.  A ring stage is one chunk of the
+ * contraction range of one tile (tile_rows rows, owned by one consumer warp): one copy per row for
+ * f32 / f16, one copy of whole 8-block groups for tiled q4_0.  Sources are in
  * a virtual address space: region k starts at LLMF90_PLAN_VBASE(k), k = 0..4 the five streamed
  * matrices (QKV, Wo, W13, W2, classifier) of this rank's shard, 5 the embedding table, 6 / 7 / 8 the
  * rms_att / rms_ffn / rms_final vectors.  The CPU test-suite uses it to check, for full-size models
@@ -183,16 +183,19 @@ typedef struct llmf90_b200_plan_info {
     int32_t sched_stride;             /* schedule entries reserved per CTA (unused ones: bytes = 0) */
     int32_t n_layers;
     int32_t rows[5], cols[5];         /* this rank's share of the five matrices                     */
+    int32_t tile_rows[5];             /* rows of a tile (the unit one consumer warp owns)           */
+    int32_t tile_chunks[5];           /* ring stages a tile's contraction range is cut into         */
     uint64_t matrix_bytes[5];         /* device bytes of one layer of each                          */
     uint64_t vector_bytes;            /* one rmsnorm weight vector                                  */
     uint64_t emb_row_bytes;           /* one row of the embedding table                             */
 } llmf90_b200_plan_info;
-typedef struct llmf90_b200_sched_stage {
-    uint64_t src;                     /* virtual source address of the stage (layer 0)              */
+typedef struct llmf90_b200_sched_stage {   /* one bulk copy (cp.async.bulk) */
+    uint64_t src;                     /* virtual source address of the copy (layer 0)               */
     uint32_t bytes;                   /* 0 = unused entry                                           */
     uint32_t layer_stride16;          /* bytes / 16 to add per layer                                */
-    uint32_t phase_start;             /* 1 on the first stage of a phase                            */
-    uint32_t reserved;
+    uint32_t phase_start;             /* 1 on the first copy of a phase                             */
+    uint32_t stage;                   /* ring stage of this CTA the copy belongs to (copies of one    */
+                                      /* stage land back to back in one ring slot)                  */
 } llmf90_b200_sched_stage;
 /* sched may be NULL (info only); otherwise it receives grid * sched_stride entries, CTA-major. */
 int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_optin,

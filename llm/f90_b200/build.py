@@ -46,13 +46,40 @@ def _cxx() -> str:
     raise RuntimeError("no g++ found")
 
 
+HOT_FUNCTIONS = ("run_tiles", "gather_x", "producer_loop")
+
+
+def _check_hot_functions(ptxas_log: str) -> None:
+    """The per-phase pieces of the decode kernel must not spill: their registers are what is left of the
+    kernel's 128 after the phase loop's live values (interprocedural allocation), and one spilled weight
+    register in the mat-vec loop costs a factor of two (measured).  Fail the build instead."""
+    lines = ptxas_log.splitlines()
+    bad = []
+    for i, ln in enumerate(lines):
+        if "Function properties for" in ln and any(h in ln for h in HOT_FUNCTIONS) and i + 1 < len(lines):
+            nxt = lines[i + 1]
+            if "spill stores" not in nxt:
+                continue
+            spilled = int(nxt.split("bytes stack frame,")[1].split("bytes spill stores")[0])
+            instrumented = "Lb1E" in ln  # the profiling instantiation (template argument PROF = true)
+            if spilled > (16 if instrumented else 0):
+                bad.append(ln.split("Function properties for ")[1][:80] + ":" + nxt.strip())
+    if bad:
+        raise RuntimeError("hot device functions spill registers:\n  " + "\n  ".join(bad))
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps = _abs(CUDA_SRCS) + _abs(CUDA_HDRS)
     if force or _newer(CUDA_LIB, deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         extra = ["-DLLMF90_WATCHDOG"] if os.environ.get("LLMF90_BUILD_WATCHDOG") else []  # debug builds only
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB] + _abs(CUDA_SRCS)
-        subprocess.run(cmd, check=True, cwd=CSRC)
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-Xptxas", "-v", "-o", CUDA_LIB] + _abs(CUDA_SRCS)
+        r = subprocess.run(cmd, cwd=CSRC, stderr=subprocess.PIPE, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stderr)
+        if r.returncode:
+            raise subprocess.CalledProcessError(r.returncode, cmd)
+        _check_hot_functions(r.stderr)
     return CUDA_LIB
 
 

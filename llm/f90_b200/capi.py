@@ -47,12 +47,13 @@ class CStats(C.Structure):
 class CPlanInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("grid", "threads", "n_slots", "slot_bytes", "smem_bytes", "sched_stride",
                                          "n_layers")] + \
-               [("rows", C.c_int32 * 5), ("cols", C.c_int32 * 5), ("matrix_bytes", C.c_uint64 * 5),
+               [("rows", C.c_int32 * 5), ("cols", C.c_int32 * 5), ("tile_rows", C.c_int32 * 5),
+                ("tile_chunks", C.c_int32 * 5), ("_pad", C.c_int32), ("matrix_bytes", C.c_uint64 * 5),
                 ("vector_bytes", C.c_uint64), ("emb_row_bytes", C.c_uint64)]
 
 
 SCHED_DTYPE = np.dtype([("src", np.uint64), ("bytes", np.uint32), ("layer_stride16", np.uint32),
-                        ("phase_start", np.uint32), ("reserved", np.uint32)])
+                        ("phase_start", np.uint32), ("stage", np.uint32)])
 B200_SMS, B200_SMEM_OPTIN = 148, 232448
 
 

@@ -79,7 +79,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// non-blocking test of a phase (profiling aid)
+// non-blocking test of a phase (the producer polls with it so that it can keep prefetching meanwhile)
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -149,16 +149,6 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
@@ -301,159 +291,6 @@ __device__ __forceinline__ void dot_rows(const uint8_t *__restrict__ w0, size_t 
     }
 }
 
-// ------------------------------------------------------------------ ring-stage dot products
-// The fused kernel's consumer path for f32 / f16 rows that sit in a shared-memory ring slot.
-// A "unit" is one 128-bit weight load of a lane: 4 f32 or 8 f16 weights.  All loads of a
-// chunk are issued before the first FMA (KU independent LDS.128 in flight per lane) and the
-// activations of the chunk live in registers, so a row costs KU LDS.128 + 4*KU (8*KU) FMAs
-// with four independent accumulator chains.
-template <int WT, int KU>
-struct XRegs {
-    float4 v[WT == WT_F16 ? 2 * KU : KU];
-};
-
-template <int WT, int KU, bool FULL>
-__device__ __forceinline__ void load_x_units(const float4 *x4, int u0, int lane, int nunits, XRegs<WT, KU> &x)
-{
-#pragma unroll
-    for (int k = 0; k < KU; k++) {
-        const int u = u0 + lane + 32 * k;
-        const bool ok = FULL || u < nunits;
-        if (WT == WT_F16) {
-            x.v[2 * k] = ok ? x4[2 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
-            x.v[2 * k + 1] = ok ? x4[2 * u + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            x.v[k] = ok ? x4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-}
-
-template <int KU, bool FULL>
-__device__ __forceinline__ void load_w_units(const uint8_t *row, int u0, int lane, int nunits, uint4 (&w)[KU])
-{
-    const uint4 *wr = reinterpret_cast<const uint4 *>(row);
-#pragma unroll
-    for (int k = 0; k < KU; k++) {
-        const int u = u0 + lane + 32 * k;
-        w[k] = (FULL || u < nunits) ? wr[u] : make_uint4(0u, 0u, 0u, 0u);
-    }
-}
-
-template <int WT, int KU>
-__device__ __forceinline__ float dot_units(const uint4 (&w)[KU], const XRegs<WT, KU> &x)
-{
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-    for (int k = 0; k < KU; k++) {
-        if (WT == WT_F16) {
-            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w[k].x));
-            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w[k].y));
-            const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w[k].z));
-            const float2 f3 = __half22float2(*reinterpret_cast<const __half2 *>(&w[k].w));
-            a0 = fmaf(f0.x, x.v[2 * k].x, a0); a1 = fmaf(f0.y, x.v[2 * k].y, a1);
-            a2 = fmaf(f1.x, x.v[2 * k].z, a2); a3 = fmaf(f1.y, x.v[2 * k].w, a3);
-            a0 = fmaf(f2.x, x.v[2 * k + 1].x, a0); a1 = fmaf(f2.y, x.v[2 * k + 1].y, a1);
-            a2 = fmaf(f3.x, x.v[2 * k + 1].z, a2); a3 = fmaf(f3.y, x.v[2 * k + 1].w, a3);
-        } else {
-            a0 = fmaf(__uint_as_float(w[k].x), x.v[k].x, a0);
-            a1 = fmaf(__uint_as_float(w[k].y), x.v[k].y, a1);
-            a2 = fmaf(__uint_as_float(w[k].z), x.v[k].z, a2);
-            a3 = fmaf(__uint_as_float(w[k].w), x.v[k].w, a3);
-        }
-    }
-    return (a0 + a1) + (a2 + a3);
-}
-
-// res[r] = partial dot(row r, x) over the units [ub, ub + nu) of each of the n rows of one ring
-// stage (one warp; with two warps per slot each takes half of the columns and the epilogue adds
-// the two partial planes).  f32 / f16 only.  Rows go in pairs so that two independent
-// load->FMA chains are in flight per warp; the latency that remains is hidden by the 14
-// consumer warps of the CTA.
-template <int WT, int KC, bool FULL>
-__device__ __forceinline__ void rows_chunked(const uint8_t *sp, size_t rs, int n, const float4 *x4, int ub,
-                                             int nu, int lane, float *res)
-{
-    const int uend = ub + nu;
-    const int nfull = ub + nu / (32 * KC) * (32 * KC);
-    int r = 0;
-    for (; r + 2 <= n; r += 2) {
-        const uint8_t *row0 = sp + (size_t)r * rs, *row1 = row0 + rs;
-        float a = 0.f, b = 0.f;
-        for (int u0 = ub; u0 < nfull; u0 += 32 * KC) {
-            XRegs<WT, KC> x;
-            uint4 w0[KC], w1[KC];
-            load_x_units<WT, KC, true>(x4, u0, lane, uend, x);
-            load_w_units<KC, true>(row0, u0, lane, uend, w0);
-            load_w_units<KC, true>(row1, u0, lane, uend, w1);
-            a += dot_units<WT, KC>(w0, x);
-            b += dot_units<WT, KC>(w1, x);
-        }
-        if (!FULL && nfull < uend) {
-            XRegs<WT, KC> x;
-            uint4 w0[KC], w1[KC];
-            load_x_units<WT, KC, false>(x4, nfull, lane, uend, x);
-            load_w_units<KC, false>(row0, nfull, lane, uend, w0);
-            load_w_units<KC, false>(row1, nfull, lane, uend, w1);
-            a += dot_units<WT, KC>(w0, x);
-            b += dot_units<WT, KC>(w1, x);
-        }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        if (lane == 0) { res[r] = a; res[r + 1] = b; }
-    }
-    if (r < n) {
-        const uint8_t *row = sp + (size_t)r * rs;
-        float a = 0.f;
-        for (int u0 = ub; u0 < nfull; u0 += 32 * KC) {
-            XRegs<WT, KC> x;
-            uint4 w[KC];
-            load_x_units<WT, KC, true>(x4, u0, lane, uend, x);
-            load_w_units<KC, true>(row, u0, lane, uend, w);
-            a += dot_units<WT, KC>(w, x);
-        }
-        if (!FULL && nfull < uend) {
-            XRegs<WT, KC> x;
-            uint4 w[KC];
-            load_x_units<WT, KC, false>(x4, nfull, lane, uend, x);
-            load_w_units<KC, false>(row, nfull, lane, uend, w);
-            a += dot_units<WT, KC>(w, x);
-        }
-        a = warp_sum(a);
-        if (lane == 0) res[r] = a;
-    }
-}
-
-template <int WT>
-__device__ __forceinline__ void stage_rows(const uint8_t *sp, size_t rs, int n, const float *__restrict__ xs,
-                                           int ub, int nu, int lane, float *res)
-{
-    constexpr int KC = (WT == WT_F32) ? 8 : 4;  // 1024 columns per chunk
-    const float4 *x4 = reinterpret_cast<const float4 *>(xs);
-    if (nu == 32 * KC) {
-        // the warp's whole column range fits in registers once: hoist x out of the row loop
-        XRegs<WT, KC> x;
-        load_x_units<WT, KC, true>(x4, ub, lane, ub + nu, x);
-        int r = 0;
-        for (; r + 2 <= n; r += 2) {
-            uint4 w0[KC], w1[KC];
-            load_w_units<KC, true>(sp + (size_t)r * rs, ub, lane, ub + nu, w0);
-            load_w_units<KC, true>(sp + (size_t)(r + 1) * rs, ub, lane, ub + nu, w1);
-            const float a = warp_sum(dot_units<WT, KC>(w0, x));
-            const float b = warp_sum(dot_units<WT, KC>(w1, x));
-            if (lane == 0) { res[r] = a; res[r + 1] = b; }
-        }
-        if (r < n) {
-            uint4 w[KC];
-            load_w_units<KC, true>(sp + (size_t)r * rs, ub, lane, ub + nu, w);
-            const float a = warp_sum(dot_units<WT, KC>(w, x));
-            if (lane == 0) res[r] = a;
-        }
-    } else if (nu % (32 * KC) == 0) {
-        rows_chunked<WT, KC, true>(sp, rs, n, x4, ub, nu, lane, res);
-    } else {
-        rows_chunked<WT, KC, false>(sp, rs, n, x4, ub, nu, lane, res);
-    }
-}
 #endif  // __CUDACC__
 
 }  // namespace llmf90

@@ -65,7 +65,9 @@ struct Engine {
     unsigned long long *d_ll = nullptr;  // all LL buffers of the fused kernel, one allocation
     SchedStage *d_sched = nullptr;       // per-CTA stage lists of the producer warps
     unsigned int launch_seq = 0;
-    float *h_logits = nullptr;  // pinned
+    size_t ll_words = 0;
+    float *h_logits = nullptr;  // pinned staging buffer (used when the caller's buffer cannot be registered)
+    float *reg_logits = nullptr;  // the caller's logits array, page-locked in place so the D2H copy lands in it directly
     int *h_tokpos = nullptr;    // pinned
     // drivers
     bool use_stream = true;
@@ -100,6 +102,7 @@ void release_all()
     for (int k = 0; k < MAX_TP; k++)
         if (E.peer[k] && E.peer[k] != E.d_shared) cudaIpcCloseMemHandle(E.peer[k]);
     if (E.d_shared) cudaFree(E.d_shared);
+    if (E.reg_logits) cudaHostUnregister(E.reg_logits);
     if (E.h_logits) cudaFreeHost(E.h_logits);
     if (E.h_tokpos) cudaFreeHost(E.h_tokpos);
     if (E.ev0) cudaEventDestroy(E.ev0);
@@ -117,7 +120,8 @@ int upload_matrix(uint8_t *dst, const void *src_host, int wtype, int src_rows, i
 {
     const size_t src_bytes = (size_t)src_rows * host_row_bytes(wtype, src_cols);
     if (src_bytes > stage_bytes) return fail("internal: staging buffer too small");
-    CK(cudaMemcpyAsync(stage, src_host, src_bytes, cudaMemcpyHostToDevice, E.st));
+    if (src_host)  // null: the staging buffer already holds this matrix (another row range of the same upload)
+        CK(cudaMemcpyAsync(stage, src_host, src_bytes, cudaMemcpyHostToDevice, E.st));
     if (tiled)  // q4_0 matrices of the fused kernel: tiled mma format (common.cuh)
         CK(launch_repack_q4_tiled(stage, src_cols, dst, dst_rows, col0, ncols, map_kind, row0, half, E.st));
     else
@@ -240,6 +244,16 @@ int enqueue_forward(int token, int pos, bool device_loop, const int *forced, int
         p.do_argmax = device_loop ? 1 : 0;
         p.forced = forced;
         p.out_tokens = out_tokens;
+        // The LL epoch (launch counter x (L + 1) + layer) is 32 bits and epoch 0 means "never written": before it
+        // can wrap, drain the stream, zero every LL buffer and restart the counter.  Tensor-parallel ranks
+        // launch in lock-step (same calls in the same order), so they all get here at the same launch.
+        if ((unsigned long long)(E.launch_seq + 2) * (unsigned)(E.cfg.n_layers + 1) >= 0xffffffffull) {
+            CK(cudaStreamSynchronize(E.st));
+            CK(cudaMemsetAsync(E.d_ll, 0, E.ll_words * 8, E.st));
+            CK(cudaMemsetAsync(E.d_shared, 0, E.sh_logits, E.st));  // partials, argmax records, flags (not the logits)
+            CK(cudaStreamSynchronize(E.st));
+            E.launch_seq = 0;
+        }
         E.launch_seq++;
         p.ep_base = E.launch_seq * (unsigned)(E.cfg.n_layers + 1);
         CK(launch_stream(p, E.plan, E.prof || p.trace != nullptr, E.st));
@@ -353,25 +367,26 @@ void stream_geometry(StreamParams &p, const llmf90_b200_config &c, int hs, int t
     p.emb = emb; p.hid = hid; p.L = c.n_layers; p.H = Hl; p.KVH = KVHl; p.V = Vl;
     p.seq = c.seq_len; p.hs = hs; p.kv = kvl; p.kv_mul = Hl / KVHl /* local heads per local KV head */; p.nqkv = nqkv; p.wtype = wt;
     p.att_dim = att; p.tp = tp; p.rank = rank; p.v_off = rank * Vl; p.v_total = c.vocab_size;
-    auto mk = [&](const uint8_t *base, int rows, int cols, int unit) {
+    auto mk = [&](const uint8_t *base, int rows, int cols) {
         PhaseW w{};
-        w.base = base; w.rows = rows; w.rows_real = rows; w.cols = cols; w.unit = unit;
+        w.base = base; w.rows_real = rows; w.cols = cols;
+        // rows go to CTAs in pairs (RoPE and SwiGLU pair rows 2i, 2i + 1; the LL stores are 16-byte pairs)
+        w.rows = (rows + 1) & ~1; w.unit = 2;
         w.rs = (unsigned)row_stride_bytes(wt, cols);
         w.layer_stride = (unsigned long long)rows * w.rs;
         if (tiled) {
             // tiled q4_0: rows go to CTAs in row groups of 16; rs = bytes of one row group
             w.rows = (rows + 15) & ~15; w.unit = 16;
-            w.ngrp = q4t_groups(cols);
-            w.rs = (unsigned)(w.ngrp * Q4T_GROUP_BYTES);
+            w.rs = (unsigned)(q4t_groups(cols) * Q4T_GROUP_BYTES);
             w.layer_stride = (unsigned long long)q4t_matrix_bytes(rows, cols);
         }
         return w;
     };
-    p.ph[0] = mk(bases[0], nqkv, emb, 2);
-    p.ph[1] = mk(bases[1], emb, att, 1);
-    p.ph[2] = mk(bases[2], 2 * hid, emb, 2);
-    p.ph[3] = mk(bases[3], emb, hid, 1);
-    p.ph[4] = mk(bases[4], Vl, emb, 1);
+    p.ph[0] = mk(bases[0], nqkv, emb);
+    p.ph[1] = mk(bases[1], emb, att);
+    p.ph[2] = mk(bases[2], 2 * hid, emb);
+    p.ph[3] = mk(bases[3], emb, hid);
+    p.ph[4] = mk(bases[4], Vl, emb);
 }
 // every CTA must own W13 rows (the LL hand-over's no-overwrite argument, stream.cu): tiny models run
 // on fewer CTAs
@@ -379,14 +394,13 @@ int stream_grid(const StreamParams &p, int n_sms, bool tiled)
 {
     return std::min(n_sms, tiled ? (2 * p.hid + 15) / 16 : p.hid);
 }
-constexpr int STREAM_MAX_SLOTS = 5;  // measured optimum (a deeper ring prefetches more but its queued bulk
-// loads delay the hand-over traffic: TinyLlama f32 4 slots 1.039, 5: 1.010, 6: 1.033, 7: 1.10 ms)
-// Stage size the planner aims for.  Tiled q4_0 splits a 16-row group into ceil(group bytes / target)
-// stages and every stage adds GW partial-sum planes to the epilogue: Llama-2-7B q4_0 measured 3.11 /
-// 2.69 / 2.56 / 2.11 / 2.06 / 2.14 ms per token at 8 / 12 / 16 / 24 / 36 / 50 KB (36 KB = one whole
-// group of a 4096-column matrix; the ring then holds 4 slots).
-inline int stream_target_slot(bool tiled) { return tiled ? 36864 : 24576; }
-constexpr int STREAM_STATIC_SMEM = 2048;  // the kernel's static shared memory (plan, RoPE row, timers)
+// The ring takes what shared memory the activation vector leaves (the kernel has no local-memory traffic
+// worth an L1): as many slots as fit, up to 16.
+constexpr int STREAM_MAX_SLOTS = 16;
+// Stage size the planner aims for: f32 / f16 a tile of 4 rows x 2048 f32 (4096 f16) columns; tiled q4_0
+// 8 groups of 16 rows x 256 columns (half a row group of a 4096-column matrix).
+inline int stream_target_slot(bool tiled) { return tiled ? 8 * Q4T_GROUP_BYTES : 32768; }
+constexpr int STREAM_STATIC_SMEM = 3072;  // the kernel's static shared memory (plan, RoPE row, timers)
 }  // namespace
 
 // ====================================================================== C ABI
@@ -479,12 +493,13 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             const uint8_t *s_w13 = (const uint8_t *)w13 + (size_t)l * 2 * hid_full * hb_e;
             const uint8_t *s_w2 = (const uint8_t *)w2 + (size_t)l * emb * hb_hf;
             uint8_t *d_qkv = E.d_wqkv + (size_t)l * mbytes(nqkv, emb);
-            // Wq rows of this rank's heads | Wk rows | Wv rows of its KV heads (read_ggml.f90:272,286,300)
+            // Wq rows of this rank's heads | Wk rows | Wv rows of its KV heads (read_ggml.f90:272,286,300):
+            // ONE host-to-device copy of the layer's fused matrix, three re-layouts out of the staging buffer
             // (att and kvl are multiples of 32, so the three pieces start on tile boundaries)
             rc |= upload_matrix(d_qkv, s_qkv, wt, nqkv_full, emb, att, 0, emb, 0, rank * att, 0, stage, stage_bytes, tiled);
-            rc |= upload_matrix(d_qkv + mbytes(att, emb), s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
+            rc |= upload_matrix(d_qkv + mbytes(att, emb), nullptr, wt, nqkv_full, emb, kvl, 0, emb, 0,
                                 emb + kv_row0, 0, stage, stage_bytes, tiled);
-            rc |= upload_matrix(d_qkv + mbytes(att + kvl, emb), s_qkv, wt, nqkv_full, emb, kvl, 0, emb, 0,
+            rc |= upload_matrix(d_qkv + mbytes(att + kvl, emb), nullptr, wt, nqkv_full, emb, kvl, 0, emb, 0,
                                 emb + kv_full + kv_row0, 0, stage, stage_bytes, tiled);
             // Wo: all rows, the input columns of this rank's heads
             rc |= upload_matrix(E.d_wo + (size_t)l * mbytes(emb, att), s_wo, wt, emb, emb, emb, rank * att, att, 0, 0, 0,
@@ -528,21 +543,18 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         StreamParams &p = E.sp;
         const uint8_t *const bases[5] = {E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls};
         stream_geometry(p, c, hs, tp, rank, tiled, bases);
-        int target_slot = stream_target_slot(tiled), max_slots = STREAM_MAX_SLOTS, cons_warps = 12;
+        int target_slot = stream_target_slot(tiled), max_slots = STREAM_MAX_SLOTS;
         if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
         if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
-        if (const char *s = getenv("LLMF90_CONS_WARPS")) cons_warps = atoi(s);
-        if (plan_stream(p, stream_grid(p, E.n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, target_slot, max_slots,
-                        cons_warps, &E.plan)) {
+        if (plan_stream(p, stream_grid(p, E.n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, target_slot, max_slots, &E.plan)) {
             release_all();
             return fail("model rows do not fit the shared-memory ring (row stride too large)");
         }
-        p.lookahead = 0;
-        if (const char *s = getenv("LLMF90_LOOKAHEAD")) p.lookahead = std::max(0, atoi(s));
-        p.pf_stages = 0;
-        if (const char *s = getenv("LLMF90_PF_STAGES")) p.pf_stages = std::max(0, atoi(s));
         p.pace = 38;  // ~1.15x the per-SM fair share of the measured HBM bandwidth (23 B/cycle)
         if (const char *s = getenv("LLMF90_PACE")) p.pace = std::max(0, atoi(s));
+        // L2 prefetch distance: ~48 MB over the 148 SMs (a third of L2) of stages ahead of the ring
+        p.pf_lead = std::max(1, (int)((48ull << 20) / ((size_t)E.n_sms * E.plan.slot_bytes)));
+        if (const char *s = getenv("LLMF90_PF_LEAD")) p.pf_lead = std::max(0, atoi(s));
         p.emb_table = E.d_emb;
         p.rms_att = E.d_rms_att; p.rms_ffn = E.d_rms_ffn; p.rms_final = E.d_rms_final;
         p.rope_tab = E.d_rope;
@@ -556,6 +568,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             p.ll_rep = rep;
             const size_t n_part = (size_t)Hl * MAX_SPLITS * (hs + 4);
             const size_t words = (size_t)rep * (2 * (size_t)att + ((hid + 1) & ~1) + 2 * (size_t)kvl) + n_part + 64;
+            E.ll_words = words;
             CK(dalloc(&E.d_ll, words));
             CK(cudaMemsetAsync(E.d_ll, 0, words * 8, E.st));
             unsigned long long *w = E.d_ll;
@@ -584,11 +597,13 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         }
         p.kc = E.d_kc; p.vc = E.d_vc;
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
-        if (const char *s = getenv("LLMF90_SMEM_PAD"))  // experiment: unused shared memory (shrinks L1)
-            E.plan.smem_bytes = std::min(E.plan.smem_bytes + atoi(s), smem_optin - STREAM_STATIC_SMEM);
-        p.lookahead = std::min(p.lookahead, E.plan.n_slots - 1);
-        p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes; p.n_cons_warps = E.plan.n_cons_warps;
-        p.xs_floats = E.plan.xs_floats; p.res_floats = E.plan.res_floats;
+        p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes;
+        p.xs_floats = E.plan.xs_floats;
+        p.tile_warps = E.plan.tile_warps;
+        if (const char *s = getenv("LLMF90_TILE_WARPS")) {
+            const int g = atoi(s);
+            if (g == 1 || g == 2 || g == 3 || g == 4) p.tile_warps = g;
+        }
         {
             SchedStage *h = nullptr;
             build_schedule(p, E.plan.grid, &h);
@@ -619,12 +634,21 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
     if (token < 1 || token > E.cfg.vocab_size) return fail("token %d out of range 1..%d", token, E.cfg.vocab_size);
     if (pos < 1 || pos > E.cfg.seq_len) return fail("pos %d out of range 1..%d", pos, E.cfg.seq_len);
     if (!logits) return fail("logits is null");
+    // The host loop passes the same logits array every token (llama2.f90:380): page-lock it in place once, so
+    // the device-to-host copy lands in the caller's memory directly (no staging copy, no second memcpy).
+    const size_t lbytes = (size_t)E.cfg.vocab_size * 4;
+    if (logits != E.reg_logits) {
+        if (E.reg_logits) { cudaHostUnregister(E.reg_logits); E.reg_logits = nullptr; }
+        if (cudaHostRegister(logits, lbytes, cudaHostRegisterDefault) == cudaSuccess) E.reg_logits = logits;
+        else cudaGetLastError();  // not registrable (e.g. read-only mapping): stage through the pinned buffer
+    }
     CK(cudaEventRecord(E.ev0, E.st));
     if (enqueue_forward(token, pos, false, nullptr, nullptr)) return 1;
     CK(cudaEventRecord(E.ev1, E.st));
-    CK(cudaMemcpyAsync(E.h_logits, logits_dev(), (size_t)E.cfg.vocab_size * 4, cudaMemcpyDeviceToHost, E.st));
+    float *dst = E.reg_logits == logits ? logits : E.h_logits;
+    CK(cudaMemcpyAsync(dst, logits_dev(), lbytes, cudaMemcpyDeviceToHost, E.st));
     CK(cudaStreamSynchronize(E.st));
-    memcpy(logits, E.h_logits, (size_t)E.cfg.vocab_size * 4);
+    if (dst != logits) memcpy(logits, E.h_logits, lbytes);
     CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
     if (!E.use_stream || !E.prof) E.host_times[3] += E.last_ms;  // no per-phase timers: whole forward in bucket 4
     return 0;
@@ -633,6 +657,7 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
 int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t *out, int32_t n_ctas)
 {
     if (!E.ready || !E.use_stream) return fail("debug_trace: needs the fused streaming engine");
+    if (!E.peers_ready) return fail("tensor-parallel engine: call llmf90_b200_tp_connect first");
     if (!out || n_ctas < E.plan.grid) return fail("debug_trace: buffer must hold %d x 128 entries", E.plan.grid);
     unsigned long long *d = nullptr;
     CK(cudaMalloc((void **)&d, (size_t)E.plan.grid * 128 * 8));
@@ -693,6 +718,7 @@ int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, 
                                 int32_t *out_tokens, float *elapsed_ms)
 {
     if (!E.ready) return fail("engine not initialised");
+    if (!E.peers_ready) return fail("tensor-parallel engine: call llmf90_b200_tp_connect first");
     if (n < 1 || n > E.cfg.seq_len) return fail("n %d out of range 1..%d", n, E.cfg.seq_len);
     if (n_prompt < 0 || (n_prompt > 0 && !prompt_tokens)) return fail("bad prompt");
     std::vector<int> forced(E.cfg.seq_len, 0);
@@ -713,6 +739,7 @@ int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, 
 int llmf90_b200_bench_device_loop(int32_t first_token, int32_t pos0, int32_t n_steps, float *elapsed_ms)
 {
     if (!E.ready) return fail("engine not initialised");
+    if (!E.peers_ready) return fail("tensor-parallel engine: call llmf90_b200_tp_connect first");
     if (pos0 < 1 || n_steps < 1 || pos0 + n_steps - 1 > E.cfg.seq_len) return fail("bad position range");
     if (first_token < 1 || first_token > E.cfg.vocab_size) return fail("bad token");
     float total = 0.f;
@@ -761,31 +788,56 @@ int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_
     p.rms_final = reinterpret_cast<const float *>(LLMF90_PLAN_VBASE(8));
     StreamPlan plan{};
     if (plan_stream(p, stream_grid(p, n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, stream_target_slot(tiled),
-                    STREAM_MAX_SLOTS, 12, &plan))
+                    STREAM_MAX_SLOTS, &plan))
         return fail("model rows do not fit the shared-memory ring (row stride too large)");
     SchedStage *h = nullptr;
     build_schedule(p, plan.grid, &h);
+    // the report lists BULK COPIES: a stage of nseg row segments becomes nseg entries
+    const unsigned long long lstride[SK_COUNT] = {p.ph[0].layer_stride, p.ph[1].layer_stride, p.ph[2].layer_stride,
+                                                  p.ph[3].layer_stride, 0ull, (unsigned long long)p.emb * 4u,
+                                                  (unsigned long long)p.emb * 4u, 0ull, 0ull};
+    int copies_max = 0;
+    for (int cta = 0; cta < plan.grid; cta++) {
+        int n = 0;
+        for (int i = 0; i < p.sched_stride; i++) n += (int)(h[(size_t)cta * p.sched_stride + i].meta & 0xffu);
+        copies_max = std::max(copies_max, n);
+    }
     memset(info, 0, sizeof *info);
     info->grid = plan.grid; info->threads = plan.threads; info->n_slots = plan.n_slots;
     info->slot_bytes = plan.slot_bytes; info->smem_bytes = plan.smem_bytes + STREAM_STATIC_SMEM;
-    info->sched_stride = p.sched_stride; info->n_layers = p.L;
+    info->sched_stride = copies_max; info->n_layers = p.L;
     for (int i = 0; i < 5; i++) {
         info->rows[i] = p.ph[i].rows_real; info->cols[i] = p.ph[i].cols;
         info->matrix_bytes[i] = tiled ? (uint64_t)q4t_matrix_bytes(p.ph[i].rows_real, p.ph[i].cols)
                                       : (uint64_t)p.ph[i].rows_real * p.ph[i].rs;
+        info->tile_rows[i] = p.ph[i].R; info->tile_chunks[i] = p.ph[i].nch;
     }
     info->vector_bytes = (uint64_t)p.emb * 4u;
     info->emb_row_bytes = (uint64_t)row_stride_bytes(p.wtype, p.emb);
-    const int64_t need = (int64_t)plan.grid * p.sched_stride;
+    const int64_t need = (int64_t)plan.grid * copies_max;
     int rc = 0;
     if (sched) {
         if (sched_entries < need) rc = fail("plan: schedule buffer too small (%lld entries needed)", (long long)need);
-        else
-            for (int64_t i = 0; i < need; i++) {
-                sched[i].src = h[i].src; sched[i].bytes = h[i].bytes;
-                sched[i].layer_stride16 = h[i].stride16 & ~SCHED_PHASE_START;
-                sched[i].phase_start = (h[i].stride16 & SCHED_PHASE_START) ? 1u : 0u;
+        else {
+            memset(sched, 0, (size_t)need * sizeof *sched);
+            for (int cta = 0; cta < plan.grid; cta++) {
+                llmf90_b200_sched_stage *o = sched + (size_t)cta * copies_max;
+                uint32_t stage = 0;
+                for (int i = 0; i < p.sched_stride; i++) {
+                    const SchedStage &e = h[(size_t)cta * p.sched_stride + i];
+                    const unsigned nseg = e.meta & 0xffu, kind = (e.meta >> 8) & 0xfu;
+                    if (!nseg) continue;
+                    const unsigned sstride = kind < 5 ? p.ph[kind].rs : 0u;
+                    for (unsigned k = 0; k < nseg; k++, o++) {
+                        o->src = e.src + (uint64_t)k * sstride; o->bytes = e.seg_bytes;
+                        o->layer_stride16 = (uint32_t)(lstride[kind] >> 4);
+                        o->phase_start = (k == 0 && (e.meta & SCHED_PHASE_START)) ? 1u : 0u;
+                        o->stage = stage;
+                    }
+                    stage++;
+                }
             }
+        }
     }
     free(h);
     return rc;

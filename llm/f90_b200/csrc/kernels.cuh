@@ -56,14 +56,17 @@ enum {
 struct PhaseW {
     const uint8_t *base;     // layer 0 base, device row format
     unsigned long long layer_stride;  // bytes between layers
-    unsigned int rs;         // row stride in bytes
+    unsigned int rs;         // f32 / f16: bytes between rows; tiled q4_0: bytes of one 16-row group
     int rows, cols;
-    int unit;                // rows are assigned to CTAs in multiples of `unit`
-    int rps;                 // rows per ring stage
-    int rows_real;           // rows of the matrix (rows is padded to a multiple of 16 for q4_0)
-    int ngrp, spg;           // q4_0 (tiled format): 8-block groups per row group, ring stages per row group
-    int ku;                  // f32 / f16: 128-bit load units per lane per row when a group of warps shares a row
-    int rows_cap;            // max rows of any CTA in this phase = stride of the partial-result planes
+    int unit;                // rows are assigned to CTAs in multiples of `unit` (2: row pairs; 16: tiled q4_0)
+    int rows_real;           // rows of the matrix (rows is padded to a multiple of `unit`)
+    // A TILE is R consecutive rows (4 for f32 / f16, one 16-row group for tiled q4_0), consumed by ONE warp.
+    // Its contraction range is cut into `nch` chunks; one chunk of one tile is one ring STAGE (R row
+    // segments of f32 / f16 weights, or a run of whole 8-block groups of the q4_0 row group).
+    int R, nch;
+    int nu;                  // f32 / f16: 16-byte weight units per row; q4_0: 8-block groups per row group
+    int cu;                  // units (groups) per chunk; the last chunk of a row has the remainder
+    int rows_cap;            // max rows of any CTA in this phase
 };
 
 constexpr int MAX_TP = 8;
@@ -71,13 +74,16 @@ constexpr int MAX_TP = 8;
 // One ring stage of a CTA's static weight-streaming schedule (built on the host once per engine,
 // copied to shared memory at kernel start): the producer warp just walks its CTA's list
 //   [embedding row][the stages of ONE layer][final norm vector + classifier stages],
-// repeating the layer section L times with src + layer * (stride16 << 4).
+// repeating the layer section L times.  A stage is `nseg` bulk copies of `seg_bytes` each, source
+// segments `kind`-specific bytes apart (the rows of a tile), landing back to back in one ring slot.
 struct SchedStage {
-    unsigned long long src;  // device address (layer 0)
-    unsigned int bytes;
-    unsigned int stride16;   // bytes between layers / 16; bit 31: first stage of a phase (SCHED_PHASE_START)
+    unsigned long long src;  // device address of the first segment (layer 0)
+    unsigned int seg_bytes;
+    unsigned int meta;       // bits 0-7: nseg; bits 8-11: kind (SK_*); bit 31: first stage of a phase
 };
 constexpr unsigned int SCHED_PHASE_START = 0x80000000u;
+// stage kinds: 0-4 = the five streamed matrices (QKV, WO, W13, W2, CLS), then the vector stages
+enum { SK_RMS_ATT = 5, SK_RMS_FFN = 6, SK_RMS_FINAL = 7, SK_EMB_ROW = 8, SK_COUNT = 9 };
 
 // All dimensions are THIS GPU's share under tensor parallelism (tp ranks): H / KVH / kv / hid / V /
 // nqkv / att_dim are local, emb is the full residual width (the residual stream is replicated).
@@ -118,31 +124,31 @@ struct StreamParams {
     const int *tokpos;       // device {token, pos} (1-based); used when token < 0
     int token, pos;          // by-value inputs (token >= 1) -- no H2D copy needed
     int n_splits;            // attention position splits
-    unsigned long long *trace;  // optional [grid][32] debug trace of layer `trace_layer` (or null)
+    unsigned long long *trace;  // optional [grid][128] globaltimer stamps at the phase edges of layer `trace_layer` (or null)
     int trace_layer;
     const SchedStage *sched; // [grid][sched_stride] per-CTA stage lists (entry 0 = embedding row 0: + (token-1) * bytes)
     int sched_stride;        // entries per CTA (padded)
-    int lookahead;           // stages of the NEXT phase the producer may issue while the consumers are still in
-                             // the current one (0 = no limit): queued bulk loads delay the hand-over traffic
-    int pf_stages;           // L2 prefetch distance beyond the ring, in stages (0 = off); used only while HBM would idle
     int pace;                // producer pacing: SM cycles per KB issued (0 = unpaced)
+    int pf_lead;             // L2 prefetch distance ahead of the ring cursor, in stages (0 = off)
     int do_argmax;           // fuse maxloc after the classifier and write tokpos = {argmax, pos+1}
     const int *forced;       // optional device array of forced next tokens (prompt), or null
     int *out_tokens;         // optional device array: out_tokens[pos-1] = chosen token
     // ring geometry
-    int n_slots, slot_bytes, n_cons_warps;
-    int xs_floats, res_floats;  // + emb floats of residual stream after the two res planes
+    int n_slots, slot_bytes;
+    int xs_floats;
+    int tile_warps;          // consumer warps per tile group (1, 2, 3 or 4)
 };
 
 struct StreamPlan {
-    int n_slots, slot_bytes, n_cons_warps, threads, smem_bytes, grid;
-    int xs_floats, res_floats;
+    int n_slots, slot_bytes, threads, smem_bytes, grid;
+    int xs_floats;
+    int tile_warps;
 };
 
-// Decide ring geometry for a model on `grid` CTAs (fills p.ph[i].spg / rps / ku / rows_cap);
+// Decide tile / ring geometry for a model on `grid` CTAs (fills p.ph[i].R / nch / nu / cu / rows_cap);
 // returns non-zero if it cannot fit.
 int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots,
-                int cons_warps, StreamPlan *out);
+                StreamPlan *out);
 // the per-CTA stage lists for `grid` CTAs: out has grid * (*stride) entries (call after plan_stream)
 void build_schedule(StreamParams &p, int grid, SchedStage **out);  // fills p.sched_stride
 cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes);

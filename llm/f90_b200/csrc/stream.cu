@@ -7,32 +7,37 @@
 // across the ~110 dependent mat-vec phases of a token.  One persistent cooperative CTA per SM:
 //
 //   * a PRODUCER warp walks the CTA's private, fully static schedule -- the token's embedding
-//     row, then for every layer the rms_att vector, its contiguous row range of Wqkv and Wo, the
-//     rms_ffn vector, its rows of W13 (gate/up rows interleaved at upload) and W2, finally the
-//     rms_final vector and its rows of Wcls -- and streams it with 1-D TMA bulk copies
-//     (cp.async.bulk, mbarrier complete_tx) into a ring of shared-memory slots.  Nothing in the
-//     schedule depends on activations, so the producer never waits for a hand-over: while the
-//     consumers finish a phase and rebuild the activation vector, the ring keeps filling.
-//   * 12 CONSUMER warps in NG groups of GW; a group owns every NG-th stage of the ring: wait on
-//     its `full` mbarrier, dot the rows in the slot with the activation vector (kept in
-//     registers for the phase; f16 / q4_0 dequantisation fused into the load, f32 accumulation,
-//     batched warp-shuffle reduction), release the slot with an `empty` mbarrier arrive.
-//   * Between phases the consumers run the tiny epilogues in place -- RoPE + KV-cache append,
-//     SwiGLU, residual add -- and publish their slice as {value, epoch} 64-bit words ("LL"
-//     buffers, the protocol NCCL uses for small messages): the next phase's prologue polls the
-//     whole vector straight out of L2 until every word carries the expected epoch.  There is NO
-//     grid barrier and no fence anywhere in the token: a phase hand-over costs one store->load
-//     trip through L2 (rmsnorm is recomputed redundantly per CTA).
+//     row, then for every layer the rms_att vector, its row range of Wqkv and Wo, the rms_ffn
+//     vector, its rows of W13 (gate/up rows interleaved at upload) and W2, finally the rms_final
+//     vector and its rows of Wcls -- and streams it with 1-D TMA bulk copies (cp.async.bulk,
+//     mbarrier complete_tx) into a ring of shared-memory slots.  Nothing in the schedule depends
+//     on activations, so the producer never waits for a hand-over: while the consumers finish a
+//     phase and rebuild the activation vector, the ring keeps filling ("banked" weights).
+//   * 12 CONSUMER warps in groups of G (1-4, as many groups as the ring has slots).  The rows of a
+//     phase are cut into TILES of R rows (4; 16 for q4_0) and a tile's contraction range into chunks
+//     of one ring stage each.  A tile belongs to ONE group (tile t -> group t mod 12/G): its warps
+//     wait on the stage's `full` mbarrier, each dots its share of the columns of the R row segments
+//     with the activation vector in shared memory (one activation load serves R rows; f16 / q4_0
+//     dequantisation fused, f32 accumulation), they hand the slot back, and after the tile's last
+//     chunk each reduces across its lanes, the group adds its G partial results through shared
+//     memory (a named barrier of the group only), and the group's first warp runs the tile's
+//     epilogue ITSELF -- RoPE + KV-cache append, SwiGLU, residual partials, logits -- publishing
+//     its rows at once.  No CTA-wide barrier follows a mat-vec: the hand-over latency is the
+//     slowest group's, not the slowest warp's plus a barrier plus a second pass; every ring slot
+//     has a group working on it, so banked stages drain at shared-memory speed (3-4x the SM's
+//     share of HBM bandwidth), which is what turns the ring's head start into time saved.
+//   * Between phases values travel as {value, epoch} 64-bit words ("LL" buffers, the protocol
+//     NCCL uses for small messages): the next phase's prologue polls the whole vector straight out
+//     of L2 until every word carries the expected epoch.  There is NO grid barrier and no fence
+//     anywhere in the token: a phase hand-over costs one store->load trip through L2 (rmsnorm is
+//     recomputed redundantly per CTA).
 //   * Attention (scores, softmax, value gather) is a phase of the same kernel: (head, split)
 //     items over the CTAs, online softmax, merged in the Wo prologue when there are splits.
 //
 // CODE SIZE IS A FIRST-CLASS CONSTRAINT.  Every piece of this kernel runs once per phase, i.e. its
-// instructions are cold each time unless one layer's worth of code fits the 32 KB L1.5
-// instruction cache; a cold 128-byte line (8 instructions) costs ~300 cycles (measured: a
-// 228 KB build of this kernel spent most of every hand-over fetching instructions).  Hence: one
-// generic prologue / consume / epilogue for all phases (data-driven, not specialised), modest
-// unrolling, profiling hooks out of line, cold paths (position splits, tensor-parallel tails)
-// in non-inlined functions.
+// instructions are cold each time unless one layer's worth of code fits the instruction caches.
+// Hence: one generic prologue / consume / epilogue for all phases (data-driven, not specialised),
+// modest unrolling, profiling hooks out of line, cold paths in non-inlined functions.
 #include <cooperative_groups.h>
 #include <cstdlib>
 
@@ -41,74 +46,58 @@
 namespace llmf90 {
 
 constexpr int MAX_SLOTS = 16;
-constexpr int MAX_CONS_WARPS = 12;  // + 1 producer warp = 416 threads -> 128 registers/thread
-constexpr int CONS_BAR = 1;         // named barrier id used by the consumer warps
-constexpr int GW = 4;               // consumer warps per group: a group of GW warps consumes one ring stage
-constexpr int NG = MAX_CONS_WARPS / GW;  // groups; group g owns the stages whose schedule index is g (mod NG)
-// Successive uses of a slot may belong to different groups, and a group may start waiting for use
-// k + 1 of a slot before use k has landed: with ONE full barrier per slot the one-bit mbarrier phase
-// parity would alias (a wait on the parity of use k + 1 returns at once while use k is in flight).
-// Every slot therefore has TWO full barriers, for its even and its odd uses: a waiter for use k + 1
-// can only be confused with use k - 1, which was consumed before use k could even be issued.
-// Use k of a slot: barrier (k & 1), parity ((k >> 1) & 1).  (The empty barriers have one waiter,
-// the producer, that sees the uses of a slot in order.)
+constexpr int NCW = 12;             // consumer warps (+ 1 producer warp = 416 threads)
+constexpr int NCT = NCW * 32;       // consumer threads
+constexpr int CONS_BAR = 1;         // named barrier id used by the consumer warps (ids 2.. : one per tile group)
+// `full` barriers are per STAGE NUMBER, not per slot: stage s (ring order, per CTA) completes barrier
+// s mod NBAR in its phase (s / NBAR) mod 2.  A warp may wait for a stage long before the stages in
+// front of it have landed (its next tile is 11 tiles ahead); the one-bit mbarrier phase parity is
+// only unambiguous if the previous use of the same barrier (stage s - NBAR) has completed by then.
+// At most n_slots stages are in flight and a warp looks at most 23 tiles x 10 chunks ahead of the
+// oldest one, less than NBAR - n_slots.
+constexpr int NBAR = 256;
+constexpr int MAX_NCH = 10;         // chunks per tile (plan_stream enforces it)
+constexpr int ATT_PSTRIDE_PAD = 4;  // attention partial record = {m, l, -, -, acc[hs]}
 
-struct SmemView {
-    uint8_t *ring;
-    float *xs, *res, *xres, *red;  // xres: this CTA's copy of the residual stream x (llama2.f90:520,605,620)
-    uint64_t *full, *empty;
-    const SchedStage *sched;  // this CTA's stage list (copied from global memory at kernel start)
-};
-
-// per-launch constants of this CTA, computed once into shared memory
+// per-launch constants of this CTA in shared memory: everything the hot loop needs comes from here
+// with one LDS (kernel parameters reached from a non-inlined function are generic loads)
 struct CtaPlan {
     PhaseW ph[5];
-    int r0[5], r1[5], nst[5];
-    // shared-memory geometry for the out-of-line pieces (they take this plan instead of a stack copy of
-    // SmemView: local memory goes through what little L1 the ring leaves)
-    int off_xs, off_res, off_xres, off_red, off_full, slot_bytes, n_slots, n_cons_warps;
-    // what the attention phase needs of the kernel parameters (in a device function they would be loads
-    // through a generic pointer that the compiler hoists into registers -- and spills)
-    struct Att {
-        float *kc, *vc;
-        unsigned long long *ll_q, *ll_kv, *ll_att, *ll_part;
-        int H, seq, kv, kv_mul, att_dim, ll_rep;
-    } att;
+    int r0[5], nrows[5], ntiles[5], nst[5];
+    unsigned long long lstride[SK_COUNT];  // bytes between layers per stage kind
+    unsigned int sstride[SK_COUNT];        // bytes between the segments of a stage per stage kind
+    int off_xs, off_xres, off_red, off_att, off_grp, off_full, off_empty, off_sched;
+    int G;                                 // consumer warps per tile group
+    int slot_bytes, n_slots;
+    unsigned int slot_magic;               // ceil(2^32 / n_slots): s mod n_slots without a division
+    int wtype, emb, hid, kv, att_dim, hs, tp, rank, ll_rep, v_off, seq, H, kv_mul, L;
+    float *kc, *vc;
+    unsigned long long *ll_q, *ll_kv, *ll_att, *ll_part, *ll_hb;
+    unsigned long long *part1[MAX_TP], *part2[MAX_TP];
+    float *logits[MAX_TP];
+    // token tail
+    unsigned long long *amax[MAX_TP], *done[MAX_TP];
+    const int *forced;
+    int *out_tokens, *tokpos;
+    unsigned int ep_last;                  // epoch of the token tail's records
+    int do_argmax;
+    volatile int prod_issued, pf_issued;   // stages copied into the ring / prefetched into L2 so far (trace)
+    float tail_best[NCW];                  // per-warp maxloc of the classifier epilogue
+    int tail_idx[NCW];
+    float2 rope[64];                       // this position's RoPE row
 };
 
-// profiling state of a CTA (shared memory): phase timers of the timer thread, trace scratch
+// profiling state of a CTA (shared memory): phase timers of the timer thread
 struct Prof {
     long long tacc[PH_COUNT];
     long long tmark;
-    long long twait[12 + 32];  // 12 accumulators + 8 clock stamps for each of the 4 layer phases
-    volatile int prod_issued;  // stages issued by the producer so far
 };
 
-__device__ __forceinline__ SmemView carve(uint8_t *smem, const StreamParams &P)
+static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int emb, int hs, int sched_entries)
 {
-    SmemView v;
-    size_t off = 0;
-    v.ring = smem;
-    off += (size_t)P.n_slots * P.slot_bytes;
-    v.xs = reinterpret_cast<float *>(smem + off);
-    off += (size_t)P.xs_floats * 4;
-    v.res = reinterpret_cast<float *>(smem + off);
-    off += (size_t)P.res_floats * 4;
-    v.xres = reinterpret_cast<float *>(smem + off);
-    off += (size_t)P.emb * 4;
-    v.red = reinterpret_cast<float *>(smem + off);
-    off += 64 * 4;
-    v.full = reinterpret_cast<uint64_t *>(smem + off);  // [2][MAX_SLOTS]: even / odd uses of a slot
-    v.empty = v.full + 2 * MAX_SLOTS;
-    off += 3 * MAX_SLOTS * 8;
-    v.sched = reinterpret_cast<const SchedStage *>(smem + off);
-    return v;
-}
-
-static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int res_floats, int emb, int sched_entries)
-{
-    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)res_floats * 4 + (size_t)emb * 4 + 64 * 4 +
-           3 * MAX_SLOTS * 8 + (size_t)sched_entries * sizeof(SchedStage);
+    return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)emb * 4 + 64 * 4 +
+           (size_t)NCW * (hs + ATT_PSTRIDE_PAD) * 4 + 2 * NCW * 16 * 4 + (NBAR + MAX_SLOTS) * 8 +
+           (size_t)sched_entries * sizeof(SchedStage);
 }
 
 __host__ __device__ inline void cta_rows(const PhaseW &ph, int cta, int G, int &r0, int &r1)
@@ -118,453 +107,105 @@ __host__ __device__ inline void cta_rows(const PhaseW &ph, int cta, int G, int &
     r1 = (int)((long long)(cta + 1) * U / G) * ph.unit;
 }
 
-// ring stages that n (a multiple of the phase's unit) rows of a phase take
-__host__ __device__ inline int phase_stages(const PhaseW &ph, int n)
-{
-    if (ph.spg > 0) return (n >> 4) * ph.spg;  // tiled q4_0: spg stages per row group of 16
-    return (n + ph.rps - 1) / ph.rps;
-}
-
-// stage index = div * n_slots + mod, advanced without division
-struct RingPos {
-    uint32_t mod, div;
-};
-__device__ __forceinline__ void ring_advance(RingPos &p, uint32_t n, uint32_t ns)
-{
-    p.mod += n;
-    while (p.mod >= ns) { p.mod -= ns; p.div++; }
-}
-
-__device__ __forceinline__ uint64_t *full_bar(uint64_t *full, uint32_t slot, uint32_t use) { return full + (use & 1u) * MAX_SLOTS + slot; }
-__device__ __forceinline__ uint32_t full_par(uint32_t use) { return (use >> 1) & 1u; }
-
-// ------------------------------------------------------------------ producer
-// Segment order of a CTA's schedule: the embedding row of the token; per layer: rms_att vector,
-// its rows of QKV, of WO, rms_ffn vector, its rows of W13, of W2; then rms_final vector, CLS.
-// The small f32 vectors and the embedding row travel through the ring like weights ("vector
-// stages", one stage each, read by all consumer warps in the prologue) so that no prologue waits
-// for a demand miss queued behind megabytes of in-flight weight requests.  The list is static
-// (nothing in it depends on activations): the host builds it once (build_schedule), the
-// producer warp walks it -- a handful of instructions per stage.
-__device__ __noinline__ void producer_loop(const StreamParams &P, const SmemView sv, const CtaPlan *cp, int token,
-                                           volatile int *issued)
-{
-    const uint64_t pol = l2_policy_evict_first();
-    const uint4 *tab = reinterpret_cast<const uint4 *>(sv.sched);
-    const uint32_t ns = (uint32_t)P.n_slots;
-    // this CTA's section sizes follow from its row ranges (the host list was built from the same cta_rows)
-    const int n_layer = 2 + cp->nst[0] + cp->nst[1] + cp->nst[2] + cp->nst[3];
-    const int e_layer_end = 1 + n_layer, total = 1 + P.L * n_layer + 1 + cp->nst[4];
-    uint32_t slot = 0, par = 1, use = 0;  // par: parity of the empty barrier to wait for; use: use count of the slots
-    int e = 0, l = 0;
-    // L2 prefetch cursor (pf_stages > 0): while the ring is full AND everything issued has landed --
-    // the consumers sit in a hand-over and HBM would idle -- the stages beyond the ring are pulled
-    // into L2, so that the ring later refills at L2 speed.
-    int ps = 0, pe = 0, pl = 0;
-    uint32_t last_slot = 0, last_use = 0;
-    uint32_t bslot = 0xffffffffu, bpar = 0, par_of_last = 0;  // empty barrier (slot, parity) of the last stage of the previous phase
-    int ahead = 0;
-    // pacing: issue at most one KB per `pace` SM cycles (0 = unpaced).  Every byte in flight
-    // beyond bandwidth x latency only adds queueing delay in front of the latency-critical LL
-    // traffic of the phase hand-overs; a paced producer keeps the queues short.
-    long long next_ok = clock64();
-    auto stage_addr = [&](int ee, int ll, int ss, uint32_t &bytes) {
-        const uint4 st = tab[ee];
-        bytes = st.z;
-        unsigned long long src = ((unsigned long long)st.y << 32 | st.x) +
-                                 ((unsigned long long)(st.w & ~SCHED_PHASE_START) << 4) * (unsigned)ll;
-        if (ss == 0) src += (unsigned long long)(token - 1) * bytes;  // the token's embedding row
-        return src;
-    };
-#pragma unroll 1
-    for (int s = 0; s < total; s++) {
-        uint32_t bytes;
-        const unsigned long long src = stage_addr(e, l, s, bytes);
-        // hand-over protection: at most `lookahead` stages of the next phase are issued before the last
-        // stage of the current phase has been released by the consumers
-        if (P.lookahead > 0 && s > 0) {
-            if (tab[e].w & SCHED_PHASE_START) { ahead = 0; bslot = last_slot; bpar = par_of_last; }
-            if (++ahead > P.lookahead && bslot != 0xffffffffu) {
-                while (!mbar_test(&sv.empty[bslot], bpar)) { }
-                bslot = 0xffffffffu;
-            }
-        }
-        if (ps <= s) { ps = s + 1; pe = e; pl = l; if (++pe == e_layer_end && pl + 1 < P.L) { pe = 1; pl++; } }
-        if (++e == e_layer_end && l + 1 < P.L) { e = 1; l++; }
-        if (P.pf_stages > 0) {
-            while (!mbar_test(&sv.empty[slot], par)) {
-                if (ps < total && ps < s + (int)ns + P.pf_stages && s > 0 && mbar_test(full_bar(sv.full, last_slot, last_use), full_par(last_use))) {
-                    long long now = clock64();
-                    if (now >= next_ok) {
-                        uint32_t pb;
-                        const unsigned long long pa = stage_addr(pe, pl, ps, pb);
-                        bulk_prefetch_l2(reinterpret_cast<const void *>(pa), pb);
-                        next_ok = now + (((long long)pb * P.pace) >> 10);
-                        ps++;
-                        if (++pe == e_layer_end && pl + 1 < P.L) { pe = 1; pl++; }
-                    }
-                }
-            }
-        } else {
-            mbar_wait(&sv.empty[slot], par, 1);
-        }
-        if (P.pace > 0) {
-            long long now = clock64();
-            while (now < next_ok) now = clock64();
-            next_ok = now + (((long long)bytes * P.pace) >> 10);
-        }
-        uint64_t *fb = full_bar(sv.full, slot, use);
-        mbar_arrive_expect_tx(fb, bytes);
-        bulk_g2s(sv.ring + (size_t)slot * P.slot_bytes, reinterpret_cast<const void *>(src), bytes, fb, pol);
-        last_slot = slot; last_use = use; par_of_last = par ^ 1u;  // its release completes the empty phase of parity (use & 1)
-        if (++slot == ns) { slot = 0; par ^= 1u; use++; }
-        *issued = s + 1;  // progress of the copy cursor, for the per-CTA trace
-    }
-}
-
-// ------------------------------------------------------------------ consumer helpers
-struct Cons {
-    int tid, warp, lane, nt, nw;  // within the consumer group
-};
-
-// ring cursor of the consumer side: the next stage of the schedule
-struct CState {
-    RingPos pos;
-    uint32_t gmod;  // schedule index of the next stage, mod NG (-> the group that owns it)
-};
-__device__ __forceinline__ void cons_advance(CState &cs, uint32_t n, uint32_t ns)
-{
-    ring_advance(cs.pos, n, ns);
-    cs.gmod = (cs.gmod + n) % (uint32_t)NG;
-}
-
-__device__ __forceinline__ void cons_sync(const Cons &c) { named_bar_sync(CONS_BAR, c.nt); }
-
-// Consume the `nst` stages of one weight phase.  The consumer warps form NG groups of GW warps;
-// group g owns the stages whose schedule index is g (mod NG) and touches no barrier of the others,
-// so a stage costs GW full-waits + GW empty-arrives, consecutive stages are in flight in different
-// groups, and slots are handed back one after the other in ring order (the producer refills
-// progressively, the phase tail is one stage of one group).
-//   f32 / f16: warp cl of a group takes the 128-bit units u = 128 k + 32 cl + lane of every row of
-//     the stage and keeps those units of the activation vector in registers for the whole phase
-//     (KUT <= 4 units per lane; wider rows stream x from shared memory).
-//     Lanes past the end of a row read a clamped (valid) unit against x = 0: no predication.
-//     Lane-partial sums of four rows are reduced together (6 shuffles instead of 20) and the slot
-//     is released as soon as its weights are in registers; partial sums go to plane cl of `res`,
-//     the epilogue adds the GW planes in a fixed order.
-//   q4_0: tensor cores, see consume_q4.
-// Not inlined on purpose: own register allocation (x stays in registers), one copy for all phases.
-struct ConsumeArgs {
-    const PhaseW *ph;      // shared memory
-    uint8_t *ring;
-    const float *xs;
-    float *res;
-    uint64_t *full, *empty;
-    long long *wait_cycles;  // optional trace accumulators (or null); warp-uniform
-    long long *stamps;       // optional 8 clock stamps of this call (trace), or null
-    int nrows, nst, slot_bytes, n_slots, slot0, use0, gmod0, warp, lane;  // use0: use count of slot0 (mod 4)
-};
-
-// four pending lane-partial sums -> four row results (see consume_phase)
-struct Pending {
-    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-    int d0 = 0, d1 = 0, d2 = 0, d3 = 0, np = 0;
-    __device__ __forceinline__ void flush(float *res, int lane)
-    {
-        const bool hi16 = lane & 16, hi8 = lane & 8;
-        float k0 = hi16 ? p2 : p0, k1 = hi16 ? p3 : p1;
-        k0 += __shfl_xor_sync(0xffffffffu, hi16 ? p0 : p2, 16);
-        k1 += __shfl_xor_sync(0xffffffffu, hi16 ? p1 : p3, 16);
-        float k = hi8 ? k1 : k0;
-        k += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
-        k += __shfl_xor_sync(0xffffffffu, k, 4);
-        k += __shfl_xor_sync(0xffffffffu, k, 2);
-        k += __shfl_xor_sync(0xffffffffu, k, 1);
-        const int r = (lane >> 3) & 3;  // which of the four pending results this lane group holds
-        const int d = r == 0 ? d0 : (r == 1 ? d1 : (r == 2 ? d2 : d3));
-        if ((lane & 7) == 0 && r < np) res[d] = k;
-        np = 0;
-    }
-    __device__ __forceinline__ void push(float v, int dst, float *res, int lane)
-    {
-        p3 = p2; p2 = p1; p1 = p0; p0 = v;
-        d3 = d2; d2 = d1; d1 = d0; d0 = dst;
-        if (++np == 4) flush(res, lane);
-    }
-};
-
-// ring walk of one group through a phase: owned stages are NG apart (PROF: trace instrumentation)
-template <bool PROF>
-struct StageWalk {
-    const ConsumeArgs &a;
-    uint32_t slot, use;
-    int s;  // phase-relative index of the group's next stage
-    long long tc0 = 0;
-    int nwaits = 0;
-    __device__ __forceinline__ void stampc(int i) const
-    {
-        if constexpr (PROF)
-            if (a.stamps && a.lane == 0) a.stamps[i] = clock64();
-    }
-    __device__ __forceinline__ StageWalk(const ConsumeArgs &a_) : a(a_)
-    {
-        stampc(1);
-        int first = (a.warp / GW) - a.gmod0;
-        if (first < 0) first += NG;
-        s = first;
-        slot = (uint32_t)a.slot0 + (uint32_t)first;
-        use = (uint32_t)a.use0;
-        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; use++; }
-    }
-    __device__ __forceinline__ bool more() const { return s < a.nst; }
-    __device__ __forceinline__ const uint8_t *wait()
-    {
-        if (PROF && a.wait_cycles) {
-            const long long w0 = clock64();
-            mbar_wait(full_bar(a.full, slot, use), full_par(use), 2);
-            tc0 = clock64();
-            if (a.lane == 0) a.wait_cycles[0] += tc0 - w0;
-            if (nwaits++ == 0) stampc(2);
-        } else {
-            mbar_wait(full_bar(a.full, slot, use), full_par(use), 2);
-        }
-        return a.ring + (size_t)slot * a.slot_bytes;
-    }
-    __device__ __forceinline__ void release()
-    {
-        __syncwarp();
-        if (PROF && a.wait_cycles && a.lane == 0) { a.wait_cycles[4] += clock64() - tc0; a.wait_cycles[8] += 1; }
-        if (a.lane == 0) mbar_arrive(&a.empty[slot]);
-        if (PROF && a.wait_cycles && nwaits == 1) stampc(3);
-        s += NG;
-        slot += NG;
-        if (slot >= (uint32_t)a.n_slots) { slot -= (uint32_t)a.n_slots; use++; }
-    }
-};
-
-template <int WT, int KUT, bool PROF>
-__device__ __forceinline__ void consume_xreg(const ConsumeArgs &a)
-{
-    const PhaseW *ph = a.ph;
-    const int nunits = ph->cols >> (WT == WT_F32 ? 2 : 3), rps = ph->rps, lane = a.lane, cl = a.warp % GW;
-    const uint32_t rs = ph->rs;
-    const float4 *x4 = reinterpret_cast<const float4 *>(a.xs);
-    float *res = a.res + (size_t)cl * ph->rows_cap;
-    XRegs<WT, KUT> x;
-    uint32_t off[KUT];  // byte offsets of this lane's units inside a row (clamped to the row)
-#pragma unroll
-    for (int k = 0; k < KUT; k++) {
-        const int u = k * (32 * GW) + cl * 32 + lane;
-        const bool ok = u < nunits;
-        off[k] = (uint32_t)min(u, nunits - 1) * 16u;
-        if (WT == WT_F16) {
-            x.v[2 * k] = ok ? x4[2 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
-            x.v[2 * k + 1] = ok ? x4[2 * u + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            x.v[k] = ok ? x4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    Pending pd;
-    StageWalk<PROF> w(a);
-    while (w.more()) {
-        const uint8_t *sp = w.wait();
-        const int base = w.s * rps, n = min(rps, a.nrows - base);
-#pragma unroll 1
-        for (int r = 0; r < n; r++) {
-            const uint8_t *row = sp + (uint32_t)r * rs;
-            // units in batches of four: four independent accumulator chains, <= 4 loads in flight
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int kb = 0; kb < KUT; kb += 4) {
-                uint4 wv[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (kb + k < KUT) wv[k] = *reinterpret_cast<const uint4 *>(row + off[kb + k]);
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (kb + k < KUT) {
-                        if (WT == WT_F16) {
-                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].x));
-                            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].y));
-                            const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].z));
-                            const float2 f3 = __half22float2(*reinterpret_cast<const __half2 *>(&wv[k].w));
-                            const float4 xa = x.v[2 * (kb + k)], xb = x.v[2 * (kb + k) + 1];
-                            a0 = fmaf(f0.x, xa.x, a0); a1 = fmaf(f0.y, xa.y, a1);
-                            a2 = fmaf(f1.x, xa.z, a2); a3 = fmaf(f1.y, xa.w, a3);
-                            a0 = fmaf(f2.x, xb.x, a0); a1 = fmaf(f2.y, xb.y, a1);
-                            a2 = fmaf(f3.x, xb.z, a2); a3 = fmaf(f3.y, xb.w, a3);
-                        } else {
-                            const float4 xa = x.v[kb + k];
-                            a0 = fmaf(__uint_as_float(wv[k].x), xa.x, a0);
-                            a1 = fmaf(__uint_as_float(wv[k].y), xa.y, a1);
-                            a2 = fmaf(__uint_as_float(wv[k].z), xa.z, a2);
-                            a3 = fmaf(__uint_as_float(wv[k].w), xa.w, a3);
-                        }
-                    }
-            }
-            pd.push((a0 + a1) + (a2 + a3), base + r, res, lane);
-        }
-        w.release();
-    }
-    if (pd.np) pd.flush(res, lane);
-}
-
-// rows wider than the register budget: the activation units come from shared memory
-template <int WT, bool PROF>
-__device__ __forceinline__ void consume_xsmem(const ConsumeArgs &a)
-{
-    constexpr int KB = 4;
-    const PhaseW *ph = a.ph;
-    const int nunits = ph->cols >> (WT == WT_F32 ? 2 : 3), rps = ph->rps, lane = a.lane, cl = a.warp % GW;
-    const uint32_t rs = ph->rs;
-    const float4 *x4 = reinterpret_cast<const float4 *>(a.xs);
-    float *res = a.res + (size_t)cl * ph->rows_cap;
-    Pending pd;
-    StageWalk<PROF> w(a);
-    while (w.more()) {
-        const uint8_t *sp = w.wait();
-        const int base = w.s * rps, n = min(rps, a.nrows - base);
-#pragma unroll 1
-        for (int r = 0; r < n; r++) {
-            const uint8_t *row = sp + (uint32_t)r * rs;
-            float acc = 0.f;
-#pragma unroll 1
-            for (int u0 = cl * 32 + lane; u0 < nunits; u0 += KB * 32 * GW) {
-                XRegs<WT, KB> x;
-                uint4 wv[KB];
-#pragma unroll
-                for (int k = 0; k < KB; k++) {
-                    const int u = u0 + k * (32 * GW);
-                    const bool ok = u < nunits;
-                    const int uc = min(u, nunits - 1);
-                    wv[k] = *reinterpret_cast<const uint4 *>(row + (uint32_t)uc * 16u);
-                    if (WT == WT_F16) {
-                        x.v[2 * k] = ok ? x4[2 * uc] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        x.v[2 * k + 1] = ok ? x4[2 * uc + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else {
-                        x.v[k] = ok ? x4[uc] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                acc += dot_units<WT, KB>(wv, x);
-            }
-            pd.push(acc, base + r, res, lane);
-        }
-        w.release();
-    }
-    if (pd.np) pd.flush(res, lane);
-}
-
-// q4_0 on the tensor cores (legacy mma.sync m16n8k16, f16 x f16 -> f32): the dequantisation is the
-// instruction bottleneck of a q4_0 mat-vec at B200's HBM rate, and on CUDA cores it costs >= 2
-// instructions per weight.  Here a nibble pair becomes a half2 {1024 + q} with ONE lop3 (the 0x6400
-// exponent trick; high nibbles give 1024 + 16 q and meet activations pre-scaled by 1/16, exact),
-// the products run on the tensor pipe, and the offsets are removed per block with the pre-computed
-// C[b] = 1032 sum(x over the low nibbles) + 72 sum(x over the high nibbles).  The block scale
-// cannot be applied inside the mma, so the n dimension separates blocks: the B operand
-// (activations) of the mma pair of block b is non-zero only in columns b and 4 + b, and D[row][b],
-// D[row][4 + b] end up holding the unscaled sums of block b against the two f16 halves x = hi + lo
-// of the activations (f16 alone would cost 3 digits: greedy tokens flip at near ties).
-// Tiled weight format: common.cuh.  A stage holds the groups [g0, g1) of one row group of 16 rows;
-// the warps of the consumer group take them round-robin and write per-warp partial sums to plane
-// (stage within the row group) * GW + warp.
-__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1)
-{
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t uint4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
-
-template <bool PROF>
-__device__ __forceinline__ void consume_q4(const ConsumeArgs &a)
-{
-    const PhaseW *ph = a.ph;
-    const int ngrp = ph->ngrp, spg = ph->spg, lane = a.lane, g = lane >> 2, t = lane & 3, cl = a.warp % GW;
-    // activations as f16 pairs x = hi + lo in B-fragment order, [half group of 4 blocks][hi | lo][block][t],
-    // then the per-block offset corrections [hi | lo][block] (store_x4)
-    const uint4 *xh4 = reinterpret_cast<const uint4 *>(a.xs);
-    const float *C = a.xs + (size_t)ngrp * 256 + (size_t)(t >> 1) * ngrp * 8;
-    StageWalk<PROF> w(a);
-    while (w.more()) {
-        const uint8_t *sp = w.wait();
-        const int rgl = w.s / spg, si = w.s - rgl * spg;
-        const int g0 = si * ngrp / spg, g1 = (si + 1) * ngrp / spg;
-        float acc0 = 0.f, acc1 = 0.f;  // rows g and g + 8 of the row group
-#pragma unroll 1
-        for (int gi = g0 + cl; gi < g1; gi += GW) {
-            const uint8_t *gp = sp + (size_t)(gi - g0) * Q4T_GROUP_BYTES;
-            uint4 cg[2], c8[2];
-            cg[0] = *reinterpret_cast<const uint4 *>(gp + lane * 16);
-            cg[1] = *reinterpret_cast<const uint4 *>(gp + 512 + lane * 16);
-            c8[0] = *reinterpret_cast<const uint4 *>(gp + 1024 + lane * 16);
-            c8[1] = *reinterpret_cast<const uint4 *>(gp + 1536 + lane * 16);
-#pragma unroll
-            for (int hb = 0; hb < 2; hb++) {
-                // four blocks per accumulation: column n = 4 p + b of D holds block b times the hi (p = 0) /
-                // lo (p = 1) part of x; this lane's B column is n = g, its D columns are 2t, 2t + 1
-                const uint4 xb = xh4[((gi * 2 + hb) * 8 + g) * 4 + t];
-                const uint2 sc = *reinterpret_cast<const uint2 *>(gp + 2048 + (g * 4 + 2 * hb + (t & 1)) * 8);
-                const float2 cc = *reinterpret_cast<const float2 *>(C + gi * 8 + 4 * hb + 2 * (t & 1));
-                // two accumulators (low / high nibbles): two independent mma chains of four
-                float d[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t wg = uint4_word(cg[hb], j), w8 = uint4_word(c8[hb], j);
-                    const uint32_t m = ((g & 3) == j) ? 0xffffffffu : 0u;
-                    const uint32_t wgs = wg >> 8, w8s = w8 >> 8;
-                    mma16816(d, (wg & 0x000f000fu) | 0x64006400u, (w8 & 0x000f000fu) | 0x64006400u,
-                             (wgs & 0x000f000fu) | 0x64006400u, (w8s & 0x000f000fu) | 0x64006400u, xb.x & m, xb.y & m);
-                    mma16816(e, (wg & 0x00f000f0u) | 0x64006400u, (w8 & 0x00f000f0u) | 0x64006400u,
-                             (wgs & 0x00f000f0u) | 0x64006400u, (w8s & 0x00f000f0u) | 0x64006400u, xb.z & m, xb.w & m);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) d[k] += e[k];
-                const float2 s01 = __half22float2(*reinterpret_cast<const __half2 *>(&sc.x));
-                const float2 s23 = __half22float2(*reinterpret_cast<const __half2 *>(&sc.y));
-                acc0 = fmaf(s01.x, d[0] - cc.x, acc0); acc0 = fmaf(s01.y, d[1] - cc.y, acc0);
-                acc1 = fmaf(s23.x, d[2] - cc.x, acc1); acc1 = fmaf(s23.y, d[3] - cc.y, acc1);
-            }
-        }
-        // sum over t: blocks 0,1 | 2,3 and the hi | lo parts
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-        if (t == 0) {
-            float *res = a.res + (size_t)(si * GW + cl) * ph->rows_cap + rgl * 16 + g;
-            res[0] = acc0;
-            res[8] = acc1;
-        }
-        w.release();
-    }
-}
-
-// Scalar parameters only (they travel in registers): a by-value struct would be written to and read
-// back from local memory by every thread, four times per layer.
-template <int WT, bool PROF>
-__device__ __noinline__ void consume_phase(const CtaPlan *cp, Prof *pf, int ph, uint32_t cursor /* slot0 | use0 << 8 | gmod0 << 16 | trace << 24 */)
+__device__ __forceinline__ uint8_t *smem_base()
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    ConsumeArgs a;
-    a.ph = &cp->ph[ph]; a.ring = smem;
-    a.xs = reinterpret_cast<const float *>(smem + cp->off_xs);
-    a.res = reinterpret_cast<float *>(smem + cp->off_res);
-    a.full = reinterpret_cast<uint64_t *>(smem + cp->off_full); a.empty = a.full + 2 * MAX_SLOTS;
-    a.nrows = cp->r1[ph] - cp->r0[ph]; a.nst = cp->nst[ph]; a.slot_bytes = cp->slot_bytes; a.n_slots = cp->n_slots;
-    a.slot0 = (int)(cursor & 255u); a.use0 = (int)((cursor >> 8) & 255u); a.gmod0 = (int)((cursor >> 16) & 255u);
-    a.warp = (int)(threadIdx.x >> 5); a.lane = (int)(threadIdx.x & 31);
-    a.wait_cycles = (PROF && (cursor >> 24)) ? &pf->twait[ph] : nullptr;
-    a.stamps = a.wait_cycles ? &pf->twait[12 + 8 * ph] : nullptr;
-    if (PROF && a.stamps && a.lane == 0) a.stamps[0] = clock64();
-    if constexpr (WT != WT_Q4_0) {
-        // units per lane per row, rounded up to an instantiated register budget
-        const int ku = a.ph->ku;
-        if (ku <= 2) consume_xreg<WT, 2, PROF>(a);
-        else if (ku <= 4) consume_xreg<WT, 4, PROF>(a);
-        else if (WT == WT_F16 && ku <= 6) consume_xreg<WT, WT == WT_F16 ? 6 : 2, PROF>(a);
-        else if (WT == WT_F32 && ku <= 12) consume_xreg<WT, WT == WT_F32 ? 12 : 2, PROF>(a);
-        else consume_xsmem<WT, PROF>(a);
-    } else {
-        consume_q4<PROF>(a);
+    return smem;
+}
+__device__ __forceinline__ uint64_t *full_bar(const CtaPlan *cp, uint32_t s)
+{
+    return reinterpret_cast<uint64_t *>(smem_base() + cp->off_full) + (s & (NBAR - 1));
+}
+__device__ __forceinline__ uint32_t full_par(uint32_t s) { return (s >> 8) & 1u; }
+static_assert(NBAR == 256, "full_par assumes 256 barriers");
+__device__ __forceinline__ uint64_t *empty_bar(const CtaPlan *cp, uint32_t slot)
+{
+    return reinterpret_cast<uint64_t *>(smem_base() + cp->off_empty) + slot;
+}
+__device__ __forceinline__ uint32_t slot_of(const CtaPlan *cp, uint32_t s)
+{
+    return s - __umulhi(s, cp->slot_magic) * (uint32_t)cp->n_slots;
+}
+__device__ __forceinline__ void cons_sync() { named_bar_sync(CONS_BAR, NCT); }
+
+// ------------------------------------------------------------------ producer
+// Walks this CTA's stage list: [embedding row][one layer's stages] x L [final norm + classifier].
+// The small f32 norm vectors and the embedding row travel through the ring like weights ("vector
+// stages", read by all consumer warps in the prologue) so that no prologue waits for a demand miss
+// queued behind megabytes of in-flight weight requests.
+//
+// Two cursors walk the list.  The RING cursor copies stage s into its slot as soon as the consumers
+// have handed the slot back.  The PREFETCH cursor runs up to `pf_lead` stages ahead of it and pulls
+// those stages into L2 (cp.async.bulk.prefetch.L2): the ring holds ~1 us of HBM time per SM, a phase
+// hand-over takes several, and while the consumers sit in one nothing else would be fetching.  L2
+// (126 MB) is the elastic buffer that keeps HBM streaming through the hand-overs; the ring then
+// refills from L2 at several times the SM's share of HBM bandwidth, and the consumers drain it at
+// shared-memory speed.  Every weight byte still crosses HBM once (the ring copy of a prefetched
+// stage hits L2, or merges with the fill in flight) and leaves L2 after its single use (evict_first
+// on the ring copy).
+// Pacing: the cursor that generates the HBM traffic issues at most one KB per `pace` SM cycles (0 =
+// unpaced).  Every byte in flight beyond bandwidth x latency only adds queueing delay in front of
+// the latency-critical LL traffic of the phase hand-overs; a paced producer keeps the queues short.
+struct SchedCursor {
+    int e, l;  // entry of the CTA's stage list, layer
+};
+__device__ __forceinline__ unsigned long long sched_stage(const CtaPlan *cp, const uint4 *tab, SchedCursor &c, int e_layer_end,
+                                                          int token, uint32_t &bytes, uint32_t &nseg, uint32_t &sstr)
+{
+    const uint4 st = tab[c.e];
+    const uint32_t kind = (st.w >> 8) & 0xfu;
+    bytes = st.z; nseg = st.w & 0xffu; sstr = cp->sstride[kind];
+    unsigned long long src = ((unsigned long long)st.y << 32 | st.x) + cp->lstride[kind] * (unsigned)c.l;
+    if (kind == SK_EMB_ROW) src += (unsigned long long)(token - 1) * bytes;
+    if (++c.e == e_layer_end && c.l + 1 < cp->L) { c.e = 1; c.l++; }
+    return src;
+}
+__device__ __noinline__ void producer_loop(CtaPlan *cp, int token, int pace, int pf_lead)
+{
+    const uint64_t pol = l2_policy_evict_first();
+    const uint4 *tab = reinterpret_cast<const uint4 *>(smem_base() + cp->off_sched);
+    const uint32_t ns = (uint32_t)cp->n_slots;
+    const int n_layer = 2 + cp->nst[0] + cp->nst[1] + cp->nst[2] + cp->nst[3];
+    const int e_layer_end = 1 + n_layer, total = 1 + cp->L * n_layer + 1 + cp->nst[4];
+    uint32_t slot = 0, par = 1;  // par: parity of the empty barrier to wait for
+    SchedCursor rc{0, 0}, pc{0, 0};
+    int s = 0, ps = 0;           // next stage of the ring cursor / of the prefetch cursor
+    int unfetched = -1;          // the stage the prefetch cursor skipped (the ring cursor had caught up with it)
+    long long next_ok = clock64();
+#pragma unroll 1
+    while (s < total) {
+        if (pf_lead > 0 && ps < total && ps <= s + pf_lead) {
+            uint32_t b, n, ss;
+            if (ps <= s) {
+                // a stage the ring cursor is about to copy anyway is not worth a prefetch: stay ahead of it
+                sched_stage(cp, tab, pc, e_layer_end, token, b, n, ss);
+                unfetched = ps++;
+                cp->pf_issued = ps;
+            } else if (clock64() >= next_ok) {
+                const unsigned long long src = sched_stage(cp, tab, pc, e_layer_end, token, b, n, ss);
+#pragma unroll 1
+                for (uint32_t i = 0; i < n; i++) bulk_prefetch_l2(reinterpret_cast<const void *>(src + (unsigned long long)i * ss), b);
+                next_ok = max(next_ok, clock64() - 2000) + (((long long)(b * n) * pace) >> 10);
+                ps++;
+                cp->pf_issued = ps;
+            }
+        }
+        if (!mbar_test(empty_bar(cp, slot), par)) continue;
+        // a copy that goes to HBM (not prefetched) shares the paced budget; one that hits L2 does not
+        const bool to_hbm = pf_lead == 0 || s == unfetched;
+        if (to_hbm && pace > 0 && clock64() < next_ok) continue;
+        uint32_t bytes, nseg, sstr;
+        const unsigned long long src = sched_stage(cp, tab, rc, e_layer_end, token, bytes, nseg, sstr);
+        if (to_hbm) next_ok = max(next_ok, clock64() - 2000) + (((long long)(bytes * nseg) * pace) >> 10);
+        uint64_t *fb = full_bar(cp, (uint32_t)s);
+        mbar_arrive_expect_tx(fb, bytes * nseg);
+        uint8_t *dst = smem_base() + (size_t)slot * cp->slot_bytes;
+#pragma unroll 1
+        for (uint32_t i = 0; i < nseg; i++)
+            bulk_g2s(dst + i * bytes, reinterpret_cast<const void *>(src + (unsigned long long)i * sstr), bytes, fb, pol);
+        if (++slot == ns) { slot = 0; par ^= 1u; }
+        s++;
+        cp->prod_issued = s;
     }
 }
 
@@ -573,7 +214,9 @@ __device__ __noinline__ void consume_phase(const CtaPlan *cp, Prof *pf, int ph, 
 // are single-copy atomic, so value and epoch always arrive together; relaxed gpu-scope accesses
 // go to L2 (never a stale L1 line).  A buffer is rewritten one layer later at the earliest, and
 // a CTA can only get there after it has seen every other CTA's output of the phases in between,
-// i.e. after every reader of the old contents is done -- no write-after-read hazard.
+// i.e. after every reader of the old contents is done (every prologue ends with a CTA-wide
+// barrier, so "a CTA has published phase p" implies all its warps finished reading phase p - 1's
+// inputs) -- no write-after-read hazard.
 __device__ __forceinline__ void ll_store(unsigned long long *buf, int i, float v, uint32_t ep)
 {
     const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)ep << 32);
@@ -590,6 +233,13 @@ __device__ __forceinline__ void ll_store2(unsigned long long *buf, int i, float 
 {
     const unsigned long long e = (unsigned long long)ep << 32;
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(buf + i), "l"(e | __float_as_uint(v0)),
+                 "l"(e | __float_as_uint(v1))
+                 : "memory");
+}
+__device__ __forceinline__ void ll_store2_sys(unsigned long long *buf, int i, float v0, float v1, uint32_t ep)
+{
+    const unsigned long long e = (unsigned long long)ep << 32;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(buf + i), "l"(e | __float_as_uint(v0)),
                  "l"(e | __float_as_uint(v1))
                  : "memory");
 }
@@ -656,20 +306,16 @@ __device__ __forceinline__ void ll_waitv(const unsigned long long *buf, int i, u
         o[0] = ll_val(a);
     }
 }
-// A thread's batch of PV float4 positions j = base + tid + k * nt of an LL vector: all requests of
+// A thread's batch of PV float4 positions j = base + tid + k * NCT of an LL vector: all requests of
 // a polling round are issued before the first check (one L2 round trip per round).  Positions
 // past the end are clamped to the last one (a harmless duplicate request).
 template <int PV>
-__device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4, int base, uint32_t ep,
-                                          const Cons &c, float4 (&v)[PV])
+__device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4, int base, uint32_t ep, float4 (&v)[PV])
 {
     unsigned long long w[PV][4];
     int jj[PV];
 #pragma unroll
-    for (int k = 0; k < PV; k++) {
-        const int j = base + c.tid + k * c.nt;
-        jj[k] = min(j, n4 - 1);
-    }
+    for (int k = 0; k < PV; k++) jj[k] = min(base + (int)threadIdx.x + k * NCT, n4 - 1);
     bool ok;
     LLMF90_WD_DECL;
     do {
@@ -689,33 +335,15 @@ __device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4,
 }
 
 // ---- vector stages: every consumer thread waits for the stage and reads what it needs; after
-// the consumer-wide barrier that ends the prologue the warps of the group that owns it hand it back
-// (the out-of-line pieces and the phase loop address shared memory through the plan's offsets instead
-// of keeping a SmemView alive: whatever is live across a call is spilled around it)
-__device__ __forceinline__ uint8_t *smem_base()
+// the consumer-wide barrier that ends the prologue one thread hands the slot back
+__device__ __forceinline__ const uint8_t *vec_stage_wait(const CtaPlan *cp, uint32_t s)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    return smem;
+    mbar_wait(full_bar(cp, s), full_par(s), 3);
+    return smem_base() + (size_t)slot_of(cp, s) * cp->slot_bytes;
 }
-__device__ __forceinline__ uint64_t *plan_full(const CtaPlan *cp) { return reinterpret_cast<uint64_t *>(smem_base() + cp->off_full); }
-__device__ __forceinline__ uint64_t *plan_empty(const CtaPlan *cp) { return plan_full(cp) + 2 * MAX_SLOTS; }
-__device__ __forceinline__ Cons plan_cons(const CtaPlan *cp)
+__device__ __forceinline__ void vec_stage_release(const CtaPlan *cp, uint32_t s)
 {
-    Cons c;
-    c.tid = (int)threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
-    c.nw = cp->n_cons_warps; c.nt = c.nw * 32;
-    return c;
-}
-__device__ __forceinline__ const uint8_t *vec_stage_wait(const CtaPlan *cp, const RingPos &at)
-{
-    mbar_wait(full_bar(plan_full(cp), at.mod, at.div), full_par(at.div), 3);
-    return smem_base() + (size_t)at.mod * cp->slot_bytes;
-}
-// call in stage order, after a cons_sync that follows the last read of the stage
-__device__ __forceinline__ void vec_stage_release(const CtaPlan *cp, CState &cs)
-{
-    if ((threadIdx.x & 31) == 0 && (uint32_t)(threadIdx.x >> 5) / GW == cs.gmod) mbar_arrive(&plan_empty(cp)[cs.pos.mod]);
-    cons_advance(cs, 1u, (uint32_t)cp->n_slots);
+    if ((int)threadIdx.x < cp->G) mbar_arrive(empty_bar(cp, slot_of(cp, s)));  // (the slot expects G arrivals)
 }
 
 // ---- activation-vector prologue, one routine for all phases.  Every CTA needs the whole vector;
@@ -770,10 +398,10 @@ __device__ __forceinline__ void store_x4(float *xs, int n, int j4, const float4 
     }
 }
 // q4_0: blocks past the end of the vector (the last group of 8 may be partial) read as zero
-__device__ __forceinline__ void q4_zero_tail(float *xs, int n, int tid, int nt)
+__device__ __forceinline__ void q4_zero_tail(float *xs, int n)
 {
     const int nblk = n >> 5, ngrp = q4t_groups(n);
-    for (int b = nblk + tid; b < ngrp * 8; b += nt) {
+    for (int b = nblk + (int)threadIdx.x; b < ngrp * 8; b += NCT) {
         uint8_t *rec = reinterpret_cast<uint8_t *>(xs) + (size_t)((b >> 2) * 8 + (b & 3)) * 64;
         uint4 *p = reinterpret_cast<uint4 *>(rec), *q = reinterpret_cast<uint4 *>(rec + 256);
         p[0] = p[1] = p[2] = p[3] = make_uint4(0u, 0u, 0u, 0u);
@@ -789,54 +417,48 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
                        row_elem(row, wtype, cols, 4 * j4 + 2), row_elem(row, wtype, cols, 4 * j4 + 3));
 }
 
-// (out of line with scalar parameters: its registers do not add to the pressure of the phase loop)
+// The previous phase's mat-vec has no closing barrier (each warp publishes its tiles and moves on), so
+// xs may still be read by a slower warp when a faster one gets here: poll first (that is the long
+// part), then one consumer-wide barrier before the first write to xs, one after the last.
 template <int WT>
 __device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long long *src, int nsrc, uint32_t ep, int n,
-                                       int norm, int wtype, const uint8_t *emb_row, const float *wn /* shared */)
+                                       int norm, const uint8_t *emb_row, const float *wn /* shared */)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    SmemView sv;
-    sv.xs = reinterpret_cast<float *>(smem + cp->off_xs);
-    sv.xres = reinterpret_cast<float *>(smem + cp->off_xres);
-    sv.red = reinterpret_cast<float *>(smem + cp->off_red);
-    Cons c;
-    c.tid = (int)threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
-    c.nw = cp->n_cons_warps; c.nt = c.nw * 32;
+    float *xs = reinterpret_cast<float *>(smem_base() + cp->off_xs);
+    float *red = reinterpret_cast<float *>(smem_base() + cp->off_red);
+    float4 *xr4 = reinterpret_cast<float4 *>(smem_base() + cp->off_xres);
+    const int tid = (int)threadIdx.x;
     constexpr int PV = 2;
     const int n4 = n >> 2;
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
-    float4 *xr4 = reinterpret_cast<float4 *>(sv.xres);
     float ss = 0.f;
 #pragma unroll 1
-    for (int base = 0; base < n4; base += PV * c.nt) {
+    for (int base = 0; base < n4; base += PV * NCT) {
         float4 v[PV];
         if (emb_row) {
 #pragma unroll
-            for (int k = 0; k < PV; k++) {
-                const int j = base + c.tid + k * c.nt;
-                v[k] = emb_row4(emb_row, wtype, n, min(j, n4 - 1));
-            }
+            for (int k = 0; k < PV; k++) v[k] = emb_row4(emb_row, cp->wtype, n, min(base + tid + k * NCT, n4 - 1));
         } else {
-            ll_gather<PV>(src, n4, base, ep, c, v);
+            ll_gather<PV>(src, n4, base, ep, v);
             if (norm) {
 #pragma unroll
                 for (int k = 0; k < PV; k++) {
-                    const int j = base + c.tid + k * c.nt;
-                    const float4 x = xr4[min(j, n4 - 1)];
+                    const float4 x = xr4[min(base + tid + k * NCT, n4 - 1)];
                     v[k].x += x.x; v[k].y += x.y; v[k].z += x.z; v[k].w += x.w;
                 }
 #pragma unroll 1
                 for (int r = 1; r < nsrc; r++) {
                     float4 t[PV];
-                    ll_gather<PV>(src + (size_t)r * n, n4, base, ep, c, t);
+                    ll_gather<PV>(src + (size_t)r * n, n4, base, ep, t);
 #pragma unroll
                     for (int k = 0; k < PV; k++) { v[k].x += t[k].x; v[k].y += t[k].y; v[k].z += t[k].z; v[k].w += t[k].w; }
                 }
             }
         }
+        if (base == 0) cons_sync();  // xs is free: every warp is past the previous phase's mat-vec
 #pragma unroll
         for (int k = 0; k < PV; k++) {
-            const int j = base + c.tid + k * c.nt;
+            const int j = base + tid + k * NCT;
             const bool valid = j < n4;
             float4 t = v[k];
             if (valid && norm) {
@@ -845,19 +467,20 @@ __device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long lo
                 const float4 w = wn4[j];
                 t.x *= w.x; t.y *= w.y; t.z *= w.z; t.w *= w.w;
             }
-            store_x4<WT>(sv.xs, n, j, t, valid);
+            store_x4<WT>(xs, n, j, t, valid);
         }
     }
-    if (WT == WT_Q4_0) q4_zero_tail(sv.xs, n, c.tid, c.nt);
+    if (WT == WT_Q4_0) q4_zero_tail(xs, n);
     if (!norm) {
-        cons_sync(c);
+        cons_sync();
         return 1.f;
     }
     ss = warp_sum(ss);
-    if (c.lane == 0) sv.red[c.warp] = ss;
-    cons_sync(c);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    cons_sync();
     float tot = 0.f;
-    for (int i = 0; i < c.nw; i++) tot += sv.red[i];
+#pragma unroll
+    for (int i = 0; i < NCW; i++) tot += red[i];
     return 1.0f / sqrtf(tot / (float)n + 1e-5f);
 }
 
@@ -870,10 +493,9 @@ __device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long lo
 //   softmax: online (running max / sum) over the 8 positions, three shuffles each
 //   values : lane <-> head dimension (hs/32 consecutive dims), p_t broadcast by shuffle
 // Positions past the end of a group read a clamped (valid) row with probability 0.
-// Warp partials merge through shared memory.  With one split the normalised head output goes
-// straight to P.att; otherwise {m, l, acc} partials go to P.att_part and the Wo prologue merges.
-constexpr int ATT_PSTRIDE_PAD = 4;  // partial record = {m, l, -, -, acc[hs]}
-
+// Warp partials merge through shared memory (a scratch area of its own: xs may still be in use by a
+// slower warp's QKV tiles).  With one split the normalised head output goes straight to ll_att;
+// otherwise {m, l, acc} partials go to ll_part and the Wo prologue merges.
 template <int VEC>
 __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 {
@@ -889,59 +511,97 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 }
 
 template <int HS>
-__device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int n_splits, int layer, int pos, uint32_t ep)
+__device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int n_splits, int layer, int pos, uint32_t ep,
+                                               unsigned long long *tr /* optional 8 trace words (profiling), or null */)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    SmemView sv;
-    sv.xs = reinterpret_cast<float *>(smem + cp->off_xs);
-    Cons c;
-    c.tid = (int)threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
-    c.nw = cp->n_cons_warps; c.nt = c.nw * 32;
+#define ASTAMP(k_) do { if (tr && threadIdx.x == 0) tr[k_] = (unsigned long long)clock64(); } while (0)
+    ASTAMP(0);
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int hs = HS, vec = HS >> 5;  // HS in {32, 64, 128}
     constexpr int q4n = HS >> 4;           // float4 per lane of a quarter head: 2, 4, 8
-    const CtaPlan::Att &T = cp->att;
     const int S = n_splits;
-    const int items = T.H * S;
-    const int npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches)
-    const int s_shift = 31 - __clz(S), kvm_shift = 31 - __clz(T.kv_mul);
-    const bool kvm_pow2 = (T.kv_mul & (T.kv_mul - 1)) == 0;
-    const int chunk = (((npast + S - 1) >> s_shift) + 7) & ~7;
-    const int pstride = hs + ATT_PSTRIDE_PAD;
+    const int H = cp->H, kv = cp->kv, kv_mul = cp->kv_mul, att_dim = cp->att_dim, ll_rep = cp->ll_rep;
+    const int items = H * S;
+    const int npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches); npast is this launch's
+    const int s_shift = 31 - __clz(S), kvm_shift = 31 - __clz(kv_mul);
+    const bool kvm_pow2 = (kv_mul & (kv_mul - 1)) == 0;
+    const int chunk = (((pos + S - 1) >> s_shift) + 7) & ~7;
+    constexpr int pstride = hs + ATT_PSTRIDE_PAD;
     const float rscale = 1.0f / sqrtf((float)hs);
-    float *sc = sv.xs;  // [nw][pstride]  (xs is dead between weight phases)
-    const float *kc = T.kc + (size_t)layer * T.seq * T.kv;
-    const float *vc = T.vc + (size_t)layer * T.seq * T.kv;
-    const int pl = c.lane >> 2, dq = c.lane & 3;
-    const int rep = (int)blockIdx.x % T.ll_rep;  // the replica of the LL vectors this CTA polls
-    const unsigned long long *ll_q = T.ll_q + (size_t)rep * T.att_dim, *ll_kv = T.ll_kv + (size_t)rep * 2 * T.kv;
+    float *sc = reinterpret_cast<float *>(smem_base() + cp->off_att);  // [NCW][pstride]
+    const float *kc = cp->kc + (size_t)layer * cp->seq * kv;
+    const float *vc = cp->vc + (size_t)layer * cp->seq * kv;
+    const int pl = lane >> 2, dq = lane & 3;
+    const int rep = (int)blockIdx.x % ll_rep;  // the replica of the LL vectors this CTA polls
+    const unsigned long long *ll_q = cp->ll_q + (size_t)rep * att_dim, *ll_kv = cp->ll_kv + (size_t)rep * 2 * kv;
 #pragma unroll 1
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         // (S is a power of two; kv_mul is one in every common model: shifts, the division is a cold path)
         const int h = item >> s_shift, sp = item & (S - 1);
-        const int g = kvm_pow2 ? h >> kvm_shift : h / T.kv_mul;
-        const int t0 = sp * chunk, t1 = min(npast, t0 + chunk);
+        const int g = kvm_pow2 ? h >> kvm_shift : h / kv_mul;
+        // this split's positions [t0, t1): the last one of the last split is the current position, whose key /
+        // value rows were produced in this launch (LL buffer) -- every other row comes from the cache
+        const int t0 = sp * chunk, t1 = min(pos, t0 + chunk);
         float m = -INFINITY, l = 0.f, acc[vec];
 #pragma unroll
         for (int i = 0; i < vec; i++) acc[i] = 0.f;
-        // this lane's quarter of the query head (written by the QKV epilogues of this launch);
-        // polled after the first group's K / V requests are in flight
         float4 qq[q4n];
         bool have_q = false;
 #pragma unroll 1
-        for (int tb = t0 + 8 * c.warp; tb < t1; tb += 8 * c.nw) {
+        for (int tb = t0 + 8 * warp; tb < t1; tb += 8 * NCW) {
             const int t = tb + pl;
             const bool valid = t < t1;
-            const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)min(t, t1 - 1) * T.kv + (size_t)g * hs +
-                                                                dq * (hs >> 2));
-            const float *vb = vc + (size_t)g * hs + c.lane * vec;
+            const int ucur = npast - tb;  // index of the current position in this group of 8 (0..7), if it is in it
+            const bool has_cur = ucur >= 0 && ucur < 8;
+            // cached rows: positions past the end (and the current one) read a clamped, valid row instead
+            const int tlast = min(t1, npast) - 1;
+            const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)max(0, min(t, tlast)) * kv + (size_t)g * hs + dq * (hs >> 2));
+            const float *vb = vc + (size_t)g * hs + lane * vec;
             float4 kk[q4n];
             float vv[8][vec];
 #pragma unroll
             for (int i = 0; i < q4n; i++) kk[i] = __ldcg(kr + i);
 #pragma unroll
-            for (int u = 0; u < 8; u++) load_vec<vec>(vb + (size_t)min(tb + u, t1 - 1) * T.kv, vv[u]);
-            if (!have_q) {
-                ll_wait4n<q4n>(ll_q, h * hs + dq * (hs >> 2), ep, qq);
+            for (int u = 0; u < 8; u++) load_vec<vec>(vb + (size_t)max(0, min(tb + u, tlast)) * kv, vv[u]);
+            if (!have_q || has_cur) {
+                // ONE polling loop for everything this launch produced: the query quarter and, in the warp that
+                // holds the current position, its key quarter and value dims (one L2 round trip, not three)
+                const unsigned long long *pq = ll_q + h * hs + dq * (hs >> 2);
+                const unsigned long long *pk = ll_kv + g * hs + dq * (hs >> 2);
+                const unsigned long long *pv = ll_kv + kv + g * hs + lane * vec;
+                const bool mine = has_cur && pl == ucur;  // the four lanes that hold the current position's key
+                bool ok;
+                LLMF90_WD_DECL;
+                do {
+                    LLMF90_WD_CHECK(102, h, ep)
+                    ok = true;
+#pragma unroll
+                    for (int k = 0; k < q4n; k++) {
+                        unsigned long long a, b, c, d;
+                        ll_load2(pq + 4 * k, a, b);
+                        ll_load2(pq + 4 * k + 2, c, d);
+                        ok = ok && ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep);
+                        qq[k] = make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
+                    }
+                    if (has_cur) {
+#pragma unroll
+                        for (int k = 0; k < q4n; k++) {
+                            unsigned long long a, b, c, d;
+                            ll_load2(pk + 4 * k, a, b);
+                            ll_load2(pk + 4 * k + 2, c, d);
+                            ok = ok && ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep);
+                            if (mine) kk[k] = make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
+                        }
+#pragma unroll
+                        for (int k = 0; k < vec; k++) {
+                            const unsigned long long a = ll_load1(pv + k);
+                            ok = ok && ll_ok(a, ep);
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (u == ucur) vv[u][k] = ll_val(a);
+                        }
+                    }
+                } while (!ok);
                 have_q = true;
             }
             float sdot = 0.f;
@@ -975,79 +635,68 @@ __device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int n_splits, 
                 for (int i = 0; i < vec; i++) acc[i] = fmaf(pt, vv[u][i], acc[i]);
             }
         }
-        if (sp == S - 1 && c.warp == 0) {
-            // the current position: its key / value rows were produced in this launch (LL buffer)
-            float4 kk[q4n];
-            float vv[vec];
-            if (!have_q) ll_wait4n<q4n>(ll_q, h * hs + dq * (hs >> 2), ep, qq);
-            ll_wait4n<q4n>(ll_kv, g * hs + dq * (hs >> 2), ep, kk);
-            ll_waitv<vec>(ll_kv, T.kv + g * hs + c.lane * vec, ep, vv);
-            float sdot = 0.f;
+        ASTAMP(3);
+        float *mine = sc + (size_t)warp * pstride;
+        if (lane == 0) { mine[0] = m; mine[1] = l; }
 #pragma unroll
-            for (int i = 0; i < q4n; i++) {
-                sdot = fmaf(qq[i].x, kk[i].x, sdot); sdot = fmaf(qq[i].y, kk[i].y, sdot);
-                sdot = fmaf(qq[i].z, kk[i].z, sdot); sdot = fmaf(qq[i].w, kk[i].w, sdot);
-            }
-            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-            sdot = sdot * rscale;  // identical in every lane (all lanes hold the same position)
-            const float mn = fmaxf(m, sdot);
-            const float corr = expf(m - mn), p = expf(sdot - mn);
-            l = fmaf(l, corr, p);
-            m = mn;
+        for (int i = 0; i < vec; i++) mine[ATT_PSTRIDE_PAD + lane * vec + i] = acc[i];
+        cons_sync();
+        ASTAMP(5);
+        // merge of the warp partials by whole warps: lane w < 12 holds warp w's {m, l} and its weight
+        // exp(m_w - M); a lane then sums its dims over the 12 records.  One warp per LL replica (S == 1) /
+        // warp 0 (partial record of a split); the merge is cheap enough to repeat per replica.
+        const int nout = S == 1 ? ll_rep : 1;
+        if (warp < nout) {
+            const float mw = lane < NCW ? sc[lane * pstride] : -INFINITY;
+            const float M = warp_max(mw);
+            const float e = mw > -INFINITY ? __expf(mw - M) : 0.f;
+            const float L = warp_sum(lane < NCW ? e * sc[lane * pstride + 1] : 0.f);
+            float ew[NCW];  // (all lanes take part in the shuffles: hs = 32 leaves half of them without a dim pair)
 #pragma unroll
-            for (int i = 0; i < vec; i++) acc[i] = fmaf(acc[i], corr, p * vv[i]);
-        }
-        float *mine = sc + (size_t)c.warp * pstride;
-        if (c.lane == 0) { mine[0] = m; mine[1] = l; }
-#pragma unroll
-        for (int i = 0; i < vec; i++) mine[ATT_PSTRIDE_PAD + c.lane * vec + i] = acc[i];
-        cons_sync(c);
-        // thread = (head dimension d, LL replica): every thread publishes one word
-        for (int w = c.tid; w < hs * (S == 1 ? T.ll_rep : 1); w += c.nt) {
-            const int d = w & (hs - 1), rr = w / hs;
-            float M = -INFINITY;
+            for (int w = 0; w < NCW; w++) ew[w] = __shfl_sync(0xffffffffu, e, w);
 #pragma unroll 1
-            for (int w = 0; w < c.nw; w++) M = fmaxf(M, sc[w * pstride]);
-            float L = 0.f, A = 0.f;
+            for (int rr = warp; rr < nout; rr += NCW) {
 #pragma unroll 1
-            for (int w = 0; w < c.nw; w++) {
-                const float mw = sc[w * pstride];
-                if (mw > -INFINITY) {
-                    const float e = __expf(mw - M);
-                    L = fmaf(sc[w * pstride + 1], e, L);
-                    A = fmaf(sc[w * pstride + ATT_PSTRIDE_PAD + d], e, A);
+                for (int d = 2 * lane; d < hs; d += 64) {
+                    float A0 = 0.f, A1 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NCW; w++) {
+                        const float2 a = *reinterpret_cast<const float2 *>(sc + w * pstride + ATT_PSTRIDE_PAD + d);
+                        A0 = fmaf(a.x, ew[w], A0); A1 = fmaf(a.y, ew[w], A1);
+                    }
+                    if (S == 1) {
+                        ll_store2(cp->ll_att + (size_t)rr * att_dim, h * hs + d, A0 / L, A1 / L, ep);
+                    } else {
+                        unsigned long long *out = cp->ll_part + (size_t)(h * S + sp) * pstride;
+                        ll_store2(out, ATT_PSTRIDE_PAD + d, A0, A1, ep);
+                        if (d == 0) ll_store2(out, 0, M, L, ep);
+                    }
                 }
             }
-            if (S == 1) {
-                ll_store(T.ll_att + (size_t)rr * T.att_dim, h * hs + d, A / L, ep);
-            } else {
-                unsigned long long *out = T.ll_part + (size_t)(h * S + sp) * pstride;
-                ll_store(out, ATT_PSTRIDE_PAD + d, A, ep);
-                if (d == 0) { ll_store(out, 0, M, ep); ll_store(out, 1, L, ep); }
-            }
         }
-        cons_sync(c);
+        ASTAMP(6);
+        cons_sync();
     }
+    ASTAMP(7);
+#undef ASTAMP
 }
 
 // xs = attention output (all heads), merging the position splits (n_splits > 1).  A thread owns one
 // float4 of the output; the {m, l} pair and the float4 of all S partial records are requested
 // together (one L2 round trip per polling round).
 template <int WT>
-__device__ __noinline__ void load_x_attn(const StreamParams &P, const CtaPlan *cp, uint32_t ep)
+__device__ __noinline__ void load_x_attn(const CtaPlan *cp, int S, uint32_t ep)
 {
-    SmemView sv;
-    sv.xs = reinterpret_cast<float *>(smem_base() + cp->off_xs);
-    const Cons c = plan_cons(cp);
-    const int S = P.n_splits;
-    const int hs = P.hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = P.att_dim >> 2;
+    float *xs = reinterpret_cast<float *>(smem_base() + cp->off_xs);
+    const int tid = (int)threadIdx.x;
+    const int hs = cp->hs, pstride = hs + ATT_PSTRIDE_PAD, n4 = cp->att_dim >> 2;
     const int hs_shift = hs == 64 ? 6 : (hs == 128 ? 7 : 5);
-    for (int jj = c.tid; jj < ((n4 + 31) & ~31); jj += c.nt) {
+    bool first = true;
+    for (int jj = tid; jj < ((n4 + 31) & ~31) || first; jj += NCT) {
         const bool valid = jj < n4;
         const int j = valid ? jj : n4 - 1;
         const int h = (4 * j) >> hs_shift, d = (4 * j) & (hs - 1);
-        const unsigned long long *part = P.ll_part + (size_t)h * S * pstride;
+        const unsigned long long *part = cp->ll_part + (size_t)h * S * pstride;
         unsigned long long ml[8][2], av[8][4];
         bool ok;
         LLMF90_WD_DECL;
@@ -1082,10 +731,12 @@ __device__ __noinline__ void load_x_attn(const StreamParams &P, const CtaPlan *c
                 num.x = fmaf(ll_val(av[s][0]), w, num.x); num.y = fmaf(ll_val(av[s][1]), w, num.y);
                 num.z = fmaf(ll_val(av[s][2]), w, num.z); num.w = fmaf(ll_val(av[s][3]), w, num.w);
             }
-        store_x4<WT>(sv.xs, P.att_dim, jj, make_float4(num.x / den, num.y / den, num.z / den, num.w / den), valid);
+        if (first) { cons_sync(); first = false; }  // xs is free (see gather_x); every thread gets here once
+        if (jj < ((n4 + 31) & ~31))
+            store_x4<WT>(xs, cp->att_dim, jj, make_float4(num.x / den, num.y / den, num.z / den, num.w / den), valid);
     }
-    if (WT == WT_Q4_0) q4_zero_tail(sv.xs, P.att_dim, c.tid, c.nt);
-    cons_sync(c);
+    if (WT == WT_Q4_0) q4_zero_tail(xs, cp->att_dim);
+    cons_sync();
 }
 
 // ------------------------------------------------------------------ profiling hooks (out of line)
@@ -1095,77 +746,56 @@ __device__ __noinline__ void prof_lap(Prof *pf, int bucket)
     pf->tacc[bucket] += now - pf->tmark;
     pf->tmark = now;
 }
-// per-CTA trace of one layer: globaltimer stamp, producer / consumer ring cursors and the number
-// of landed stages at phase edge k
-__device__ __noinline__ void prof_stamp(const StreamParams &P, const CtaPlan *cp, uint32_t pos_mod, uint32_t pos_div, Prof *pf, int k)
+// per-CTA trace of one layer: globaltimer stamp at phase edge k
+__device__ __noinline__ void prof_stamp(unsigned long long *trace, int k)
 {
-    SmemView sv;
-    sv.full = plan_full(cp);
-    CState cs;
-    cs.pos.mod = pos_mod; cs.pos.div = pos_div;
-    unsigned long long *row = P.trace + (size_t)blockIdx.x * 128;
-    row[k] = globaltimer_ns();
-    row[32 + k] = (unsigned long long)pf->prod_issued;
-    RingPos at = cs.pos;
-    int landed = 0;
-    for (int i = 0; i < P.n_slots; i++) {
-        landed += mbar_test(full_bar(sv.full, at.mod, at.div), full_par(at.div)) ? 1 : 0;
-        ring_advance(at, 1u, (uint32_t)P.n_slots);
-    }
-    row[48 + k] = (unsigned long long)(cs.pos.div * (uint32_t)P.n_slots + cs.pos.mod) | ((unsigned long long)landed << 32);
+    trace[(size_t)blockIdx.x * 128 + k] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------ token tail (once per launch)
 // all-gathered logits must have landed on every rank before any rank's kernel ends (tp > 1), then
 // maxloc(logits) (llama2.f90:388): first maximum wins at every reduction level
-__device__ __noinline__ void token_tail(const StreamParams &P, const CtaPlan *cp, float best, int bidx, int pos)
+__device__ __noinline__ void token_tail(const CtaPlan *cp, int pos)
 {
-    SmemView sv;
-    sv.red = reinterpret_cast<float *>(smem_base() + cp->off_red);
-    const Cons c = plan_cons(cp);
-    const uint32_t epl = P.ep_base + (uint32_t)P.L + 1u;
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t epl = cp->ep_last;
+    const int tp = cp->tp, rank = cp->rank;
     const int G = (int)gridDim.x;
-    if (P.tp > 1) {
+    if (tp > 1) {
         // each CTA flags every rank once its rows are stored, CTA 0 of every rank collects the flags
-        cons_sync(c);
-        if (c.tid == 0) {
+        cons_sync();
+        if (tid == 0) {
             asm volatile("fence.acq_rel.sys;" ::: "memory");
-            for (int k = 0; k < P.tp; k++) ll_store_sys(P.done[k], P.rank * G + (int)blockIdx.x, 0.f, epl);
+            for (int k = 0; k < tp; k++) ll_store_sys(cp->done[k], rank * G + (int)blockIdx.x, 0.f, epl);
         }
         if (blockIdx.x == 0) {
-            for (int i = c.tid; i < P.tp * G; i += c.nt) {
+            for (int i = tid; i < tp * G; i += NCT) {
                 float t[1];
-                ll_waitv<1>(P.done[P.rank], i, epl, t);
+                ll_waitv<1>(cp->done[rank], i, epl, t);
             }
             asm volatile("fence.acq_rel.sys;" ::: "memory");
         }
     }
-    if (!P.do_argmax) return;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-    }
-    float *rv = sv.red;
-    int *ri = reinterpret_cast<int *>(sv.red + 32);
-    if (c.lane == 0) { rv[c.warp] = best; ri[c.warp] = bidx; }
-    cons_sync(c);
-    if (c.tid == 0) {
-        for (int w = 1; w < c.nw; w++)
-            if (rv[w] > best || (rv[w] == best && ri[w] < bidx)) { best = rv[w]; bidx = ri[w]; }
-        for (int k = 0; k < P.tp; k++) {
-            unsigned long long *dst = P.amax[k] + (size_t)(P.rank * G + (int)blockIdx.x) * 2;
+    if (!cp->do_argmax) return;
+    cons_sync();  // every warp's maxloc record (run_tiles) is in shared memory
+    if (tid == 0) {
+        float best = cp->tail_best[0];
+        int bidx = cp->tail_idx[0];
+        for (int w = 1; w < NCW; w++)
+            if (cp->tail_best[w] > best || (cp->tail_best[w] == best && cp->tail_idx[w] < bidx)) { best = cp->tail_best[w]; bidx = cp->tail_idx[w]; }
+        for (int k = 0; k < tp; k++) {
+            unsigned long long *dst = cp->amax[k] + (size_t)(rank * G + (int)blockIdx.x) * 2;
             ll_store_sys(dst, 0, best, epl);
             ll_store_sys(dst, 1, __int_as_float(bidx), epl);
         }
     }
-    if (blockIdx.x == 0 && c.warp == 0) {
+    if (blockIdx.x == 0 && warp == 0) {
         // every rank reduces the same tp * grid records in the same order -> the same token
-        best = -INFINITY; bidx = 0x7fffffff;
-        for (int i = c.lane; i < P.tp * G; i += 32) {
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int i = lane; i < tp * G; i += 32) {
             float rec[2];
-            ll_waitv<2>(P.amax[P.rank], 2 * i, epl, rec);
+            ll_waitv<2>(cp->amax[rank], 2 * i, epl, rec);
             const float v = rec[0];
             const int ix = __float_as_int(rec[1]);
             if (v > best || (v == best && ix < bidx)) { best = v; bidx = ix; }
@@ -1176,81 +806,443 @@ __device__ __noinline__ void token_tail(const StreamParams &P, const CtaPlan *cp
             const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
             if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
         }
-        if (c.lane == 0) {
-            int next = bidx + 1;
-            if (P.forced && P.forced[pos - 1] > 0) next = P.forced[pos - 1];
-            if (P.out_tokens) P.out_tokens[pos - 1] = next;
-            int *tp = const_cast<int *>(P.tokpos);
-            tp[0] = next;
-            tp[1] = pos + 1;
+        if (lane == 0) {
+            // (NaN logits compare false everywhere: bidx stays the sentinel -- fall back to token 1 instead
+            // of indexing the embedding table out of bounds in the next launch)
+            int next = bidx == 0x7fffffff ? 1 : bidx + 1;
+            if (cp->forced && cp->forced[pos - 1] > 0) next = cp->forced[pos - 1];
+            if (cp->out_tokens) cp->out_tokens[pos - 1] = next;
+            cp->tokpos[0] = next;
+            cp->tokpos[1] = pos + 1;
         }
+    }
+}
+
+// ------------------------------------------------------------------ the mat-vec of one tile chunk
+// f32 / f16: the warp's 32 lanes split the chunk's 16-byte units; one activation load (two for f16: 8
+// weights need 8 floats) serves the four rows of the tile.  Rows past the tile's valid count hold stale
+// shared memory: their sums are computed and thrown away (no branch in the loop).
+// The loads are volatile asm on purpose: the compiler otherwise sinks every row's load next to its
+// FMAs and reuses one register quad for all rows -- five serialised shared-memory latencies per step
+// (measured: 300 cycles per step, 7 bytes/cycle/warp).  In program order all loads of a step (and of
+// the next step: the loop is software-pipelined by hand) are issued before the FMAs of this one.
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+template <int WT>
+struct TileRegs {
+    uint4 w[4];
+    uint4 x[WT == WT_F16 ? 2 : 1];
+};
+template <int WT>
+__device__ __forceinline__ void tile_load(TileRegs<WT> &r, uint32_t wp, uint32_t cs, uint32_t xp)
+{
+    r.w[0] = lds128(wp); r.w[1] = lds128(wp + cs); r.w[2] = lds128(wp + 2 * cs); r.w[3] = lds128(wp + 3 * cs);
+    r.x[0] = lds128(xp);
+    if constexpr (WT == WT_F16) r.x[1] = lds128(xp + 16);
+}
+template <int WT>
+__device__ __forceinline__ void tile_fma(const TileRegs<WT> &r, float (&acc)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint4 w = r.w[i];
+        float a = acc[i];
+        if constexpr (WT == WT_F32) {
+            a = fmaf(__uint_as_float(w.x), __uint_as_float(r.x[0].x), a);
+            a = fmaf(__uint_as_float(w.y), __uint_as_float(r.x[0].y), a);
+            a = fmaf(__uint_as_float(w.z), __uint_as_float(r.x[0].z), a);
+            a = fmaf(__uint_as_float(w.w), __uint_as_float(r.x[0].w), a);
+        } else {
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+            const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w.z));
+            const float2 f3 = __half22float2(*reinterpret_cast<const __half2 *>(&w.w));
+            a = fmaf(f0.x, __uint_as_float(r.x[0].x), a); a = fmaf(f0.y, __uint_as_float(r.x[0].y), a);
+            a = fmaf(f1.x, __uint_as_float(r.x[0].z), a); a = fmaf(f1.y, __uint_as_float(r.x[0].w), a);
+            a = fmaf(f2.x, __uint_as_float(r.x[1].x), a); a = fmaf(f2.y, __uint_as_float(r.x[1].y), a);
+            a = fmaf(f3.x, __uint_as_float(r.x[1].z), a); a = fmaf(f3.y, __uint_as_float(r.x[1].w), a);
+        }
+        acc[i] = a;
+    }
+}
+// sp: the stage in its ring slot (rows cs bytes apart); x: the chunk's first activation; nu: 16-byte
+// weight units per row in this chunk.  Two register sets in rotation: a set is reloaded right after its
+// FMAs and used one set of FMAs later (the rest of the shared-memory latency is covered by the other
+// warps; a third set costs 20 registers, which this function does not have: it must not spill).
+template <int WT>
+__device__ __forceinline__ void tile_dot(const uint8_t *sp, uint32_t cs, const float *x, int nu, int lane, float (&acc)[4])
+{
+    constexpr uint32_t XB = WT == WT_F16 ? 32u : 16u;  // activation bytes per weight unit
+    uint32_t wp = smem_u32(sp) + (uint32_t)lane * 16u, xp = smem_u32(x) + (uint32_t)lane * XB;
+    const int nfull = nu >> 5;  // steps in which every lane has a unit
+    TileRegs<WT> r0, r1;
+    if (nfull > 0) tile_load<WT>(r0, wp, cs, xp);
+    if (nfull > 1) tile_load<WT>(r1, wp + 512u, cs, xp + 32u * XB);
+#pragma unroll 1
+    for (int i = 0; i < nfull; i += 2) {
+        tile_fma<WT>(r0, acc);
+        if (i + 2 < nfull) tile_load<WT>(r0, wp + 1024u, cs, xp + 64u * XB);
+        if (i + 1 < nfull) {
+            tile_fma<WT>(r1, acc);
+            if (i + 3 < nfull) tile_load<WT>(r1, wp + 1536u, cs, xp + 96u * XB);
+        }
+        wp += 1024u; xp += 64u * XB;
+    }
+    if (lane < (nu & 31)) {  // the last, partial step of a row whose unit count is not a multiple of 32
+        const uint32_t o = (uint32_t)nfull;
+        tile_load<WT>(r0, smem_u32(sp) + (o * 32u + (uint32_t)lane) * 16u, cs, smem_u32(x) + (o * 32u + (uint32_t)lane) * XB);
+        tile_fma<WT>(r0, acc);
+    }
+}
+
+// q4_0 on the tensor cores (legacy mma.sync m16n8k16, f16 x f16 -> f32): the dequantisation is the
+// instruction bottleneck of a q4_0 mat-vec at B200's HBM rate, and on CUDA cores it costs >= 2
+// instructions per weight.  Here a nibble pair becomes a half2 {1024 + q} with ONE lop3 (the 0x6400
+// exponent trick; high nibbles give 1024 + 16 q and meet activations pre-scaled by 1/16, exact),
+// the products run on the tensor pipe, and the offsets are removed per block with the pre-computed
+// C[b] = 1032 sum(x over the low nibbles) + 72 sum(x over the high nibbles).  The block scale
+// cannot be applied inside the mma, so the n dimension separates blocks: the B operand
+// (activations) of the mma pair of block b is non-zero only in columns b and 4 + b, and D[row][b],
+// D[row][4 + b] end up holding the unscaled sums of block b against the two f16 halves x = hi + lo
+// of the activations (f16 alone would cost 3 digits: greedy tokens flip at near ties).
+// Tiled weight format: common.cuh.  A stage holds the 8-block groups [g0, g0 + ng) of one row group of
+// 16 rows; lane = 4 g + t accumulates rows g and g + 8 over its blocks.
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t uint4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+__device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, int ngrp, int g0, int ng, int lane,
+                                            float &acc0, float &acc1)
+{
+    const int g = lane >> 2, t = lane & 3;
+    // activations as f16 pairs x = hi + lo in B-fragment order, [half group of 4 blocks][hi | lo][block][t],
+    // then the per-block offset corrections [hi | lo][block] (store_x4)
+    const uint4 *xh4 = reinterpret_cast<const uint4 *>(xs);
+    const float *C = xs + (size_t)ngrp * 256 + (size_t)(t >> 1) * ngrp * 8;
+#pragma unroll 1
+    for (int gi = g0; gi < g0 + ng; gi++) {
+        const uint8_t *gp = sp + (size_t)(gi - g0) * Q4T_GROUP_BYTES;
+        uint4 cg[2], c8[2];
+        cg[0] = *reinterpret_cast<const uint4 *>(gp + lane * 16);
+        cg[1] = *reinterpret_cast<const uint4 *>(gp + 512 + lane * 16);
+        c8[0] = *reinterpret_cast<const uint4 *>(gp + 1024 + lane * 16);
+        c8[1] = *reinterpret_cast<const uint4 *>(gp + 1536 + lane * 16);
+#pragma unroll
+        for (int hb = 0; hb < 2; hb++) {
+            // four blocks per accumulation: column n = 4 p + b of D holds block b times the hi (p = 0) /
+            // lo (p = 1) part of x; this lane's B column is n = g, its D columns are 2t, 2t + 1
+            const uint4 xb = xh4[((gi * 2 + hb) * 8 + g) * 4 + t];
+            const uint2 sc = *reinterpret_cast<const uint2 *>(gp + 2048 + (g * 4 + 2 * hb + (t & 1)) * 8);
+            const float2 cc = *reinterpret_cast<const float2 *>(C + gi * 8 + 4 * hb + 2 * (t & 1));
+            // two accumulators (low / high nibbles): two independent mma chains of four
+            float d[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t wg = uint4_word(cg[hb], j), w8 = uint4_word(c8[hb], j);
+                const uint32_t m = ((g & 3) == j) ? 0xffffffffu : 0u;
+                const uint32_t wgs = wg >> 8, w8s = w8 >> 8;
+                mma16816(d, (wg & 0x000f000fu) | 0x64006400u, (w8 & 0x000f000fu) | 0x64006400u,
+                         (wgs & 0x000f000fu) | 0x64006400u, (w8s & 0x000f000fu) | 0x64006400u, xb.x & m, xb.y & m);
+                mma16816(e, (wg & 0x00f000f0u) | 0x64006400u, (w8 & 0x00f000f0u) | 0x64006400u,
+                         (wgs & 0x00f000f0u) | 0x64006400u, (w8s & 0x00f000f0u) | 0x64006400u, xb.z & m, xb.w & m);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[k] += e[k];
+            const float2 s01 = __half22float2(*reinterpret_cast<const __half2 *>(&sc.x));
+            const float2 s23 = __half22float2(*reinterpret_cast<const __half2 *>(&sc.y));
+            acc0 = fmaf(s01.x, d[0] - cc.x, acc0); acc0 = fmaf(s01.y, d[1] - cc.y, acc0);
+            acc1 = fmaf(s23.x, d[2] - cc.x, acc1); acc1 = fmaf(s23.y, d[3] - cc.y, acc1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the tiles of one phase
+// This warp's tiles of phase `ph` (tile t -> warp t mod 12): the mat-vec over the tile's chunks as they
+// land in the ring, the cross-lane reduction, and the tile's epilogue -- every lane ends up holding one
+// row PAIR (rows 2i, 2i + 1: what RoPE and SwiGLU combine, and one 16-byte LL store), and the lanes
+// that share a pair split its destinations (LL replicas x tensor-parallel ranks) between them.
+// Out of line on purpose: its own register allocation, nothing live across it in the phase loop, and
+// all constants come from the plan in shared memory.  `s0` = ring stage number of the phase's first
+// stage; rscale = the 1 / rms factor of the phase's rmsnorm (the mat-vec is linear).
+template <int WT, bool PROF>
+__device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float rscale, uint32_t ep, int l, int pos,
+                                       unsigned long long *tr /* PROF: this CTA's 8 trace words of the phase, or null */)
+{
+#define TSTAMP(k_) do { if constexpr (PROF) { if (tr && threadIdx.x == 0 && !tdone) tr[k_] = (unsigned long long)clock64(); } } while (0)
+    bool tdone = false;
+    uint8_t *smem = smem_base();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PhaseW &W = cp->ph[ph];
+    const int ntiles = cp->ntiles[ph], nch = W.nch, rows_real = W.rows_real, cu = W.cu, nu_row = W.nu;
+    const int r0 = cp->r0[ph], nr = cp->nrows[ph];
+    const float *xs = reinterpret_cast<const float *>(smem + cp->off_xs);
+    const int nrep = cp->ll_rep, tp = cp->tp, att_dim = cp->att_dim, kv = cp->kv;
+    float best = -INFINITY;  // running maxloc of this lane's logits (classifier epilogue)
+    int bidx = 0x7fffffff;
+    if constexpr (PROF) {
+        if (tr && threadIdx.x == 0) {
+            tr[5] = (unsigned long long)(unsigned)cp->prod_issued | ((unsigned long long)(unsigned)cp->pf_issued << 32);
+            tr[6] = s0;
+        }
+    }
+    TSTAMP(0);
+    const int G = cp->G, grp = warp / G, cl = warp - grp * G, ngrp = NCW / G;
+    float *gsc = reinterpret_cast<float *>(smem + cp->off_grp);  // [2][NCW][16]
+    int buf = 0;
+#pragma unroll 1
+    for (int t = grp; t < ntiles; t += ngrp) {
+        uint32_t s = s0 + (uint32_t)(t * nch);
+        float va, vb;  // this lane's row pair after the reduction
+        int i, sub, nsl;  // first row of the pair (within the CTA's range); destination lane index / count
+        if constexpr (WT != WT_Q4_0) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            int u0 = 0;
+#pragma unroll 1
+            for (int c = 0; c < nch; c++, s++) {
+                const int nu = min(cu, nu_row - u0);
+                // this warp's share of the chunk's columns: whole lane rounds [b0, b1) of 32 units
+                const int rounds = (nu + 31) >> 5, b0 = (cl * rounds) / G, b1 = ((cl + 1) * rounds) / G;
+                const int ub = b0 << 5, un = min(nu, b1 << 5) - ub;
+                const uint32_t slot = slot_of(cp, s);
+                mbar_wait(full_bar(cp, s), full_par(s), 2);
+                if (c == 0) TSTAMP(1);
+                if (un > 0)
+                    tile_dot<WT>(smem + (size_t)slot * cp->slot_bytes + (size_t)ub * 16, (uint32_t)nu * 16u,
+                                 xs + (WT == WT_F16 ? 8 : 4) * (u0 + ub), un, lane, acc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(cp, slot));
+                u0 += nu;
+            }
+            TSTAMP(2);
+            // transposing reduction: 4 lane-partial sums -> row pair h = lane / 16 in every lane
+            const bool hi16 = lane & 16, hi8 = lane & 8;
+            float k0 = hi16 ? acc[2] : acc[0], k1 = hi16 ? acc[3] : acc[1];
+            k0 += __shfl_xor_sync(0xffffffffu, hi16 ? acc[0] : acc[2], 16);
+            k1 += __shfl_xor_sync(0xffffffffu, hi16 ? acc[1] : acc[3], 16);
+            float k = hi8 ? k1 : k0;
+            k += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+            k += __shfl_xor_sync(0xffffffffu, k, 4);
+            k += __shfl_xor_sync(0xffffffffu, k, 2);
+            k += __shfl_xor_sync(0xffffffffu, k, 1);
+            const float o = __shfl_xor_sync(0xffffffffu, k, 8);
+            va = hi8 ? o : k; vb = hi8 ? k : o;
+            if (G > 1) {
+                // the group's partial results meet in shared memory: warp cl > 0 leaves its two pairs, the
+                // group's named barrier, warp 0 adds them (in warp order: deterministic) and goes on alone
+                float *mine = gsc + (buf * NCW + warp) * 16;
+                if (cl > 0 && (lane & 15) == 0) *reinterpret_cast<float2 *>(mine + (lane >> 3)) = make_float2(va, vb);
+                named_bar_sync(2 + grp, 32 * G);
+                if (cl > 0) { buf ^= 1; continue; }
+#pragma unroll 1
+                for (int w = 1; w < G; w++) {
+                    const float2 pp = *reinterpret_cast<const float2 *>(mine + w * 16 + ((lane >> 4) << 1));
+                    va += pp.x; vb += pp.y;
+                }
+                buf ^= 1;
+            }
+            i = t * 4 + 2 * (lane >> 4); sub = lane & 15; nsl = 16;
+        } else {
+            float acc0 = 0.f, acc1 = 0.f;
+            int g0 = 0;
+#pragma unroll 1
+            for (int c = 0; c < nch; c++, s++) {
+                const int ng = min(cu, nu_row - g0);
+                const int b0 = (cl * ng) / G, b1 = ((cl + 1) * ng) / G;  // this warp's 8-block groups of the chunk
+                const uint32_t slot = slot_of(cp, s);
+                mbar_wait(full_bar(cp, s), full_par(s), 2);
+                if (c == 0) TSTAMP(1);
+                tile_dot_q4(smem + (size_t)slot * cp->slot_bytes + (size_t)b0 * Q4T_GROUP_BYTES, xs, nu_row, g0 + b0, b1 - b0, lane, acc0, acc1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(cp, slot));
+                g0 += ng;
+            }
+            TSTAMP(2);
+            // sum over t (blocks 0,1 | 2,3 and the hi | lo parts): rows g, g + 8 in all four t lanes
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+            const int g = lane >> 2;
+            if (G > 1) {
+                float *mine = gsc + (buf * NCW + warp) * 16;
+                if (cl > 0 && (lane & 3) == 0) { mine[g] = acc0; mine[g + 8] = acc1; }
+                named_bar_sync(2 + grp, 32 * G);
+                if (cl > 0) { buf ^= 1; continue; }
+#pragma unroll 1
+                for (int w = 1; w < G; w++) { acc0 += mine[w * 16 + g]; acc1 += mine[w * 16 + g + 8]; }
+                buf ^= 1;
+            }
+            // the even-g lanes take the pair (g, g + 1), the odd-g lanes the pair (g + 7, g + 8)
+            const float p0 = __shfl_xor_sync(0xffffffffu, acc0, 4), p1 = __shfl_xor_sync(0xffffffffu, acc1, 4);
+            const bool odd = g & 1;
+            va = odd ? p1 : acc0; vb = odd ? acc1 : p0;
+            i = t * 16 + (odd ? g + 7 : g); sub = lane & 3; nsl = 4;
+        }
+
+        // ---- epilogue of the row pair (i, i + 1): `nsl` lanes hold it, lane `sub` serves the
+        // destinations sub, sub + nsl, ... (LL replicas x ranks)
+        const int r = r0 + i;
+        TSTAMP(3);
+        if (i >= nr || r >= rows_real) continue;  // rows past the CTA's range / padding rows of the matrix
+        const bool two = r + 1 < rows_real;
+        const float a = va * rscale, b = vb * rscale;
+        if (ph == 0) {
+            // RoPE on q and k (reference quirks Q1/Q2 are in the table), KV append (llama2.f90:543-565)
+            const bool isq = r < att_dim, isv = r >= att_dim + kv;
+            const int rk = isq ? r : (isv ? r - att_dim - kv : r - att_dim);
+            const float2 cs2 = isv ? make_float2(1.f, 0.f) : cp->rope[(rk >> 1) & ((cp->hs >> 1) - 1)];
+            const float o0 = a * cs2.x - b * cs2.y, o1 = a * cs2.y + b * cs2.x;
+#pragma unroll 1
+            for (int d = sub; d < nrep; d += nsl) {
+                unsigned long long *dst = isq ? cp->ll_q + (size_t)d * att_dim
+                                              : cp->ll_kv + (size_t)d * 2 * kv + (isv ? kv : 0);
+                ll_store2(dst, rk, o0, o1, ep);
+            }
+            if (!isq && sub == nsl - 1) {
+                // the cache row serves later launches, the LL copy this launch's attention
+                float *cache = (isv ? cp->vc : cp->kc) + ((size_t)l * cp->seq + (pos - 1)) * kv;
+                *reinterpret_cast<float2 *>(cache + rk) = make_float2(o0, o1);
+            }
+        } else if (ph == 2) {
+            // SwiGLU on the interleaved gate/up rows (llama2.f90:613-616)
+            const float hv = (a * (1.0f / (1.0f + expf(-a)))) * b;
+            const int hb_stride = (cp->hid + 1) & ~1;
+#pragma unroll 1
+            for (int d = sub; d < nrep; d += nsl) ll_store(cp->ll_hb + (size_t)d * hb_stride, r >> 1, hv, ep);
+        } else if (ph == 4) {
+            // logits rows of this rank go to every rank's full logits buffer (all-gather)
+            const int gi = cp->v_off + r;
+#pragma unroll 1
+            for (int k = sub; k < tp; k += nsl) {
+                cp->logits[k][gi] = a;
+                if (two) cp->logits[k][gi + 1] = b;
+            }
+            if (sub == 0) {
+                if (a > best) { best = a; bidx = gi; }
+                if (two && b > best) { best = b; bidx = gi + 1; }
+            }
+        } else {
+            // Wo / W2 (llama2.f90:603-605, :618-620): publish this rank's partial sums to every
+            // rank; the residual add happens in the next norm prologue, on every CTA's copy of x
+            const int rep_shift = 31 - __clz(nrep);
+#pragma unroll 1
+            for (int d = sub; d < nrep * tp; d += nsl) {
+                const int k = d >> rep_shift, rr = d & (nrep - 1);  // destination rank, replica
+                unsigned long long *dst = (ph == 1 ? cp->part1[k] : cp->part2[k]) + ((size_t)rr * tp + cp->rank) * cp->emb;
+                if (two) ll_store2_sys(dst, r, a, b, ep);
+                else ll_store_sys(dst, r, a, ep);
+            }
+        }
+        TSTAMP(4);
+        tdone = true;
+    }
+    tdone = false;
+    TSTAMP(7);
+    if constexpr (PROF) {
+        if (tr && threadIdx.x == 0)
+            tr[3] = (tr[3] & 0xffffffffull) | ((unsigned long long)(unsigned)(cp->pf_issued - (int)s0) << 48) |
+                    ((unsigned long long)(unsigned)(cp->prod_issued - (int)s0) << 32);  // cursors when warp 0 is done
+    }
+#undef TSTAMP
+    if (ph == 4) {
+        // maxloc of this warp's logits (llama2.f90:388: the first maximum wins), for the token tail
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if (lane == 0) { cp->tail_best[warp] = best; cp->tail_idx[warp] = bidx; }
     }
 }
 
 // ------------------------------------------------------------------ the kernel
 // PROF = false is the production kernel; PROF = true adds the phase timers of CTA 0 and the optional
-// per-CTA trace (the instrumentation alone costs 5-8 % of the token time: measured).
+// per-CTA phase-edge trace.
 template <int WT, bool PROF>
 __global__ void __launch_bounds__(416, 1)
 stream_decode_kernel(const __grid_constant__ StreamParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const SmemView sv = carve(smem, P);
-    const int n_cons_warps = P.n_cons_warps;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     __shared__ CtaPlan cp;
-    __shared__ float2 rope[64];
     __shared__ Prof pf;
-    if (threadIdx.x == 0) pf.prod_issued = 0;
+    // ---- shared-memory map: ring | xs | xres | red | attention scratch | full[NBAR] | empty[MAX_SLOTS] | stage list
+    const int off_xs = P.n_slots * P.slot_bytes, off_xres = off_xs + P.xs_floats * 4, off_red = off_xres + P.emb * 4;
+    const int off_att = off_red + 64 * 4, off_grp = off_att + NCW * (P.hs + ATT_PSTRIDE_PAD) * 4;
+    const int off_full = off_grp + 2 * NCW * 16 * 4;  // [2][NCW][16] partial results of a tile group's warps
+    const int off_empty = off_full + NBAR * 8, off_sched = off_empty + MAX_SLOTS * 8;
     if (threadIdx.x == 5) {
-        cp.off_xs = (int)(reinterpret_cast<uint8_t *>(sv.xs) - smem);
-        cp.off_res = (int)(reinterpret_cast<uint8_t *>(sv.res) - smem);
-        cp.off_xres = (int)(reinterpret_cast<uint8_t *>(sv.xres) - smem);
-        cp.off_red = (int)(reinterpret_cast<uint8_t *>(sv.red) - smem);
-        cp.off_full = (int)(reinterpret_cast<uint8_t *>(sv.full) - smem);
-        cp.slot_bytes = P.slot_bytes; cp.n_slots = P.n_slots; cp.n_cons_warps = P.n_cons_warps;
-        cp.att.kc = P.kc; cp.att.vc = P.vc; cp.att.ll_q = P.ll_q; cp.att.ll_kv = P.ll_kv; cp.att.ll_att = P.ll_att;
-        cp.att.ll_part = P.ll_part; cp.att.H = P.H; cp.att.seq = P.seq; cp.att.kv = P.kv; cp.att.kv_mul = P.kv_mul;
-        cp.att.att_dim = P.att_dim; cp.att.ll_rep = P.ll_rep;
+        cp.off_xs = off_xs; cp.off_xres = off_xres; cp.off_red = off_red; cp.off_att = off_att; cp.off_grp = off_grp;
+        cp.G = P.tile_warps;
+        cp.off_full = off_full; cp.off_empty = off_empty; cp.off_sched = off_sched;
+        cp.slot_bytes = P.slot_bytes; cp.n_slots = P.n_slots;
+        cp.slot_magic = 0xffffffffu / (uint32_t)P.n_slots + 1u;
+        cp.wtype = P.wtype; cp.emb = P.emb; cp.hid = P.hid; cp.kv = P.kv; cp.att_dim = P.att_dim; cp.hs = P.hs;
+        cp.tp = P.tp; cp.rank = P.rank; cp.ll_rep = P.ll_rep; cp.v_off = P.v_off; cp.seq = P.seq; cp.H = P.H;
+        cp.kv_mul = P.kv_mul; cp.L = P.L;
+        cp.kc = P.kc; cp.vc = P.vc; cp.ll_q = P.ll_q; cp.ll_kv = P.ll_kv; cp.ll_att = P.ll_att;
+        cp.ll_part = P.ll_part; cp.ll_hb = P.ll_hb;
+    }
+    if (threadIdx.x >= 8 && threadIdx.x < 8 + MAX_TP) {
+        const int k = threadIdx.x - 8;
+        cp.part1[k] = P.part1[k]; cp.part2[k] = P.part2[k]; cp.logits[k] = P.logits[k];
+        cp.amax[k] = P.amax[k]; cp.done[k] = P.done[k];
+    }
+    if (threadIdx.x == 7) {
+        cp.forced = P.forced; cp.out_tokens = P.out_tokens; cp.tokpos = const_cast<int *>(P.tokpos);
+        cp.ep_last = P.ep_base + (uint32_t)P.L + 1u; cp.do_argmax = P.do_argmax;
     }
     if (threadIdx.x < 5) {
         const int i = threadIdx.x;
         cp.ph[i] = P.ph[i];
         int r0, r1;
         cta_rows(P.ph[i], blockIdx.x, gridDim.x, r0, r1);
-        cp.r0[i] = r0; cp.r1[i] = r1;
-        cp.nst[i] = phase_stages(P.ph[i], r1 - r0);
+        cp.r0[i] = r0; cp.nrows[i] = r1 - r0;
+        const int nt = (r1 - r0 + P.ph[i].R - 1) / P.ph[i].R;
+        cp.ntiles[i] = nt; cp.nst[i] = nt * P.ph[i].nch;
+        cp.lstride[i] = i < 4 ? P.ph[i].layer_stride : 0ull;
+        cp.sstride[i] = P.ph[i].rs;
+    }
+    if (threadIdx.x == 6) {
+        cp.lstride[SK_RMS_ATT] = cp.lstride[SK_RMS_FFN] = (unsigned long long)P.emb * 4u;
+        cp.lstride[SK_RMS_FINAL] = cp.lstride[SK_EMB_ROW] = 0ull;
+        cp.sstride[SK_RMS_ATT] = cp.sstride[SK_RMS_FFN] = cp.sstride[SK_RMS_FINAL] = cp.sstride[SK_EMB_ROW] = 0u;
     }
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(P.sched + (size_t)blockIdx.x * P.sched_stride);
-        uint4 *d = reinterpret_cast<uint4 *>(const_cast<SchedStage *>(sv.sched));
+        uint4 *d = reinterpret_cast<uint4 *>(smem + off_sched);
         for (int i = threadIdx.x; i < P.sched_stride; i += blockDim.x) d[i] = __ldg(g + i);
     }
-    if (threadIdx.x == 32) {
-        for (int i = 0; i < P.n_slots; i++) {
-            mbar_init(&sv.full[i], 1);
-            mbar_init(&sv.full[MAX_SLOTS + i], 1);
-            mbar_init(&sv.empty[i], (uint32_t)GW);
-        }
+    if (threadIdx.x < NBAR + P.n_slots) {
+        uint64_t *bars = reinterpret_cast<uint64_t *>(smem + off_full);
+        if (threadIdx.x < NBAR) mbar_init(&bars[threadIdx.x], 1);
+        else mbar_init(&bars[threadIdx.x], (uint32_t)P.tile_warps);  // empty[slot]: one arrive per warp of the tile's group
         fence_mbar_init();
     }
     const int token = P.token > 0 ? P.token : P.tokpos[0];
     const int pos = P.token > 0 ? P.pos : P.tokpos[1];
     // this position's RoPE row (a cold HBM read, issued first thing, used after the QKV phase)
-    if (threadIdx.x < (P.hs >> 1)) rope[threadIdx.x] = P.rope_tab[(size_t)(pos - 1) * (P.hs >> 1) + threadIdx.x];
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + (P.hs >> 1))
+        cp.rope[threadIdx.x - 64] = P.rope_tab[(size_t)(pos - 1) * (P.hs >> 1) + threadIdx.x - 64];
     __syncthreads();
 
-    if (warp == n_cons_warps) {
+    if (warp == NCW) {
         // ===================== producer warp =====================
-        if (lane == 0) producer_loop(P, sv, &cp, token, &pf.prod_issued);
+        if (lane == 0) producer_loop(&cp, token, P.pace, P.pf_lead);
         return;
     }
 
     // ===================== consumer warps =====================
-    const int tid = (int)threadIdx.x, nt = n_cons_warps * 32;
-    CState cs;
-    cs.pos.mod = 0; cs.pos.div = 0; cs.gmod = 0;
+    const int tid = (int)threadIdx.x;
     // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh;
     // optional per-CTA trace of one layer (debug/profiling)
     const bool timer = PROF && (blockIdx.x == 0 && tid == 0);
@@ -1261,19 +1253,14 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         for (int i = 0; i < PH_COUNT; i++) pf.tacc[i] = 0;
         pf.tmark = t_c0;
     }
-    if (tracing && tid == 0)
-        for (int i = 0; i < 44; i++) pf.twait[i] = 0;
 #define LAP(b) do { if constexpr (PROF) { if (timer) prof_lap(&pf, (b)); } } while (0)
-#define STAMP(l_, k_) do { if constexpr (PROF) { if (tracing && tid == 0 && (l_) == P.trace_layer) prof_stamp(P, &cp, cs.pos.mod, cs.pos.div, &pf, (k_)); } } while (0)
-    const int half_mask = (P.hs >> 1) - 1;
-    const uint32_t ns = (uint32_t)P.n_slots;
-    const int nrep = P.ll_rep, rep = (int)blockIdx.x % nrep;  // LL vector replicas; the one this CTA polls
+#define STAMP(l_, k_) do { if constexpr (PROF) { if (tracing && tid == 0 && (l_) == P.trace_layer) prof_stamp(P.trace, (k_)); } } while (0)
+    const int rep = (int)blockIdx.x % P.ll_rep;  // LL vector replicas; the one this CTA polls
     const int hb_stride = (P.hid + 1) & ~1;
-    float best = -INFINITY;  // running maxloc of this thread's logits (classifier epilogue)
-    int bidx = 0x7fffffff;
+    uint32_t s0 = 0;  // ring stage number of the next stage of this CTA's schedule (identical in every thread)
 
     // One loop over the 4 L + 1 weight phases (q = 4 l + {0 QKV, 1 WO, 2 W13, 3 W2}; q = 4 L is the
-    // classifier): prologue -> ring consumption -> epilogue (-> attention).  A single copy of
+    // classifier): prologue -> tiles (mat-vec + epilogue per warp) (-> attention).  A single copy of
     // every piece serves all phases.
     const int nq = 4 * P.L + 1;
 #pragma unroll 1
@@ -1282,7 +1269,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         const uint32_t ep = P.ep_base + (uint32_t)l + 1u;  // epoch of everything layer l publishes
         const int tb = ph == 0 ? 0 : 2 + 3 * ph;  // timer bucket / trace stamp base of this phase
         const bool norm = !(ph & 1);
-        const int r0 = cp.r0[ph], nr = cp.r1[ph] - cp.r0[ph];
+        const int nr = cp.nrows[ph];
         if (ph == 0) STAMP(l, 0);
 
         // ---- prologue: the activation vector of this phase, in shared memory
@@ -1291,121 +1278,43 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
             // rmsnorm (llama2.f90:527, :608, :627); layer 0 starts from the embedding row (:520);
             // adds the tp partial outputs of the phase before (Wo of this layer / W2 of the previous one)
             const uint8_t *emb_row = nullptr;
-            RingPos at = cs.pos;
-            if (q == 0) {
-                emb_row = vec_stage_wait(&cp, at);
-                ring_advance(at, 1u, ns);
-            }
-            const float *wn = reinterpret_cast<const float *>(vec_stage_wait(&cp, at));
-            rscale = gather_x<WT>(&cp, (ph == 2 ? P.part1[P.rank] : P.part2[P.rank]) + (size_t)rep * P.tp * P.emb, P.tp,
-                                  ph == 2 ? ep : ep - 1u, P.emb, 1, P.wtype, emb_row, wn);
-            if (q == 0) vec_stage_release(&cp, cs);
-            vec_stage_release(&cp, cs);
+            if (q == 0) emb_row = vec_stage_wait(&cp, s0++);
+            const float *wn = reinterpret_cast<const float *>(vec_stage_wait(&cp, s0));
+            rscale = gather_x<WT>(&cp, (ph == 2 ? cp.part1[P.rank] : cp.part2[P.rank]) + (size_t)rep * P.tp * P.emb, P.tp,
+                                  ph == 2 ? ep : ep - 1u, P.emb, 1, emb_row, wn);
+            if (q == 0) vec_stage_release(&cp, s0 - 1);
+            vec_stage_release(&cp, s0++);
         } else if (nr > 0) {
             // (a CTA without rows in a Wo / W2 phase does not need its input vector: skipping the poll
             // also keeps it from ever lagging behind on a buffer nobody waits for it to have read)
-            if (ph == 1 && P.n_splits > 1) load_x_attn<WT>(P, &cp, ep);
-            else gather_x<WT>(&cp, ph == 1 ? P.ll_att + (size_t)rep * P.att_dim : P.ll_hb + (size_t)rep * hb_stride, 1, ep,
-                              ph == 1 ? P.att_dim : P.hid, 0, P.wtype, nullptr, nullptr);
+            if (ph == 1 && P.n_splits > 1) load_x_attn<WT>(&cp, P.n_splits, ep);
+            else gather_x<WT>(&cp, ph == 1 ? cp.ll_att + (size_t)rep * P.att_dim : cp.ll_hb + (size_t)rep * hb_stride, 1, ep,
+                              ph == 1 ? P.att_dim : P.hid, 0, nullptr, nullptr);
         }
         LAP(tb);
         STAMP(l, ph == 0 ? 1 : 3 + 3 * ph);
 
-        // ---- the mat-vec: consume this CTA's stages of the phase from the ring
-        {
-            const bool trace_me = tracing && warp == 0 && l == P.trace_layer && ph < 4;
-            const uint32_t cursor = cs.pos.mod | ((cs.pos.div & 3u) << 8) | (cs.gmod << 16) | (trace_me ? 1u << 24 : 0u);
-            if (trace_me && lane == 0) pf.twait[12 + 8 * ph + 7] = clock64();  // before the call
-            consume_phase<WT, PROF>(&cp, &pf, ph, cursor);
-            if (trace_me && lane == 0) pf.twait[12 + 8 * ph + 4] = clock64();  // after the return
-            cons_advance(cs, (uint32_t)cp.nst[ph], ns);
-        }
-        STAMP(l, ph == 0 ? 2 : 4 + 3 * ph);
-        named_bar_sync(CONS_BAR, nt);
-        if (tracing && tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 5] = clock64();
+        // ---- the mat-vec: this warp's tiles of the phase, each followed by its epilogue
+        run_tiles<WT, PROF>(&cp, ph, s0, rscale, ep, l, pos,
+                            (tracing && l == P.trace_layer && ph < 4) ? P.trace + (size_t)blockIdx.x * 128 + 16 + 8 * ph : nullptr);
+        s0 += (uint32_t)cp.nst[ph];
         LAP(tb + 1);
-
-        // ---- epilogue.  A work item is (row pair, LL replica [, destination rank]): the planes of
-        // partial sums are added in a fixed order, times the 1 / rms factor of the phase's rmsnorm,
-        // and every thread publishes ONE 16-byte LL record -- relaxed gpu-scope stores are slow one
-        // after the other from one thread, so they are spread over the threads instead.
-        {
-            const int cap = cp.ph[ph].rows_cap, rows_real = cp.ph[ph].rows_real;
-            const int planes = (WT == WT_Q4_0) ? cp.ph[ph].spg * GW : GW;
-            // (replica and rank counts are powers of two: shifts)
-            const int nsub = ph == 4 ? 1 : ((ph & 1) ? nrep * P.tp : nrep), npairs = (nr + 1) >> 1;
-            const int sub_shift = 31 - __clz(nsub);
-            const float *res = reinterpret_cast<const float *>(smem_base() + cp.off_res);
-#pragma unroll 1
-            for (int w = tid; w < npairs * nsub; w += nt) {
-                const int pair = w >> sub_shift, sub = w & (nsub - 1), i = 2 * pair;
-                if (r0 + i >= rows_real) continue;  // padding rows of a tiled q4_0 matrix
-                const bool two = i + 1 < nr && r0 + i + 1 < rows_real;
-                float a = res[i], b = two ? res[i + 1] : 0.f;
-#pragma unroll 4
-                for (int p = 1; p < planes; p++) {
-                    a += res[p * cap + i];
-                    b += two ? res[p * cap + i + 1] : 0.f;
-                }
-                a *= rscale; b *= rscale;
-                const int r = r0 + i;
-                if (ph == 0) {
-                    // RoPE on q and k (reference quirks Q1/Q2 are in the table), KV append (llama2.f90:543-565)
-                    const bool isq = r < P.att_dim, isv = r >= P.att_dim + P.kv;
-                    const int rk = isq ? r : (isv ? r - P.att_dim - P.kv : r - P.att_dim);
-                    const float2 cs2 = isv ? make_float2(1.f, 0.f) : rope[(rk >> 1) & half_mask];
-                    const float o0 = a * cs2.x - b * cs2.y, o1 = a * cs2.y + b * cs2.x;
-                    if (!isq && sub == 0) {
-                        // the cache row serves later launches, the LL copy this launch's attention
-                        float *cache = (isv ? P.vc : P.kc) + ((size_t)l * P.seq + (pos - 1)) * P.kv;
-                        *reinterpret_cast<float2 *>(cache + rk) = make_float2(o0, o1);
-                    }
-                    unsigned long long *dst = isq ? P.ll_q + (size_t)sub * P.att_dim
-                                                  : P.ll_kv + (size_t)sub * 2 * P.kv + (isv ? P.kv : 0);
-                    ll_store2(dst, rk, o0, o1, ep);
-                } else if (ph == 2) {
-                    // SwiGLU on the interleaved gate/up rows (llama2.f90:613-616)
-                    ll_store(P.ll_hb + (size_t)sub * hb_stride, r >> 1, (a * (1.0f / (1.0f + expf(-a)))) * b, ep);
-                } else if (ph == 4) {
-                    // logits rows of this rank go to every rank's full logits buffer (all-gather)
-                    const int gi = P.v_off + r;
-                    for (int k = 0; k < P.tp; k++) {
-                        P.logits[k][gi] = a;
-                        if (two) P.logits[k][gi + 1] = b;
-                    }
-                    if (a > best) { best = a; bidx = gi; }
-                    if (two && b > best) { best = b; bidx = gi + 1; }
-                } else {
-                    // Wo / W2 (llama2.f90:603-605, :618-620): publish this rank's partial sums to every
-                    // rank; the residual add happens in the next norm prologue, on every CTA's copy of x
-                    const int k = sub >> (31 - __clz(nrep)), rr = sub & (nrep - 1);  // destination rank, replica
-                    unsigned long long *dst = (ph == 1 ? P.part1[k] : P.part2[k]) + ((size_t)rr * P.tp + P.rank) * P.emb;
-                    ll_store_sys(dst, r, a, ep);  // (r may be odd here: no 16-byte store)
-                    if (two) ll_store_sys(dst, r + 1, b, ep);
-                }
-            }
-        }
-        if (tracing && tid == 0 && l == P.trace_layer && ph < 4) pf.twait[12 + 8 * ph + 6] = clock64();
+        STAMP(l, ph == 0 ? 2 : 4 + 3 * ph);
         if (ph == 4) break;
-        LAP(tb + 2);
-        STAMP(l, ph == 0 ? 3 : 5 + 3 * ph);
 
         if (ph == 0) {
             // ---- attention (llama2.f90:574-598)
-            if (P.hs == 64) attention_phase_t<64>(&cp, P.n_splits, l, pos, ep);
-            else if (P.hs == 128) attention_phase_t<128>(&cp, P.n_splits, l, pos, ep);
-            else attention_phase_t<32>(&cp, P.n_splits, l, pos, ep);
+            unsigned long long *atr = nullptr;
+            if constexpr (PROF) { if (tracing && l == P.trace_layer) atr = P.trace + (size_t)blockIdx.x * 128 + 48; }
+            if (P.hs == 64) attention_phase_t<64>(&cp, P.n_splits, l, pos, ep, atr);
+            else if (P.hs == 128) attention_phase_t<128>(&cp, P.n_splits, l, pos, ep, atr);
+            else attention_phase_t<32>(&cp, P.n_splits, l, pos, ep, atr);
             LAP(PH_ATT);
             STAMP(l, 4);
-            STAMP(l, 5);
         }
-        if (ph == 3 && tracing && tid == 0 && l == P.trace_layer)
-            for (int i = 0; i < 44; i++)
-                P.trace[(size_t)blockIdx.x * 128 + (i < 12 ? 16 + i : 64 + i - 12)] = (unsigned long long)pf.twait[i];
     }
-    LAP(PH_CLS_MV);
 
-    token_tail(P, &cp, best, bidx, pos);
+    token_tail(&cp, pos);
     if (timer) {
         prof_lap(&pf, PH_ARGMAX);
         for (int i = 0; i < PH_COUNT; i++) P.phase_cycles[i] += (unsigned long long)pf.tacc[i];
@@ -1418,74 +1327,67 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
 
 // ------------------------------------------------------------------ host side
 // stages a CTA can have in the layer section / after it (upper bounds over all CTAs)
+static int tiles_of(const PhaseW &w, int nrows) { return (nrows + w.R - 1) / w.R; }
 static void sched_caps(const StreamParams &p, int *layer, int *post)
 {
     int per_layer = 2, cls = 0;
     for (int i = 0; i < 5; i++) {
-        const int st = phase_stages(p.ph[i], p.ph[i].rows_cap);
+        const int st = tiles_of(p.ph[i], p.ph[i].rows_cap) * p.ph[i].nch;
         if (i < 4) per_layer += st; else cls = st;
     }
     *layer = per_layer;
     *post = 1 + cls;
 }
 
-int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots,
-                int cons_warps, StreamPlan *out)
+int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_bytes, int max_slots, StreamPlan *out)
 {
-    cons_warps = MAX_CONS_WARPS;  // NG groups of GW warps
-    const bool tiled = p.ph[0].ngrp > 0;  // q4_0 in the tiled mma format
-    unsigned int rs_max = (unsigned)p.emb * 4u;  // f32 vector stages
-    if ((unsigned)row_stride_bytes(p.wtype, p.emb) > rs_max) rs_max = (unsigned)row_stride_bytes(p.wtype, p.emb);
-    for (int i = 0; i < 5; i++) {
-        PhaseW &w = p.ph[i];
-        if (tiled) {
-            // split a row group into stages of whole 8-block groups that fit the target slot
-            w.spg = (int)((w.rs + (unsigned)target_slot_bytes - 1) / (unsigned)target_slot_bytes);
-            const unsigned stage = (unsigned)((w.ngrp + w.spg - 1) / w.spg) * Q4T_GROUP_BYTES;
-            if (stage > rs_max) rs_max = stage;
-        } else {
-            w.spg = 0;
-            if (w.rs > rs_max) rs_max = w.rs;
-        }
-    }
-    int slot = (!tiled && target_slot_bytes > (int)rs_max) ? target_slot_bytes : (int)rs_max;
-    slot = (slot + 127) & ~127;
-    int res_floats = 0;
+    const bool tiled = p.wtype == WT_Q4_0;  // q4_0 in the tiled mma format
+    // a slot holds one stage: a chunk of a tile, a norm vector, or an embedding row
+    unsigned int slot = (unsigned)p.emb * 4u;
+    if ((unsigned)row_stride_bytes(p.wtype, p.emb) > slot) slot = (unsigned)row_stride_bytes(p.wtype, p.emb);
+    const unsigned min_chunk = tiled ? Q4T_GROUP_BYTES : 4u * 32u * 16u;  // one group / one unit per lane of 4 rows
+    if (slot < min_chunk) slot = min_chunk;
+    if ((unsigned)target_slot_bytes > slot) slot = (unsigned)target_slot_bytes;
+    slot = (slot + 127u) & ~127u;
     for (int i = 0; i < 5; i++) {
         PhaseW &w = p.ph[i];
         const int U = w.rows / w.unit;
         w.rows_cap = ((U + grid - 1) / grid) * w.unit;
-        const int nunits = w.cols >> (p.wtype == WT_F32 ? 2 : 3);
-        w.ku = tiled ? 0 : (nunits + 32 * GW - 1) / (32 * GW);
-        const int planes = tiled ? w.spg * GW : GW;
-        if (planes * w.rows_cap > res_floats) res_floats = planes * w.rows_cap;
+        if (tiled) {
+            w.R = 16;
+            w.nu = q4t_groups(w.cols);
+            const int cu_max = (int)(slot / Q4T_GROUP_BYTES);
+            w.nch = (w.nu + cu_max - 1) / cu_max;
+            w.cu = (w.nu + w.nch - 1) / w.nch;
+        } else {
+            w.R = 4;
+            w.nu = (int)(row_stride_bytes(p.wtype, w.cols) / 16);
+            const int cu_max = (int)(slot / (4u * 16u)) & ~31;  // whole lane rounds
+            w.nch = (w.nu + cu_max - 1) / cu_max;
+            w.cu = (((w.nu + w.nch - 1) / w.nch) + 31) & ~31;
+        }
+        if (w.nch > MAX_NCH) return 1;
     }
     int xs_floats = p.emb > p.hid ? p.emb : p.hid;
     if (tiled)  // f16 hi + lo activations in fragment order + two corrections per block (store_x4)
-        for (int i = 0; i < 5; i++) xs_floats = xs_floats > p.ph[i].ngrp * 272 ? xs_floats : p.ph[i].ngrp * 272;
-    // attention scratch ([consumer warps][hs+4] partials) also lives in xs
-    const int att_scratch = MAX_SLOTS * (p.hs + 4);
-    if (att_scratch > xs_floats) xs_floats = att_scratch;
+        for (int i = 0; i < 5; i++) xs_floats = xs_floats > p.ph[i].nu * 272 ? xs_floats : p.ph[i].nu * 272;
     xs_floats = (xs_floats + 31) & ~31;
-    res_floats = (res_floats + 31) & ~31;
     if (max_slots > MAX_SLOTS) max_slots = MAX_SLOTS;
-    for (int i = 0; i < 5; i++) p.ph[i].rps = (!tiled && slot / (int)p.ph[i].rs > 0) ? slot / (int)p.ph[i].rs : 1;
     int cap_layer, cap_post;
     sched_caps(p, &cap_layer, &cap_post);
     const int sched_entries = 1 + cap_layer + cap_post + 1;
     int n_slots = max_slots;
-    while (n_slots > 0 &&
-           smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb, sched_entries) > (size_t)max_smem_optin)
+    while (n_slots > 0 && smem_bytes_for(n_slots, (int)slot, xs_floats, p.emb, p.hs, sched_entries) > (size_t)max_smem_optin)
         n_slots--;
-    if (n_slots < NG) return 1;
+    if (n_slots < 3) return 1;
     out->n_slots = n_slots;
-    out->slot_bytes = slot;
-    out->n_cons_warps = cons_warps;
-    out->threads = (cons_warps + 1) * 32;
-    out->smem_bytes = (int)smem_bytes_for(n_slots, slot, xs_floats, res_floats, p.emb, sched_entries);
+    out->slot_bytes = (int)slot;
+    out->threads = (NCW + 1) * 32;
+    out->smem_bytes = (int)smem_bytes_for(n_slots, (int)slot, xs_floats, p.emb, p.hs, sched_entries);
     out->grid = grid;
     out->xs_floats = xs_floats;
-    out->res_floats = res_floats;
+    // warps per tile: every ring slot should have a group working on it (more groups than slots would idle)
+    out->tile_warps = NCW / n_slots < 1 ? 1 : (NCW / n_slots > 4 ? 4 : NCW / n_slots);
     return 0;
 }
 
@@ -1496,14 +1398,15 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
     int cap_layer, cap_post;
     sched_caps(p, &cap_layer, &cap_post);
     const int cap = 1 + cap_layer + cap_post + 1;
+    const bool tiled = p.wtype == WT_Q4_0;
     SchedStage *tab = (SchedStage *)calloc((size_t)grid * cap, sizeof(SchedStage));
     for (int cta = 0; cta < grid; cta++) {
         SchedStage *t = tab + (size_t)cta * cap;
         int n = 0;
         bool start = true;  // the next stage pushed is the first of a phase (its vector stage, if it has one)
-        auto vec = [&](const void *ptr, unsigned bytes, size_t layer_stride) {
-            t[n].src = (unsigned long long)ptr; t[n].bytes = bytes;
-            t[n].stride16 = (unsigned)(layer_stride >> 4) | (start ? SCHED_PHASE_START : 0u);
+        auto push = [&](const void *ptr, unsigned seg_bytes, unsigned nseg, unsigned kind) {
+            t[n].src = (unsigned long long)ptr; t[n].seg_bytes = seg_bytes;
+            t[n].meta = nseg | (kind << 8) | (start ? SCHED_PHASE_START : 0u);
             start = false;
             n++;
         };
@@ -1511,33 +1414,32 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
             int r0, r1;
             cta_rows(p.ph[ph], cta, grid, r0, r1);
             const PhaseW &w = p.ph[ph];
-            const size_t ls = ph < 4 ? (size_t)w.layer_stride : 0;
             if (ph == 1 || ph == 3) start = true;  // Wo / W2 have no vector stage: the phase starts with its rows
-            if (w.spg > 0) {
-                // tiled q4_0: spg stages per row group of 16, stage i = groups [i ngrp / spg, (i + 1) ngrp / spg)
-                for (int rg = r0 >> 4; rg < (r1 >> 4); rg++)
-                    for (int i = 0; i < w.spg; i++) {
-                        const int g0 = i * w.ngrp / w.spg, g1 = (i + 1) * w.ngrp / w.spg;
-                        vec(w.base + ((size_t)rg * w.ngrp + g0) * Q4T_GROUP_BYTES, (unsigned)(g1 - g0) * Q4T_GROUP_BYTES, ls);
+            for (int r = r0; r < r1; r += w.R)
+                for (int c = 0; c < w.nch; c++) {
+                    const int u0 = c * w.cu, nu = (w.nu - u0) < w.cu ? (w.nu - u0) : w.cu;
+                    if (tiled) {
+                        // one run of whole 8-block groups of the row group
+                        push(w.base + ((size_t)(r >> 4) * w.nu + u0) * Q4T_GROUP_BYTES, (unsigned)nu * Q4T_GROUP_BYTES, 1u, (unsigned)ph);
+                    } else {
+                        // the chunk's segment of every valid row of the tile
+                        int valid = (r1 < w.rows_real ? r1 : w.rows_real) - r;
+                        if (valid > w.R) valid = w.R;
+                        push(w.base + (size_t)r * w.rs + (size_t)u0 * 16, (unsigned)nu * 16u, (unsigned)valid, (unsigned)ph);
                     }
-                return;
-            }
-            for (int r = r0; r < r1; r += w.rps) {
-                const int k = r1 - r < w.rps ? r1 - r : w.rps;
-                vec(w.base + (size_t)r * w.rs, (unsigned)k * w.rs, ls);
-            }
+                }
         };
-        vec(p.emb_table, (unsigned)row_stride_bytes(p.wtype, p.emb), 0);  // row 0; the kernel adds (token - 1) rows
+        push(p.emb_table, (unsigned)row_stride_bytes(p.wtype, p.emb), 1u, SK_EMB_ROW);  // row 0; the kernel adds (token - 1) rows
         start = true;
-        vec(p.rms_att, (unsigned)p.emb * 4u, (size_t)p.emb * 4u);
+        push(p.rms_att, (unsigned)p.emb * 4u, 1u, SK_RMS_ATT);
         rows(0);
         rows(1);
         start = true;
-        vec(p.rms_ffn, (unsigned)p.emb * 4u, (size_t)p.emb * 4u);
+        push(p.rms_ffn, (unsigned)p.emb * 4u, 1u, SK_RMS_FFN);
         rows(2);
         rows(3);
         start = true;
-        vec(p.rms_final, (unsigned)p.emb * 4u, 0);
+        push(p.rms_final, (unsigned)p.emb * 4u, 1u, SK_RMS_FINAL);
         rows(4);
     }
     p.sched_stride = cap;

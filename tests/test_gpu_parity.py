@@ -265,5 +265,7 @@ def test_profile_flag_selects_the_instrumented_kernel():
         ph = eng.phase_times()
         assert ph["w13_mv"] > 0 and ph["qkv_pro"] > 0 and ph["cls_mv"] > 0
         t = eng.times()
-        assert (t > 0).all()
+        # bucket 2 (RoPE + KV append, llama2.f90:543-565) is part of the QKV tiles' epilogue here: it reads 0,
+        # like the reference's own transcript (README.md:77-82: 26.67 / 0.0 / 0.0 / 192.0 / 17.33)
+        assert (t[[0, 2, 3, 4]] > 0).all() and t[1] >= 0
     assert all(np.array_equal(x, y) for x, y in zip(a, b))

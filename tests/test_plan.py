@@ -5,7 +5,8 @@ takes.  A wrong list does not fail loudly on the device -- a misaligned or overs
 a row streamed twice or never gives wrong logits only for some shapes -- so the properties are pinned
 here for the full-size models of BASELINE.json and every tensor-parallel split:
 
-  * every stage is 16-byte aligned (cp.async.bulk), non-empty and fits one ring slot;
+  * every bulk copy is 16-byte aligned (cp.async.bulk) and non-empty, and the copies of one ring stage
+    (the row segments of a tile's chunk) fit one ring slot together;
   * the stages of all CTAs cover each of the five streamed matrices exactly once (llama2.f90:529-531,
     :603-605, :610-612, :618-620, :634-636 read every row once per token);
   * the per-layer stride stays inside the matrix' allocation for the last layer;
@@ -52,6 +53,12 @@ def test_plan_covers_every_matrix_once(model, wt, tp):
         # ---- every bulk copy: aligned, fits a slot
         assert (used["src"] % 16 == 0).all() and (used["bytes"] % 16 == 0).all()
         assert (used["bytes"] <= info["slot_bytes"]).all()
+        assert max(info["tile_chunks"]) <= 10 and all(r in (4, 16) for r in info["tile_rows"])
+        for cta in (0, info["grid"] // 2, info["grid"] - 1):
+            row = st[cta][st[cta]["bytes"] > 0]
+            per_stage = np.bincount(row["stage"], weights=row["bytes"])
+            assert per_stage.max() <= info["slot_bytes"] and (per_stage > 0).all()
+            assert (np.diff(row["stage"].astype(np.int64)) >= 0).all()
         reg = _region(used["src"])
         assert reg.min() >= 0 and reg.max() <= 8
         # ---- the five matrices: the union of all CTAs' stages is the matrix, nothing twice
@@ -95,14 +102,14 @@ def test_plan_rejects_what_init_rejects():
 
 
 def test_plan_balance_is_within_one_unit():
-    """Rows go to CTAs in units (1 row, 2 for the interleaved W13 / fused QKV, 16 for tiled q4_0):
-    no CTA has more than one unit more than another in any phase."""
+    """Rows go to CTAs in units (row pairs; 16 rows for tiled q4_0): no CTA has more than one unit more
+    than another in any phase."""
     for wt in (WT_F32, WT_Q4_0):
         info, st = capi.plan(Config(**LLAMA2_7B, wtype=wt))
         reg = np.where(st["bytes"] > 0, _region(st["src"]), -1)
         for k in range(5):
             per_cta = np.where(reg == k, st["bytes"], 0).sum(axis=1).astype(np.int64)
             rows = info["rows"][k]
-            unit = 16 if wt == WT_Q4_0 else (2 if k in (0, 2) else 1)
+            unit = 16 if wt == WT_Q4_0 else 2
             per_unit = info["matrix_bytes"][k] / (((rows + unit - 1) // unit))
             assert per_cta.max() - per_cta.min() <= per_unit + 1e-6

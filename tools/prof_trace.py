@@ -1,4 +1,4 @@
-"""Per-CTA phase trace of one layer of the fused kernel (profiling aid).
+"""Per-CTA phase-edge trace of one layer of the fused kernel (profiling aid; instrumented kernel).
 usage: python tools/prof_trace.py <tinyllama|llama2-7b> <f32|f16|q4_0> [layer] [pos]"""
 import sys
 import numpy as np
@@ -13,33 +13,46 @@ w = fx.synth_weights_tiled(cfg, 0)
 eng = capi.Engine(w)
 toks, _ = eng.generate_greedy([5, 6, 7], npos)
 tr = eng.debug_trace(int(toks[-1]), npos + 1, layer).astype(np.int64)
-t = tr[:, :15] - tr[:, :1].min()
-names = ["start", "qkv_pro", "qkv_mv", "bar", "att", "bar", "wo_pro", "wo_mv", "bar", "w13_pro", "w13_mv", "bar",
-         "w2_pro", "w2_mv", "bar"]
-print("edge            min     p50     max   (us since the first CTA entered the layer)")
-for k, nme in enumerate(names):
-    col = t[:, k] / 1000.0
-    print(f"{k:2d} {nme:8s} {col.min():8.2f}{np.median(col):8.2f}{col.max():8.2f}")
-d = np.diff(t, axis=1) / 1000.0
-print("per-CTA durations (us): min p50 max")
-for k in range(14):
-    print(f"   {names[k+1]:8s} {d[:, k].min():7.2f}{np.median(d[:, k]):7.2f}{d[:, k].max():7.2f}")
-wait = tr[:, 16:20]
-print("warp-0 wait cycles in mv phases (qkv, wo, w13, w2): p50", np.median(wait, axis=0), "max", wait.max(axis=0))
-print("warp-0 compute cycles: p50", np.median(tr[:, 20:24], axis=0), "max", tr[:, 20:24].max(axis=0))
-print("warp-0 stages: p50", np.median(tr[:, 24:28], axis=0), "max", tr[:, 24:28].max(axis=0))
-landed = (tr[:, 48:63] >> 32).astype(np.int64)
-tr[:, 48:63] &= 0xffffffff
-lead = tr[:, 32:47] - tr[:, 48:63]
-print("stages already landed in the ring at each edge: min p50 max")
-for k, nme in enumerate(names):
-    print(f"{k:2d} {nme:8s} {landed[:, k].min():4d} {int(np.median(landed[:, k])):4d} {landed[:, k].max():4d}")
-print("producer lead (stages issued - stages consumed) at each edge: min p50 max")
-for k, nme in enumerate(names):
-    print(f"{k:2d} {nme:8s} {lead[:, k].min():4d} {int(np.median(lead[:, k])):4d} {lead[:, k].max():4d}   issued p50 {int(np.median(tr[:, 32 + k]))} consumed p50 {int(np.median(tr[:, 48 + k]))}")
-st = tr[:, 64:96].reshape(-1, 4, 8).astype(np.int64)
-print("warp-0 consume stamps (cycles since 'before call', p50 over CTAs): entry, walk-ctor, 1st wait done, 1st stage released, returned, after cons_sync, after epilogue")
-for phi, nme in enumerate(["qkv", "wo", "w13", "w2"]):
-    b = st[:, phi, 7]
-    print(f"   {nme:4s}", [int(np.median(st[:, phi, i] - b)) for i in (0, 1, 2, 3, 4, 5, 6)])
+# thread 0 of every CTA stamps globaltimer (ns) when IT passes an edge: after a prologue (the activation
+# vector is complete: includes the wait for the slowest publisher), after its own warp's tiles of a phase
+edges = [(0, "layer start"), (1, "qkv prologue done"), (2, "qkv tiles done (warp 0)"), (4, "attention done"),
+         (6, "wo prologue done"), (7, "wo tiles done (warp 0)"), (9, "w13 prologue done"),
+         (10, "w13 tiles done (warp 0)"), (12, "w2 prologue done"), (13, "w2 tiles done (warp 0)")]
+t0 = tr[:, 0].min()
+print("edge                         min     p50     max   (us since the first CTA entered the layer)")
+prev = None
+for k, name in edges:
+    col = (tr[:, k] - t0) / 1000.0
+    d = "" if prev is None else f"   step p50 {np.median((tr[:, k] - tr[:, prev]) / 1000.0):6.2f}  min {((tr[:, k] - tr[:, prev]) / 1000.0).min():6.2f}  max {((tr[:, k] - tr[:, prev]) / 1000.0).max():6.2f}"
+    print(f"{k:2d} {name:24s} {col.min():7.2f} {np.median(col):7.2f} {col.max():7.2f}{d}")
+    prev = k
 np.save("gpurun_out/trace.npy", tr)
+# warp 0's first tile of each mat-vec phase: SM clocks relative to entering run_tiles
+print("warp 0, first tile (cycles since run_tiles entry, p50 / max over CTAs): first stage landed, mat-vec done, reduced, "
+      "published | all own tiles done | at entry: ring lead / prefetch lead (stages ahead of the phase's first) p50 | "
+      "when warp 0 is done: ring / prefetch cursor - phase start, stages of the phase")
+info = eng.stats()
+for ph, name in enumerate(["qkv", "wo", "w13", "w2"]):
+    b = tr[:, 16 + 8 * ph: 24 + 8 * ph].copy()
+    ok = b[:, 1] > 0  # CTAs whose warp 0 had a tile
+    if not ok.any():
+        continue
+    end_ring = (b[ok, 3] >> 32) & 0xffff
+    end_pf = (b[ok, 3] >> 48) & 0xffff
+    b[:, 3] &= 0xffffffff
+    e = b[ok, 0]
+    lo = e & 0xffffffff
+    cols = [b[ok, k] - e for k in (1, 2, 4, 7)]
+    red = (b[ok, 3] - lo) & 0xffffffff
+    lead = (b[ok, 5] & 0xffffffff) - b[ok, 6]
+    pfl = (b[ok, 5] >> 32) - b[ok, 6]
+    print(f"   {name:4s}", " ".join(f"{int(np.median(c)):6d}/{int(c.max()):6d}" for c in cols), f"(reduced {int(np.median(red))})",
+          f"| lead {int(np.median(lead))} / pf {int(np.median(pfl))} | end ring {int(np.median(end_ring))} pf {int(np.median(end_pf))}")
+# attention phase of the CTAs that had an item: cycles since entering attention_phase_t
+a = tr[:, 48:56]
+ok = a[:, 2] > 0
+if ok.any():
+    e = a[ok, 0]
+    names = ["K/V loads issued", "q arrived", "positions done", "current position done", "merge barrier passed", "published", "left"]
+    print(f"attention CTAs ({int(ok.sum())}): cycles since entry, p50 / max:",
+          "; ".join(f"{n} {int(np.median(a[ok, k + 1] - e))}/{int((a[ok, k + 1] - e).max())}" for k, n in enumerate(names)))
