@@ -185,6 +185,8 @@ typedef struct llmf90_b200_plan_info {
     int32_t rows[5], cols[5];         /* this rank's share of the five matrices                     */
     int32_t tile_rows[5];             /* rows of a tile (the unit one consumer warp owns)           */
     int32_t tile_chunks[5];           /* ring stages a tile's contraction range is cut into         */
+    int32_t tile_warps[5];            /* consumer warps that share one tile (a divisor of 12)       */
+    int32_t reserved0;
     uint64_t matrix_bytes[5];         /* device bytes of one layer of each                          */
     uint64_t vector_bytes;            /* one rmsnorm weight vector                                  */
     uint64_t emb_row_bytes;           /* one row of the embedding table                             */

@@ -62,7 +62,7 @@ def _check_hot_functions(ptxas_log: str) -> None:
                 continue
             spilled = int(nxt.split("bytes stack frame,")[1].split("bytes spill stores")[0])
             instrumented = "Lb1E" in ln  # the profiling instantiation (template argument PROF = true)
-            if spilled > (16 if instrumented else 0):
+            if spilled > (160 if instrumented else 0):
                 bad.append(ln.split("Function properties for ")[1][:80] + ":" + nxt.strip())
     if bad:
         raise RuntimeError("hot device functions spill registers:\n  " + "\n  ".join(bad))
@@ -73,6 +73,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if force or _newer(CUDA_LIB, deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         extra = ["-DLLMF90_WATCHDOG"] if os.environ.get("LLMF90_BUILD_WATCHDOG") else []  # debug builds only
+        if os.environ.get("LLMF90_BUILD_PROBE"):
+            extra.append("-DLLMF90_COLD_CODE_PROBE")  # experiment: time a second, warm pass of the attention merge
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-Xptxas", "-v", "-o", CUDA_LIB] + _abs(CUDA_SRCS)
         r = subprocess.run(cmd, cwd=CSRC, stderr=subprocess.PIPE, text=True)
         if verbose or r.returncode:

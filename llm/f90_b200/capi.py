@@ -48,7 +48,8 @@ class CPlanInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("grid", "threads", "n_slots", "slot_bytes", "smem_bytes", "sched_stride",
                                          "n_layers")] + \
                [("rows", C.c_int32 * 5), ("cols", C.c_int32 * 5), ("tile_rows", C.c_int32 * 5),
-                ("tile_chunks", C.c_int32 * 5), ("_pad", C.c_int32), ("matrix_bytes", C.c_uint64 * 5),
+                ("tile_chunks", C.c_int32 * 5), ("tile_warps", C.c_int32 * 5), ("reserved0", C.c_int32),
+                ("matrix_bytes", C.c_uint64 * 5),
                 ("vector_bytes", C.c_uint64), ("emb_row_bytes", C.c_uint64)]
 
 

@@ -136,13 +136,13 @@ struct StreamParams {
     // ring geometry
     int n_slots, slot_bytes;
     int xs_floats;
-    int tile_warps;          // consumer warps per tile group (1, 2, 3 or 4)
+    int tile_warps[5];       // consumer warps per tile group, per phase (a divisor of 12)
 };
 
 struct StreamPlan {
     int n_slots, slot_bytes, threads, smem_bytes, grid;
     int xs_floats;
-    int tile_warps;
+    int tile_warps[5];
 };
 
 // Decide tile / ring geometry for a model on `grid` CTAs (fills p.ph[i].R / nch / nu / cu / rows_cap);

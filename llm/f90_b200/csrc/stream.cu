@@ -58,6 +58,7 @@ constexpr int CONS_BAR = 1;         // named barrier id used by the consumer war
 constexpr int NBAR = 256;
 constexpr int MAX_NCH = 10;         // chunks per tile (plan_stream enforces it)
 constexpr int ATT_PSTRIDE_PAD = 4;  // attention partial record = {m, l, -, -, acc[hs]}
+constexpr int ATT_MAX_CHUNK = 288;  // positions of one attention split: <= 256 rounded up to groups of 16, + slack
 
 // per-launch constants of this CTA in shared memory: everything the hot loop needs comes from here
 // with one LDS (kernel parameters reached from a non-inlined function are generic loads)
@@ -67,10 +68,22 @@ struct CtaPlan {
     unsigned long long lstride[SK_COUNT];  // bytes between layers per stage kind
     unsigned int sstride[SK_COUNT];        // bytes between the segments of a stage per stage kind
     int off_xs, off_xres, off_red, off_att, off_grp, off_full, off_empty, off_sched;
-    int G;                                 // consumer warps per tile group
+    int G[5];                              // consumer warps per tile group, per phase (1, 2, 3, 4, 6 or 12)
     int slot_bytes, n_slots;
     unsigned int slot_magic;               // ceil(2^32 / n_slots): s mod n_slots without a division
     int wtype, emb, hid, kv, att_dim, hs, tp, rank, ll_rep, v_off, seq, H, kv_mul, L;
+    int rep;                               // the replica of the LL vectors this CTA polls (blockIdx % ll_rep)
+    int pos, n_splits;                     // this launch's position (1-based) and attention split count
+    unsigned int ep_base;                  // epoch of layer l = ep_base + l + 1
+    // ring stage numbers (per CTA): stage 0 is the embedding row, layer l's section starts at 1 + l * n_layer;
+    // voff / toff: offsets of a phase's vector stage / first tile stage inside its section (classifier: after
+    // the last layer)
+    int n_layer, voff[5], toff[5];
+    unsigned long long *trace;             // profiling kernel: this CTA's 128 trace words while the traced layer runs, else null
+    unsigned long long *trace_base, *phase_cycles;  // profiling kernel: the trace buffer [grid][128] (or null), the timer accumulators
+    int trace_layer;
+    unsigned int kvmul_inv16;              // ceil(65536 / kv_mul): h / kv_mul without a division
+    float inv_emb;                         // 1 / emb (rmsnorm mean)
     float *kc, *vc;
     unsigned long long *ll_q, *ll_kv, *ll_att, *ll_part, *ll_hb;
     unsigned long long *part1[MAX_TP], *part2[MAX_TP];
@@ -82,6 +95,8 @@ struct CtaPlan {
     unsigned int ep_last;                  // epoch of the token tail's records
     int do_argmax;
     volatile int prod_issued, pf_issued;   // stages copied into the ring / prefetched into L2 so far (trace)
+    unsigned long long *gx_trace;          // where gather_x leaves its clock stamps (profiling kernel), or null
+    volatile int qw[NCW];                  // per warp: the phase it is in (the phase loop keeps NOTHING in registers across calls)
     float tail_best[NCW];                  // per-warp maxloc of the classifier epilogue
     int tail_idx[NCW];
     float2 rope[64];                       // this position's RoPE row
@@ -96,7 +111,7 @@ struct Prof {
 static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int emb, int hs, int sched_entries)
 {
     return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)emb * 4 + 64 * 4 +
-           (size_t)NCW * (hs + ATT_PSTRIDE_PAD) * 4 + 2 * NCW * 16 * 4 + (NBAR + MAX_SLOTS) * 8 +
+           (size_t)(ATT_MAX_CHUNK + NCW * hs) * 4 + 2 * NCW * 16 * 4 + (NBAR + MAX_SLOTS) * 8 +
            (size_t)sched_entries * sizeof(SchedStage);
 }
 
@@ -174,6 +189,7 @@ __device__ __noinline__ void producer_loop(CtaPlan *cp, int token, int pace, int
     long long next_ok = clock64();
 #pragma unroll 1
     while (s < total) {
+        bool busy = false;
         if (pf_lead > 0 && ps < total && ps <= s + pf_lead) {
             uint32_t b, n, ss;
             if (ps <= s) {
@@ -181,6 +197,7 @@ __device__ __noinline__ void producer_loop(CtaPlan *cp, int token, int pace, int
                 sched_stage(cp, tab, pc, e_layer_end, token, b, n, ss);
                 unfetched = ps++;
                 cp->pf_issued = ps;
+                busy = true;
             } else if (clock64() >= next_ok) {
                 const unsigned long long src = sched_stage(cp, tab, pc, e_layer_end, token, b, n, ss);
 #pragma unroll 1
@@ -188,24 +205,29 @@ __device__ __noinline__ void producer_loop(CtaPlan *cp, int token, int pace, int
                 next_ok = max(next_ok, clock64() - 2000) + (((long long)(b * n) * pace) >> 10);
                 ps++;
                 cp->pf_issued = ps;
+                busy = true;
             }
         }
-        if (!mbar_test(empty_bar(cp, slot), par)) continue;
         // a copy that goes to HBM (not prefetched) shares the paced budget; one that hits L2 does not
         const bool to_hbm = pf_lead == 0 || s == unfetched;
-        if (to_hbm && pace > 0 && clock64() < next_ok) continue;
-        uint32_t bytes, nseg, sstr;
-        const unsigned long long src = sched_stage(cp, tab, rc, e_layer_end, token, bytes, nseg, sstr);
-        if (to_hbm) next_ok = max(next_ok, clock64() - 2000) + (((long long)(bytes * nseg) * pace) >> 10);
-        uint64_t *fb = full_bar(cp, (uint32_t)s);
-        mbar_arrive_expect_tx(fb, bytes * nseg);
-        uint8_t *dst = smem_base() + (size_t)slot * cp->slot_bytes;
+        if (mbar_test(empty_bar(cp, slot), par) && !(to_hbm && pace > 0 && clock64() < next_ok)) {
+            uint32_t bytes, nseg, sstr;
+            const unsigned long long src = sched_stage(cp, tab, rc, e_layer_end, token, bytes, nseg, sstr);
+            if (to_hbm) next_ok = max(next_ok, clock64() - 2000) + (((long long)(bytes * nseg) * pace) >> 10);
+            uint64_t *fb = full_bar(cp, (uint32_t)s);
+            mbar_arrive_expect_tx(fb, bytes * nseg);
+            uint8_t *dst = smem_base() + (size_t)slot * cp->slot_bytes;
 #pragma unroll 1
-        for (uint32_t i = 0; i < nseg; i++)
-            bulk_g2s(dst + i * bytes, reinterpret_cast<const void *>(src + (unsigned long long)i * sstr), bytes, fb, pol);
-        if (++slot == ns) { slot = 0; par ^= 1u; }
-        s++;
-        cp->prod_issued = s;
+            for (uint32_t i = 0; i < nseg; i++)
+                bulk_g2s(dst + i * bytes, reinterpret_cast<const void *>(src + (unsigned long long)i * sstr), bytes, fb, pol);
+            if (++slot == ns) { slot = 0; par ^= 1u; }
+            s++;
+            cp->prod_issued = s;
+            busy = true;
+        }
+        // Nothing to do right now: sleep instead of spinning.  This warp has the highest index of its scheduler
+        // partition, i.e. issue priority over three consumer warps -- a tight polling loop here steals their slots.
+        if (!busy) __nanosleep(64);
     }
 }
 
@@ -343,7 +365,7 @@ __device__ __forceinline__ const uint8_t *vec_stage_wait(const CtaPlan *cp, uint
 }
 __device__ __forceinline__ void vec_stage_release(const CtaPlan *cp, uint32_t s)
 {
-    if ((int)threadIdx.x < cp->G) mbar_arrive(empty_bar(cp, slot_of(cp, s)));  // (the slot expects G arrivals)
+    if (threadIdx.x == 0) mbar_arrive_n(empty_bar(cp, slot_of(cp, s)), (uint32_t)NCW);
 }
 
 // ---- activation-vector prologue, one routine for all phases.  Every CTA needs the whole vector;
@@ -421,7 +443,7 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
 // xs may still be read by a slower warp when a faster one gets here: poll first (that is the long
 // part), then one consumer-wide barrier before the first write to xs, one after the last.
 template <int WT>
-__device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long long *src, int nsrc, uint32_t ep, int n,
+__device__ __forceinline__ float gather_x(const CtaPlan *cp, const unsigned long long *src, int nsrc, uint32_t ep, int n,
                                        int norm, const uint8_t *emb_row, const float *wn /* shared */)
 {
     float *xs = reinterpret_cast<float *>(smem_base() + cp->off_xs);
@@ -432,6 +454,9 @@ __device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long lo
     const int n4 = n >> 2;
     const float4 *wn4 = reinterpret_cast<const float4 *>(wn);
     float ss = 0.f;
+    unsigned long long *gtr = cp->gx_trace;
+#define GSTAMP(k_) do { if (gtr && tid == 0) gtr[k_] = (unsigned long long)clock64(); } while (0)
+    GSTAMP(0);
 #pragma unroll 1
     for (int base = 0; base < n4; base += PV * NCT) {
         float4 v[PV];
@@ -455,7 +480,11 @@ __device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long lo
                 }
             }
         }
-        if (base == 0) cons_sync();  // xs is free: every warp is past the previous phase's mat-vec
+        if (base == 0) {
+            GSTAMP(1);
+            cons_sync();  // xs is free: every warp is past the previous phase's mat-vec
+            GSTAMP(2);
+        }
 #pragma unroll
         for (int k = 0; k < PV; k++) {
             const int j = base + tid + k * NCT;
@@ -471,31 +500,42 @@ __device__ __noinline__ float gather_x(const CtaPlan *cp, const unsigned long lo
         }
     }
     if (WT == WT_Q4_0) q4_zero_tail(xs, n);
+    GSTAMP(3);
     if (!norm) {
         cons_sync();
+        GSTAMP(4);
         return 1.f;
     }
     ss = warp_sum(ss);
     if ((tid & 31) == 0) red[tid >> 5] = ss;
     cons_sync();
+    GSTAMP(4);
     float tot = 0.f;
 #pragma unroll
     for (int i = 0; i < NCW; i++) tot += red[i];
-    return 1.0f / sqrtf(tot / (float)n + 1e-5f);
+    return rsqrtf(fmaf(tot, cp->inv_emb, 1e-5f));  // 1 / sqrt(mean(x^2) + 1e-5), llama2.f90:454-456 (n == emb)
+#undef GSTAMP
 }
 
 // ------------------------------------------------------------------ attention phase
 // (head, split) items over the CTAs (llama2.f90:574-598); a split is a run of positions (<= 256
-// up to 2048 positions of context).  Inside an item each consumer warp takes groups of 8
-// positions; lane = 4 * (position in group) + (quarter of the head dimension):
-//   scores : each lane dots its quarter of q_h with its quarter of one K row (q, K and V requests
-//            are all issued up front: ONE L2 round trip per group), two shuffles finish the dot
-//   softmax: online (running max / sum) over the 8 positions, three shuffles each
-//   values : lane <-> head dimension (hs/32 consecutive dims), p_t broadcast by shuffle
-// Positions past the end of a group read a clamped (valid) row with probability 0.
-// Warp partials merge through shared memory (a scratch area of its own: xs may still be in use by a
-// slower warp's QKV tiles).  With one split the normalised head output goes straight to ll_att;
-// otherwise {m, l, acc} partials go to ll_part and the Wo prologue merges.
+// up to 2048 positions of context).  The phase is a pure latency chain between the QKV tiles and the
+// Wo prologue, so it is organised for few dependent steps and little code, not for throughput:
+//   scores : each warp takes groups of 8 positions; lane = 4 * (position in group) + (quarter of the
+//            head dimension) dots its quarter of q_h with its quarter of one K row (the K requests go out
+//            before the poll for q: ONE L2 round trip), two shuffles finish the dot, the score goes to
+//            shared memory.  The V rows of the group are requested right after (lane <-> head
+//            dimensions) and arrive while the CTA meets at the barrier.
+//   softmax: every warp computes the maximum and the normaliser of ALL scores of the item itself (a few
+//            shared-memory reads and two warp reductions: cheaper than exchanging them) -- no running
+//            maximum, no rescaling (softmax :468-478)
+//   values : acc = sum_t exp(s_t - max) v_t over the warp's positions, one partial vector per warp in
+//            shared memory; after the second barrier thread d adds the partials of dimension d.
+// Positions past the end of a group read a clamped (valid) row and are skipped.  The last position
+// is this launch's own: its key / value rows come from the LL buffer, polled in the same loop as q by
+// the warp whose group holds it.  With one split the normalised head output goes straight to ll_att;
+// otherwise {max, normaliser, acc} partials go to ll_part and the Wo prologue merges.
+
 template <int VEC>
 __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
 {
@@ -510,168 +550,180 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
     }
 }
 
+// The current position of an item: its query and key quarters and its value dims all come from the LL
+// buffers (one polling loop: one L2 round trip).  Run by one warp; writes the score to *sc_out and parks
+// the value dims in v_out.  (Inlined: a call inside the attention phase would spill everything that is live
+// across it -- and it is a branch of its own, so its 2 x 16 LL words per lane do not add to the others.)
 template <int HS>
-__device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int n_splits, int layer, int pos, uint32_t ep,
-                                               unsigned long long *tr /* optional 8 trace words (profiling), or null */)
+__device__ __forceinline__ void attention_current(const unsigned long long *pq, const unsigned long long *pk,
+                                               const unsigned long long *pv, uint32_t ep, float *sc_out, float *v_out)
 {
+    constexpr int LP = HS >> 4, vec = HS >> 5;  // lanes per position (16 dims each); value dims per lane
+    constexpr float rscale = HS == 32 ? 0.17677669529663687f : (HS == 64 ? 0.125f : 0.08838834764831845f);  // 1 / sqrt(hs)
+    const int lane = threadIdx.x & 31, dq = lane & (LP - 1);
+    pq += dq * 16; pk += dq * 16; pv += lane * vec;
+    float sdot, v[vec];
+    bool ok;
+    LLMF90_WD_DECL;
+    do {
+        LLMF90_WD_CHECK(102, 0, ep)
+        ok = true;
+        sdot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned long long a, b, c, d, e, f, g, h;
+            ll_load2(pq + 4 * k, a, b);
+            ll_load2(pq + 4 * k + 2, c, d);
+            ll_load2(pk + 4 * k, e, f);
+            ll_load2(pk + 4 * k + 2, g, h);
+            ok = ok && ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep) && ll_ok(e, ep) && ll_ok(f, ep) &&
+                 ll_ok(g, ep) && ll_ok(h, ep);
+            sdot = fmaf(ll_val(a), ll_val(e), sdot); sdot = fmaf(ll_val(b), ll_val(f), sdot);
+            sdot = fmaf(ll_val(c), ll_val(g), sdot); sdot = fmaf(ll_val(d), ll_val(h), sdot);
+        }
+#pragma unroll
+        for (int k = 0; k < vec; k++) {
+            const unsigned long long a = ll_load1(pv + k);
+            ok = ok && ll_ok(a, ep);
+            v[k] = ll_val(a);
+        }
+    } while (!ok);
+#pragma unroll
+    for (int o = 1; o < LP; o <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+    if (lane == 0) *sc_out = sdot * rscale;
+#pragma unroll
+    for (int k = 0; k < vec; k++) v_out[lane * vec + k] = v[k];
+}
+
+template <int HS>
+__device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int layer)
+{
+    const int n_splits = cp->n_splits, pos = cp->pos;
+    const uint32_t ep = cp->ep_base + (uint32_t)layer + 1u;
+    unsigned long long *tr = cp->trace ? cp->trace + 48 : nullptr;  // 8 trace words (profiling kernel)
 #define ASTAMP(k_) do { if (tr && threadIdx.x == 0) tr[k_] = (unsigned long long)clock64(); } while (0)
     ASTAMP(0);
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int hs = HS, vec = HS >> 5;  // HS in {32, 64, 128}
-    constexpr int q4n = HS >> 4;           // float4 per lane of a quarter head: 2, 4, 8
+    // a position is held by LP lanes of 16 head dimensions each; a warp takes PG positions at a time
+    constexpr int hs = HS, vec = HS >> 5, LP = HS >> 4, PG = 32 / LP;  // HS in {32, 64, 128}: LP 2 / 4 / 8, PG 16 / 8 / 4
+    constexpr int lp_shift = HS == 32 ? 1 : (HS == 64 ? 2 : 3);
+    constexpr float rscale = HS == 32 ? 0.17677669529663687f : (HS == 64 ? 0.125f : 0.08838834764831845f);  // 1 / sqrt(hs)
     const int S = n_splits;
-    const int H = cp->H, kv = cp->kv, kv_mul = cp->kv_mul, att_dim = cp->att_dim, ll_rep = cp->ll_rep;
-    const int items = H * S;
+    const int kv = cp->kv, att_dim = cp->att_dim;
+    const int items = cp->H * S;
     const int npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches); npast is this launch's
-    const int s_shift = 31 - __clz(S), kvm_shift = 31 - __clz(kv_mul);
-    const bool kvm_pow2 = (kv_mul & (kv_mul - 1)) == 0;
-    const int chunk = (((pos + S - 1) >> s_shift) + 7) & ~7;
-    constexpr int pstride = hs + ATT_PSTRIDE_PAD;
-    const float rscale = 1.0f / sqrtf((float)hs);
-    float *sc = reinterpret_cast<float *>(smem_base() + cp->off_att);  // [NCW][pstride]
-    const float *kc = cp->kc + (size_t)layer * cp->seq * kv;
-    const float *vc = cp->vc + (size_t)layer * cp->seq * kv;
-    const int pl = lane >> 2, dq = lane & 3;
-    const int rep = (int)blockIdx.x % ll_rep;  // the replica of the LL vectors this CTA polls
-    const unsigned long long *ll_q = cp->ll_q + (size_t)rep * att_dim, *ll_kv = cp->ll_kv + (size_t)rep * 2 * kv;
+    const int s_shift = 31 - __clz(S);
+    const int chunk = (((pos + S - 1) >> s_shift) + 15) & ~15;
+    float *sc = reinterpret_cast<float *>(smem_base() + cp->off_att);  // [ATT_MAX_CHUNK] scores
+    float *part = sc + ATT_MAX_CHUNK;                                    // [NCW][hs] partial outputs
+    const int pl = lane >> lp_shift, dq = lane & (LP - 1);
+    const int rep = cp->rep;  // the replica of the LL vectors this CTA polls
 #pragma unroll 1
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        // (S is a power of two; kv_mul is one in every common model: shifts, the division is a cold path)
+        // (S is a power of two; h / kv_mul by multiplication: llama2.f90:581 maps head h to KV head h / kv_mul)
         const int h = item >> s_shift, sp = item & (S - 1);
-        const int g = kvm_pow2 ? h >> kvm_shift : h / kv_mul;
-        // this split's positions [t0, t1): the last one of the last split is the current position, whose key /
-        // value rows were produced in this launch (LL buffer) -- every other row comes from the cache
-        const int t0 = sp * chunk, t1 = min(pos, t0 + chunk);
-        float m = -INFINITY, l = 0.f, acc[vec];
-#pragma unroll
-        for (int i = 0; i < vec; i++) acc[i] = 0.f;
-        float4 qq[q4n];
-        bool have_q = false;
+        const int g = (int)(((uint32_t)h * cp->kvmul_inv16) >> 16);
+        const int t0 = sp * chunk, t1 = min(pos, t0 + chunk);  // this split's positions
+        const int tc1 = min(t1, npast);                        // ... of which [t0, tc1) are cached rows
+        const bool cur_here = npast >= t0 && npast < t1;       // the split ends with this launch's own position:
+        const int nwg = cur_here ? NCW - 1 : NCW;              // the last warp takes it, the others the cached rows
+        const bool cur_warp = cur_here && warp == NCW - 1;
+        const unsigned long long *pq = cp->ll_q + (size_t)rep * att_dim + h * hs;
+        const float *kbase = cp->kc + ((size_t)layer * cp->seq * kv + g * hs + dq * 16);
+        const float *vbase = cp->vc + ((size_t)layer * cp->seq * kv + g * hs + lane * vec);
+        const int tb0 = t0 + PG * warp;  // the warp's first group
+        float vv[PG][vec];               // value rows of the warp's first group
+        // ---- scores
+        if (cur_warp) {
+            const unsigned long long *pk = cp->ll_kv + (size_t)rep * 2 * kv + g * hs;
+            attention_current<HS>(pq, pk, pk + kv, ep, sc + (npast - t0), part + warp * hs);
+        } else if (tb0 < tc1) {
+            float4 qq[4];
 #pragma unroll 1
-        for (int tb = t0 + 8 * warp; tb < t1; tb += 8 * NCW) {
-            const int t = tb + pl;
-            const bool valid = t < t1;
-            const int ucur = npast - tb;  // index of the current position in this group of 8 (0..7), if it is in it
-            const bool has_cur = ucur >= 0 && ucur < 8;
-            // cached rows: positions past the end (and the current one) read a clamped, valid row instead
-            const int tlast = min(t1, npast) - 1;
-            const float4 *kr = reinterpret_cast<const float4 *>(kc + (size_t)max(0, min(t, tlast)) * kv + (size_t)g * hs + dq * (hs >> 2));
-            const float *vb = vc + (size_t)g * hs + lane * vec;
-            float4 kk[q4n];
-            float vv[8][vec];
+            for (int tb = tb0; tb < tc1; tb += PG * nwg) {
+                const int t = tb + pl;
+                const float4 *kr = reinterpret_cast<const float4 *>(kbase + (uint32_t)(min(t, tc1 - 1) * kv));
+                float4 kk[4];
 #pragma unroll
-            for (int i = 0; i < q4n; i++) kk[i] = __ldcg(kr + i);
+                for (int i = 0; i < 4; i++) kk[i] = __ldcg(kr + i);
+                if (tb == tb0) {
+                    // first group: the value rows are requested now and used after the barrier; then the query
+                    // (written by the QKV epilogues of this launch) is polled: one L2 round trip for all three
 #pragma unroll
-            for (int u = 0; u < 8; u++) load_vec<vec>(vb + (size_t)max(0, min(tb + u, tlast)) * kv, vv[u]);
-            if (!have_q || has_cur) {
-                // ONE polling loop for everything this launch produced: the query quarter and, in the warp that
-                // holds the current position, its key quarter and value dims (one L2 round trip, not three)
-                const unsigned long long *pq = ll_q + h * hs + dq * (hs >> 2);
-                const unsigned long long *pk = ll_kv + g * hs + dq * (hs >> 2);
-                const unsigned long long *pv = ll_kv + kv + g * hs + lane * vec;
-                const bool mine = has_cur && pl == ucur;  // the four lanes that hold the current position's key
-                bool ok;
-                LLMF90_WD_DECL;
-                do {
-                    LLMF90_WD_CHECK(102, h, ep)
-                    ok = true;
+                    for (int u = 0; u < PG; u++) load_vec<vec>(vbase + (uint32_t)(min(tb0 + u, tc1 - 1) * kv), vv[u]);
+                    ASTAMP(1);
+                    ll_wait4n<4>(pq, dq * 16, ep, qq);
+                    ASTAMP(2);
+                }
+                float sdot = 0.f;
 #pragma unroll
-                    for (int k = 0; k < q4n; k++) {
-                        unsigned long long a, b, c, d;
-                        ll_load2(pq + 4 * k, a, b);
-                        ll_load2(pq + 4 * k + 2, c, d);
-                        ok = ok && ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep);
-                        qq[k] = make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
-                    }
-                    if (has_cur) {
+                for (int i = 0; i < 4; i++) {
+                    sdot = fmaf(qq[i].x, kk[i].x, sdot); sdot = fmaf(qq[i].y, kk[i].y, sdot);
+                    sdot = fmaf(qq[i].z, kk[i].z, sdot); sdot = fmaf(qq[i].w, kk[i].w, sdot);
+                }
 #pragma unroll
-                        for (int k = 0; k < q4n; k++) {
-                            unsigned long long a, b, c, d;
-                            ll_load2(pk + 4 * k, a, b);
-                            ll_load2(pk + 4 * k + 2, c, d);
-                            ok = ok && ll_ok(a, ep) && ll_ok(b, ep) && ll_ok(c, ep) && ll_ok(d, ep);
-                            if (mine) kk[k] = make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
-                        }
-#pragma unroll
-                        for (int k = 0; k < vec; k++) {
-                            const unsigned long long a = ll_load1(pv + k);
-                            ok = ok && ll_ok(a, ep);
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if (u == ucur) vv[u][k] = ll_val(a);
-                        }
-                    }
-                } while (!ok);
-                have_q = true;
-            }
-            float sdot = 0.f;
-#pragma unroll
-            for (int i = 0; i < q4n; i++) {
-                sdot = fmaf(qq[i].x, kk[i].x, sdot); sdot = fmaf(qq[i].y, kk[i].y, sdot);
-                sdot = fmaf(qq[i].z, kk[i].z, sdot); sdot = fmaf(qq[i].w, kk[i].w, sdot);
-            }
-            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-            sdot = valid ? sdot * rscale : -INFINITY;  // dot_product(q_t,k_t)/sqrt(head_size), :582
-            float bm = sdot;
-            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
-            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
-            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
-            const float mn = fmaxf(m, bm);
-            const float corr = expf(m - mn);
-            const float p = valid ? expf(sdot - mn) : 0.f;
-            float ps = p;  // every position is held by 4 lanes: sum over the position bits only
-            ps += __shfl_xor_sync(0xffffffffu, ps, 4);
-            ps += __shfl_xor_sync(0xffffffffu, ps, 8);
-            ps += __shfl_xor_sync(0xffffffffu, ps, 16);
-            l = fmaf(l, corr, ps);
-            m = mn;
-#pragma unroll
-            for (int i = 0; i < vec; i++) acc[i] *= corr;
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const float pt = __shfl_sync(0xffffffffu, p, 4 * u);
-#pragma unroll
-                for (int i = 0; i < vec; i++) acc[i] = fmaf(pt, vv[u][i], acc[i]);
+                for (int o = 1; o < LP; o <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+                if (dq == 0 && t < tc1) sc[t - t0] = sdot * rscale;  // dot_product(q_t,k_t)/sqrt(head_size), :582
             }
         }
         ASTAMP(3);
-        float *mine = sc + (size_t)warp * pstride;
-        if (lane == 0) { mine[0] = m; mine[1] = l; }
+        cons_sync();
+        // ---- softmax statistics of the whole item, in every warp (:468-478)
+        const int n = t1 - t0;
+        float M = -INFINITY;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) M = fmaxf(M, sc[i]);
+        M = warp_max(M);
+        float L = 0.f;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) L += __expf(sc[i] - M);
+        L = warp_sum(L);
+        // ---- values: acc = sum over the warp's positions of exp(s_t - M) v_t
+        float acc[vec];
 #pragma unroll
-        for (int i = 0; i < vec; i++) mine[ATT_PSTRIDE_PAD + lane * vec + i] = acc[i];
+        for (int i = 0; i < vec; i++) acc[i] = 0.f;
+        if (cur_warp) {
+            const float p = __expf(sc[npast - t0] - M);
+#pragma unroll
+            for (int i = 0; i < vec; i++) acc[i] = p * part[warp * hs + lane * vec + i];  // (parked by attention_current)
+        } else {
+#pragma unroll 1
+            for (int tb = tb0; tb < tc1; tb += PG * nwg) {
+                if (tb != tb0) {
+#pragma unroll
+                    for (int u = 0; u < PG; u++) load_vec<vec>(vbase + (uint32_t)(min(tb + u, tc1 - 1) * kv), vv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < PG; u++)
+                    if (tb + u < tc1) {
+                        const float p = __expf(sc[tb + u - t0] - M);
+#pragma unroll
+                        for (int i = 0; i < vec; i++) acc[i] = fmaf(p, vv[u][i], acc[i]);
+                    }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < vec; i++) part[warp * hs + lane * vec + i] = acc[i];
         cons_sync();
         ASTAMP(5);
-        // merge of the warp partials by whole warps: lane w < 12 holds warp w's {m, l} and its weight
-        // exp(m_w - M); a lane then sums its dims over the 12 records.  One warp per LL replica (S == 1) /
-        // warp 0 (partial record of a split); the merge is cheap enough to repeat per replica.
-        const int nout = S == 1 ? ll_rep : 1;
-        if (warp < nout) {
-            const float mw = lane < NCW ? sc[lane * pstride] : -INFINITY;
-            const float M = warp_max(mw);
-            const float e = mw > -INFINITY ? __expf(mw - M) : 0.f;
-            const float L = warp_sum(lane < NCW ? e * sc[lane * pstride + 1] : 0.f);
-            float ew[NCW];  // (all lanes take part in the shuffles: hs = 32 leaves half of them without a dim pair)
+        // ---- thread (dimension pair, LL replica): add the 12 partial vectors, publish
+        const int nout = S == 1 ? cp->ll_rep : 1;
+        if (tid < (hs >> 1) * nout) {
+            const int d = (tid & ((hs >> 1) - 1)) << 1, rr = tid >> (HS == 32 ? 4 : (HS == 64 ? 5 : 6));
+            const float invL = __fdividef(1.0f, L);
+            float A0 = 0.f, A1 = 0.f;
 #pragma unroll
-            for (int w = 0; w < NCW; w++) ew[w] = __shfl_sync(0xffffffffu, e, w);
-#pragma unroll 1
-            for (int rr = warp; rr < nout; rr += NCW) {
-#pragma unroll 1
-                for (int d = 2 * lane; d < hs; d += 64) {
-                    float A0 = 0.f, A1 = 0.f;
-#pragma unroll
-                    for (int w = 0; w < NCW; w++) {
-                        const float2 a = *reinterpret_cast<const float2 *>(sc + w * pstride + ATT_PSTRIDE_PAD + d);
-                        A0 = fmaf(a.x, ew[w], A0); A1 = fmaf(a.y, ew[w], A1);
-                    }
-                    if (S == 1) {
-                        ll_store2(cp->ll_att + (size_t)rr * att_dim, h * hs + d, A0 / L, A1 / L, ep);
-                    } else {
-                        unsigned long long *out = cp->ll_part + (size_t)(h * S + sp) * pstride;
-                        ll_store2(out, ATT_PSTRIDE_PAD + d, A0, A1, ep);
-                        if (d == 0) ll_store2(out, 0, M, L, ep);
-                    }
-                }
+            for (int w = 0; w < NCW; w++) {
+                const float2 a = *reinterpret_cast<const float2 *>(part + w * hs + d);
+                A0 += a.x; A1 += a.y;
+            }
+            if (S == 1) {
+                ll_store2(cp->ll_att + (size_t)rr * att_dim, h * hs + d, A0 * invL, A1 * invL, ep);
+            } else {
+                unsigned long long *out = cp->ll_part + (size_t)(h * S + sp) * (hs + ATT_PSTRIDE_PAD);
+                ll_store2(out, ATT_PSTRIDE_PAD + d, A0, A1, ep);
+                if (d == 0) ll_store2(out, 0, n > 0 ? M : -INFINITY, L, ep);
             }
         }
         ASTAMP(6);
@@ -965,18 +1017,58 @@ __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, 
     }
 }
 
+// ------------------------------------------------------------------ the prologue of one phase
+// The activation vector of phase q into shared memory; returns the 1 / rms factor of a norm phase (1 else).
+//   QKV / W13 / classifier: rmsnorm (llama2.f90:527, :608, :627) of the residual stream plus the tp partial
+//     outputs of the phase before (Wo of this layer / W2 of the previous one); layer 0 starts from the
+//     embedding row (:520).  The norm weights (and the embedding row) arrive through the ring.
+//   Wo / W2: the attention output (merging position splits) / the SwiGLU output.  A CTA without rows in
+//     such a phase does not need its input vector: skipping the poll also keeps it from ever lagging
+//     behind on a buffer nobody waits for it to have read.
+template <int WT>
+__device__ __forceinline__ float phase_prologue(CtaPlan *cp, int q)
+{
+    const int ph = q < 4 * cp->L ? (q & 3) : 4, l = q >> 2;
+    const uint32_t ep = cp->ep_base + (uint32_t)l + 1u;
+    const int rep = cp->rep, tp = cp->tp, emb = cp->emb;
+    if constexpr (true) {
+        if (cp->trace && threadIdx.x == 0) cp->gx_trace = (ph == 2 || ph == 3) ? cp->trace + 72 + 8 * (ph - 2) : nullptr;
+    }
+    if (!(ph & 1)) {
+        const uint32_t sv = 1u + (uint32_t)((ph < 4 ? l : cp->L) * cp->n_layer + cp->voff[ph]);  // the norm vector's stage
+        const uint8_t *emb_row = q == 0 ? vec_stage_wait(cp, 0u) : nullptr;
+        const float *wn = reinterpret_cast<const float *>(vec_stage_wait(cp, sv));
+        const float rs = gather_x<WT>(cp, (ph == 2 ? cp->part1[cp->rank] : cp->part2[cp->rank]) + (size_t)rep * tp * emb, tp,
+                                      ph == 2 ? ep : ep - 1u, emb, 1, emb_row, wn);
+        if (q == 0) vec_stage_release(cp, 0u);
+        vec_stage_release(cp, sv);
+        return rs;
+    }
+    if (cp->nrows[ph] > 0) {
+        if (ph == 1 && cp->n_splits > 1) load_x_attn<WT>(cp, cp->n_splits, ep);
+        else gather_x<WT>(cp, ph == 1 ? cp->ll_att + (size_t)rep * cp->att_dim : cp->ll_hb + (size_t)rep * ((cp->hid + 1) & ~1), 1, ep,
+                          ph == 1 ? cp->att_dim : cp->hid, 0, nullptr, nullptr);
+    }
+    return 1.f;
+}
+
 // ------------------------------------------------------------------ the tiles of one phase
 // This warp's tiles of phase `ph` (tile t -> warp t mod 12): the mat-vec over the tile's chunks as they
 // land in the ring, the cross-lane reduction, and the tile's epilogue -- every lane ends up holding one
 // row PAIR (rows 2i, 2i + 1: what RoPE and SwiGLU combine, and one 16-byte LL store), and the lanes
 // that share a pair split its destinations (LL replicas x tensor-parallel ranks) between them.
-// Out of line on purpose: its own register allocation, nothing live across it in the phase loop, and
-// all constants come from the plan in shared memory.  `s0` = ring stage number of the phase's first
-// stage; rscale = the 1 / rms factor of the phase's rmsnorm (the mat-vec is linear).
+// Out of line on purpose: its own register allocation, nothing live across it in the phase loop (the
+// loop carries the phase number and nothing else: whatever is live across a call is spilled around it,
+// and local memory is an L2 round trip in this kernel), all constants come from the plan in shared
+// memory.  rscale = the 1 / rms factor of the phase's rmsnorm (the mat-vec is linear).
 template <int WT, bool PROF>
-__device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float rscale, uint32_t ep, int l, int pos,
-                                       unsigned long long *tr /* PROF: this CTA's 8 trace words of the phase, or null */)
+__device__ __forceinline__ void run_tiles(CtaPlan *cp, int q, float rscale)
 {
+    const int ph = q < 4 * cp->L ? (q & 3) : 4, l = q >> 2, pos = cp->pos;
+    const uint32_t ep = cp->ep_base + (uint32_t)l + 1u;  // epoch of everything layer l publishes
+    const uint32_t s0 = 1u + (uint32_t)((ph < 4 ? l : cp->L) * cp->n_layer + cp->toff[ph]);  // the phase's first tile stage
+    unsigned long long *tr = nullptr;  // PROF: this CTA's 8 trace words of the phase
+    if constexpr (PROF) { if (cp->trace && ph < 4) tr = cp->trace + 16 + 8 * ph; }
 #define TSTAMP(k_) do { if constexpr (PROF) { if (tr && threadIdx.x == 0 && !tdone) tr[k_] = (unsigned long long)clock64(); } } while (0)
     bool tdone = false;
     uint8_t *smem = smem_base();
@@ -995,7 +1087,11 @@ __device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float r
         }
     }
     TSTAMP(0);
-    const int G = cp->G, grp = warp / G, cl = warp - grp * G, ngrp = NCW / G;
+    const int G = cp->G[ph];
+    const uint32_t ginv = (65535u + (uint32_t)G) / (uint32_t)G;  // ceil(65536 / G): x / G = (x * ginv) >> 16 for x < 32768
+#define DIV_G(x_) ((int)(((uint32_t)(x_) * ginv) >> 16))
+    const int grp = DIV_G(warp), cl = warp - grp * G, ngrp = DIV_G(NCW);
+    const uint32_t gweight = (uint32_t)ngrp;  // this warp's weight in the slot's empty barrier (12 arrivals in all)
     float *gsc = reinterpret_cast<float *>(smem + cp->off_grp);  // [2][NCW][16]
     int buf = 0;
 #pragma unroll 1
@@ -1010,7 +1106,7 @@ __device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float r
             for (int c = 0; c < nch; c++, s++) {
                 const int nu = min(cu, nu_row - u0);
                 // this warp's share of the chunk's columns: whole lane rounds [b0, b1) of 32 units
-                const int rounds = (nu + 31) >> 5, b0 = (cl * rounds) / G, b1 = ((cl + 1) * rounds) / G;
+                const int rounds = (nu + 31) >> 5, b0 = DIV_G(cl * rounds), b1 = DIV_G((cl + 1) * rounds);
                 const int ub = b0 << 5, un = min(nu, b1 << 5) - ub;
                 const uint32_t slot = slot_of(cp, s);
                 mbar_wait(full_bar(cp, s), full_par(s), 2);
@@ -1019,7 +1115,7 @@ __device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float r
                     tile_dot<WT>(smem + (size_t)slot * cp->slot_bytes + (size_t)ub * 16, (uint32_t)nu * 16u,
                                  xs + (WT == WT_F16 ? 8 : 4) * (u0 + ub), un, lane, acc);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty_bar(cp, slot));
+                if (lane == 0) mbar_arrive_n(empty_bar(cp, slot), gweight);
                 u0 += nu;
             }
             TSTAMP(2);
@@ -1056,13 +1152,13 @@ __device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float r
 #pragma unroll 1
             for (int c = 0; c < nch; c++, s++) {
                 const int ng = min(cu, nu_row - g0);
-                const int b0 = (cl * ng) / G, b1 = ((cl + 1) * ng) / G;  // this warp's 8-block groups of the chunk
+                const int b0 = DIV_G(cl * ng), b1 = DIV_G((cl + 1) * ng);  // this warp's 8-block groups of the chunk
                 const uint32_t slot = slot_of(cp, s);
                 mbar_wait(full_bar(cp, s), full_par(s), 2);
                 if (c == 0) TSTAMP(1);
                 tile_dot_q4(smem + (size_t)slot * cp->slot_bytes + (size_t)b0 * Q4T_GROUP_BYTES, xs, nu_row, g0 + b0, b1 - b0, lane, acc0, acc1);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty_bar(cp, slot));
+                if (lane == 0) mbar_arrive_n(empty_bar(cp, slot), gweight);
                 g0 += ng;
             }
             TSTAMP(2);
@@ -1112,7 +1208,7 @@ __device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float r
             }
         } else if (ph == 2) {
             // SwiGLU on the interleaved gate/up rows (llama2.f90:613-616)
-            const float hv = (a * (1.0f / (1.0f + expf(-a)))) * b;
+            const float hv = (a * __fdividef(1.0f, 1.0f + __expf(-a))) * b;
             const int hb_stride = (cp->hid + 1) & ~1;
 #pragma unroll 1
             for (int d = sub; d < nrep; d += nsl) ll_store(cp->ll_hb + (size_t)d * hb_stride, r >> 1, hv, ep);
@@ -1151,6 +1247,7 @@ __device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float r
                     ((unsigned long long)(unsigned)(cp->prod_issued - (int)s0) << 32);  // cursors when warp 0 is done
     }
 #undef TSTAMP
+#undef DIV_G
     if (ph == 4) {
         // maxloc of this warp's logits (llama2.f90:388: the first maximum wins), for the token tail
 #pragma unroll
@@ -1161,6 +1258,81 @@ __device__ __noinline__ void run_tiles(CtaPlan *cp, int ph, uint32_t s0, float r
         }
         if (lane == 0) { cp->tail_best[warp] = best; cp->tail_idx[warp] = bidx; }
     }
+}
+
+// ------------------------------------------------------------------ the consumer warps' phase loop
+// One loop over the 4 L + 1 weight phases (q = 4 l + {0 QKV, 1 WO, 2 W13, 3 W2}; q = 4 L is the
+// classifier): prologue -> tiles (mat-vec + epilogue per group) (-> attention).  A single copy of every
+// piece serves all phases.  The loop is a function of its own and carries nothing but q: the pieces are
+// allocated the registers their caller does not hold, and what they cannot keep in registers they spill to
+// local memory -- which is an L2 round trip in this kernel (shared memory leaves the L1 next to nothing).
+// PROF = true adds the phase timers of CTA 0 (SM cycles per bucket, PH_* in kernels.cuh) and the optional
+// per-CTA trace of one layer.
+template <int WT, bool PROF>
+__device__ __noinline__ void consumer_main(CtaPlan *cp, Prof *pf)
+{
+    const bool timer = PROF && (blockIdx.x == 0 && threadIdx.x == 0);
+    const bool tracing = PROF && cp->trace_base != nullptr;
+    const unsigned long long t_ns0 = timer ? globaltimer_ns() : 0ull;
+    const long long t_c0 = timer ? clock64() : 0ll;
+    if (timer) {
+        for (int i = 0; i < PH_COUNT; i++) pf->tacc[i] = 0;
+        pf->tmark = t_c0;
+    }
+#define LAP(b) do { if constexpr (PROF) { if (timer) prof_lap(pf, (b)); } } while (0)
+#define STAMP(l_, k_) do { if constexpr (PROF) { if (tracing && threadIdx.x == 0 && (l_) == cp->trace_layer) prof_stamp(cp->trace_base, (k_)); } } while (0)
+    // The phase number lives in shared memory (one word per warp) and is re-read after every call: a value
+    // kept in a register across a call has to be saved and restored around it by somebody, through local
+    // memory, and local memory is an L2 round trip here.
+#define Q_NOW (cp->qw[threadIdx.x >> 5])
+    if ((threadIdx.x & 31) == 0) Q_NOW = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (;;) {
+        {
+            const int q = Q_NOW, nq = 4 * cp->L + 1;
+            if (q >= nq) break;
+            if constexpr (PROF) {
+                const int ph = q < nq - 1 ? (q & 3) : 4, l = q >> 2;
+                if (threadIdx.x == 0 && (q & 3) == 0) cp->trace = (tracing && l == cp->trace_layer && ph < 4) ? cp->trace_base + (size_t)blockIdx.x * 128 : nullptr;
+                if ((q & 3) == 0) cons_sync();
+                if (ph == 0) STAMP(l, 0);
+            }
+        }
+        const float rscale = phase_prologue<WT>(cp, Q_NOW);
+        if constexpr (PROF) {
+            const int q = Q_NOW, ph = q < 4 * cp->L ? (q & 3) : 4;
+            LAP(ph == 0 ? 0 : 2 + 3 * ph);
+            STAMP(q >> 2, ph == 0 ? 1 : 3 + 3 * ph);
+        }
+        run_tiles<WT, PROF>(cp, Q_NOW, rscale);
+        if constexpr (PROF) {
+            const int q = Q_NOW, ph = q < 4 * cp->L ? (q & 3) : 4;
+            LAP((ph == 0 ? 0 : 2 + 3 * ph) + 1);
+            STAMP(q >> 2, ph == 0 ? 2 : 4 + 3 * ph);
+        }
+        if ((Q_NOW & 3) == 0 && Q_NOW < 4 * cp->L) {
+            // ---- attention (llama2.f90:574-598)
+            if (cp->hs == 64) attention_phase_t<64>(cp, Q_NOW >> 2);
+            else if (cp->hs == 128) attention_phase_t<128>(cp, Q_NOW >> 2);
+            else attention_phase_t<32>(cp, Q_NOW >> 2);
+            LAP(PH_ATT);
+            STAMP(Q_NOW >> 2, 4);
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) Q_NOW = Q_NOW + 1;
+        __syncwarp();
+    }
+#undef Q_NOW
+    token_tail(cp, cp->pos);
+    if (timer) {
+        prof_lap(pf, PH_ARGMAX);
+        for (int i = 0; i < PH_COUNT; i++) cp->phase_cycles[i] += (unsigned long long)pf->tacc[i];
+        cp->phase_cycles[PH_COUNT] += (unsigned long long)(clock64() - t_c0);
+        cp->phase_cycles[PH_COUNT + 1] += globaltimer_ns() - t_ns0;
+    }
+#undef LAP
+#undef STAMP
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -1177,18 +1349,23 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     __shared__ Prof pf;
     // ---- shared-memory map: ring | xs | xres | red | attention scratch | full[NBAR] | empty[MAX_SLOTS] | stage list
     const int off_xs = P.n_slots * P.slot_bytes, off_xres = off_xs + P.xs_floats * 4, off_red = off_xres + P.emb * 4;
-    const int off_att = off_red + 64 * 4, off_grp = off_att + NCW * (P.hs + ATT_PSTRIDE_PAD) * 4;
+    const int off_att = off_red + 64 * 4, off_grp = off_att + (ATT_MAX_CHUNK + NCW * P.hs) * 4;
     const int off_full = off_grp + 2 * NCW * 16 * 4;  // [2][NCW][16] partial results of a tile group's warps
     const int off_empty = off_full + NBAR * 8, off_sched = off_empty + MAX_SLOTS * 8;
     if (threadIdx.x == 5) {
         cp.off_xs = off_xs; cp.off_xres = off_xres; cp.off_red = off_red; cp.off_att = off_att; cp.off_grp = off_grp;
-        cp.G = P.tile_warps;
+        for (int i = 0; i < 5; i++) cp.G[i] = P.tile_warps[i];
         cp.off_full = off_full; cp.off_empty = off_empty; cp.off_sched = off_sched;
         cp.slot_bytes = P.slot_bytes; cp.n_slots = P.n_slots;
         cp.slot_magic = 0xffffffffu / (uint32_t)P.n_slots + 1u;
         cp.wtype = P.wtype; cp.emb = P.emb; cp.hid = P.hid; cp.kv = P.kv; cp.att_dim = P.att_dim; cp.hs = P.hs;
         cp.tp = P.tp; cp.rank = P.rank; cp.ll_rep = P.ll_rep; cp.v_off = P.v_off; cp.seq = P.seq; cp.H = P.H;
         cp.kv_mul = P.kv_mul; cp.L = P.L;
+        cp.rep = (int)(blockIdx.x % (unsigned)P.ll_rep);
+        cp.n_splits = P.n_splits; cp.ep_base = P.ep_base; cp.trace = nullptr;
+        cp.trace_base = P.trace; cp.trace_layer = P.trace_layer; cp.phase_cycles = P.phase_cycles;
+        cp.kvmul_inv16 = (65535u + (unsigned)P.kv_mul) / (unsigned)P.kv_mul;
+        cp.inv_emb = 1.0f / (float)P.emb;
         cp.kc = P.kc; cp.vc = P.vc; cp.ll_q = P.ll_q; cp.ll_kv = P.ll_kv; cp.ll_att = P.ll_att;
         cp.ll_part = P.ll_part; cp.ll_hb = P.ll_hb;
     }
@@ -1198,6 +1375,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         cp.amax[k] = P.amax[k]; cp.done[k] = P.done[k];
     }
     if (threadIdx.x == 7) {
+        cp.gx_trace = nullptr;
         cp.forced = P.forced; cp.out_tokens = P.out_tokens; cp.tokpos = const_cast<int *>(P.tokpos);
         cp.ep_last = P.ep_base + (uint32_t)P.L + 1u; cp.do_argmax = P.do_argmax;
     }
@@ -1225,11 +1403,24 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     if (threadIdx.x < NBAR + P.n_slots) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + off_full);
         if (threadIdx.x < NBAR) mbar_init(&bars[threadIdx.x], 1);
-        else mbar_init(&bars[threadIdx.x], (uint32_t)P.tile_warps);  // empty[slot]: one arrive per warp of the tile's group
+        else mbar_init(&bars[threadIdx.x], (uint32_t)NCW);  // empty[slot]: a group of G warps arrives with weight 12 / G each
         fence_mbar_init();
     }
     const int token = P.token > 0 ? P.token : P.tokpos[0];
     const int pos = P.token > 0 ? P.pos : P.tokpos[1];
+    if (threadIdx.x == 6) {
+        cp.pos = pos;
+        int nst[5];
+        for (int i = 0; i < 5; i++) {
+            int r0, r1;
+            cta_rows(P.ph[i], blockIdx.x, gridDim.x, r0, r1);
+            nst[i] = ((r1 - r0 + P.ph[i].R - 1) / P.ph[i].R) * P.ph[i].nch;
+        }
+        cp.n_layer = 2 + nst[0] + nst[1] + nst[2] + nst[3];
+        cp.voff[0] = 0; cp.toff[0] = 1; cp.voff[1] = 0; cp.toff[1] = 1 + nst[0];
+        cp.voff[2] = 1 + nst[0] + nst[1]; cp.toff[2] = cp.voff[2] + 1; cp.voff[3] = 0; cp.toff[3] = cp.toff[2] + nst[2];
+        cp.voff[4] = 0; cp.toff[4] = 1;
+    }
     // this position's RoPE row (a cold HBM read, issued first thing, used after the QKV phase)
     if (threadIdx.x >= 64 && threadIdx.x < 64 + (P.hs >> 1))
         cp.rope[threadIdx.x - 64] = P.rope_tab[(size_t)(pos - 1) * (P.hs >> 1) + threadIdx.x - 64];
@@ -1242,87 +1433,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     }
 
     // ===================== consumer warps =====================
-    const int tid = (int)threadIdx.x;
-    // phase timers (CTA 0, thread 0): SM cycles per fine-grained bucket, see PH_* in kernels.cuh;
-    // optional per-CTA trace of one layer (debug/profiling)
-    const bool timer = PROF && (blockIdx.x == 0 && tid == 0);
-    const bool tracing = PROF && P.trace != nullptr;
-    const unsigned long long t_ns0 = timer ? globaltimer_ns() : 0ull;
-    const long long t_c0 = timer ? clock64() : 0ll;
-    if (timer) {
-        for (int i = 0; i < PH_COUNT; i++) pf.tacc[i] = 0;
-        pf.tmark = t_c0;
-    }
-#define LAP(b) do { if constexpr (PROF) { if (timer) prof_lap(&pf, (b)); } } while (0)
-#define STAMP(l_, k_) do { if constexpr (PROF) { if (tracing && tid == 0 && (l_) == P.trace_layer) prof_stamp(P.trace, (k_)); } } while (0)
-    const int rep = (int)blockIdx.x % P.ll_rep;  // LL vector replicas; the one this CTA polls
-    const int hb_stride = (P.hid + 1) & ~1;
-    uint32_t s0 = 0;  // ring stage number of the next stage of this CTA's schedule (identical in every thread)
-
-    // One loop over the 4 L + 1 weight phases (q = 4 l + {0 QKV, 1 WO, 2 W13, 3 W2}; q = 4 L is the
-    // classifier): prologue -> tiles (mat-vec + epilogue per warp) (-> attention).  A single copy of
-    // every piece serves all phases.
-    const int nq = 4 * P.L + 1;
-#pragma unroll 1
-    for (int q = 0; q < nq; q++) {
-        const int ph = q < 4 * P.L ? (q & 3) : 4, l = q >> 2;
-        const uint32_t ep = P.ep_base + (uint32_t)l + 1u;  // epoch of everything layer l publishes
-        const int tb = ph == 0 ? 0 : 2 + 3 * ph;  // timer bucket / trace stamp base of this phase
-        const bool norm = !(ph & 1);
-        const int nr = cp.nrows[ph];
-        if (ph == 0) STAMP(l, 0);
-
-        // ---- prologue: the activation vector of this phase, in shared memory
-        float rscale = 1.f;
-        if (norm) {
-            // rmsnorm (llama2.f90:527, :608, :627); layer 0 starts from the embedding row (:520);
-            // adds the tp partial outputs of the phase before (Wo of this layer / W2 of the previous one)
-            const uint8_t *emb_row = nullptr;
-            if (q == 0) emb_row = vec_stage_wait(&cp, s0++);
-            const float *wn = reinterpret_cast<const float *>(vec_stage_wait(&cp, s0));
-            rscale = gather_x<WT>(&cp, (ph == 2 ? cp.part1[P.rank] : cp.part2[P.rank]) + (size_t)rep * P.tp * P.emb, P.tp,
-                                  ph == 2 ? ep : ep - 1u, P.emb, 1, emb_row, wn);
-            if (q == 0) vec_stage_release(&cp, s0 - 1);
-            vec_stage_release(&cp, s0++);
-        } else if (nr > 0) {
-            // (a CTA without rows in a Wo / W2 phase does not need its input vector: skipping the poll
-            // also keeps it from ever lagging behind on a buffer nobody waits for it to have read)
-            if (ph == 1 && P.n_splits > 1) load_x_attn<WT>(&cp, P.n_splits, ep);
-            else gather_x<WT>(&cp, ph == 1 ? cp.ll_att + (size_t)rep * P.att_dim : cp.ll_hb + (size_t)rep * hb_stride, 1, ep,
-                              ph == 1 ? P.att_dim : P.hid, 0, nullptr, nullptr);
-        }
-        LAP(tb);
-        STAMP(l, ph == 0 ? 1 : 3 + 3 * ph);
-
-        // ---- the mat-vec: this warp's tiles of the phase, each followed by its epilogue
-        run_tiles<WT, PROF>(&cp, ph, s0, rscale, ep, l, pos,
-                            (tracing && l == P.trace_layer && ph < 4) ? P.trace + (size_t)blockIdx.x * 128 + 16 + 8 * ph : nullptr);
-        s0 += (uint32_t)cp.nst[ph];
-        LAP(tb + 1);
-        STAMP(l, ph == 0 ? 2 : 4 + 3 * ph);
-        if (ph == 4) break;
-
-        if (ph == 0) {
-            // ---- attention (llama2.f90:574-598)
-            unsigned long long *atr = nullptr;
-            if constexpr (PROF) { if (tracing && l == P.trace_layer) atr = P.trace + (size_t)blockIdx.x * 128 + 48; }
-            if (P.hs == 64) attention_phase_t<64>(&cp, P.n_splits, l, pos, ep, atr);
-            else if (P.hs == 128) attention_phase_t<128>(&cp, P.n_splits, l, pos, ep, atr);
-            else attention_phase_t<32>(&cp, P.n_splits, l, pos, ep, atr);
-            LAP(PH_ATT);
-            STAMP(l, 4);
-        }
-    }
-
-    token_tail(&cp, pos);
-    if (timer) {
-        prof_lap(&pf, PH_ARGMAX);
-        for (int i = 0; i < PH_COUNT; i++) P.phase_cycles[i] += (unsigned long long)pf.tacc[i];
-        P.phase_cycles[PH_COUNT] += (unsigned long long)(clock64() - t_c0);
-        P.phase_cycles[PH_COUNT + 1] += globaltimer_ns() - t_ns0;
-    }
-#undef LAP
-#undef STAMP
+    consumer_main<WT, PROF>(&cp, &pf);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1386,8 +1497,27 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
     out->smem_bytes = (int)smem_bytes_for(n_slots, (int)slot, xs_floats, p.emb, p.hs, sched_entries);
     out->grid = grid;
     out->xs_floats = xs_floats;
-    // warps per tile: every ring slot should have a group working on it (more groups than slots would idle)
-    out->tile_warps = NCW / n_slots < 1 ? 1 : (NCW / n_slots > 4 ? 4 : NCW / n_slots);
+    // Warps per tile group, per phase.  Measured on B200 with one value for all phases: 3 (four groups) is
+    // the best or within 1 % of it for every benchmark configuration (TinyLlama f32 1.006 / 0.949 / 0.930 /
+    // 0.951 ms per token with 1 / 2 / 3 / 4 warps, Llama-2-7B f16 4.29 / 3.34 / 3.19 / 3.20, q4_0 3.02 / 2.30 /
+    // 2.24 / 2.15): a stage is drained in a third of the time, so a slot spends its life in flight, not
+    // waiting for its warp.  A short phase (a handful of tiles per CTA, all banked in the ring before it
+    // starts) is a latency chain instead: its time is rounds x (fixed part + mat-vec / G), so prefer the
+    // group size that takes the fewest rounds.
+    for (int i = 0; i < 5; i++) {
+        const int tiles = tiles_of(p.ph[i], p.ph[i].rows_cap), big = tiled ? 4 : 3;
+        int best = big;
+        if (tiles <= NCW && tiles * p.ph[i].nch <= n_slots) {  // the whole phase of a CTA fits the ring
+            long best_cost = -1;
+            const int cand[4] = {4, 3, 2, 1};
+            for (int k = 0; k < 4; k++) {
+                const int g = cand[k], rounds = (tiles + NCW / g - 1) / (NCW / g);
+                const long cost = (long)rounds * (1500 + 4500 / g);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = g; }
+            }
+        }
+        out->tile_warps[i] = best;
+    }
     return 0;
 }
 

@@ -48,11 +48,28 @@ for ph, name in enumerate(["qkv", "wo", "w13", "w2"]):
     pfl = (b[ok, 5] >> 32) - b[ok, 6]
     print(f"   {name:4s}", " ".join(f"{int(np.median(c)):6d}/{int(c.max()):6d}" for c in cols), f"(reduced {int(np.median(red))})",
           f"| lead {int(np.median(lead))} / pf {int(np.median(pfl))} | end ring {int(np.median(end_ring))} pf {int(np.median(end_pf))}")
-# attention phase of the CTAs that had an item: cycles since entering attention_phase_t
+# attention phase of the CTAs that had an item: cycles since entering attention_phase_t (thread 0 = warp 0)
 a = tr[:, 48:56]
-ok = a[:, 2] > 0
+ok = a[:, 6] > 0
 if ok.any():
     e = a[ok, 0]
-    names = ["K/V loads issued", "q arrived", "positions done", "current position done", "merge barrier passed", "published", "left"]
+    names = {1: "K/V loads issued, poll starts", 2: "q (+ current k, v) arrived", 3: "positions done", 5: "merge barrier passed",
+             4: "(probe build: first merge pass done)", 6: "published", 7: "left"}
     print(f"attention CTAs ({int(ok.sum())}): cycles since entry, p50 / max:",
-          "; ".join(f"{n} {int(np.median(a[ok, k + 1] - e))}/{int((a[ok, k + 1] - e).max())}" for k, n in enumerate(names)))
+          "; ".join(f"{n} {int(np.median(a[ok, k] - e))}/{int((a[ok, k] - e).max())}" for k, n in names.items() if (a[ok, k] > 0).any()))
+# the activation-vector prologue (gather_x) of W13 and W2: cycles since entry (thread 0)
+for k, name in ((72, "w13 prologue"), (80, "w2 prologue")):
+    g = tr[:, k:k + 5]
+    ok = g[:, 4] > 0
+    if ok.any():
+        e = g[ok, 0]
+        print(f"{name}: first batch polled {int(np.median(g[ok, 1] - e))}/{int((g[ok, 1] - e).max())}; barrier A passed "
+              f"{int(np.median(g[ok, 2] - e))}; vector stored {int(np.median(g[ok, 3] - e))}; barrier B passed "
+              f"{int(np.median(g[ok, 4] - e))}/{int((g[ok, 4] - e).max())}   (p50[/max] over {int(ok.sum())} CTAs)")
+# probe build (LLMF90_BUILD_PROBE=1): the attention phase run a second time on complete inputs, warm code
+a2 = tr[:, 56:64]
+ok = a2[:, 7] > 0
+if ok.any():
+    e = a2[ok, 0]
+    print("attention, second (warm) call: cycles since entry p50/max:",
+          "; ".join(f"[{k}] {int(np.median(a2[ok, k] - e))}/{int((a2[ok, k] - e).max())}" for k in (1, 2, 3, 5, 6, 7) if (a2[ok, k] > 0).any()))
