@@ -69,6 +69,7 @@ struct Engine {
     float *h_logits = nullptr;  // pinned staging buffer (used when the caller's buffer cannot be registered)
     float *reg_logits = nullptr;  // the caller's logits array, page-locked in place so the D2H copy lands in it directly
     int *h_tokpos = nullptr;    // pinned
+    int *h_err = nullptr, *d_err = nullptr;  // host-mapped error word the kernel sets when a tensor-parallel poll times out
     // drivers
     bool use_stream = true;
     bool prof = false;  // instrumented fused kernel (LLMF90_FLAG_PROFILE / LLMF90_PROFILE=1)
@@ -105,6 +106,7 @@ void release_all()
     if (E.reg_logits) cudaHostUnregister(E.reg_logits);
     if (E.h_logits) cudaFreeHost(E.h_logits);
     if (E.h_tokpos) cudaFreeHost(E.h_tokpos);
+    if (E.h_err) cudaFreeHost(E.h_err);
     if (E.ev0) cudaEventDestroy(E.ev0);
     if (E.ev1) cudaEventDestroy(E.ev1);
     if (E.ev2) cudaEventDestroy(E.ev2);
@@ -276,6 +278,17 @@ int enqueue_forward(int token, int pos, bool device_loop, const int *forced, int
     return 0;
 }
 
+// after a stream synchronisation: did a kernel give up waiting for a tensor-parallel peer?
+int check_peers()
+{
+    if (E.h_err && *E.h_err) {
+        *E.h_err = 0;
+        return fail("a tensor-parallel rank stopped answering (a poll for its partial sums timed out): the forward "
+                    "pass is invalid; every rank must make the same calls in the same order after tp_connect");
+    }
+    return 0;
+}
+
 int device_loop(int first_token, int pos0, int n, const int *d_forced, int *d_out, float *ms_after_first,
                 float *ms_total)
 {
@@ -288,6 +301,7 @@ int device_loop(int first_token, int pos0, int n, const int *d_forced, int *d_ou
     }
     CK(cudaEventRecord(E.ev2, E.st));
     CK(cudaStreamSynchronize(E.st));
+    if (check_peers()) return 1;
     float a = 0, b = 0;
     CK(cudaEventElapsedTime(&a, E.ev0, E.ev2));
     CK(cudaEventElapsedTime(&b, E.ev1, E.ev2));
@@ -405,6 +419,11 @@ constexpr int STREAM_MAX_SLOTS = 16;
 inline int stream_target_slot(bool tiled, int wtype, int emb)
 {
     if (tiled) return 16 * Q4T_GROUP_BYTES;
+    if (wtype == WT_F16) {
+        // tensor-core tiles of 8 rows, row segments of at most 4096 bytes (2048 columns)
+        const int seg = std::min((int)row_stride_bytes(wtype, emb), 4096);
+        return std::max(8 * seg, 8192);
+    }
     const int tile = 4 * (int)row_stride_bytes(wtype, emb);
     return tile < 16384 ? 16384 : (tile > 32768 ? 32768 : tile);
 }
@@ -486,15 +505,47 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     E.active_bytes = (size_t)L * ((size_t)(nqkv + 2 * hid) * hb_e + (size_t)emb * host_row_bytes(wt, att) +
                                   (size_t)emb * host_row_bytes(wt, hid) + 2 * (size_t)emb * 4) +
                      (size_t)Vl * hb_e + (size_t)emb * 4 + hb_e;
+    if (E.use_stream) {
+        // the fused kernel's plan comes first: the f32 / f16 matrices are laid out in the order it streams them
+        int coop = 0, smem_optin = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
+        CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
+        if (!coop) { release_all(); return fail("device does not support cooperative launch"); }
+        const uint8_t *const bases[5] = {E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls};
+        stream_geometry(E.sp, c, hs, tp, rank, tiled, bases);
+        int target_slot = stream_target_slot(tiled, wt, emb), max_slots = STREAM_MAX_SLOTS;
+        if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
+        if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
+        if (plan_stream(E.sp, stream_grid(E.sp, E.n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, target_slot, max_slots, &E.plan)) {
+            release_all();
+            return fail("model rows do not fit the shared-memory ring (row stride too large)");
+        }
+    }
     {
         const int nqkv_full = emb + 2 * kv_full;
         size_t stage_bytes = std::max({(size_t)V * hb_e, (size_t)2 * hid_full * hb_e, (size_t)emb * hb_hf,
                                        (size_t)nqkv_full * hb_e});
-        uint8_t *stage = nullptr;
+        uint8_t *stage = nullptr, *tmp = nullptr;
         CK(dalloc(&stage, stage_bytes));
+        // f32 / f16 matrices of the fused kernel: plain rows -> tile-major (stream.cu: tile_pass_kernel), one layer
+        // of one matrix at a time through a scratch copy
+        const bool tile_major = E.use_stream && !tiled;
+        if (tile_major) {
+            size_t tb = 0;
+            for (int i = 0; i < 5; i++) tb = std::max(tb, (size_t)E.sp.ph[i].layer_stride);
+            CK(dalloc(&tmp, tb));
+        }
+        auto to_tiles = [&](int phase, uint8_t *layer) -> int {
+            if (!tile_major) return 0;
+            CK(cudaMemcpyAsync(tmp, layer, (size_t)E.sp.ph[phase].layer_stride, cudaMemcpyDeviceToDevice, E.st));
+            CK(launch_tile_pass(E.sp, phase, E.plan.grid, tmp, layer, E.st));
+            CK(cudaStreamSynchronize(E.st));
+            return 0;
+        };
         int rc = 0;
         rc |= upload_matrix(E.d_emb, tok_emb, wt, V, emb, V, 0, emb, 0, 0, 0, stage, stage_bytes);
         rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, Vl, 0, emb, 0, rank * Vl, 0, stage, stage_bytes, tiled);
+        if (!rc) rc |= to_tiles(4, E.d_wcls);
         for (int l = 0; l < L && !rc; l++) {
             const uint8_t *s_qkv = (const uint8_t *)wqkv + (size_t)l * nqkv_full * hb_e;
             const uint8_t *s_wo = (const uint8_t *)wo + (size_t)l * emb * hb_e;
@@ -509,17 +560,22 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
                                 emb + kv_row0, 0, stage, stage_bytes, tiled);
             rc |= upload_matrix(d_qkv + mbytes(att + kvl, emb), nullptr, wt, nqkv_full, emb, kvl, 0, emb, 0,
                                 emb + kv_full + kv_row0, 0, stage, stage_bytes, tiled);
+            if (!rc) rc |= to_tiles(0, d_qkv);
             // Wo: all rows, the input columns of this rank's heads
             rc |= upload_matrix(E.d_wo + (size_t)l * mbytes(emb, att), s_wo, wt, emb, emb, emb, rank * att, att, 0, 0, 0,
                                 stage, stage_bytes, tiled);
+            if (!rc) rc |= to_tiles(1, E.d_wo + (size_t)l * mbytes(emb, att));
             // gate/up rows of this rank's FFN slice, interleaved: row 2i = W1 row i, row 2i+1 = W3 row i
             rc |= upload_matrix(E.d_w13 + (size_t)l * mbytes(2 * hid, emb), s_w13, wt, 2 * hid_full, emb, 2 * hid, 0,
                                 emb, 1, rank * hid, hid_full, stage, stage_bytes, tiled);
+            if (!rc) rc |= to_tiles(2, E.d_w13 + (size_t)l * mbytes(2 * hid, emb));
             // W2: all rows, the input columns of this rank's FFN slice
             rc |= upload_matrix(E.d_w2 + (size_t)l * mbytes(emb, hid), s_w2, wt, emb, hid_full, emb, rank * hid, hid, 0, 0,
                                 0, stage, stage_bytes, tiled);
+            if (!rc) rc |= to_tiles(3, E.d_w2 + (size_t)l * mbytes(emb, hid));
         }
         cudaFree(stage);
+        if (tmp) cudaFree(tmp);
         if (rc) { release_all(); return 1; }
     }
     CK(cudaMemcpy(E.d_rms_att, rms_att, (size_t)L * emb * 4, cudaMemcpyHostToDevice));
@@ -542,22 +598,12 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     E.launch_seq = 0;
     CK(cudaMallocHost((void **)&E.h_logits, (size_t)V * 4));
     CK(cudaMallocHost((void **)&E.h_tokpos, 64));
+    CK(cudaHostAlloc((void **)&E.h_err, 64, cudaHostAllocMapped));
+    *E.h_err = 0;
+    CK(cudaHostGetDevicePointer((void **)&E.d_err, E.h_err, 0));
 
     if (E.use_stream) {
-        int coop = 0, smem_optin = 0;
-        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
-        CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
-        if (!coop) { release_all(); return fail("device does not support cooperative launch"); }
         StreamParams &p = E.sp;
-        const uint8_t *const bases[5] = {E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls};
-        stream_geometry(p, c, hs, tp, rank, tiled, bases);
-        int target_slot = stream_target_slot(tiled, wt, emb), max_slots = STREAM_MAX_SLOTS;
-        if (const char *s = getenv("LLMF90_SLOT_BYTES")) target_slot = atoi(s);
-        if (const char *s = getenv("LLMF90_MAX_SLOTS")) max_slots = atoi(s);
-        if (plan_stream(p, stream_grid(p, E.n_sms, tiled), smem_optin - STREAM_STATIC_SMEM, target_slot, max_slots, &E.plan)) {
-            release_all();
-            return fail("model rows do not fit the shared-memory ring (row stride too large)");
-        }
         p.pace = 38;  // ~1.15x the per-SM fair share of the measured HBM bandwidth (23 B/cycle)
         if (const char *s = getenv("LLMF90_PACE")) p.pace = std::max(0, atoi(s));
         // L2 prefetch distance: ~48 MB over the 148 SMs (a third of L2) of stages ahead of the ring
@@ -604,6 +650,7 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             bind_peers();
         }
         p.kc = E.d_kc; p.vc = E.d_vc;
+        p.err_flag = E.d_err;
         p.phase_cycles = E.d_times; p.tokpos = E.d_tokpos;
         p.n_slots = E.plan.n_slots; p.slot_bytes = E.plan.slot_bytes;
         p.xs_floats = E.plan.xs_floats;
@@ -660,6 +707,7 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
     float *dst = E.reg_logits == logits ? logits : E.h_logits;
     CK(cudaMemcpyAsync(dst, logits_dev(), lbytes, cudaMemcpyDeviceToHost, E.st));
     CK(cudaStreamSynchronize(E.st));
+    if (check_peers()) return 1;
     if (dst != logits) memcpy(logits, E.h_logits, lbytes);
     CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
     if (!E.use_stream || !E.prof) E.host_times[3] += E.last_ms;  // no per-phase timers: whole forward in bucket 4
@@ -943,6 +991,14 @@ int llmf90_b200_tp_connect(const void *handles, int32_t n)
         E.peer[k] = (uint8_t *)ptr;
     }
     bind_peers();
+    // Every rank restarts its launch counter (the LL epochs derive from it) and clears its hand-over buffers
+    // here: launches made before the connection (warm-ups, a debug trace on one rank) no longer matter, the
+    // ranks are in step from this call on as long as they make the same calls in the same order.
+    CK(cudaStreamSynchronize(E.st));
+    CK(cudaMemsetAsync(E.d_ll, 0, E.ll_words * 8, E.st));
+    CK(cudaMemsetAsync(E.d_shared, 0, E.sh_logits, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    E.launch_seq = 0;
     E.peers_ready = true;
     return 0;
 }

@@ -133,6 +133,7 @@ struct StreamParams {
     int do_argmax;           // fuse maxloc after the classifier and write tokpos = {argmax, pos+1}
     const int *forced;       // optional device array of forced next tokens (prompt), or null
     int *out_tokens;         // optional device array: out_tokens[pos-1] = chosen token
+    int *err_flag;           // host-mapped error word: set when a tensor-parallel poll timed out (a peer is gone)
     // ring geometry
     int n_slots, slot_bytes;
     int xs_floats;
@@ -154,5 +155,8 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out);  // fills p.sc
 cudaError_t prepare_stream_kernel(int wtype, int threads, int smem_bytes);
 // prof: the instrumented kernel (phase timers of CTA 0, optional per-CTA trace) instead of the production one
 cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, bool prof, cudaStream_t st);
+// f32 / f16: one layer of streamed matrix `phase` from plain rows (src) to the tile-major order the decode kernel
+// streams (dst, same size; not in place); call after plan_stream
+cudaError_t launch_tile_pass(const StreamParams &p, int phase, int grid, const uint8_t *src, uint8_t *dst, cudaStream_t st);
 
 }  // namespace llmf90

@@ -56,7 +56,7 @@ constexpr int CONS_BAR = 1;         // named barrier id used by the consumer war
 // At most n_slots stages are in flight and a warp looks at most 23 tiles x 10 chunks ahead of the
 // oldest one, less than NBAR - n_slots.
 constexpr int NBAR = 256;
-constexpr int MAX_NCH = 10;         // chunks per tile (plan_stream enforces it)
+constexpr int MAX_NCH = 24;         // chunks per tile (plan_stream enforces it)
 constexpr int ATT_PSTRIDE_PAD = 4;  // attention partial record = {m, l, -, -, acc[hs]}
 constexpr int ATT_MAX_CHUNK = 288;  // positions of one attention split: <= 256 rounded up to groups of 16, + slack
 
@@ -96,6 +96,8 @@ struct CtaPlan {
     int do_argmax;
     volatile int prod_issued, pf_issued;   // stages copied into the ring / prefetched into L2 so far (trace)
     unsigned long long *gx_trace;          // where gather_x leaves its clock stamps (profiling kernel), or null
+    volatile int abort;                    // a tensor-parallel poll timed out: the peers are gone, stop waiting for them
+    int *err_flag;                         // host-visible error word (0 = ok)
     volatile int qw[NCW];                  // per warp: the phase it is in (the phase loop keeps NOTHING in registers across calls)
     float tail_best[NCW];                  // per-warp maxloc of the classifier epilogue
     int tail_idx[NCW];
@@ -387,8 +389,22 @@ __device__ __forceinline__ void vec_stage_release(const CtaPlan *cp, uint32_t s)
 template <int WT>
 __device__ __forceinline__ void store_x4(float *xs, int n, int j4, const float4 v, bool valid)
 {
-    if constexpr (WT != WT_Q4_0) {
+    if constexpr (WT == WT_F32) {
         if (valid) reinterpret_cast<float4 *>(xs)[j4] = v;
+    } else if constexpr (WT == WT_F16) {
+        // f16 weights run on the tensor cores (tile_dot_f16): the activations are two f16 planes x = hi + lo
+        // (hi = rn(x), lo = rn(x - hi): 22 bits of x, the products with f16 weights are exact in the f32
+        // accumulators), hi[n] then lo[n], each in column order
+        if (valid) {
+            const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t *>(&h01); o.y = *reinterpret_cast<const uint32_t *>(&h23);
+            reinterpret_cast<uint2 *>(xs)[j4] = o;
+            o.x = *reinterpret_cast<const uint32_t *>(&l01); o.y = *reinterpret_cast<const uint32_t *>(&l23);
+            reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(xs) + n)[j4] = o;
+        }
     } else {
         const int B = j4 >> 3, i = j4 & 7, t = i & 3, ngrp = q4t_groups(n);
         const bool hi_nib = i >= 4;
@@ -439,6 +455,48 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
                        row_elem(row, wtype, cols, 4 * j4 + 2), row_elem(row, wtype, cols, 4 * j4 + 3));
 }
 
+// Tensor parallelism: x += the partial Wo / W2 outputs of ALL ranks (the fused all-reduce).  Every rank stored
+// its partial vector into this GPU's [tp][emb] buffer (peer stores over NVLink); a thread takes its float4
+// positions one at a time, requests that position from all tp vectors at once (one local L2 round trip per
+// polling round, whatever tp is) and adds them in rank order -- every GPU adds the same numbers in the same
+// order, the replicated residual stream stays bit-identical.  The sums go to the CTA's copy of x in shared
+// memory.  Out of line: the 8 x 4 LL words in flight per lane would otherwise set the register budget of the
+// single-GPU phase loop.  A poll that sees nothing for seconds means a peer is gone: flag it and stop waiting.
+constexpr long long TP_POLL_TIMEOUT_CYCLES = 8000000000ll;  // ~4 s at 2 GHz
+__device__ __noinline__ void gather_tp(CtaPlan *cp, const unsigned long long *src, int nsrc, uint32_t ep, int n4)
+{
+    float4 *xr4 = reinterpret_cast<float4 *>(smem_base() + cp->off_xres);
+    const int n = n4 << 2;
+#pragma unroll 1
+    for (int j = (int)threadIdx.x; j < n4; j += NCT) {
+        unsigned long long w[MAX_TP][4];
+        bool ok;
+        const long long t0 = clock64();
+        do {
+#pragma unroll
+            for (int r = 0; r < MAX_TP; r++)
+                if (r < nsrc) {
+                    ll_load2(src + (size_t)r * n + 4 * j, w[r][0], w[r][1]);
+                    ll_load2(src + (size_t)r * n + 4 * j + 2, w[r][2], w[r][3]);
+                }
+            ok = true;
+#pragma unroll
+            for (int r = 0; r < MAX_TP; r++)
+                if (r < nsrc) ok = ok && ll_ok(w[r][0], ep) && ll_ok(w[r][1], ep) && ll_ok(w[r][2], ep) && ll_ok(w[r][3], ep);
+            if (!ok && (cp->abort || clock64() - t0 > TP_POLL_TIMEOUT_CYCLES)) {
+                cp->abort = 1;
+                if (cp->err_flag) *cp->err_flag = 1;
+                break;
+            }
+        } while (!ok);
+        float4 v = xr4[j];
+#pragma unroll
+        for (int r = 0; r < MAX_TP; r++)
+            if (r < nsrc) { v.x += ll_val(w[r][0]); v.y += ll_val(w[r][1]); v.z += ll_val(w[r][2]); v.w += ll_val(w[r][3]); }
+        xr4[j] = v;
+    }
+}
+
 // The previous phase's mat-vec has no closing barrier (each warp publishes its tiles and moves on), so
 // xs may still be read by a slower warp when a faster one gets here: poll first (that is the long
 // part), then one consumer-wide barrier before the first write to xs, one after the last.
@@ -457,12 +515,17 @@ __device__ __forceinline__ float gather_x(const CtaPlan *cp, const unsigned long
     unsigned long long *gtr = cp->gx_trace;
 #define GSTAMP(k_) do { if (gtr && tid == 0) gtr[k_] = (unsigned long long)clock64(); } while (0)
     GSTAMP(0);
+    if (nsrc > 1 && !emb_row) gather_tp(const_cast<CtaPlan *>(cp), src, nsrc, ep, n4);
 #pragma unroll 1
     for (int base = 0; base < n4; base += PV * NCT) {
         float4 v[PV];
         if (emb_row) {
 #pragma unroll
             for (int k = 0; k < PV; k++) v[k] = emb_row4(emb_row, cp->wtype, n, min(base + tid + k * NCT, n4 - 1));
+        } else if (nsrc > 1) {
+            // tensor parallel: gather_tp has already added every rank's partials to this thread's positions of x
+#pragma unroll
+            for (int k = 0; k < PV; k++) v[k] = xr4[min(base + tid + k * NCT, n4 - 1)];
         } else {
             ll_gather<PV>(src, n4, base, ep, v);
             if (norm) {
@@ -470,13 +533,6 @@ __device__ __forceinline__ float gather_x(const CtaPlan *cp, const unsigned long
                 for (int k = 0; k < PV; k++) {
                     const float4 x = xr4[min(base + tid + k * NCT, n4 - 1)];
                     v[k].x += x.x; v[k].y += x.y; v[k].z += x.z; v[k].w += x.w;
-                }
-#pragma unroll 1
-                for (int r = 1; r < nsrc; r++) {
-                    float4 t[PV];
-                    ll_gather<PV>(src + (size_t)r * n, n4, base, ep, t);
-#pragma unroll
-                    for (int k = 0; k < PV; k++) { v[k].x += t[k].x; v[k].y += t[k].y; v[k].z += t[k].z; v[k].w += t[k].w; }
                 }
             }
         }
@@ -822,8 +878,13 @@ __device__ __noinline__ void token_tail(const CtaPlan *cp, int pos)
         }
         if (blockIdx.x == 0) {
             for (int i = tid; i < tp * G; i += NCT) {
-                float t[1];
-                ll_waitv<1>(cp->done[rank], i, epl, t);
+                const long long t0 = clock64();
+                while (!ll_ok(ll_load1(cp->done[rank] + i), epl)) {
+                    if (cp->abort || clock64() - t0 > TP_POLL_TIMEOUT_CYCLES) {  // a peer is gone (see gather_tp)
+                        if (cp->err_flag) *cp->err_flag = 1;
+                        break;
+                    }
+                }
             }
             asm volatile("fence.acq_rel.sys;" ::: "memory");
         }
@@ -846,10 +907,18 @@ __device__ __noinline__ void token_tail(const CtaPlan *cp, int pos)
         float best = -INFINITY;
         int bidx = 0x7fffffff;
         for (int i = lane; i < tp * G; i += 32) {
-            float rec[2];
-            ll_waitv<2>(cp->amax[rank], 2 * i, epl, rec);
-            const float v = rec[0];
-            const int ix = __float_as_int(rec[1]);
+            unsigned long long ra, rb;
+            const long long t0 = clock64();
+            for (;;) {
+                ll_load2(cp->amax[rank] + 2 * i, ra, rb);
+                if (ll_ok(ra, epl) && ll_ok(rb, epl)) break;
+                if (tp > 1 && (cp->abort || clock64() - t0 > TP_POLL_TIMEOUT_CYCLES)) {
+                    if (cp->err_flag) *cp->err_flag = 1;
+                    break;
+                }
+            }
+            const float v = ll_val(ra);
+            const int ix = __float_as_int(ll_val(rb));
             if (v > best || (v == best && ix < bidx)) { best = v; bidx = ix; }
         }
 #pragma unroll
@@ -951,6 +1020,59 @@ __device__ __forceinline__ void tile_dot(const uint8_t *sp, uint32_t cs, const f
     }
 }
 
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// f16 on the tensor cores (legacy mma.sync m16n8k16, f16 x f16 -> f32).  On the FMA pipe an f16 weight costs a
+// conversion and an FMA (13 instructions per 16 bytes of weights: the mat-vec is issue-bound at a third of the
+// shared-memory rate); here the WEIGHTS are the B operand -- n = the 8 rows of the tile, k = 16 columns -- and
+// the activations the A operand: row 0 = the hi plane, row 1 = the lo plane of x = hi + lo (store_x4), the other
+// 14 rows zero.  D[0][n] + D[1][n] = dot(row n, x): two instructions per 512 bytes of weights.  The contraction
+// index inside a k-step may be permuted freely as long as both operands agree, so lane (g, t) takes 16
+// CONTIGUOUS bytes of row g -- columns c0 .. c0 + 7, c0 = 32 step + 8 t -- for two mmas (b0 / b1 of the first =
+// halves 0,1 / 2,3, of the second = 4,5 / 6,7) and the lanes g < 2 the same 8 columns of the hi / lo plane
+// (a0 / a2 likewise): one 128-bit load each.
+// Layout of a stage (tile_pass_kernel wrote the matrix that way, the bulk copy moves it verbatim): k-step major,
+// [step][row][64 bytes], so a warp's load is 512 contiguous bytes -- no bank conflicts; a row whose unit count
+// is not a multiple of 4 ends with a short step [row][rem x 16 bytes].  A tile of v < 8 rows has v rows per step;
+// the lanes g >= v then read the following steps' bytes: finite or not, they only reach the D columns n >= v,
+// whose rows do not exist and are dropped in the epilogue.
+// sp: the stage; xh: the hi plane at the chunk's first column, the lo plane xl_off bytes further; this warp takes
+// the k-steps [s0, s1) of the chunk's (nu + 3) / 4.
+__device__ __forceinline__ void tile_dot_f16(const uint8_t *sp, uint32_t v, const __half *xh, uint32_t xl_off, int nu,
+                                             int s0, int s1, int lane, float (&dA)[4], float (&dB)[4])
+{
+    const int g = lane >> 2, t = lane & 3, nfull = nu >> 2;
+    const uint32_t sstep = v * 64u;
+    uint32_t wp = smem_u32(sp) + (uint32_t)s0 * sstep + (uint32_t)lane * 16u;
+    uint32_t xp = smem_u32(xh) + (g == 1 ? xl_off : 0u) + (uint32_t)(s0 * 4 + t) * 16u;
+    const bool ax = g < 2;  // the lanes that hold rows 0 (hi) and 1 (lo) of the A operand
+    const int e = min(s1, nfull);
+#pragma unroll 2
+    for (int st = s0; st < e; st++) {
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 w = lds128(wp);
+        if (ax) x = lds128(xp);
+        mma16816(dA, x.x, 0u, x.y, 0u, w.x, w.y);
+        mma16816(dB, x.z, 0u, x.w, 0u, w.z, w.w);
+        wp += sstep; xp += 64u;
+    }
+    if (s1 > nfull) {  // the short last step of the row: rem units per row, rows rem x 16 bytes apart
+        const int rem = nu & 3;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u), x = make_uint4(0u, 0u, 0u, 0u);
+        if (t < rem) {
+            w = lds128(smem_u32(sp) + (uint32_t)nfull * sstep + (uint32_t)(g * rem + t) * 16u);
+            if (ax) x = lds128(smem_u32(xh) + (g == 1 ? xl_off : 0u) + (uint32_t)(nfull * 4 + t) * 16u);
+        }
+        mma16816(dA, x.x, 0u, x.y, 0u, w.x, w.y);
+        mma16816(dB, x.z, 0u, x.w, 0u, w.z, w.w);
+    }
+}
+
 // q4_0 on the tensor cores (legacy mma.sync m16n8k16, f16 x f16 -> f32): the dequantisation is the
 // instruction bottleneck of a q4_0 mat-vec at B200's HBM rate, and on CUDA cores it costs >= 2
 // instructions per weight.  Here a nibble pair becomes a half2 {1024 + q} with ONE lop3 (the 0x6400
@@ -963,13 +1085,6 @@ __device__ __forceinline__ void tile_dot(const uint8_t *sp, uint32_t cs, const f
 // of the activations (f16 alone would cost 3 digits: greedy tokens flip at near ties).
 // Tiled weight format: common.cuh.  A stage holds the 8-block groups [g0, g0 + ng) of one row group of
 // 16 rows; lane = 4 g + t accumulates rows g and g + 8 over its blocks.
-__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1)
-{
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ uint32_t uint4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, int ngrp, int g0, int ng, int lane,
@@ -1099,7 +1214,45 @@ __device__ __forceinline__ void run_tiles(CtaPlan *cp, int q, float rscale)
         uint32_t s = s0 + (uint32_t)(t * nch);
         float va, vb;  // this lane's row pair after the reduction
         int i, sub, nsl;  // first row of the pair (within the CTA's range); destination lane index / count
-        if constexpr (WT != WT_Q4_0) {
+        if constexpr (WT == WT_F16) {
+            float dA[4] = {0.f, 0.f, 0.f, 0.f}, dB[4] = {0.f, 0.f, 0.f, 0.f};
+            int u0 = 0;
+            const int vrows = min(8, min(nr, rows_real - r0) - t * 8);  // rows of this tile (the schedule's `valid`)
+#pragma unroll 1
+            for (int c = 0; c < nch; c++, s++) {
+                const int nu = min(cu, nu_row - u0);
+                const int nsteps = (nu + 3) >> 2, b0 = DIV_G(cl * nsteps), b1 = DIV_G((cl + 1) * nsteps);  // this warp's k-steps
+                const uint32_t slot = slot_of(cp, s);
+                mbar_wait(full_bar(cp, s), full_par(s), 2);
+                if (c == 0) TSTAMP(1);
+                tile_dot_f16(smem + (size_t)slot * cp->slot_bytes, (uint32_t)vrows,
+                             reinterpret_cast<const __half *>(xs) + 8 * u0, (uint32_t)W.cols * 2u, nu, b0, b1, lane, dA, dB);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_n(empty_bar(cp, slot), gweight);
+                u0 += nu;
+            }
+            TSTAMP(2);
+            // D rows 0 (lanes g = 0) and 1 (g = 1) hold the hi / lo parts of rows 2t, 2t + 1 of the tile: add them,
+            // then every lane of column t takes the pair (lane g serves destination g)
+            float k0 = dA[0] + dB[0], k1 = dA[1] + dB[1];
+            k0 += __shfl_xor_sync(0xffffffffu, k0, 4);
+            k1 += __shfl_xor_sync(0xffffffffu, k1, 4);
+            va = __shfl_sync(0xffffffffu, k0, lane & 3);
+            vb = __shfl_sync(0xffffffffu, k1, lane & 3);
+            if (G > 1) {
+                float *mine = gsc + (buf * NCW + warp) * 16;
+                if (cl > 0 && lane < 4) *reinterpret_cast<float2 *>(mine + 2 * lane) = make_float2(va, vb);
+                named_bar_sync(2 + grp, 32 * G);
+                if (cl > 0) { buf ^= 1; continue; }
+#pragma unroll 1
+                for (int w = 1; w < G; w++) {
+                    const float2 pp = *reinterpret_cast<const float2 *>(mine + w * 16 + 2 * (lane & 3));
+                    va += pp.x; vb += pp.y;
+                }
+                buf ^= 1;
+            }
+            i = t * 8 + 2 * (lane & 3); sub = lane >> 2; nsl = 8;
+        } else if constexpr (WT == WT_F32) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             int u0 = 0;
 #pragma unroll 1
@@ -1375,7 +1528,7 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
         cp.amax[k] = P.amax[k]; cp.done[k] = P.done[k];
     }
     if (threadIdx.x == 7) {
-        cp.gx_trace = nullptr;
+        cp.gx_trace = nullptr; cp.abort = 0; cp.err_flag = P.err_flag;
         cp.forced = P.forced; cp.out_tokens = P.out_tokens; cp.tokpos = const_cast<int *>(P.tokpos);
         cp.ep_last = P.ep_base + (uint32_t)P.L + 1u; cp.do_argmax = P.do_argmax;
     }
@@ -1456,7 +1609,7 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
     // a slot holds one stage: a chunk of a tile, a norm vector, or an embedding row
     unsigned int slot = (unsigned)p.emb * 4u;
     if ((unsigned)row_stride_bytes(p.wtype, p.emb) > slot) slot = (unsigned)row_stride_bytes(p.wtype, p.emb);
-    const unsigned min_chunk = tiled ? Q4T_GROUP_BYTES : 4u * 32u * 16u;  // one group / one unit per lane of 4 rows
+    const unsigned min_chunk = tiled ? Q4T_GROUP_BYTES : (p.wtype == WT_F16 ? 8u * 64u : 4u * 32u * 16u);  // one group / one k-step of 8 rows / one unit per lane of 4 rows
     if (slot < min_chunk) slot = min_chunk;
     if ((unsigned)target_slot_bytes > slot) slot = (unsigned)target_slot_bytes;
     slot = (slot + 127u) & ~127u;
@@ -1470,6 +1623,14 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
             const int cu_max = (int)(slot / Q4T_GROUP_BYTES);
             w.nch = (w.nu + cu_max - 1) / cu_max;
             w.cu = (w.nu + w.nch - 1) / w.nch;
+        } else if (p.wtype == WT_F16) {
+            // f16 on the tensor cores (tile_dot_f16): 8 rows = the n dimension of one mma; chunks of whole
+            // k-steps (4 units = 32 columns)
+            w.R = 8;
+            w.nu = (int)(row_stride_bytes(p.wtype, w.cols) / 16);
+            const int cu_max = (int)(slot / (8u * 16u)) & ~3;
+            w.nch = (w.nu + cu_max - 1) / cu_max;
+            w.cu = (((w.nu + w.nch - 1) / w.nch) + 3) & ~3;
         } else {
             w.R = 4;
             w.nu = (int)(row_stride_bytes(p.wtype, w.cols) / 16);
@@ -1552,10 +1713,11 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
                         // one run of whole 8-block groups of the row group
                         push(w.base + ((size_t)(r >> 4) * w.nu + u0) * Q4T_GROUP_BYTES, (unsigned)nu * Q4T_GROUP_BYTES, 1u, (unsigned)ph);
                     } else {
-                        // the chunk's segment of every valid row of the tile
+                        // tile-major matrix (tile_pass_kernel): the chunk's segments of the tile's valid rows are
+                        // one contiguous run -- ONE bulk copy per stage
                         int valid = (r1 < w.rows_real ? r1 : w.rows_real) - r;
                         if (valid > w.R) valid = w.R;
-                        push(w.base + (size_t)r * w.rs + (size_t)u0 * 16, (unsigned)nu * 16u, (unsigned)valid, (unsigned)ph);
+                        push(w.base + ((size_t)r * w.nu + (size_t)valid * u0) * 16, (unsigned)(valid * nu) * 16u, 1u, (unsigned)ph);
                     }
                 }
         };
@@ -1574,6 +1736,45 @@ void build_schedule(StreamParams &p, int grid, SchedStage **out)
     }
     p.sched_stride = cap;
     *out = tab;
+}
+
+// ------------------------------------------------------------------ tile-major weights
+// A bulk copy costs its issuing thread ~100 SM cycles whatever its size (measured: tools/ubench/bulk_issue.cu), and an L2
+// prefetch as much again: with one copy per ROW of a stage the producer thread -- not HBM, not the consumers --
+// set the pace of the kernel (8 rows per f16 stage: ~2200 cycles per stage against ~1400 cycles of HBM time for
+// its 32 KB).  So the streamed matrices are re-laid out once at init in the order the kernel consumes them: for
+// every CTA's row range, tile after tile, chunk after chunk, the chunk's segment of every valid row -- f32 row
+// after row, f16 k-step after k-step (tile_dot_f16) -- and a stage is ONE contiguous run.  The permutation stays
+// inside a tile's rows x row_bytes block, so a CTA's data still starts at row r0 and no byte is added.
+// src: one layer of the matrix, plain rows; dst: the same bytes, tile-major.  grid (CTAs of the decode kernel, y).
+__global__ void tile_pass_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, PhaseW w, int grid, int step_major)
+{
+    int r0, r1;
+    cta_rows(w, blockIdx.x, grid, r0, r1);
+    const int nr = min(r1, w.rows_real) - r0;
+    const long long total = (long long)nr * w.nu;
+    for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.y * blockDim.x) {
+        const int jr = (int)(idx / w.nu), u = (int)(idx - (long long)jr * w.nu);
+        const int t = jr / w.R, j = jr - t * w.R, v = min(w.R, nr - t * w.R);
+        const int c = u / w.cu, u0 = c * w.cu, nuc = min(w.cu, w.nu - u0), uu = u - u0;
+        const size_t base = (size_t)(r0 + t * w.R) * w.nu + (size_t)v * u0;
+        size_t off;
+        if (!step_major) {
+            off = base + (size_t)j * nuc + uu;
+        } else {
+            const int st = uu >> 2, nfull = nuc >> 2;
+            off = st < nfull ? base + (size_t)(st * v + j) * 4 + (uu & 3) : base + (size_t)nfull * v * 4 + (size_t)j * (nuc & 3) + (uu & 3);
+        }
+        dst[off] = src[(size_t)(r0 + jr) * w.nu + u];
+    }
+}
+
+cudaError_t launch_tile_pass(const StreamParams &p, int phase, int grid, const uint8_t *src, uint8_t *dst, cudaStream_t st)
+{
+    if (p.wtype == WT_Q4_0) return cudaErrorInvalidValue;  // q4_0 has its own tiled format (repack_q4_tiled_kernel)
+    tile_pass_kernel<<<dim3(grid, 16), 256, 0, st>>>(reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), p.ph[phase], grid,
+                                                    p.wtype == WT_F16 ? 1 : 0);
+    return cudaGetLastError();
 }
 
 static const void *kernel_for(int wtype, bool prof)

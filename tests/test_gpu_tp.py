@@ -29,7 +29,7 @@ def free_port():
 KV1 = dict(SMALL, n_kv_heads=1)  # fewer KV heads than ranks: the KV head is replicated
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("wt,shape", [(F32, SMALL), (F16, MID), (Q4_0, MID), (F32, KV1)],
                          ids=["f32-small", "f16-mid", "q4-mid", "f32-small-kv1"])
 def test_tp_matches_oracle(tmp_path, built, wt, shape, world):
