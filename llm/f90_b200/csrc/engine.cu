@@ -150,11 +150,16 @@ float *logits_dev() { return reinterpret_cast<float *>(E.d_shared + E.sh_logits)
 
 int n_splits_for(int pos)
 {
-    // a power of two (the kernel splits items with shifts): runs of <= 256 positions up to 2048, and
-    // enough (head, split) items to occupy the SMs (only H CTAs work otherwise) while a split keeps
-    // at least 16 positions
+    // a power of two (the kernel splits items with shifts).  Hard rule: runs of <= 256 positions (the score
+    // buffer).  Then: an item whose cached positions fit ONE group per warp (11 warps x 512 / head_size
+    // positions) has all its K rows in flight before the query arrives and its V rows before the softmax
+    // statistics -- every further round is a serial L2 round trip on the layer's critical path -- so split
+    // further while that is not the case and (head, split) items still map one-to-one onto CTAs.
     int s = 1;
     while (s < MAX_SPLITS && s * 256 < pos) s *= 2;
+    static const int one_round = getenv("LLMF90_ATT_ONE_ROUND") ? atoi(getenv("LLMF90_ATT_ONE_ROUND")) : 1;
+    const int per_round = 11 * (512 / E.hs);
+    while (one_round && s < MAX_SPLITS && E.sp.H * s * 2 <= E.plan.grid && (pos + s - 1) / s > per_round) s *= 2;
     static const int min_items = getenv("LLMF90_ATT_ITEMS") ? atoi(getenv("LLMF90_ATT_ITEMS")) : 0;
     while (s < MAX_SPLITS && E.sp.H * s * 2 <= min_items && (pos - 1) / (2 * s) >= 16) s *= 2;
     return s;

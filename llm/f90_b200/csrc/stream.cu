@@ -110,6 +110,13 @@ struct Prof {
     long long tmark;
 };
 
+// One plan / one timer block per CTA at FILE scope: their shared-memory addresses are compile-time constants, so no
+// device function needs a register (or, across a call, a local-memory slot) to find them.
+__shared__ CtaPlan g_cp;
+__shared__ Prof g_pf;
+#define cp (&g_cp)
+#define pf (&g_pf)
+
 static size_t smem_bytes_for(int n_slots, int slot_bytes, int xs_floats, int emb, int hs, int sched_entries)
 {
     return (size_t)n_slots * slot_bytes + (size_t)xs_floats * 4 + (size_t)emb * 4 + 64 * 4 +
@@ -129,17 +136,17 @@ __device__ __forceinline__ uint8_t *smem_base()
     extern __shared__ __align__(128) uint8_t smem[];
     return smem;
 }
-__device__ __forceinline__ uint64_t *full_bar(const CtaPlan *cp, uint32_t s)
+__device__ __forceinline__ uint64_t *full_bar(const CtaPlan *, uint32_t s)
 {
     return reinterpret_cast<uint64_t *>(smem_base() + cp->off_full) + (s & (NBAR - 1));
 }
 __device__ __forceinline__ uint32_t full_par(uint32_t s) { return (s >> 8) & 1u; }
 static_assert(NBAR == 256, "full_par assumes 256 barriers");
-__device__ __forceinline__ uint64_t *empty_bar(const CtaPlan *cp, uint32_t slot)
+__device__ __forceinline__ uint64_t *empty_bar(const CtaPlan *, uint32_t slot)
 {
     return reinterpret_cast<uint64_t *>(smem_base() + cp->off_empty) + slot;
 }
-__device__ __forceinline__ uint32_t slot_of(const CtaPlan *cp, uint32_t s)
+__device__ __forceinline__ uint32_t slot_of(const CtaPlan *, uint32_t s)
 {
     return s - __umulhi(s, cp->slot_magic) * (uint32_t)cp->n_slots;
 }
@@ -166,7 +173,7 @@ __device__ __forceinline__ void cons_sync() { named_bar_sync(CONS_BAR, NCT); }
 struct SchedCursor {
     int e, l;  // entry of the CTA's stage list, layer
 };
-__device__ __forceinline__ unsigned long long sched_stage(const CtaPlan *cp, const uint4 *tab, SchedCursor &c, int e_layer_end,
+__device__ __forceinline__ unsigned long long sched_stage(const CtaPlan *, const uint4 *tab, SchedCursor &c, int e_layer_end,
                                                           int token, uint32_t &bytes, uint32_t &nseg, uint32_t &sstr)
 {
     const uint4 st = tab[c.e];
@@ -177,7 +184,7 @@ __device__ __forceinline__ unsigned long long sched_stage(const CtaPlan *cp, con
     if (++c.e == e_layer_end && c.l + 1 < cp->L) { c.e = 1; c.l++; }
     return src;
 }
-__device__ __noinline__ void producer_loop(CtaPlan *cp, int token, int pace, int pf_lead)
+__device__ __noinline__ void producer_loop(CtaPlan *, int token, int pace, int pf_lead)
 {
     const uint64_t pol = l2_policy_evict_first();
     const uint4 *tab = reinterpret_cast<const uint4 *>(smem_base() + cp->off_sched);
@@ -360,12 +367,12 @@ __device__ __forceinline__ void ll_gather(const unsigned long long *buf, int n4,
 
 // ---- vector stages: every consumer thread waits for the stage and reads what it needs; after
 // the consumer-wide barrier that ends the prologue one thread hands the slot back
-__device__ __forceinline__ const uint8_t *vec_stage_wait(const CtaPlan *cp, uint32_t s)
+__device__ __forceinline__ const uint8_t *vec_stage_wait(const CtaPlan *, uint32_t s)
 {
     mbar_wait(full_bar(cp, s), full_par(s), 3);
     return smem_base() + (size_t)slot_of(cp, s) * cp->slot_bytes;
 }
-__device__ __forceinline__ void vec_stage_release(const CtaPlan *cp, uint32_t s)
+__device__ __forceinline__ void vec_stage_release(const CtaPlan *, uint32_t s)
 {
     if (threadIdx.x == 0) mbar_arrive_n(empty_bar(cp, slot_of(cp, s)), (uint32_t)NCW);
 }
@@ -463,7 +470,7 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
 // memory.  Out of line: the 8 x 4 LL words in flight per lane would otherwise set the register budget of the
 // single-GPU phase loop.  A poll that sees nothing for seconds means a peer is gone: flag it and stop waiting.
 constexpr long long TP_POLL_TIMEOUT_CYCLES = 8000000000ll;  // ~4 s at 2 GHz
-__device__ __noinline__ void gather_tp(CtaPlan *cp, const unsigned long long *src, int nsrc, uint32_t ep, int n4)
+__device__ __noinline__ void gather_tp(CtaPlan *, const unsigned long long *src, int nsrc, uint32_t ep, int n4)
 {
     float4 *xr4 = reinterpret_cast<float4 *>(smem_base() + cp->off_xres);
     const int n = n4 << 2;
@@ -501,7 +508,7 @@ __device__ __noinline__ void gather_tp(CtaPlan *cp, const unsigned long long *sr
 // xs may still be read by a slower warp when a faster one gets here: poll first (that is the long
 // part), then one consumer-wide barrier before the first write to xs, one after the last.
 template <int WT>
-__device__ __forceinline__ float gather_x(const CtaPlan *cp, const unsigned long long *src, int nsrc, uint32_t ep, int n,
+__device__ __forceinline__ float gather_x(const CtaPlan *, const unsigned long long *src, int nsrc, uint32_t ep, int n,
                                        int norm, const uint8_t *emb_row, const float *wn /* shared */)
 {
     float *xs = reinterpret_cast<float *>(smem_base() + cp->off_xs);
@@ -606,6 +613,8 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
     }
 }
 
+__device__ __forceinline__ void prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // The current position of an item: its query and key quarters and its value dims all come from the LL
 // buffers (one polling loop: one L2 round trip).  Run by one warp; writes the score to *sc_out and parks
 // the value dims in v_out.  (Inlined: a call inside the attention phase would spill everything that is live
@@ -651,135 +660,202 @@ __device__ __forceinline__ void attention_current(const unsigned long long *pq, 
     for (int k = 0; k < vec; k++) v_out[lane * vec + k] = v[k];
 }
 
-template <int HS>
-__device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int layer)
+// Fields of the CTA plan read with a VOLATILE shared-memory load: the value cannot be hoisted above the asm
+// volatile barrier in front of it nor merged with an earlier load of the same field.  The attention phase is three
+// stages separated by CTA barriers; each stage re-derives what it needs from (item, layer) and fresh plan loads,
+// so nothing but the loop counter is live across a barrier -- left to itself the compiler computes every pointer
+// and index at the top, spills them around the 32-register poll for q and reloads them one by one after each
+// barrier, and a local-memory load is an L2 round trip here (the ring leaves ~20 KB of L1): measured 3.7 K
+// cycles for the 12-term sum + publish of the last stage alone.
+__device__ __forceinline__ uint32_t plan_u32(const void *p)
 {
-    const int n_splits = cp->n_splits, pos = cp->pos;
-    const uint32_t ep = cp->ep_base + (uint32_t)layer + 1u;
-    unsigned long long *tr = cp->trace ? cp->trace + 48 : nullptr;  // 8 trace words (profiling kernel)
-#define ASTAMP(k_) do { if (tr && threadIdx.x == 0) tr[k_] = (unsigned long long)clock64(); } while (0)
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long plan_u64(const void *p)
+{
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+#define PLAN_I(f_) ((int)plan_u32(&cp->f_))
+#define PLAN_P(T_, f_) (reinterpret_cast<T_>(plan_u64(&cp->f_)))
+
+// the positions of attention item (head h, split sp) at position `pos` with S splits
+struct AttItem {
+    int h, sp, t0, t1, tc1, npast;
+    bool cur_here;
+};
+__device__ __forceinline__ AttItem att_item(int item, int S, int pos)
+{
+    AttItem a;
+    const int s_shift = 31 - __clz(S);
+    const int chunk = (((pos + S - 1) >> s_shift) + 15) & ~15;
+    a.h = item >> s_shift; a.sp = item & (S - 1);
+    a.npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches); npast is this launch's
+    a.t0 = a.sp * chunk; a.t1 = min(pos, a.t0 + chunk);  // this split's positions
+    a.tc1 = min(a.t1, a.npast);                           // ... of which [t0, tc1) are cached rows
+    a.cur_here = a.npast >= a.t0 && a.npast < a.t1;       // the split ends with this launch's own position
+    return a;
+}
+
+template <int HS, bool PROF>
+__device__ __noinline__ void attention_phase_t(const CtaPlan *, int layer)
+{
+    // 8 trace words (profiling kernel)
+#define ASTAMP(k_) do { if constexpr (PROF) { unsigned long long *tr_ = PLAN_P(unsigned long long *, trace); if (tr_ && threadIdx.x == 0) tr_[48 + (k_)] = (unsigned long long)clock64(); } } while (0)
     ASTAMP(0);
-    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // a position is held by LP lanes of 16 head dimensions each; a warp takes PG positions at a time
     constexpr int hs = HS, vec = HS >> 5, LP = HS >> 4, PG = 32 / LP;  // HS in {32, 64, 128}: LP 2 / 4 / 8, PG 16 / 8 / 4
     constexpr int lp_shift = HS == 32 ? 1 : (HS == 64 ? 2 : 3);
     constexpr float rscale = HS == 32 ? 0.17677669529663687f : (HS == 64 ? 0.125f : 0.08838834764831845f);  // 1 / sqrt(hs)
-    const int S = n_splits;
-    const int kv = cp->kv, att_dim = cp->att_dim;
-    const int items = cp->H * S;
-    const int npast = pos - 1;  // positions 0 .. pos-2 come from the cache (earlier launches); npast is this launch's
-    const int s_shift = 31 - __clz(S);
-    const int chunk = (((pos + S - 1) >> s_shift) + 15) & ~15;
-    float *sc = reinterpret_cast<float *>(smem_base() + cp->off_att);  // [ATT_MAX_CHUNK] scores
-    float *part = sc + ATT_MAX_CHUNK;                                    // [NCW][hs] partial outputs
-    const int pl = lane >> lp_shift, dq = lane & (LP - 1);
-    const int rep = cp->rep;  // the replica of the LL vectors this CTA polls
 #pragma unroll 1
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        // (S is a power of two; h / kv_mul by multiplication: llama2.f90:581 maps head h to KV head h / kv_mul)
-        const int h = item >> s_shift, sp = item & (S - 1);
-        const int g = (int)(((uint32_t)h * cp->kvmul_inv16) >> 16);
-        const int t0 = sp * chunk, t1 = min(pos, t0 + chunk);  // this split's positions
-        const int tc1 = min(t1, npast);                        // ... of which [t0, tc1) are cached rows
-        const bool cur_here = npast >= t0 && npast < t1;       // the split ends with this launch's own position:
-        const int nwg = cur_here ? NCW - 1 : NCW;              // the last warp takes it, the others the cached rows
-        const bool cur_warp = cur_here && warp == NCW - 1;
-        const unsigned long long *pq = cp->ll_q + (size_t)rep * att_dim + h * hs;
-        const float *kbase = cp->kc + ((size_t)layer * cp->seq * kv + g * hs + dq * 16);
-        const float *vbase = cp->vc + ((size_t)layer * cp->seq * kv + g * hs + lane * vec);
-        const int tb0 = t0 + PG * warp;  // the warp's first group
-        float vv[PG][vec];               // value rows of the warp's first group
-        // ---- scores
-        if (cur_warp) {
-            const unsigned long long *pk = cp->ll_kv + (size_t)rep * 2 * kv + g * hs;
-            attention_current<HS>(pq, pk, pk + kv, ep, sc + (npast - t0), part + warp * hs);
-        } else if (tb0 < tc1) {
-            float4 qq[4];
+    for (int item = blockIdx.x; item < PLAN_I(H) * PLAN_I(n_splits); item += gridDim.x) {
+        // value row quarter (position tb0 + pl, dims 16 dq ..) of the warp's first group: requested in stage 1, used in
+        // stage 2 (same lane mapping as the key rows: 4 x float4 per lane)
+        float4 vq[4];
+        // ================================================================ stage 1: scores
+        {
+            const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+            const int pl = lane >> lp_shift, dq = lane & (LP - 1);
+            const int kv = PLAN_I(kv);
+            const AttItem a = att_item(item, PLAN_I(n_splits), PLAN_I(pos));
+            // (h / kv_mul by multiplication: llama2.f90:581 maps head h to KV head h / kv_mul)
+            const int g = (int)(((uint32_t)a.h * plan_u32(&cp->kvmul_inv16)) >> 16);
+            const int nwg = a.cur_here ? NCW - 1 : NCW;  // the last warp takes the current position, the others the cached rows
+            const bool cur_warp = a.cur_here && warp == NCW - 1;
+            const uint32_t ep = plan_u32(&cp->ep_base) + (uint32_t)layer + 1u;
+            float *sc = reinterpret_cast<float *>(smem_base() + PLAN_I(off_att));  // [ATT_MAX_CHUNK] scores
+            const size_t row0 = (size_t)layer * PLAN_I(seq) * kv + g * hs;
+            const float *kbase = PLAN_P(const float *, kc) + row0 + dq * 16;
+            const float *vc = PLAN_P(const float *, vc) + row0;
+            const unsigned long long *pq = PLAN_P(const unsigned long long *, ll_q) + (size_t)PLAN_I(rep) * PLAN_I(att_dim) + a.h * hs;
+            const int tb0 = a.t0 + PG * warp;  // the warp's first group
+            if (cur_warp) {
+                const unsigned long long *pk = PLAN_P(const unsigned long long *, ll_kv) + (size_t)PLAN_I(rep) * 2 * kv + g * hs;
+                attention_current<HS>(pq, pk, pk + kv, ep, sc + (a.npast - a.t0), sc + ATT_MAX_CHUNK + warp * hs);
+            } else if (tb0 < a.tc1) {
+                // all K / V rows of the warp are pulled into L2 now (no destination register); only the query poll's
+                // 32 registers are live while waiting
 #pragma unroll 1
-            for (int tb = tb0; tb < tc1; tb += PG * nwg) {
-                const int t = tb + pl;
-                const float4 *kr = reinterpret_cast<const float4 *>(kbase + (uint32_t)(min(t, tc1 - 1) * kv));
-                float4 kk[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) kk[i] = __ldcg(kr + i);
-                if (tb == tb0) {
-                    // first group: the value rows are requested now and used after the barrier; then the query
-                    // (written by the QKV epilogues of this launch) is polled: one L2 round trip for all three
-#pragma unroll
-                    for (int u = 0; u < PG; u++) load_vec<vec>(vbase + (uint32_t)(min(tb0 + u, tc1 - 1) * kv), vv[u]);
-                    ASTAMP(1);
-                    ll_wait4n<4>(pq, dq * 16, ep, qq);
-                    ASTAMP(2);
+                for (int tb = tb0; tb < a.tc1; tb += PG * nwg) {
+                    const uint32_t ro = (uint32_t)(min(tb + pl, a.tc1 - 1) * kv);
+                    prefetch_l2_line(kbase + ro);
+                    prefetch_l2_line(vc + dq * 16 + ro);
                 }
-                float sdot = 0.f;
+                float4 qq[4];
+                ASTAMP(1);
+                ll_wait4n<4>(pq, dq * 16, ep, qq);  // (written by the QKV epilogues of this launch)
+                ASTAMP(2);
+#pragma unroll 1
+                for (int tb = tb0; tb < a.tc1; tb += PG * nwg) {
+                    const float4 *kr = reinterpret_cast<const float4 *>(kbase + (uint32_t)(min(tb + pl, a.tc1 - 1) * kv));
+                    float4 kk[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    sdot = fmaf(qq[i].x, kk[i].x, sdot); sdot = fmaf(qq[i].y, kk[i].y, sdot);
-                    sdot = fmaf(qq[i].z, kk[i].z, sdot); sdot = fmaf(qq[i].w, kk[i].w, sdot);
+                    for (int i = 0; i < 4; i++) kk[i] = __ldcg(kr + i);
+                    float sdot = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        sdot = fmaf(qq[i].x, kk[i].x, sdot); sdot = fmaf(qq[i].y, kk[i].y, sdot);
+                        sdot = fmaf(qq[i].z, kk[i].z, sdot); sdot = fmaf(qq[i].w, kk[i].w, sdot);
+                    }
+#pragma unroll
+                    for (int o = 1; o < LP; o <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+                    if (dq == 0 && tb + pl < a.tc1) sc[tb + pl - a.t0] = sdot * rscale;  // dot_product(q_t,k_t)/sqrt(head_size), :582
                 }
+                const float4 *vr = reinterpret_cast<const float4 *>(vc + dq * 16 + (uint32_t)(min(tb0 + pl, a.tc1 - 1) * kv));
 #pragma unroll
-                for (int o = 1; o < LP; o <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
-                if (dq == 0 && t < tc1) sc[t - t0] = sdot * rscale;  // dot_product(q_t,k_t)/sqrt(head_size), :582
+                for (int i = 0; i < 4; i++) vq[i] = __ldcg(vr + i);
             }
         }
         ASTAMP(3);
         cons_sync();
-        // ---- softmax statistics of the whole item, in every warp (:468-478)
-        const int n = t1 - t0;
-        float M = -INFINITY;
+        // ================================================================ stage 2: softmax statistics, values
+        float M = -INFINITY, L = 0.f;
+        {
+            const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+            const AttItem a = att_item(item, PLAN_I(n_splits), PLAN_I(pos));
+            const float *sc = reinterpret_cast<const float *>(smem_base() + PLAN_I(off_att));
+            float *part = reinterpret_cast<float *>(smem_base() + PLAN_I(off_att)) + ATT_MAX_CHUNK;  // [NCW][hs] partial outputs
+            // the statistics of the whole item, in every warp (:468-478)
+            const int n = a.t1 - a.t0;
 #pragma unroll 1
-        for (int i = lane; i < n; i += 32) M = fmaxf(M, sc[i]);
-        M = warp_max(M);
-        float L = 0.f;
+            for (int i = lane; i < n; i += 32) M = fmaxf(M, sc[i]);
+            M = warp_max(M);
 #pragma unroll 1
-        for (int i = lane; i < n; i += 32) L += __expf(sc[i] - M);
-        L = warp_sum(L);
-        // ---- values: acc = sum over the warp's positions of exp(s_t - M) v_t
-        float acc[vec];
+            for (int i = lane; i < n; i += 32) L += __expf(sc[i] - M);
+            L = warp_sum(L);
+            // acc = sum over the warp's positions of exp(s_t - M) v_t: lane (pl, dq) adds up its positions' quarter
+            // rows, the PG position groups are folded with shuffles, the lanes pl = 0 hold the warp's partial vector
+            if (a.cur_here && warp == NCW - 1) {
+                const float p = __expf(sc[a.npast - a.t0] - M);
 #pragma unroll
-        for (int i = 0; i < vec; i++) acc[i] = 0.f;
-        if (cur_warp) {
-            const float p = __expf(sc[npast - t0] - M);
+                for (int i = 0; i < vec; i++) part[warp * hs + lane * vec + i] *= p;  // (parked by attention_current)
+            } else {
+                const int pl = lane >> lp_shift, dq = lane & (LP - 1);
+                const int nwg = a.cur_here ? NCW - 1 : NCW;
+                const int tb0 = a.t0 + PG * warp;
+                float4 acc[4];
 #pragma unroll
-            for (int i = 0; i < vec; i++) acc[i] = p * part[warp * hs + lane * vec + i];  // (parked by attention_current)
-        } else {
+                for (int i = 0; i < 4; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-            for (int tb = tb0; tb < tc1; tb += PG * nwg) {
-                if (tb != tb0) {
+                for (int tb = tb0; tb < a.tc1; tb += PG * nwg) {
+                    if (tb != tb0) {
+                        const int kv = PLAN_I(kv);
+                        const int g = (int)(((uint32_t)a.h * plan_u32(&cp->kvmul_inv16)) >> 16);
+                        const float4 *vr = reinterpret_cast<const float4 *>(
+                            PLAN_P(const float *, vc) + ((size_t)layer * PLAN_I(seq) * kv + g * hs + dq * 16) + (uint32_t)(min(tb + pl, a.tc1 - 1) * kv));
 #pragma unroll
-                    for (int u = 0; u < PG; u++) load_vec<vec>(vbase + (uint32_t)(min(tb + u, tc1 - 1) * kv), vv[u]);
+                        for (int i = 0; i < 4; i++) vq[i] = __ldcg(vr + i);
+                    }
+                    const float p = tb + pl < a.tc1 ? __expf(sc[tb + pl - a.t0] - M) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        acc[i].x = fmaf(p, vq[i].x, acc[i].x); acc[i].y = fmaf(p, vq[i].y, acc[i].y);
+                        acc[i].z = fmaf(p, vq[i].z, acc[i].z); acc[i].w = fmaf(p, vq[i].w, acc[i].w);
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < PG; u++)
-                    if (tb + u < tc1) {
-                        const float p = __expf(sc[tb + u - t0] - M);
+                for (int o = LP; o < 32; o <<= 1)
 #pragma unroll
-                        for (int i = 0; i < vec; i++) acc[i] = fmaf(p, vv[u][i], acc[i]);
+                    for (int i = 0; i < 4; i++) {
+                        acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o); acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
+                        acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, o); acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, o);
                     }
+                if (pl == 0) {
+                    float4 *dst = reinterpret_cast<float4 *>(part + warp * hs + dq * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) dst[i] = acc[i];
+                }
             }
         }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < vec; i++) part[warp * hs + lane * vec + i] = acc[i];
         cons_sync();
         ASTAMP(5);
-        // ---- thread (dimension pair, LL replica): add the 12 partial vectors, publish
-        const int nout = S == 1 ? cp->ll_rep : 1;
-        if (tid < (hs >> 1) * nout) {
-            const int d = (tid & ((hs >> 1) - 1)) << 1, rr = tid >> (HS == 32 ? 4 : (HS == 64 ? 5 : 6));
-            const float invL = __fdividef(1.0f, L);
-            float A0 = 0.f, A1 = 0.f;
+        // ================================================================ stage 3: thread (dimension pair, LL replica): add the 12 partial vectors, publish
+        {
+            const int tid = (int)threadIdx.x;
+            const int S = PLAN_I(n_splits);
+            const int nout = S == 1 ? PLAN_I(ll_rep) : 1;
+            if (tid < (hs >> 1) * nout) {
+                const float *part = reinterpret_cast<const float *>(smem_base() + PLAN_I(off_att)) + ATT_MAX_CHUNK;
+                const int d = (tid & ((hs >> 1) - 1)) << 1, rr = tid >> (HS == 32 ? 4 : (HS == 64 ? 5 : 6));
+                float A0 = 0.f, A1 = 0.f;
 #pragma unroll
-            for (int w = 0; w < NCW; w++) {
-                const float2 a = *reinterpret_cast<const float2 *>(part + w * hs + d);
-                A0 += a.x; A1 += a.y;
-            }
-            if (S == 1) {
-                ll_store2(cp->ll_att + (size_t)rr * att_dim, h * hs + d, A0 * invL, A1 * invL, ep);
-            } else {
-                unsigned long long *out = cp->ll_part + (size_t)(h * S + sp) * (hs + ATT_PSTRIDE_PAD);
-                ll_store2(out, ATT_PSTRIDE_PAD + d, A0, A1, ep);
-                if (d == 0) ll_store2(out, 0, n > 0 ? M : -INFINITY, L, ep);
+                for (int w = 0; w < NCW; w++) {
+                    const float2 p2 = *reinterpret_cast<const float2 *>(part + w * hs + d);
+                    A0 += p2.x; A1 += p2.y;
+                }
+                const uint32_t ep = plan_u32(&cp->ep_base) + (uint32_t)layer + 1u;
+                const int s_shift = 31 - __clz(S), h = item >> s_shift, sp = item & (S - 1);
+                if (S == 1) {
+                    const float invL = __fdividef(1.0f, L);
+                    ll_store2(PLAN_P(unsigned long long *, ll_att) + (size_t)rr * PLAN_I(att_dim), h * hs + d, A0 * invL, A1 * invL, ep);
+                } else {
+                    unsigned long long *out = PLAN_P(unsigned long long *, ll_part) + (size_t)(h * S + sp) * (hs + ATT_PSTRIDE_PAD);
+                    ll_store2(out, ATT_PSTRIDE_PAD + d, A0, A1, ep);
+                    if (d == 0) ll_store2(out, 0, M, L, ep);  // (a split always has at least one position: M is finite)
+                }
             }
         }
         ASTAMP(6);
@@ -792,8 +868,8 @@ __device__ __noinline__ void attention_phase_t(const CtaPlan *cp, int layer)
 // xs = attention output (all heads), merging the position splits (n_splits > 1).  A thread owns one
 // float4 of the output; the {m, l} pair and the float4 of all S partial records are requested
 // together (one L2 round trip per polling round).
-template <int WT>
-__device__ __noinline__ void load_x_attn(const CtaPlan *cp, int S, uint32_t ep)
+template <int WT, int S>
+__device__ __noinline__ void load_x_attn_s(const CtaPlan *, uint32_t ep)
 {
     float *xs = reinterpret_cast<float *>(smem_base() + cp->off_xs);
     const int tid = (int)threadIdx.x;
@@ -805,50 +881,58 @@ __device__ __noinline__ void load_x_attn(const CtaPlan *cp, int S, uint32_t ep)
         const int j = valid ? jj : n4 - 1;
         const int h = (4 * j) >> hs_shift, d = (4 * j) & (hs - 1);
         const unsigned long long *part = cp->ll_part + (size_t)h * S * pstride;
-        unsigned long long ml[8][2], av[8][4];
+        unsigned long long ml[S][2], av[S][4];
         bool ok;
         LLMF90_WD_DECL;
         do {
             LLMF90_WD_CHECK(107, j, ep)
 #pragma unroll
-            for (int s = 0; s < 8; s++)
-                if (s < S) {
-                    const unsigned long long *rec = part + (size_t)s * pstride;
-                    ll_load2(rec, ml[s][0], ml[s][1]);
-                    ll_load2(rec + ATT_PSTRIDE_PAD + d, av[s][0], av[s][1]);
-                    ll_load2(rec + ATT_PSTRIDE_PAD + d + 2, av[s][2], av[s][3]);
-                }
+            for (int s = 0; s < S; s++) {
+                const unsigned long long *rec = part + (size_t)s * pstride;
+                ll_load2(rec, ml[s][0], ml[s][1]);
+                ll_load2(rec + ATT_PSTRIDE_PAD + d, av[s][0], av[s][1]);
+                ll_load2(rec + ATT_PSTRIDE_PAD + d + 2, av[s][2], av[s][3]);
+            }
             ok = true;
 #pragma unroll
-            for (int s = 0; s < 8; s++)
-                if (s < S)
-                    ok = ok && ll_ok(ml[s][0], ep) && ll_ok(ml[s][1], ep) && ll_ok(av[s][0], ep) && ll_ok(av[s][1], ep) &&
-                         ll_ok(av[s][2], ep) && ll_ok(av[s][3], ep);
+            for (int s = 0; s < S; s++)
+                ok = ok && ll_ok(ml[s][0], ep) && ll_ok(ml[s][1], ep) && ll_ok(av[s][0], ep) && ll_ok(av[s][1], ep) &&
+                     ll_ok(av[s][2], ep) && ll_ok(av[s][3], ep);
         } while (!ok);
         float M = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < 8; s++)
-            if (s < S) M = fmaxf(M, ll_val(ml[s][0]));
+        for (int s = 0; s < S; s++) M = fmaxf(M, ll_val(ml[s][0]));
         float den = 0.f;
         float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int s = 0; s < 8; s++)
-            if (s < S && ll_val(ml[s][0]) > -INFINITY) {
-                const float w = expf(ll_val(ml[s][0]) - M);
+        for (int s = 0; s < S; s++)
+            if (ll_val(ml[s][0]) > -INFINITY) {
+                const float w = __expf(ll_val(ml[s][0]) - M);
                 den = fmaf(ll_val(ml[s][1]), w, den);
                 num.x = fmaf(ll_val(av[s][0]), w, num.x); num.y = fmaf(ll_val(av[s][1]), w, num.y);
                 num.z = fmaf(ll_val(av[s][2]), w, num.z); num.w = fmaf(ll_val(av[s][3]), w, num.w);
             }
         if (first) { cons_sync(); first = false; }  // xs is free (see gather_x); every thread gets here once
+        const float rden = __fdividef(1.0f, den);
         if (jj < ((n4 + 31) & ~31))
-            store_x4<WT>(xs, cp->att_dim, jj, make_float4(num.x / den, num.y / den, num.z / den, num.w / den), valid);
+            store_x4<WT>(xs, cp->att_dim, jj, make_float4(num.x * rden, num.y * rden, num.z * rden, num.w * rden), valid);
     }
     if (WT == WT_Q4_0) q4_zero_tail(xs, cp->att_dim);
     cons_sync();
 }
 
+// (one instantiation per split count: the S records of a thread's float4 stay in registers -- arrays sized for the
+// maximum and guarded by a run-time count went to local memory)
+template <int WT>
+__device__ __noinline__ void load_x_attn(const CtaPlan *, int S, uint32_t ep)
+{
+    if (S == 2) load_x_attn_s<WT, 2>(cp, ep);
+    else if (S == 4) load_x_attn_s<WT, 4>(cp, ep);
+    else load_x_attn_s<WT, 8>(cp, ep);
+}
+
 // ------------------------------------------------------------------ profiling hooks (out of line)
-__device__ __noinline__ void prof_lap(Prof *pf, int bucket)
+__device__ __noinline__ void prof_lap(Prof *, int bucket)
 {
     const long long now = clock64();
     pf->tacc[bucket] += now - pf->tmark;
@@ -863,7 +947,7 @@ __device__ __noinline__ void prof_stamp(unsigned long long *trace, int k)
 // ------------------------------------------------------------------ token tail (once per launch)
 // all-gathered logits must have landed on every rank before any rank's kernel ends (tp > 1), then
 // maxloc(logits) (llama2.f90:388): first maximum wins at every reduction level
-__device__ __noinline__ void token_tail(const CtaPlan *cp, int pos)
+__device__ __noinline__ void token_tail(const CtaPlan *, int pos)
 {
     const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t epl = cp->ep_last;
@@ -1044,26 +1128,34 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 // sp: the stage; xh: the hi plane at the chunk's first column, the lo plane xl_off bytes further; this warp takes
 // the k-steps [s0, s1) of the chunk's (nu + 3) / 4.
 __device__ __forceinline__ void tile_dot_f16(const uint8_t *sp, uint32_t v, const __half *xh, uint32_t xl_off, int nu,
-                                             int s0, int s1, int lane, float (&dA)[4], float (&dB)[4])
+                                             int s0, int s1, int lane, float (&dA)[4], float (&dB)[4], uint32_t zero16)
 {
     const int g = lane >> 2, t = lane & 3, nfull = nu >> 2;
     const uint32_t sstep = v * 64u;
     uint32_t wp = smem_u32(sp) + (uint32_t)s0 * sstep + (uint32_t)lane * 16u;
-    uint32_t xp = smem_u32(xh) + (g == 1 ? xl_off : 0u) + (uint32_t)(s0 * 4 + t) * 16u;
-    const bool ax = g < 2;  // the lanes that hold rows 0 (hi) and 1 (lo) of the A operand
+    // the lanes g >= 2 hold the zero rows 2 .. 15 of the A operand: they read 16 zero bytes (zero16, stride 0)
+    // instead of branching on the lane in the loop -- every value the loop needs then fits a register that is
+    // only live here (the compiler kept `lane` in local memory and reloaded it every step)
+    const bool ax = g < 2;
+    uint32_t xp = ax ? smem_u32(xh) + (g == 1 ? xl_off : 0u) + (uint32_t)(s0 * 4 + t) * 16u : zero16;
+    const uint32_t xstep = ax ? 64u : 0u;
     const int e = min(s1, nfull);
+    // software-pipelined by hand (the loads are volatile asm: in program order the next step's are issued before
+    // this step's mmas wait for theirs)
+    uint4 w = make_uint4(0u, 0u, 0u, 0u), x = make_uint4(0u, 0u, 0u, 0u);
+    if (s0 < e) { w = lds128(wp); x = lds128(xp); }
 #pragma unroll 2
     for (int st = s0; st < e; st++) {
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        const uint4 w = lds128(wp);
-        if (ax) x = lds128(xp);
+        wp += sstep; xp += xstep;
+        uint4 wn = w, xn = x;
+        if (st + 1 < e) { wn = lds128(wp); xn = lds128(xp); }
         mma16816(dA, x.x, 0u, x.y, 0u, w.x, w.y);
         mma16816(dB, x.z, 0u, x.w, 0u, w.z, w.w);
-        wp += sstep; xp += 64u;
+        w = wn; x = xn;
     }
     if (s1 > nfull) {  // the short last step of the row: rem units per row, rows rem x 16 bytes apart
         const int rem = nu & 3;
-        uint4 w = make_uint4(0u, 0u, 0u, 0u), x = make_uint4(0u, 0u, 0u, 0u);
+        w = make_uint4(0u, 0u, 0u, 0u); x = make_uint4(0u, 0u, 0u, 0u);
         if (t < rem) {
             w = lds128(smem_u32(sp) + (uint32_t)nfull * sstep + (uint32_t)(g * rem + t) * 16u);
             if (ax) x = lds128(smem_u32(xh) + (g == 1 ? xl_off : 0u) + (uint32_t)(nfull * 4 + t) * 16u);
@@ -1141,7 +1233,7 @@ __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, 
 //     such a phase does not need its input vector: skipping the poll also keeps it from ever lagging
 //     behind on a buffer nobody waits for it to have read.
 template <int WT>
-__device__ __forceinline__ float phase_prologue(CtaPlan *cp, int q)
+__device__ __forceinline__ float phase_prologue(CtaPlan *, int q)
 {
     const int ph = q < 4 * cp->L ? (q & 3) : 4, l = q >> 2;
     const uint32_t ep = cp->ep_base + (uint32_t)l + 1u;
@@ -1177,7 +1269,7 @@ __device__ __forceinline__ float phase_prologue(CtaPlan *cp, int q)
 // and local memory is an L2 round trip in this kernel), all constants come from the plan in shared
 // memory.  rscale = the 1 / rms factor of the phase's rmsnorm (the mat-vec is linear).
 template <int WT, bool PROF>
-__device__ __forceinline__ void run_tiles(CtaPlan *cp, int q, float rscale)
+__device__ __forceinline__ void run_tiles(CtaPlan *, int q, float rscale)
 {
     const int ph = q < 4 * cp->L ? (q & 3) : 4, l = q >> 2, pos = cp->pos;
     const uint32_t ep = cp->ep_base + (uint32_t)l + 1u;  // epoch of everything layer l publishes
@@ -1226,7 +1318,8 @@ __device__ __forceinline__ void run_tiles(CtaPlan *cp, int q, float rscale)
                 mbar_wait(full_bar(cp, s), full_par(s), 2);
                 if (c == 0) TSTAMP(1);
                 tile_dot_f16(smem + (size_t)slot * cp->slot_bytes, (uint32_t)vrows,
-                             reinterpret_cast<const __half *>(xs) + 8 * u0, (uint32_t)W.cols * 2u, nu, b0, b1, lane, dA, dB);
+                             reinterpret_cast<const __half *>(xs) + 8 * u0, (uint32_t)W.cols * 2u, nu, b0, b1, lane, dA, dB,
+                             smem_u32(smem + cp->off_red) + 192u);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_n(empty_bar(cp, slot), gweight);
                 u0 += nu;
@@ -1422,7 +1515,7 @@ __device__ __forceinline__ void run_tiles(CtaPlan *cp, int q, float rscale)
 // PROF = true adds the phase timers of CTA 0 (SM cycles per bucket, PH_* in kernels.cuh) and the optional
 // per-CTA trace of one layer.
 template <int WT, bool PROF>
-__device__ __noinline__ void consumer_main(CtaPlan *cp, Prof *pf)
+__device__ __noinline__ void consumer_main(CtaPlan *, Prof *)
 {
     const bool timer = PROF && (blockIdx.x == 0 && threadIdx.x == 0);
     const bool tracing = PROF && cp->trace_base != nullptr;
@@ -1466,9 +1559,9 @@ __device__ __noinline__ void consumer_main(CtaPlan *cp, Prof *pf)
         }
         if ((Q_NOW & 3) == 0 && Q_NOW < 4 * cp->L) {
             // ---- attention (llama2.f90:574-598)
-            if (cp->hs == 64) attention_phase_t<64>(cp, Q_NOW >> 2);
-            else if (cp->hs == 128) attention_phase_t<128>(cp, Q_NOW >> 2);
-            else attention_phase_t<32>(cp, Q_NOW >> 2);
+            if (cp->hs == 64) attention_phase_t<64, PROF>(cp, Q_NOW >> 2);
+            else if (cp->hs == 128) attention_phase_t<128, PROF>(cp, Q_NOW >> 2);
+            else attention_phase_t<32, PROF>(cp, Q_NOW >> 2);
             LAP(PH_ATT);
             STAMP(Q_NOW >> 2, 4);
         }
@@ -1498,55 +1591,53 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    __shared__ CtaPlan cp;
-    __shared__ Prof pf;
     // ---- shared-memory map: ring | xs | xres | red | attention scratch | full[NBAR] | empty[MAX_SLOTS] | stage list
     const int off_xs = P.n_slots * P.slot_bytes, off_xres = off_xs + P.xs_floats * 4, off_red = off_xres + P.emb * 4;
     const int off_att = off_red + 64 * 4, off_grp = off_att + (ATT_MAX_CHUNK + NCW * P.hs) * 4;
     const int off_full = off_grp + 2 * NCW * 16 * 4;  // [2][NCW][16] partial results of a tile group's warps
     const int off_empty = off_full + NBAR * 8, off_sched = off_empty + MAX_SLOTS * 8;
     if (threadIdx.x == 5) {
-        cp.off_xs = off_xs; cp.off_xres = off_xres; cp.off_red = off_red; cp.off_att = off_att; cp.off_grp = off_grp;
-        for (int i = 0; i < 5; i++) cp.G[i] = P.tile_warps[i];
-        cp.off_full = off_full; cp.off_empty = off_empty; cp.off_sched = off_sched;
-        cp.slot_bytes = P.slot_bytes; cp.n_slots = P.n_slots;
-        cp.slot_magic = 0xffffffffu / (uint32_t)P.n_slots + 1u;
-        cp.wtype = P.wtype; cp.emb = P.emb; cp.hid = P.hid; cp.kv = P.kv; cp.att_dim = P.att_dim; cp.hs = P.hs;
-        cp.tp = P.tp; cp.rank = P.rank; cp.ll_rep = P.ll_rep; cp.v_off = P.v_off; cp.seq = P.seq; cp.H = P.H;
-        cp.kv_mul = P.kv_mul; cp.L = P.L;
-        cp.rep = (int)(blockIdx.x % (unsigned)P.ll_rep);
-        cp.n_splits = P.n_splits; cp.ep_base = P.ep_base; cp.trace = nullptr;
-        cp.trace_base = P.trace; cp.trace_layer = P.trace_layer; cp.phase_cycles = P.phase_cycles;
-        cp.kvmul_inv16 = (65535u + (unsigned)P.kv_mul) / (unsigned)P.kv_mul;
-        cp.inv_emb = 1.0f / (float)P.emb;
-        cp.kc = P.kc; cp.vc = P.vc; cp.ll_q = P.ll_q; cp.ll_kv = P.ll_kv; cp.ll_att = P.ll_att;
-        cp.ll_part = P.ll_part; cp.ll_hb = P.ll_hb;
+        g_cp.off_xs = off_xs; g_cp.off_xres = off_xres; g_cp.off_red = off_red; g_cp.off_att = off_att; g_cp.off_grp = off_grp;
+        for (int i = 0; i < 5; i++) g_cp.G[i] = P.tile_warps[i];
+        g_cp.off_full = off_full; g_cp.off_empty = off_empty; g_cp.off_sched = off_sched;
+        g_cp.slot_bytes = P.slot_bytes; g_cp.n_slots = P.n_slots;
+        g_cp.slot_magic = 0xffffffffu / (uint32_t)P.n_slots + 1u;
+        g_cp.wtype = P.wtype; g_cp.emb = P.emb; g_cp.hid = P.hid; g_cp.kv = P.kv; g_cp.att_dim = P.att_dim; g_cp.hs = P.hs;
+        g_cp.tp = P.tp; g_cp.rank = P.rank; g_cp.ll_rep = P.ll_rep; g_cp.v_off = P.v_off; g_cp.seq = P.seq; g_cp.H = P.H;
+        g_cp.kv_mul = P.kv_mul; g_cp.L = P.L;
+        g_cp.rep = (int)(blockIdx.x % (unsigned)P.ll_rep);
+        g_cp.n_splits = P.n_splits; g_cp.ep_base = P.ep_base; g_cp.trace = nullptr;
+        g_cp.trace_base = P.trace; g_cp.trace_layer = P.trace_layer; g_cp.phase_cycles = P.phase_cycles;
+        g_cp.kvmul_inv16 = (65535u + (unsigned)P.kv_mul) / (unsigned)P.kv_mul;
+        g_cp.inv_emb = 1.0f / (float)P.emb;
+        g_cp.kc = P.kc; g_cp.vc = P.vc; g_cp.ll_q = P.ll_q; g_cp.ll_kv = P.ll_kv; g_cp.ll_att = P.ll_att;
+        g_cp.ll_part = P.ll_part; g_cp.ll_hb = P.ll_hb;
     }
     if (threadIdx.x >= 8 && threadIdx.x < 8 + MAX_TP) {
         const int k = threadIdx.x - 8;
-        cp.part1[k] = P.part1[k]; cp.part2[k] = P.part2[k]; cp.logits[k] = P.logits[k];
-        cp.amax[k] = P.amax[k]; cp.done[k] = P.done[k];
+        g_cp.part1[k] = P.part1[k]; g_cp.part2[k] = P.part2[k]; g_cp.logits[k] = P.logits[k];
+        g_cp.amax[k] = P.amax[k]; g_cp.done[k] = P.done[k];
     }
     if (threadIdx.x == 7) {
-        cp.gx_trace = nullptr; cp.abort = 0; cp.err_flag = P.err_flag;
-        cp.forced = P.forced; cp.out_tokens = P.out_tokens; cp.tokpos = const_cast<int *>(P.tokpos);
-        cp.ep_last = P.ep_base + (uint32_t)P.L + 1u; cp.do_argmax = P.do_argmax;
+        g_cp.gx_trace = nullptr; g_cp.abort = 0; g_cp.err_flag = P.err_flag;
+        g_cp.forced = P.forced; g_cp.out_tokens = P.out_tokens; g_cp.tokpos = const_cast<int *>(P.tokpos);
+        g_cp.ep_last = P.ep_base + (uint32_t)P.L + 1u; g_cp.do_argmax = P.do_argmax;
     }
     if (threadIdx.x < 5) {
         const int i = threadIdx.x;
-        cp.ph[i] = P.ph[i];
+        g_cp.ph[i] = P.ph[i];
         int r0, r1;
         cta_rows(P.ph[i], blockIdx.x, gridDim.x, r0, r1);
-        cp.r0[i] = r0; cp.nrows[i] = r1 - r0;
+        g_cp.r0[i] = r0; g_cp.nrows[i] = r1 - r0;
         const int nt = (r1 - r0 + P.ph[i].R - 1) / P.ph[i].R;
-        cp.ntiles[i] = nt; cp.nst[i] = nt * P.ph[i].nch;
-        cp.lstride[i] = i < 4 ? P.ph[i].layer_stride : 0ull;
-        cp.sstride[i] = P.ph[i].rs;
+        g_cp.ntiles[i] = nt; g_cp.nst[i] = nt * P.ph[i].nch;
+        g_cp.lstride[i] = i < 4 ? P.ph[i].layer_stride : 0ull;
+        g_cp.sstride[i] = P.ph[i].rs;
     }
     if (threadIdx.x == 6) {
-        cp.lstride[SK_RMS_ATT] = cp.lstride[SK_RMS_FFN] = (unsigned long long)P.emb * 4u;
-        cp.lstride[SK_RMS_FINAL] = cp.lstride[SK_EMB_ROW] = 0ull;
-        cp.sstride[SK_RMS_ATT] = cp.sstride[SK_RMS_FFN] = cp.sstride[SK_RMS_FINAL] = cp.sstride[SK_EMB_ROW] = 0u;
+        g_cp.lstride[SK_RMS_ATT] = g_cp.lstride[SK_RMS_FFN] = (unsigned long long)P.emb * 4u;
+        g_cp.lstride[SK_RMS_FINAL] = g_cp.lstride[SK_EMB_ROW] = 0ull;
+        g_cp.sstride[SK_RMS_ATT] = g_cp.sstride[SK_RMS_FFN] = g_cp.sstride[SK_RMS_FINAL] = g_cp.sstride[SK_EMB_ROW] = 0u;
     }
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(P.sched + (size_t)blockIdx.x * P.sched_stride);
@@ -1562,31 +1653,33 @@ stream_decode_kernel(const __grid_constant__ StreamParams P)
     const int token = P.token > 0 ? P.token : P.tokpos[0];
     const int pos = P.token > 0 ? P.pos : P.tokpos[1];
     if (threadIdx.x == 6) {
-        cp.pos = pos;
+        g_cp.pos = pos;
         int nst[5];
         for (int i = 0; i < 5; i++) {
             int r0, r1;
             cta_rows(P.ph[i], blockIdx.x, gridDim.x, r0, r1);
             nst[i] = ((r1 - r0 + P.ph[i].R - 1) / P.ph[i].R) * P.ph[i].nch;
         }
-        cp.n_layer = 2 + nst[0] + nst[1] + nst[2] + nst[3];
-        cp.voff[0] = 0; cp.toff[0] = 1; cp.voff[1] = 0; cp.toff[1] = 1 + nst[0];
-        cp.voff[2] = 1 + nst[0] + nst[1]; cp.toff[2] = cp.voff[2] + 1; cp.voff[3] = 0; cp.toff[3] = cp.toff[2] + nst[2];
-        cp.voff[4] = 0; cp.toff[4] = 1;
+        g_cp.n_layer = 2 + nst[0] + nst[1] + nst[2] + nst[3];
+        g_cp.voff[0] = 0; g_cp.toff[0] = 1; g_cp.voff[1] = 0; g_cp.toff[1] = 1 + nst[0];
+        g_cp.voff[2] = 1 + nst[0] + nst[1]; g_cp.toff[2] = g_cp.voff[2] + 1; g_cp.voff[3] = 0; g_cp.toff[3] = g_cp.toff[2] + nst[2];
+        g_cp.voff[4] = 0; g_cp.toff[4] = 1;
     }
+    if (threadIdx.x >= 32 && threadIdx.x < 36)  // 16 zero bytes (the zero rows of tile_dot_f16's A operand)
+        reinterpret_cast<float *>(smem_base() + off_red)[48 + threadIdx.x - 32] = 0.f;
     // this position's RoPE row (a cold HBM read, issued first thing, used after the QKV phase)
     if (threadIdx.x >= 64 && threadIdx.x < 64 + (P.hs >> 1))
-        cp.rope[threadIdx.x - 64] = P.rope_tab[(size_t)(pos - 1) * (P.hs >> 1) + threadIdx.x - 64];
+        g_cp.rope[threadIdx.x - 64] = P.rope_tab[(size_t)(pos - 1) * (P.hs >> 1) + threadIdx.x - 64];
     __syncthreads();
 
     if (warp == NCW) {
         // ===================== producer warp =====================
-        if (lane == 0) producer_loop(&cp, token, P.pace, P.pf_lead);
+        if (lane == 0) producer_loop(cp, token, P.pace, P.pf_lead);
         return;
     }
 
     // ===================== consumer warps =====================
-    consumer_main<WT, PROF>(&cp, &pf);
+    consumer_main<WT, PROF>(cp, pf);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1652,6 +1745,20 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
     while (n_slots > 0 && smem_bytes_for(n_slots, (int)slot, xs_floats, p.emb, p.hs, sched_entries) > (size_t)max_smem_optin)
         n_slots--;
     if (n_slots < 3) return 1;
+    // Shared memory and L1 share 256 KB per SM, and the carve-out comes in steps (.. 164, 196, 228 KB).  The kernel
+    // is capped at 128 registers (13 warps: four on one scheduler partition) and the compiler parks a few dozen
+    // words per thread in local memory; with the 228 KB carve-out the ~28 KB of L1 left do not hold them and
+    // every reload is an L2 round trip.  Giving up one ring slot to fall under the 196 KB step (60 KB of L1)
+    // pays whenever enough ring is left -- measured, ms per token with n / n - 1 slots: TinyLlama f32 0.904 /
+    // 0.889, f16 0.765 / 0.695, Llama-2-7B q4_0 1.871 / 1.768, but f16 (4 x 32 KB -> 3) 3.40 / 3.53.
+    if (max_slots >= MAX_SLOTS) {  // (an explicit LLMF90_MAX_SLOTS is taken as given)
+        const size_t step = 196 * 1024 - 1024 - 3072;  // the step, minus the per-CTA reservation and the static part
+        const size_t min_ring = tiled ? 100 * 1024 : 120 * 1024;
+        if (smem_bytes_for(n_slots, (int)slot, xs_floats, p.emb, p.hs, sched_entries) > step &&
+            smem_bytes_for(n_slots - 1, (int)slot, xs_floats, p.emb, p.hs, sched_entries) <= step &&
+            (size_t)(n_slots - 1) * slot >= min_ring)
+            n_slots--;
+    }
     out->n_slots = n_slots;
     out->slot_bytes = (int)slot;
     out->threads = (NCW + 1) * 32;
@@ -1666,7 +1773,10 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
     // starts) is a latency chain instead: its time is rounds x (fixed part + mat-vec / G), so prefer the
     // group size that takes the fewest rounds.
     for (int i = 0; i < 5; i++) {
-        const int tiles = tiles_of(p.ph[i], p.ph[i].rows_cap), big = tiled ? 4 : 3;
+        // (f16 / q4_0 run on the tensor pipe: few instructions per byte, so a tile's warps are latency-bound and more
+        // of them per tile pay -- Llama-2-7B f16 3.40 / 3.09 / 2.99 ms per token with 3 / 4 / 6, q4_0 1.93 / 1.77 / 1.75)
+        const int tiles = tiles_of(p.ph[i], p.ph[i].rows_cap);
+        const int big = tiled ? (p.emb >= 4096 ? 6 : 4) : (p.wtype == WT_F16 ? (p.ph[i].nch >= 2 ? 6 : 4) : 3);
         int best = big;
         if (tiles <= NCW && tiles * p.ph[i].nch <= n_slots) {  // the whole phase of a CTA fits the ring
             long best_cost = -1;
