@@ -19,8 +19,10 @@ llama2.f90:376-402) on synthetic weights of the named architecture.
   cpu_baseline the C restatement of llama2.f90 (oracle/, 1 thread like the reference) on a bounded
                sample of the same workload, on this box's host cores.
 
---impl reference times that CPU restatement with all host threads (the Fortran binary cannot be
-built: no Fortran compiler in the image).  Under torchrun only rank 0 runs it.
+--impl reference times that CPU restatement (the Fortran binary cannot be built: no Fortran compiler
+in the image) on a bounded sample of the same workload: `value` is the 1-thread figure -- the reference is a
+single-threaded program -- and cpu_baseline.all_cores the same code with OpenMP on every host core.  Under
+torchrun only rank 0 runs it.
 """
 from __future__ import annotations
 
@@ -40,6 +42,11 @@ sys.path.insert(0, ROOT)
 N_POS = 128
 PROMPT = "I stopped posting on knitting forums because"  # README.md:42
 METRIC = "tokens/sec decode (128-tok gen)"
+# the arithmetic of the mat-vecs per weight storage type (activations, accumulators and everything else are f32)
+DTYPE = {"f32": "f32", "f16": "f16", "q4_0": "q4_0"}
+ARITHMETIC = {"f32": "f32 FMA (weights f32)",
+              "f16": "f16 weights x (hi + lo f16 planes of the f32 activations) on mma.sync, f32 accumulate",
+              "q4_0": "q4_0 nibbles -> f16 x (hi + lo f16 planes of the activations) on mma.sync, f32 scales / accumulate"}
 
 
 def model_config(name: str, wtype: str):
@@ -223,7 +230,17 @@ def main():
     cfg = model_config(model, wtype)
     workload = f"{model}-{wtype} {N_POS}-position greedy decode, synthetic weights (seed 0)"
 
+    def config_of(parallelism: str, n_prompt: int) -> dict:
+        return {"workload": workload, "emb_dim": cfg.emb_dim, "hidden_dim": cfg.hidden_dim,
+                "n_layers": cfg.n_layers, "n_heads": cfg.n_heads, "n_kv_heads": cfg.n_kv_heads,
+                "vocab_size": cfg.vocab_size, "weight_storage": wtype, "positions_per_step": N_POS,
+                "prompt_tokens": n_prompt, "parallelism": parallelism,
+                "arithmetic": ARITHMETIC[wtype]}
+
     if a.impl == "reference":
+        # The reference is a single-threaded program (llama2.f90:93 has `use omp_lib` commented out; README.md:97
+        # "single thread 32-bit operation"): `value` is the 1-thread figure the north star names; the same C
+        # restatement with OpenMP over rows on every host core is reported beside it.
         if rank != 0:
             return 0
         cores = host_cores()
@@ -231,21 +248,27 @@ def main():
         prompt = prompt_tokens(cfg)
         n_pos = a.cpu_sample_pos or {"tinyllama": 12, "llama2-7b": 4, "small": N_POS}[model]
         for _ in range(a.warmup):
-            cpu_oracle_run(w, prompt, min(n_pos, 3), cores)
+            cpu_oracle_run(w, prompt, min(n_pos, 3), 1)
         tps, walls = [], []
         for _ in range(a.steps):
-            t, wall = cpu_oracle_run(w, prompt, n_pos, cores)
+            t, wall = cpu_oracle_run(w, prompt, n_pos, 1)
             tps.append(t)
             walls.append(wall)
         val = float(len(tps) * (n_pos - 1) / sum((n_pos - 1) / t for t in tps))
-        sample = f"{n_pos} positions per step (of the {N_POS}-position workload), (n-1)/(t_end-t_after_first)"
+        all_tps, _ = cpu_oracle_run(w, prompt, n_pos, cores)
+        sample = (f"positions 1..{n_pos} of the {N_POS}-position workload per step (the sample: a CPU pass over all "
+                  f"{N_POS} would take minutes), tokens/s by the reference's formula (n-1)/(t_end-t_after_first)")
+        cfgd = config_of("cpu, 1 thread", len(prompt))
+        cfgd["positions_per_step_sampled"] = n_pos
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * sum(walls) / len(walls),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": workload},
-                "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample,
-                                 "note": "C restatement of llama2.f90 (oracle/), OpenMP over rows; the Fortran "
-                                         "binary cannot be built in this image (no Fortran compiler)"},
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[wtype],
+                "data": "synthetic", "config": cfgd,
+                "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": 1, "kind": "port", "sample": sample,
+                                 "all_cores": {"value": all_tps, "unit": "tokens/s", "cores": cores,
+                                               "how": "same restatement, OpenMP over rows, one step"},
+                                 "note": "C restatement of llama2.f90 (oracle/); the Fortran binary cannot be built "
+                                         "in this image (no Fortran compiler)"},
                 "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -332,11 +355,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "emb_dim": cfg.emb_dim, "hidden_dim": cfg.hidden_dim,
-                   "n_layers": cfg.n_layers, "n_heads": cfg.n_heads, "n_kv_heads": cfg.n_kv_heads,
-                   "vocab_size": cfg.vocab_size, "weight_storage": wtype, "positions_per_step": N_POS,
-                   "prompt_tokens": len(prompt), "parallelism": f"tp{world}",
+        "vs_baseline": None, "dtype": DTYPE[wtype], "data": "synthetic",
+        "config": {**config_of(f"tp{world}", len(prompt)),
                    "l2": f"inputs larger than L2: {act_bytes / 1e6:.0f} MB of weights streamed per token vs 126 MB L2",
                    "tokens_per_s_reference_formula": ref_formula,
                    "wall_ms_timed_region": wall_ms},

@@ -137,7 +137,12 @@ Model load_gguf(const std::string &path, bool verbose, bool print_offset)
             default: v = r.get<double>(); break;
             }
             num[key] = v;
-            if (key == "general.alignment") alignment = (uint32_t)v;
+            if (key == "general.alignment") {
+                // (a zero or non-power-of-two alignment would divide by zero / misplace the tensor data below)
+                if (!(v >= 1 && v <= 65536) || ((uint32_t)v & ((uint32_t)v - 1)))
+                    throw std::runtime_error("GGUF: general.alignment " + std::to_string(v) + " is not a power of two in 1..65536");
+                alignment = (uint32_t)v;
+            }
             if (verbose) printf(" %s = %g\n", key.c_str(), v);
         } else {
             throw std::runtime_error("GGUF: unsupported value type " + std::to_string(t) + " for key " + key);

@@ -129,12 +129,15 @@ static cudaError_t launch_matvec_t(const uint8_t *W, int rows, int cols, const f
                                    const float *residual, float *y, cudaStream_t st)
 {
     const size_t smem = (size_t)cols * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // (function attributes are per device: one flag per device, not one per process)
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(matvec_kernel<WT, NR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const int grid = (rows + MV_WARPS * NR - 1) / (MV_WARPS * NR);
     matvec_kernel<WT, NR><<<grid, MV_WARPS * 32, smem, st>>>(W, row_stride_bytes(WT, cols), rows,
@@ -320,8 +323,20 @@ cudaError_t launch_attention(const float *q, const float *kc_layer, const float 
                              const int *tokpos, float *out, int n_heads, int kv_mul, int hs, int kv,
                              int seq, cudaStream_t st)
 {
-    attention_kernel<<<n_heads, ATT_THREADS, (size_t)seq * sizeof(float), st>>>(
-        q, kc_layer, vc_layer, tokpos, out, kv_mul, hs, kv);
+    const size_t smem = (size_t)seq * sizeof(float);  // one score per position
+    if (smem > 48 * 1024) {
+        // beyond the default 48 KB a kernel has to opt in (seq_len > 12288); the attribute is per device
+        if (smem > 200 * 1024) return cudaErrorInvalidValue;
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
+    }
+    attention_kernel<<<n_heads, ATT_THREADS, smem, st>>>(q, kc_layer, vc_layer, tokpos, out, kv_mul, hs, kv);
     return cudaGetLastError();
 }
 
