@@ -470,38 +470,55 @@ __device__ __forceinline__ float4 emb_row4(const uint8_t *row, int wtype, int co
 // memory.  Out of line: the 8 x 4 LL words in flight per lane would otherwise set the register budget of the
 // single-GPU phase loop.  A poll that sees nothing for seconds means a peer is gone: flag it and stop waiting.
 constexpr long long TP_POLL_TIMEOUT_CYCLES = 8000000000ll;  // ~4 s at 2 GHz
-__device__ __noinline__ void gather_tp(CtaPlan *, const unsigned long long *src, int nsrc, uint32_t ep, int n4)
+// poll position j of NS consecutive source vectors (n floats apart) and add them to v in source order
+template <int NS>
+__device__ __forceinline__ void tp_poll_add(const unsigned long long *src, int n, int j, uint32_t ep, float4 &v)
+{
+    unsigned long long w[NS][4];
+    bool ok;
+    const long long t0 = clock64();
+    do {
+#pragma unroll
+        for (int r = 0; r < NS; r++) {
+            ll_load2(src + (size_t)r * n + 4 * j, w[r][0], w[r][1]);
+            ll_load2(src + (size_t)r * n + 4 * j + 2, w[r][2], w[r][3]);
+        }
+        ok = true;
+#pragma unroll
+        for (int r = 0; r < NS; r++) ok = ok && ll_ok(w[r][0], ep) && ll_ok(w[r][1], ep) && ll_ok(w[r][2], ep) && ll_ok(w[r][3], ep);
+        if (!ok && (cp->abort || clock64() - t0 > TP_POLL_TIMEOUT_CYCLES)) {
+            cp->abort = 1;
+            if (cp->err_flag) *cp->err_flag = 1;
+            break;
+        }
+    } while (!ok);
+#pragma unroll
+    for (int r = 0; r < NS; r++) { v.x += ll_val(w[r][0]); v.y += ll_val(w[r][1]); v.z += ll_val(w[r][2]); v.w += ll_val(w[r][3]); }
+}
+// (one instantiation per world size: the words in flight stay in registers; 8 sources are polled as two groups of
+// four -- 64 registers of LL words do not fit beside the rest -- in rank order, so the sum is the same on every GPU)
+template <int NS>
+__device__ __noinline__ void gather_tp_n(const unsigned long long *src, uint32_t ep, int n4)
 {
     float4 *xr4 = reinterpret_cast<float4 *>(smem_base() + cp->off_xres);
     const int n = n4 << 2;
 #pragma unroll 1
     for (int j = (int)threadIdx.x; j < n4; j += NCT) {
-        unsigned long long w[MAX_TP][4];
-        bool ok;
-        const long long t0 = clock64();
-        do {
-#pragma unroll
-            for (int r = 0; r < MAX_TP; r++)
-                if (r < nsrc) {
-                    ll_load2(src + (size_t)r * n + 4 * j, w[r][0], w[r][1]);
-                    ll_load2(src + (size_t)r * n + 4 * j + 2, w[r][2], w[r][3]);
-                }
-            ok = true;
-#pragma unroll
-            for (int r = 0; r < MAX_TP; r++)
-                if (r < nsrc) ok = ok && ll_ok(w[r][0], ep) && ll_ok(w[r][1], ep) && ll_ok(w[r][2], ep) && ll_ok(w[r][3], ep);
-            if (!ok && (cp->abort || clock64() - t0 > TP_POLL_TIMEOUT_CYCLES)) {
-                cp->abort = 1;
-                if (cp->err_flag) *cp->err_flag = 1;
-                break;
-            }
-        } while (!ok);
         float4 v = xr4[j];
-#pragma unroll
-        for (int r = 0; r < MAX_TP; r++)
-            if (r < nsrc) { v.x += ll_val(w[r][0]); v.y += ll_val(w[r][1]); v.z += ll_val(w[r][2]); v.w += ll_val(w[r][3]); }
+        if constexpr (NS == 8) {
+            tp_poll_add<4>(src, n, j, ep, v);
+            tp_poll_add<4>(src + (size_t)4 * n, n, j, ep, v);
+        } else {
+            tp_poll_add<NS>(src, n, j, ep, v);
+        }
         xr4[j] = v;
     }
+}
+__device__ __forceinline__ void gather_tp(CtaPlan *, const unsigned long long *src, int nsrc, uint32_t ep, int n4)
+{
+    if (nsrc == 2) gather_tp_n<2>(src, ep, n4);
+    else if (nsrc == 4) gather_tp_n<4>(src, ep, n4);
+    else gather_tp_n<8>(src, ep, n4);
 }
 
 // The previous phase's mat-vec has no closing barrier (each warp publishes its tiles and moves on), so
