@@ -12,13 +12,19 @@ cfg = Config(**(TINYLLAMA if model == 'tinyllama' else LLAMA2_7B), wtype=WTYPE_B
 w = fx.synth_weights_tiled(cfg, 0)
 prompt = [5, 6, 7, 8, 9, 10, 11, 12, 13]
 ref = None
+touched = set()
 for v in sys.argv[4:]:
+    for k in touched:  # every point starts from the caller's environment
+        os.environ.pop(k, None)
+    touched.clear()
     if name == "MULTI":
         for kv in v.split(","):
             k, x = kv.split("=")
             os.environ[k] = x
+            touched.add(k)
     else:
         os.environ[name] = v
+        touched.add(name)
     eng = capi.Engine(w)
     for _ in range(3):
         eng.generate_greedy(prompt, 128)
