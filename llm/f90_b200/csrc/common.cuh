@@ -136,44 +136,6 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-// KV-cache accesses: keep the lines in L2 (evict_last) -- a layer's rows are read again one token later, with
-// gigabytes of evict_first weight traffic in between
-#ifdef LLMF90_NO_KEEP
-__device__ __forceinline__ float4 ldg_keep_f4(const float4 *p, uint64_t) { return __ldcg(p); }
-__device__ __forceinline__ float2 ldg_keep_f2(const float2 *p, uint64_t) { return __ldcg(p); }
-__device__ __forceinline__ float ldg_keep_f1(const float *p, uint64_t) { return __ldcg(p); }
-__device__ __forceinline__ void stg_keep_f2(float2 *p, float2 v, uint64_t) { *p = v; }
-#else
-__device__ __forceinline__ float4 ldg_keep_f4(const float4 *p, uint64_t pol)
-{
-    float4 v;
-    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float2 ldg_keep_f2(const float2 *p, uint64_t pol)
-{
-    float2 v;
-    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ldg_keep_f1(const float *p, uint64_t pol)
-{
-    float v;
-    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void stg_keep_f2(float2 *p, float2 v, uint64_t pol)
-{
-    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
-}
-#endif
 // 1-D bulk copy global -> shared through the TMA engine, completion on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                          uint64_t *bar, uint64_t policy)

@@ -318,25 +318,6 @@ __device__ __forceinline__ void ll_wait4n(const unsigned long long *buf, int i, 
         }
     } while (!ok);
 }
-// poll NV (<= 4) consecutive floats (i % NV == 0)
-template <int NV>
-__device__ __forceinline__ void ll_waitv(const unsigned long long *buf, int i, uint32_t ep, float (&o)[NV])
-{
-    if (NV == 4) {
-        const float4 t = ll_wait4(buf, i, ep);
-        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-    } else if (NV == 2) {
-        unsigned long long a, b;
-        LLMF90_WD_DECL;
-        do { ll_load2(buf + i, a, b); LLMF90_WD_CHECK(103, i, ep) } while (!(ll_ok(a, ep) && ll_ok(b, ep)));
-        o[0] = ll_val(a); o[1] = ll_val(b);
-    } else {
-        unsigned long long a;
-        LLMF90_WD_DECL;
-        do { a = ll_load1(buf + i); LLMF90_WD_CHECK(104, i, ep) } while (!ll_ok(a, ep));
-        o[0] = ll_val(a);
-    }
-}
 // A thread's batch of PV float4 positions j = base + tid + k * NCT of an LL vector: all requests of
 // a polling round are issued before the first check (one L2 round trip per round).  Positions
 // past the end are clamped to the last one (a harmless duplicate request).
@@ -598,37 +579,25 @@ __device__ __forceinline__ float gather_x(const CtaPlan *, const unsigned long l
 }
 
 // ------------------------------------------------------------------ attention phase
-// (head, split) items over the CTAs (llama2.f90:574-598); a split is a run of positions (<= 256
-// up to 2048 positions of context).  The phase is a pure latency chain between the QKV tiles and the
-// Wo prologue, so it is organised for few dependent steps and little code, not for throughput:
-//   scores : each warp takes groups of 8 positions; lane = 4 * (position in group) + (quarter of the
-//            head dimension) dots its quarter of q_h with its quarter of one K row (the K requests go out
-//            before the poll for q: ONE L2 round trip), two shuffles finish the dot, the score goes to
-//            shared memory.  The V rows of the group are requested right after (lane <-> head
-//            dimensions) and arrive while the CTA meets at the barrier.
+// (head, split) items over the CTAs (llama2.f90:574-598); a split is a run of positions, chosen so that its
+// cached rows fit one group per warp where the grid allows (engine.cu: n_splits_for; <= 256 in any case).  The
+// phase is a pure latency chain between the QKV tiles and the Wo prologue, so it is organised for few dependent
+// steps, not for throughput -- three stages separated by CTA barriers:
+//   scores : a position is held by hs / 16 lanes (16 head dimensions each), a warp takes 512 / hs positions at a
+//            time; all K / V rows of the warp are pulled into L2 first (prefetch: no destination registers while
+//            the 32-register poll for q is in flight), then q is polled, the K quarters are loaded and dotted,
+//            shuffles finish the dot, the score goes to shared memory; the V quarters of the warp's first group
+//            are requested right after and arrive while the CTA meets at the barrier.  The last position is this
+//            launch's own: the last warp polls its q, k and v from the LL buffers (attention_current).
 //   softmax: every warp computes the maximum and the normaliser of ALL scores of the item itself (a few
 //            shared-memory reads and two warp reductions: cheaper than exchanging them) -- no running
-//            maximum, no rescaling (softmax :468-478)
-//   values : acc = sum_t exp(s_t - max) v_t over the warp's positions, one partial vector per warp in
-//            shared memory; after the second barrier thread d adds the partials of dimension d.
-// Positions past the end of a group read a clamped (valid) row and are skipped.  The last position
-// is this launch's own: its key / value rows come from the LL buffer, polled in the same loop as q by
-// the warp whose group holds it.  With one split the normalised head output goes straight to ll_att;
-// otherwise {max, normaliser, acc} partials go to ll_part and the Wo prologue merges.
-
-template <int VEC>
-__device__ __forceinline__ void load_vec(const float *p, float (&o)[VEC])
-{
-    if (VEC == 4) {
-        const float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
-        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-    } else if (VEC == 2) {
-        const float2 t = __ldcg(reinterpret_cast<const float2 *>(p));
-        o[0] = t.x; o[1] = t.y;
-    } else {
-        o[0] = __ldcg(p);
-    }
-}
+//            maximum, no rescaling (softmax :468-478); then acc = sum_t exp(s_t - max) v_t over the warp's
+//            positions in the same lane mapping, the position groups folded with shuffles, one partial vector
+//            per warp in shared memory.
+//   publish: thread d adds the 12 partials of dimension pair d.  With one split the normalised head output goes
+//            straight to ll_att; otherwise {max, normaliser, acc} partials go to ll_part and the Wo prologue
+//            merges (load_x_attn_s).
+// Positions past the end of a group read a clamped (valid) row and get weight 0.
 
 __device__ __forceinline__ void prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
