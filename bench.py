@@ -135,6 +135,51 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s), "how": self.how}
 
 
+# ------------------------------------------------------------------ NVLink counters
+def nvlink_kib(index: int):
+    """(tx, rx) data KiB this GPU has moved over NVLink so far (NVML throughput counters, summed over the links),
+    or None when the driver does not expose them.  Read before and after the timed region of a tensor-parallel run:
+    the only NVLink traffic in between is the decode kernel's own peer stores (partial Wo / W2 vectors, logits rows,
+    argmax records) -- no NCCL call is inside it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        out = []
+        for fid in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX):
+            tot, seen = 0, False
+            try:  # scope UINT_MAX = all links
+                v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])[0]
+                if v.nvmlReturn == 0:
+                    tot, seen = int(v.value.ullVal), True
+            except Exception:
+                pass
+            if not seen:
+                for link in range(18):
+                    try:
+                        v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, link)])[0]
+                        if v.nvmlReturn == 0:
+                            tot += int(v.value.ullVal)
+                            seen = True
+                    except Exception:
+                        break
+            if not seen:
+                raise RuntimeError("NVML NVLink throughput fields not supported")
+            out.append(tot)
+        return tuple(out)
+    except Exception:
+        pass
+    try:  # the same counters through the CLI: "Link 3: Data Tx: 1234 KiB"
+        import re
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=10).stdout
+        tx = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt)]
+        rx = [int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt)]
+        return (sum(tx), sum(rx)) if tx and rx else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------ CPU legs
 def host_cores() -> int:
     try:
@@ -304,6 +349,7 @@ def main():
     barrier()
     l0 = eng.stats()["kernel_launches"]
     dev_ms, after_first = [], []
+    nvl0 = nvlink_kib(dev) if world > 1 else None
     t0 = time.perf_counter()
     with ClockSampler(dev) as clk:
         for _ in range(a.steps):
@@ -313,6 +359,7 @@ def main():
             after_first.append(af)
         barrier()
     wall_ms = (time.perf_counter() - t0) * 1000.0
+    nvl1 = nvlink_kib(dev) if world > 1 else None
     launches = eng.stats()["kernel_launches"] - l0
     tot_ms = float(sum(dev_ms))
     if world > 1:
@@ -384,6 +431,22 @@ def main():
                                 "sample": f"first {n_pos} of the {N_POS} positions, 1 thread, {wall:.1f} s wall; "
                                           f"C restatement of llama2.f90 (no Fortran compiler in the image); "
                                           f"box has {host_cores()} host cores"}
+    if world > 1:
+        # what the fused all-reduce should move per token and GPU: twice per layer the rank's partial vector (emb LL
+        # words of 8 bytes) to each of the other ranks, times the hand-over replicas; + its logits rows to each peer
+        rep = 2 if world == 2 else 1
+        expect = (2 * cfg.n_layers * cfg.emb_dim * 8 * rep + (cfg.vocab_size // world) * 4) * (world - 1)
+        nv = {"expected_tx_bytes_per_token_per_gpu": int(expect),
+              "how": "NVML NVLINK_THROUGHPUT_DATA_TX / _RX of rank 0's GPU before / after the timed region (device loop)"}
+        if nvl0 and nvl1:
+            toks_timed = a.steps * N_POS
+            nv["tx_bytes_per_token"] = (nvl1[0] - nvl0[0]) * 1024.0 / toks_timed
+            nv["rx_bytes_per_token"] = (nvl1[1] - nvl0[1]) * 1024.0 / toks_timed
+        else:
+            nv["tx_bytes_per_token"] = nv["rx_bytes_per_token"] = None
+            nv["unavailable"] = ("the driver does not expose the NVLink throughput counters here (NVML field values "
+                                 "unsupported, `nvidia-smi nvlink -gt d` prints N/A)")
+        line["nvlink"] = nv
     if (world > 1 and not a.no_tp1) or a.force_tp1:
         v1, note = tp1_same_workload(model, wtype, a.steps, local_rank)
         line["config"]["tp1_same_workload"] = {"value": v1, "unit": "tokens/s", "how": note}
