@@ -1163,6 +1163,13 @@ __device__ __forceinline__ void tile_dot_f16(const uint8_t *sp, uint32_t v, cons
 // of the activations (f16 alone would cost 3 digits: greedy tokens flip at near ties).
 // Tiled weight format: common.cuh.  A stage holds the 8-block groups [g0, g0 + ng) of one row group of
 // 16 rows; lane = 4 g + t accumulates rows g and g + 8 over its blocks.
+// (w & mask) | bias in ONE instruction: two nibbles of w -> half2 {1024 + q, 1024 + q'} (or 1024 + 16 q for the high mask)
+__device__ __forceinline__ uint32_t nib_half2(uint32_t w, uint32_t mask, uint32_t bias)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "r"(mask), "r"(bias));
+    return d;
+}
 __device__ __forceinline__ uint32_t uint4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, int ngrp, int g0, int ng, int lane,
@@ -1173,6 +1180,12 @@ __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, 
     // then the per-block offset corrections [hi | lo][block] (store_x4)
     const uint4 *xh4 = reinterpret_cast<const uint4 *>(xs);
     const float *C = xs + (size_t)ngrp * 256 + (size_t)(t >> 1) * ngrp * 8;
+    // the two nibble masks and the exponent bias live in registers (opaque to the compiler, which would otherwise
+    // fold them into immediates and need an AND and an OR per half2: LOP3 takes one immediate)
+    uint32_t mlo, mhi, bias;
+    asm volatile("mov.b32 %0, 0x000f000f;" : "=r"(mlo));
+    asm volatile("mov.b32 %0, 0x00f000f0;" : "=r"(mhi));
+    asm volatile("mov.b32 %0, 0x64006400;" : "=r"(bias));
 #pragma unroll 1
     for (int gi = g0; gi < g0 + ng; gi++) {
         const uint8_t *gp = sp + (size_t)(gi - g0) * Q4T_GROUP_BYTES;
@@ -1195,10 +1208,10 @@ __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, 
                 const uint32_t wg = uint4_word(cg[hb], j), w8 = uint4_word(c8[hb], j);
                 const uint32_t m = ((g & 3) == j) ? 0xffffffffu : 0u;
                 const uint32_t wgs = wg >> 8, w8s = w8 >> 8;
-                mma16816(d, (wg & 0x000f000fu) | 0x64006400u, (w8 & 0x000f000fu) | 0x64006400u,
-                         (wgs & 0x000f000fu) | 0x64006400u, (w8s & 0x000f000fu) | 0x64006400u, xb.x & m, xb.y & m);
-                mma16816(e, (wg & 0x00f000f0u) | 0x64006400u, (w8 & 0x00f000f0u) | 0x64006400u,
-                         (wgs & 0x00f000f0u) | 0x64006400u, (w8s & 0x00f000f0u) | 0x64006400u, xb.z & m, xb.w & m);
+                mma16816(d, nib_half2(wg, mlo, bias), nib_half2(w8, mlo, bias), nib_half2(wgs, mlo, bias), nib_half2(w8s, mlo, bias),
+                         xb.x & m, xb.y & m);
+                mma16816(e, nib_half2(wg, mhi, bias), nib_half2(w8, mhi, bias), nib_half2(wgs, mhi, bias), nib_half2(w8s, mhi, bias),
+                         xb.z & m, xb.w & m);
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) d[k] += e[k];
