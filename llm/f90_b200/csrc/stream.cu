@@ -1173,7 +1173,7 @@ __device__ __forceinline__ uint32_t nib_half2(uint32_t w, uint32_t mask, uint32_
 __device__ __forceinline__ uint32_t uint4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, int ngrp, int g0, int ng, int lane,
-                                            float &acc0, float &acc1)
+                                            float &acc0, float &acc1, uint32_t zero16)
 {
     const int g = lane >> 2, t = lane & 3;
     // activations as f16 pairs x = hi + lo in B-fragment order, [half group of 4 blocks][hi | lo][block][t],
@@ -1198,7 +1198,10 @@ __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, 
         for (int hb = 0; hb < 2; hb++) {
             // four blocks per accumulation: column n = 4 p + b of D holds block b times the hi (p = 0) /
             // lo (p = 1) part of x; this lane's B column is n = g, its D columns are 2t, 2t + 1
-            const uint4 xb = xh4[((gi * 2 + hb) * 8 + g) * 4 + t];
+            // this lane's B column is n = g: in the mma pair of block j it is x (hi for g < 4, lo for g >= 4) if
+            // j == g & 3 and zero otherwise -- the lanes of the other blocks read a 16-byte zero block instead of
+            // masking four registers per block
+            const uint32_t xaddr = smem_u32(xh4 + ((gi * 2 + hb) * 8 + g) * 4 + t);
             const uint2 sc = *reinterpret_cast<const uint2 *>(gp + 2048 + (g * 4 + 2 * hb + (t & 1)) * 8);
             const float2 cc = *reinterpret_cast<const float2 *>(C + gi * 8 + 4 * hb + 2 * (t & 1));
             // two accumulators (low / high nibbles): two independent mma chains of four
@@ -1206,12 +1209,12 @@ __device__ __forceinline__ void tile_dot_q4(const uint8_t *sp, const float *xs, 
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t wg = uint4_word(cg[hb], j), w8 = uint4_word(c8[hb], j);
-                const uint32_t m = ((g & 3) == j) ? 0xffffffffu : 0u;
+                const uint4 xb = lds128((g & 3) == j ? xaddr : zero16);
                 const uint32_t wgs = wg >> 8, w8s = w8 >> 8;
                 mma16816(d, nib_half2(wg, mlo, bias), nib_half2(w8, mlo, bias), nib_half2(wgs, mlo, bias), nib_half2(w8s, mlo, bias),
-                         xb.x & m, xb.y & m);
+                         xb.x, xb.y);
                 mma16816(e, nib_half2(wg, mhi, bias), nib_half2(w8, mhi, bias), nib_half2(wgs, mhi, bias), nib_half2(w8s, mhi, bias),
-                         xb.z & m, xb.w & m);
+                         xb.z, xb.w);
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) d[k] += e[k];
@@ -1401,7 +1404,8 @@ __device__ __forceinline__ void run_tiles(CtaPlan *, int q, float rscale)
                 const uint32_t slot = slot_of(cp, s);
                 mbar_wait(full_bar(cp, s), full_par(s), 2);
                 if (c == 0) TSTAMP(1);
-                tile_dot_q4(smem + (size_t)slot * cp->slot_bytes + (size_t)b0 * Q4T_GROUP_BYTES, xs, nu_row, g0 + b0, b1 - b0, lane, acc0, acc1);
+                tile_dot_q4(smem + (size_t)slot * cp->slot_bytes + (size_t)b0 * Q4T_GROUP_BYTES, xs, nu_row, g0 + b0, b1 - b0, lane, acc0, acc1,
+                            smem_u32(smem + cp->off_red) + 192u);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_n(empty_bar(cp, slot), gweight);
                 g0 += ng;
