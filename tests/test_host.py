@@ -230,6 +230,23 @@ print("FUZZ", len(blobs), ok, err)
 '''
 
 
+@pytest.mark.parametrize("alignment", [0, 24])
+def test_loader_rejects_a_bad_alignment(tmp_path, alignment):
+    """general.alignment is divided by (read_ggml.f90:176-196): zero would be a SIGFPE, a value that is not a
+    power of two misplaces the tensor data -- an error, not a crash"""
+    cfg = Config(**TINY)
+    p = str(tmp_path / "align.gguf")
+    fx.write_gguf(p, cfg, fx.synth_tensors(cfg, 0), alignment=64)
+    raw = bytearray(open(p, "rb").read())
+    key = b"general.alignment"
+    i = raw.index(key) + len(key) + 4  # key bytes, then the u32 value type, then the value
+    assert int.from_bytes(raw[i:i + 4], "little") == 64
+    raw[i:i + 4] = alignment.to_bytes(4, "little")
+    open(p, "wb").write(bytes(raw))
+    with pytest.raises(hostapi.HostError, match="alignment"):
+        hostapi.HostModel(p)
+
+
 def test_loader_survives_truncated_and_corrupted_files(tmp_path):
     """The reference prints a message and stops on a bad file (read_ggml.f90:122-125); the mirror must
     do the same -- an error, never a crash or an unbounded allocation -- whatever the bytes are.  Runs in
