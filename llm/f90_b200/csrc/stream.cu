@@ -374,6 +374,9 @@ __device__ __forceinline__ void vec_stage_release(const CtaPlan *, uint32_t s)
 // C[hi | lo][block] = 1032 sum(low elements) + 72 sum(high elements) (sums of the ROUNDED values, so
 // that the offset 1024 + q -> q - 8 cancels exactly).  All 32 lanes call it together: an aligned
 // group of 8 lanes holds the 8 float4 of one block.
+// f16 activations: byte offset of the lo plane behind the hi plane of an n-vector -- 64 bytes past a multiple of 128,
+// so that the four lanes reading hi and the four reading lo in one quarter-warp hit different banks (one wavefront)
+__host__ __device__ __forceinline__ uint32_t f16_lo_off(int n) { return (((uint32_t)n * 2u + 127u) & ~127u) + 64u; }
 template <int WT>
 __device__ __forceinline__ void store_x4(float *xs, int n, int j4, const float4 v, bool valid)
 {
@@ -382,7 +385,7 @@ __device__ __forceinline__ void store_x4(float *xs, int n, int j4, const float4 
     } else if constexpr (WT == WT_F16) {
         // f16 weights run on the tensor cores (tile_dot_f16): the activations are two f16 planes x = hi + lo
         // (hi = rn(x), lo = rn(x - hi): 22 bits of x, the products with f16 weights are exact in the f32
-        // accumulators), hi[n] then lo[n], each in column order
+        // accumulators), hi[n] then lo[n] (f16_lo_off bytes further), each in column order
         if (valid) {
             const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -391,7 +394,7 @@ __device__ __forceinline__ void store_x4(float *xs, int n, int j4, const float4 
             o.x = *reinterpret_cast<const uint32_t *>(&h01); o.y = *reinterpret_cast<const uint32_t *>(&h23);
             reinterpret_cast<uint2 *>(xs)[j4] = o;
             o.x = *reinterpret_cast<const uint32_t *>(&l01); o.y = *reinterpret_cast<const uint32_t *>(&l23);
-            reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(xs) + n)[j4] = o;
+            reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(xs) + f16_lo_off(n))[j4] = o;
         }
     } else {
         const int B = j4 >> 3, i = j4 & 7, t = i & 3, ngrp = q4t_groups(n);
@@ -1320,7 +1323,7 @@ __device__ __forceinline__ void run_tiles(CtaPlan *, int q, float rscale)
                 mbar_wait(full_bar(cp, s), full_par(s), 2);
                 if (c == 0) TSTAMP(1);
                 tile_dot_f16(smem + (size_t)slot * cp->slot_bytes, (uint32_t)vrows,
-                             reinterpret_cast<const __half *>(xs) + 8 * u0, (uint32_t)W.cols * 2u, nu, b0, b1, lane, dA, dB,
+                             reinterpret_cast<const __half *>(xs) + 8 * u0, f16_lo_off(W.cols), nu, b0, b1, lane, dA, dB,
                              smem_u32(smem + cp->off_red) + 192u);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_n(empty_bar(cp, slot), gweight);
@@ -1737,6 +1740,7 @@ int plan_stream(StreamParams &p, int grid, int max_smem_optin, int target_slot_b
         if (w.nch > MAX_NCH) return 1;
     }
     int xs_floats = p.emb > p.hid ? p.emb : p.hid;
+    if (p.wtype == WT_F16) xs_floats += 64;  // (the lo plane starts up to 192 bytes past the hi plane: f16_lo_off)
     if (tiled)  // f16 hi + lo activations in fragment order + two corrections per block (store_x4)
         for (int i = 0; i < 5; i++) xs_floats = xs_floats > p.ph[i].nu * 272 ? xs_floats : p.ph[i].nu * 272;
     xs_floats = (xs_floats + 31) & ~31;
