@@ -13,12 +13,12 @@
 //     mbarrier complete_tx) into a ring of shared-memory slots.  Nothing in the schedule depends
 //     on activations, so the producer never waits for a hand-over: while the consumers finish a
 //     phase and rebuild the activation vector, the ring keeps filling ("banked" weights).
-//   * 12 CONSUMER warps in groups of G (1-4, as many groups as the ring has slots).  The rows of a
-//     phase are cut into TILES of R rows (4; 16 for q4_0) and a tile's contraction range into chunks
+//   * 12 CONSUMER warps in groups of G (a divisor of 12, per phase).  The rows of a phase are cut
+//     into TILES of R rows (4 f32, 8 f16, 16 q4_0) and a tile's contraction range into chunks
 //     of one ring stage each.  A tile belongs to ONE group (tile t -> group t mod 12/G): its warps
 //     wait on the stage's `full` mbarrier, each dots its share of the columns of the R row segments
 //     with the activation vector in shared memory (one activation load serves R rows; f16 / q4_0
-//     dequantisation fused, f32 accumulation), they hand the slot back, and after the tile's last
+//     on mma.sync with the dequantisation fused, f32 accumulation), they hand the slot back, and after the tile's last
 //     chunk each reduces across its lanes, the group adds its G partial results through shared
 //     memory (a named barrier of the group only), and the group's first warp runs the tile's
 //     epilogue ITSELF -- RoPE + KV-cache append, SwiGLU, residual partials, logits -- publishing
@@ -53,10 +53,11 @@ constexpr int CONS_BAR = 1;         // named barrier id used by the consumer war
 // s mod NBAR in its phase (s / NBAR) mod 2.  A warp may wait for a stage long before the stages in
 // front of it have landed (its next tile is 11 tiles ahead); the one-bit mbarrier phase parity is
 // only unambiguous if the previous use of the same barrier (stage s - NBAR) has completed by then.
-// At most n_slots stages are in flight and a warp looks at most 23 tiles x 10 chunks ahead of the
-// oldest one, less than NBAR - n_slots.
+// At most n_slots stages are in flight and a warp looks at most 11 tiles (the other groups') x MAX_NCH chunks
+// ahead of the oldest one: 11 x 20 + 16 slots < NBAR.
 constexpr int NBAR = 256;
-constexpr int MAX_NCH = 24;         // chunks per tile (plan_stream enforces it)
+constexpr int MAX_NCH = 20;         // chunks per tile (plan_stream enforces it)
+static_assert((NCW - 1) * MAX_NCH + MAX_SLOTS < NBAR, "a full barrier could be waited on before its previous use completed");
 constexpr int ATT_PSTRIDE_PAD = 4;  // attention partial record = {m, l, -, -, acc[hs]}
 constexpr int ATT_MAX_CHUNK = 288;  // positions of one attention split: <= 256 rounded up to groups of 16, + slack
 

@@ -53,7 +53,7 @@ def test_plan_covers_every_matrix_once(model, wt, tp):
         # ---- every bulk copy: aligned, fits a slot
         assert (used["src"] % 16 == 0).all() and (used["bytes"] % 16 == 0).all()
         assert (used["bytes"] <= info["slot_bytes"]).all()
-        assert max(info["tile_chunks"]) <= 24 and all(r in (4, 8, 16) for r in info["tile_rows"])
+        assert max(info["tile_chunks"]) <= 20 and all(r in (4, 8, 16) for r in info["tile_rows"])
         for cta in (0, info["grid"] // 2, info["grid"] - 1):
             row = st[cta][st[cta]["bytes"] > 0]
             per_stage = np.bincount(row["stage"], weights=row["bytes"])
