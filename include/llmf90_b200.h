@@ -167,8 +167,9 @@ int llmf90_b200_get_stats(llmf90_b200_stats *out);
  * the list of bulk copies one token takes -- [embedding row][one layer: rms_att, its QKV rows, its Wo
  * rows, rms_ffn, its W13 rows, its W2 rows][rms_final, its classifier rows]; the kernel walks the layer
  * section n_layers times adding layer_stride16 * 16 bytes per layer.  A ring stage is one chunk of the
- * contraction range of one tile (tile_rows rows, owned by one consumer warp): one copy per row for
- * f32 / f16, one copy of whole 8-block groups for tiled q4_0.  Sources are in
+ * contraction range of one tile (tile_rows rows, owned by one group of tile_warps consumer warps) and ONE
+ * bulk copy: the f32 / f16 matrices are stored tile-major on the device (the chunk's segments of the
+ * tile's rows are contiguous), tiled q4_0 in whole 8-block groups.  Sources are in
  * a virtual address space: region k starts at LLMF90_PLAN_VBASE(k), k = 0..4 the five streamed
  * matrices (QKV, Wo, W13, W2, classifier) of this rank's shard, 5 the embedding table, 6 / 7 / 8 the
  * rms_att / rms_ffn / rms_final vectors.  The CPU test-suite uses it to check, for full-size models
@@ -183,7 +184,7 @@ typedef struct llmf90_b200_plan_info {
     int32_t sched_stride;             /* schedule entries reserved per CTA (unused ones: bytes = 0) */
     int32_t n_layers;
     int32_t rows[5], cols[5];         /* this rank's share of the five matrices                     */
-    int32_t tile_rows[5];             /* rows of a tile (the unit one consumer warp owns)           */
+    int32_t tile_rows[5];             /* rows of a tile (the unit one group of consumer warps owns) */
     int32_t tile_chunks[5];           /* ring stages a tile's contraction range is cut into         */
     int32_t tile_warps[5];            /* consumer warps that share one tile (a divisor of 12)       */
     int32_t reserved0;
