@@ -54,6 +54,9 @@ extern "C" {
                                     reference buckets of llmf90_b200_times); costs 5-8 % of the token
                                     time, so it is off by default: all forward time then goes to bucket 4.
                                     Also switched on by the environment variable LLMF90_PROFILE=1 */
+#define LLMF90_FLAG_PREFILL  4u  /* keep a second copy of the layer matrices in tensor-core operand order
+                                    (f16 hi / lo planes) so that llmf90_b200_prefill can run the prompt
+                                    positions as one batched tcgen05 pass; single-GPU */
 
 /* mirror of `type Config` (weight_module.f90:28-31) + dtype and placement */
 typedef struct llmf90_b200_config {
@@ -121,9 +124,26 @@ const char *llmf90_b200_last_error(void);
 int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, int32_t n,
                                 int32_t *out_tokens, float *elapsed_ms);
 
+/* The forced prompt positions of llama2.f90:379-385 as ONE batched pass (needs LLMF90_FLAG_PREFILL): after the
+ * call the KV cache holds the key / value rows of positions pos0 .. pos0 + n_tokens - 1 (1-based) for the input
+ * tokens tokens[0 .. n_tokens) -- what n_tokens calls of llmf90_b200_transformer would have left there; their
+ * logits, which the reference discards (llama2.f90:383-385), are not computed.  The caller continues with
+ * llmf90_b200_transformer(next_token, pos0 + n_tokens, logits).  llmf90_b200_generate_greedy does this itself for
+ * its prompt when the flag is set.  Prompts longer than 128 positions are taken in passes of 128. */
+int llmf90_b200_prefill(const int32_t *tokens, int32_t n_tokens, int32_t pos0);
+
+/* test aid: the key and value rows (n_kv_heads * head_size floats each; this rank's share under tensor
+ * parallelism) of cache position pos (1-based) in `layer` (0-based) */
+int llmf90_b200_debug_read_kv(int32_t layer, int32_t pos, float *k, float *v);
+
 /* ---- the inner subroutines as separately callable operators (host pointers in/out) ---- */
 /* y(ix) = dot_product(x, w(:,ix)), ix = 1..rows; w is `rows` rows of `cols` weights of `wtype` */
 int llmf90_b200_matvec(const void *w, int32_t wtype, int32_t rows, int32_t cols, const float *x,
+                       float *y);
+/* the same dot products for n_pos (1..128) activation vectors at once -- the GEMM of the batched prompt pass
+ * (tcgen05 tensor cores, f16 hi + lo operand planes, f32 accumulation): y[p][ix] = dot_product(x[p][:], w(:,ix));
+ * x is [n_pos][cols], y is [n_pos][rows] */
+int llmf90_b200_matmul(const void *w, int32_t wtype, int32_t rows, int32_t cols, const float *x, int32_t n_pos,
                        float *y);
 /* llama2.f90:450-457 */
 int llmf90_b200_rmsnorm(const float *x, const float *w, int32_t n, float *out);

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
-CUDA_SRCS = ["ops.cu", "stream.cu", "engine.cu"]
+CUDA_SRCS = ["ops.cu", "stream.cu", "prefill.cu", "engine.cu"]
 CUDA_HDRS = ["common.cuh", "kernels.cuh", os.path.join(ROOT, "include", "llmf90_b200.h")]
 CUDA_LIB = os.path.join(HERE, "libllmf90_b200.so")
 HOST_LIB = os.path.join(HERE, "libllmf90_host.so")

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "libllmf90_b200.so")
 
 FLAG_GRANULAR = 1
 FLAG_PROFILE = 2  # fused kernel with per-phase timers (slower; phase_times / debug_trace tools)
+FLAG_PREFILL = 4  # second copy of the layer matrices in tensor-core operand order: batched prompt pass
 
 EXPORTS = [
     "llmf90_b200_init", "llmf90_b200_transformer", "llmf90_b200_times", "llmf90_b200_reset",
@@ -25,7 +26,7 @@ EXPORTS = [
     "llmf90_b200_matvec", "llmf90_b200_rmsnorm", "llmf90_b200_softmax", "llmf90_b200_rope",
     "llmf90_b200_tp_export", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
     "llmf90_b200_bench_device_loop", "llmf90_b200_phase_times", "llmf90_b200_debug_trace",
-    "llmf90_b200_plan",
+    "llmf90_b200_plan", "llmf90_b200_prefill", "llmf90_b200_debug_read_kv", "llmf90_b200_matmul",
 ]
 
 
@@ -95,6 +96,9 @@ def load() -> C.CDLL:
     L.llmf90_b200_tp_connect.argtypes = [vp, C.c_int32]
     L.llmf90_b200_get_stats.argtypes = [C.POINTER(CStats)]
     L.llmf90_b200_bench_device_loop.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp]
+    L.llmf90_b200_prefill.argtypes = [ip, C.c_int32, C.c_int32]
+    L.llmf90_b200_debug_read_kv.argtypes = [C.c_int32, C.c_int32, fp, fp]
+    L.llmf90_b200_matmul.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, C.c_int32, fp]
     L.llmf90_b200_plan.argtypes = [C.POINTER(CConfig), C.c_int32, C.c_int32, C.POINTER(CPlanInfo), vp, C.c_int64]
     for name in EXPORTS:
         if name != "llmf90_b200_last_error":
@@ -122,14 +126,15 @@ class Engine:
     """The process-wide engine singleton behind the C ABI."""
 
     def __init__(self, weights: Weights, device: int = 0, granular: bool = False, tp_rank: int = 0,
-                 tp_size: int = 1, profile: bool = False):
+                 tp_size: int = 1, profile: bool = False, prefill: bool = False):
         self.L = load()
         c = weights.cfg
         self.cfg = c
         self.tp_rank, self.tp_size = tp_rank, tp_size
         cc = CConfig(c.emb_dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads, c.vocab_size,
                      c.seq_len, c.wtype, device, tp_rank, tp_size,
-                     (FLAG_GRANULAR if granular else 0) | (FLAG_PROFILE if profile else 0))
+                     (FLAG_GRANULAR if granular else 0) | (FLAG_PROFILE if profile else 0) |
+                     (FLAG_PREFILL if prefill else 0))
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
         _check(self.L.llmf90_b200_init(C.byref(cc), ptr(weights.token_embedding_table),
                                        ptr(weights.rms_att_weight), ptr(weights.wqkv), ptr(weights.wo),
@@ -156,6 +161,18 @@ class Engine:
             out = np.empty(self.cfg.vocab_size, np.float32)
         _check(self.L.llmf90_b200_transformer(token, pos, _fp(out)))
         return out
+
+    def prefill(self, tokens, pos0: int = 1) -> None:
+        """KV rows of positions pos0.. for the input tokens, as one batched tcgen05 pass (llama2.f90:379-385)."""
+        t = np.ascontiguousarray(tokens, np.int32)
+        _check(self.L.llmf90_b200_prefill(_ip(t), len(t), pos0))
+
+    def read_kv(self, layer: int, pos: int):
+        """The key and value rows of cache position pos (1-based) in `layer` (0-based)."""
+        n = self.cfg.n_kv_heads * (self.cfg.emb_dim // self.cfg.n_heads) // max(1, min(self.tp_size, self.cfg.n_kv_heads))
+        k, v = np.empty(n, np.float32), np.empty(n, np.float32)
+        _check(self.L.llmf90_b200_debug_read_kv(layer, pos, _fp(k), _fp(v)))
+        return k, v
 
     def generate_greedy(self, prompt_tokens, n: int):
         pt = np.ascontiguousarray(prompt_tokens, np.int32)
@@ -249,6 +266,15 @@ def matvec(w: np.ndarray, wtype: int, rows: int, cols: int, x: np.ndarray) -> np
     y = np.empty(rows, np.float32)
     w = np.ascontiguousarray(w)
     _check(load().llmf90_b200_matvec(w.ctypes.data_as(C.c_void_p), wtype, rows, cols, _fp(x), _fp(y)))
+    return y
+
+
+def matmul(w: np.ndarray, wtype: int, rows: int, cols: int, x: np.ndarray) -> np.ndarray:
+    """y[p] = W x[p] for the rows of x at once: the tcgen05 GEMM of the batched prompt pass."""
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty((x.shape[0], rows), np.float32)
+    w = np.ascontiguousarray(w)
+    _check(load().llmf90_b200_matmul(w.ctypes.data_as(C.c_void_p), wtype, rows, cols, _fp(x), x.shape[0], _fp(y)))
     return y
 
 

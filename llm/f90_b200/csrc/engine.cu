@@ -76,6 +76,7 @@ struct Engine {
     StreamParams sp{};
     StreamPlan plan{};
     cudaGraphExec_t graph = nullptr;
+    Prefill *pf = nullptr;  // batched prompt pass (LLMF90_FLAG_PREFILL), prefill.cu
     int graph_kernels = 0;
     // stats
     uint64_t launches = 0, forwards = 0, weight_bytes = 0, active_bytes = 0;
@@ -94,6 +95,7 @@ cudaError_t dalloc(T **p, size_t n)
 void release_all()
 {
     if (E.graph) cudaGraphExecDestroy(E.graph);
+    prefill_destroy(E.pf);
     void *ptrs[] = {E.d_emb, E.d_wqkv, E.d_wo, E.d_w13, E.d_w2, E.d_wcls, E.d_rms_att, E.d_rms_ffn,
                     E.d_rms_final, E.d_rope, E.d_kc, E.d_vc, E.d_x, E.d_xb, E.d_qkv, E.d_att,
                     E.d_att_part, E.d_h13, E.d_hb, (void *)E.d_times, E.d_tokpos, E.d_forced,
@@ -435,6 +437,30 @@ inline int stream_target_slot(bool tiled, int wtype, int emb)
 constexpr int STREAM_STATIC_SMEM = 3072;  // the kernel's static shared memory (plan, RoPE row, timers)
 }  // namespace
 
+// ---- the batched prompt pass: positions pos0 .. pos0 + n - 1 of host tokens, in passes of prefill_max_positions()
+namespace {
+int prefill_positions(const int32_t *tokens, int n, int pos0, float *ms)
+{
+    const int maxp = prefill_max_positions();
+    const PrefillRun r{E.d_emb, E.d_rms_att, E.d_rms_ffn, E.d_rope, E.d_kc, E.d_vc};
+    CK(cudaEventRecord(E.ev0, E.st));
+    for (int off = 0; off < n; off += maxp) {
+        const int m = std::min(maxp, n - off);
+        CK(cudaMemcpyAsync(prefill_token_buffer(E.pf), tokens + off, (size_t)m * 4, cudaMemcpyHostToDevice, E.st));
+        int k = 0;
+        CK(prefill_run(E.pf, r, m, pos0 + off, E.st, &k));
+        E.launches += (uint64_t)k;
+    }
+    CK(cudaEventRecord(E.ev1, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, E.ev0, E.ev1));
+    E.host_times[3] += t;
+    if (ms) *ms = t;
+    return 0;
+}
+}  // namespace
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -526,6 +552,14 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             return fail("model rows do not fit the shared-memory ring (row stride too large)");
         }
     }
+    if (c.flags & LLMF90_FLAG_PREFILL) {
+        // a second copy of the four layer matrices, f16 planes in tensor-core operand order (prefill.cu)
+        if (tp > 1) { release_all(); return fail("LLMF90_FLAG_PREFILL: the batched prompt pass is single-GPU"); }
+        const PrefillDims pd{emb, hid_full, L, c.n_heads, c.n_kv_heads, hs, kv_full, emb + 2 * kv_full, c.seq_len, wt};
+        cudaError_t e = prefill_create(&E.pf, pd, E.n_sms);
+        if (e != cudaSuccess) { release_all(); return fail("prefill_create: %s", cudaGetErrorString(e)); }
+        E.weight_bytes += prefill_weight_bytes(pd);
+    }
     {
         const int nqkv_full = emb + 2 * kv_full;
         size_t stage_bytes = std::max({(size_t)V * hb_e, (size_t)2 * hid_full * hb_e, (size_t)emb * hb_hf,
@@ -566,18 +600,28 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
             rc |= upload_matrix(d_qkv + mbytes(att + kvl, emb), nullptr, wt, nqkv_full, emb, kvl, 0, emb, 0,
                                 emb + kv_full + kv_row0, 0, stage, stage_bytes, tiled);
             if (!rc) rc |= to_tiles(0, d_qkv);
+            auto pf_pack = [&](int m) -> int {  // the staging buffer holds the layer's host-format matrix m
+                if (!E.pf || rc) return 0;
+                CK(prefill_pack_weights(E.pf, m, l, stage, E.st));
+                CK(cudaStreamSynchronize(E.st));
+                return 0;
+            };
+            rc |= pf_pack(0);
             // Wo: all rows, the input columns of this rank's heads
             rc |= upload_matrix(E.d_wo + (size_t)l * mbytes(emb, att), s_wo, wt, emb, emb, emb, rank * att, att, 0, 0, 0,
                                 stage, stage_bytes, tiled);
             if (!rc) rc |= to_tiles(1, E.d_wo + (size_t)l * mbytes(emb, att));
+            rc |= pf_pack(1);
             // gate/up rows of this rank's FFN slice, interleaved: row 2i = W1 row i, row 2i+1 = W3 row i
             rc |= upload_matrix(E.d_w13 + (size_t)l * mbytes(2 * hid, emb), s_w13, wt, 2 * hid_full, emb, 2 * hid, 0,
                                 emb, 1, rank * hid, hid_full, stage, stage_bytes, tiled);
             if (!rc) rc |= to_tiles(2, E.d_w13 + (size_t)l * mbytes(2 * hid, emb));
+            rc |= pf_pack(2);
             // W2: all rows, the input columns of this rank's FFN slice
             rc |= upload_matrix(E.d_w2 + (size_t)l * mbytes(emb, hid), s_w2, wt, emb, hid_full, emb, rank * hid, hid, 0, 0,
                                 0, stage, stage_bytes, tiled);
             if (!rc) rc |= to_tiles(3, E.d_w2 + (size_t)l * mbytes(emb, hid));
+            rc |= pf_pack(3);
         }
         cudaFree(stage);
         if (tmp) cudaFree(tmp);
@@ -797,11 +841,53 @@ int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, 
     }
     CK(cudaMemcpyAsync(E.d_forced, forced.data(), (size_t)E.cfg.seq_len * 4, cudaMemcpyHostToDevice, E.st));
     CK(cudaStreamSynchronize(E.st));
+    // With the batched prompt pass the forced positions (inputs BOS, prompt[0 .. m-2]; llama2.f90:376-385) are one
+    // pass over the weights; the loop then starts at the first position whose logits are used.  At least one
+    // position is left to the loop.
+    const int m = E.pf ? std::min(n_prompt, n - 1) : 0;
+    if (m >= 1) {
+        std::vector<int32_t> in(m);
+        in[0] = 2;  // BOS
+        for (int i = 1; i < m; i++) in[i] = prompt_tokens[i - 1];
+        float pf_ms = 0.f, loop_ms = 0.f;
+        if (prefill_positions(in.data(), m, 1, &pf_ms)) return 1;
+        if (device_loop(prompt_tokens[m - 1], m + 1, n - m, E.d_forced, E.d_out_tokens, nullptr, &loop_ms)) return 1;
+        CK(cudaMemcpy(out_tokens, E.d_out_tokens, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) out_tokens[i] = prompt_tokens[i];
+        if (elapsed_ms) *elapsed_ms = pf_ms + loop_ms;  // every position is inside: there is no separate first token to leave out
+        return 0;
+    }
     float after_first = 0.f;
     if (device_loop(2 /* BOS, llama2.f90:376 */, 1, n, E.d_forced, E.d_out_tokens, &after_first, nullptr))
         return 1;
     CK(cudaMemcpy(out_tokens, E.d_out_tokens, (size_t)n * 4, cudaMemcpyDeviceToHost));
     if (elapsed_ms) *elapsed_ms = after_first;
+    return 0;
+}
+
+// ---------------------------------------------------------------- batched prompt pass (prefill.cu)
+
+int llmf90_b200_prefill(const int32_t *tokens, int32_t n_tokens, int32_t pos0)
+{
+    if (!E.ready) return fail("llmf90_b200_prefill: engine not initialised");
+    if (!E.pf) return fail("llmf90_b200_prefill: initialise the engine with LLMF90_FLAG_PREFILL");
+    if (!tokens || n_tokens < 1) return fail("prefill: no tokens");
+    if (pos0 < 1 || pos0 + n_tokens - 1 > E.cfg.seq_len)
+        return fail("prefill: positions %d..%d out of range 1..%d", pos0, pos0 + n_tokens - 1, E.cfg.seq_len);
+    if ((size_t)(pos0 + n_tokens) * 4 > 200 * 1024) return fail("prefill: more than 51199 positions of attention scores");
+    for (int i = 0; i < n_tokens; i++)
+        if (tokens[i] < 1 || tokens[i] > E.cfg.vocab_size) return fail("prefill: token %d out of range 1..%d", tokens[i], E.cfg.vocab_size);
+    return prefill_positions(tokens, n_tokens, pos0, nullptr);
+}
+
+int llmf90_b200_debug_read_kv(int32_t layer, int32_t pos, float *k, float *v)
+{
+    if (!E.ready) return fail("engine not initialised");
+    if (layer < 0 || layer >= E.cfg.n_layers || pos < 1 || pos > E.cfg.seq_len || !k || !v) return fail("read_kv: bad argument");
+    CK(cudaStreamSynchronize(E.st));
+    const size_t off = ((size_t)layer * E.cfg.seq_len + (size_t)(pos - 1)) * E.kv;
+    CK(cudaMemcpy(k, E.d_kc + off, (size_t)E.kv * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v, E.d_vc + off, (size_t)E.kv * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -930,6 +1016,28 @@ int llmf90_b200_matvec(const void *w, int32_t wtype, int32_t rows, int32_t cols,
     CK(launch_repack(d_src, wtype, cols, d_w, rows, 0, cols, 0, 0, 0, t.s));
     CK(launch_matvec(d_w, wtype, rows, cols, d_x, nullptr, d_y, t.s));
     CK(cudaMemcpyAsync(y, d_y, (size_t)rows * 4, cudaMemcpyDeviceToHost, t.s));
+    CK(cudaStreamSynchronize(t.s));
+    return 0;
+}
+
+int llmf90_b200_matmul(const void *w, int32_t wtype, int32_t rows, int32_t cols, const float *x, int32_t n_pos, float *y)
+{
+    if (!w || !x || !y || rows <= 0 || cols <= 0) return fail("matmul: bad argument");
+    if (wtype < 0 || wtype > 2) return fail("matmul: unknown wtype");
+    if (n_pos < 1 || n_pos > prefill_max_positions()) return fail("matmul: n_pos must be 1..%d", prefill_max_positions());
+    const int colmul = wtype == WT_Q4_0 ? 32 : (wtype == WT_F16 ? 8 : 4);
+    if (cols % colmul) return fail("matmul: cols must be a multiple of %d", colmul);
+    TmpStream t;
+    if (op_begin(t)) return 1;
+    int dev = 0, n_sms = 148;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    uint8_t *d_w; float *d_x, *d_y;
+    if (op_buf(t, &d_w, (size_t)rows * host_row_bytes(wtype, cols), w)) return 1;
+    if (op_buf(t, &d_x, (size_t)n_pos * cols, x)) return 1;
+    if (op_buf(t, &d_y, (size_t)n_pos * rows, nullptr)) return 1;
+    CK(prefill_gemm_op(d_w, wtype, rows, cols, d_x, n_pos, d_y, n_sms, t.s));
+    CK(cudaMemcpyAsync(y, d_y, (size_t)n_pos * rows * 4, cudaMemcpyDeviceToHost, t.s));
     CK(cudaStreamSynchronize(t.s));
     return 0;
 }

@@ -159,4 +159,27 @@ cudaError_t launch_stream(const StreamParams &p, const StreamPlan &plan, bool pr
 // streams (dst, same size; not in place); call after plan_stream
 cudaError_t launch_tile_pass(const StreamParams &p, int phase, int grid, const uint8_t *src, uint8_t *dst, cudaStream_t st);
 
+// ---------------------------------------------------------------- batched prompt pass (prefill.cu)
+// The KV rows of up to prefill_max_positions() prompt positions per call, GEMMs on tcgen05 (see prefill.cu).
+struct PrefillDims { int emb, hid, L, H, KVH, hs, kv, nqkv, seq, wtype; };
+struct PrefillRun {
+    const uint8_t *emb_table;            // device row format (plain rows)
+    const float *rms_att, *rms_ffn;      // [L][emb]
+    const float2 *rope_tab;              // [seq][hs/2]
+    float *kc, *vc;                      // [L][seq][kv]
+};
+struct Prefill;
+size_t prefill_weight_bytes(const PrefillDims &d);   // HBM the operand-order copy of the layer matrices takes
+cudaError_t prefill_create(Prefill **out, const PrefillDims &d, int n_sms);
+void prefill_destroy(Prefill *pf);
+int prefill_max_positions();
+int *prefill_token_buffer(Prefill *pf);              // device int[prefill_max_positions()]: the input tokens of a pass
+// matrix 0 QKV, 1 Wo, 2 W1|W3, 3 W2 of `layer`, from the HOST-format matrix already copied to the device
+cudaError_t prefill_pack_weights(Prefill *pf, int matrix, int layer, const uint8_t *src_host_format, cudaStream_t st);
+// cache rows of positions pos0 .. pos0 + n - 1 (1-based) of every layer; *launches = kernels enqueued
+cudaError_t prefill_run(Prefill *pf, const PrefillRun &r, int n, int pos0, cudaStream_t st, int *launches);
+// the tcgen05 GEMM on its own: y[P][N] = x[P][K] . W^T, W in host format on the device (synchronises `st`)
+cudaError_t prefill_gemm_op(const uint8_t *w_host_format, int wtype, int N, int K, const float *x, int P, float *y,
+                            int n_sms, cudaStream_t st);
+
 }  // namespace llmf90
