@@ -58,6 +58,13 @@ extern "C" {
                                     (f16 hi / lo planes) so that llmf90_b200_prefill can run the prompt
                                     positions as one batched tcgen05 pass; single-GPU */
 
+#define LLMF90_FLAG_CLS_Q6K  8u  /* wcls points at ggml Q6_K super-blocks (type 14: 210 bytes per 256 weights, as in the
+                                    file) instead of `wtype` rows: the output.weight of stock llama.cpp q4_0 GGUFs,
+                                    which the reference's type switch stops at (read_ggml.f90:613-635).  The fused
+                                    kernel streams ONE storage type, so such a model runs on the granular engine
+                                    (the flag implies LLMF90_FLAG_GRANULAR); single-GPU; emb_dim % 256 == 0 */
+#define LLMF90_WTYPE_Q6_K 14  /* accepted by llmf90_b200_matvec only */
+
 /* mirror of `type Config` (weight_module.f90:28-31) + dtype and placement */
 typedef struct llmf90_b200_config {
     int32_t emb_dim;      /* llama2.f90:102 */

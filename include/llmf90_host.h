@@ -15,6 +15,7 @@ typedef struct llmf90_host_model llmf90_host_model;
 
 typedef struct llmf90_host_config {
     int32_t emb_dim, hidden_dim, n_layers, n_heads, n_kv_heads, vocab_size, seq_len, wtype;
+    int32_t cls_wtype; /* storage of tensor 8 (wcls): wtype, or 14 = ggml Q6_K blocks (stock llama.cpp q4_0 files) */
 } llmf90_host_config;
 
 /* NULL on failure; llmf90_host_last_error() says why.  verbose: 1 = the reference's -v listing,

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "libllmf90_b200.so")
 
 FLAG_GRANULAR = 1
 FLAG_PROFILE = 2  # fused kernel with per-phase timers (slower; phase_times / debug_trace tools)
+FLAG_CLS_Q6K = 8  # wcls is ggml Q6_K super-blocks (stock llama.cpp q4_0 files); implies the granular engine
 FLAG_PREFILL = 4  # second copy of the layer matrices in tensor-core operand order: batched prompt pass
 
 EXPORTS = [
@@ -134,7 +135,8 @@ class Engine:
         cc = CConfig(c.emb_dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads, c.vocab_size,
                      c.seq_len, c.wtype, device, tp_rank, tp_size,
                      (FLAG_GRANULAR if granular else 0) | (FLAG_PROFILE if profile else 0) |
-                     (FLAG_PREFILL if prefill else 0))
+                     (FLAG_PREFILL if prefill else 0) |
+                     (FLAG_CLS_Q6K if getattr(weights, "cls_wtype", c.wtype) == 14 else 0))
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
         _check(self.L.llmf90_b200_init(C.byref(cc), ptr(weights.token_embedding_table),
                                        ptr(weights.rms_att_weight), ptr(weights.wqkv), ptr(weights.wo),

@@ -72,6 +72,7 @@ struct Engine {
     int *h_err = nullptr, *d_err = nullptr;  // host-mapped error word the kernel sets when a tensor-parallel poll times out
     // drivers
     bool use_stream = true;
+    bool cls_q6k = false;  // wcls is ggml Q6_K super-blocks (LLMF90_FLAG_CLS_Q6K): granular engine, Q6_K classifier kernel
     bool prof = false;  // instrumented fused kernel (LLMF90_FLAG_PROFILE / LLMF90_PROFILE=1)
     StreamParams sp{};
     StreamPlan plan{};
@@ -205,7 +206,9 @@ int enqueue_granular(bool count)
         CK(launch_matvec(E.d_w2 + (size_t)l * emb * rs_h, wt, emb, hid, E.d_hb, E.d_x, E.d_x, E.st)); k++;
     }
     CK(launch_rmsnorm(E.d_x, E.d_rms_final, E.d_xb, emb, E.st)); k++;
-    CK(launch_matvec(E.d_wcls, wt, c.vocab_size, emb, E.d_xb, nullptr, logits_dev(), E.st)); k++;
+    if (E.cls_q6k) CK(launch_matvec_q6k(E.d_wcls, c.vocab_size, emb, E.d_xb, logits_dev(), E.st));
+    else CK(launch_matvec(E.d_wcls, wt, c.vocab_size, emb, E.d_xb, nullptr, logits_dev(), E.st));
+    k++;
     if (count) E.graph_kernels = k;
     return 0;
 }
@@ -363,7 +366,7 @@ int check_config(const llmf90_b200_config &c, int *hs_out, int *tp_out, int *ran
     if (tp != 1 && tp != 2 && tp != 4 && tp != 8) return fail("config: tp_size %d not in {1,2,4,8}", tp);
     if (rank < 0 || rank >= tp) return fail("config: tp_rank %d out of range", rank);
     if (tp > 1) {
-        if (c.flags & LLMF90_FLAG_GRANULAR) return fail("the granular forward is single-GPU only");
+        if (c.flags & (LLMF90_FLAG_GRANULAR | LLMF90_FLAG_CLS_Q6K)) return fail("the granular forward (and with it a Q6_K classifier) is single-GPU only");
         // fewer KV heads than ranks: each KV head is replicated on tp / n_kv_heads ranks
         if (c.n_heads % tp || (c.n_kv_heads % tp && tp % c.n_kv_heads))
             return fail("config: n_heads %d must be a multiple of tp_size %d, n_kv_heads %d a multiple or a divisor",
@@ -371,6 +374,8 @@ int check_config(const llmf90_b200_config &c, int *hs_out, int *tp_out, int *ran
         if (c.hidden_dim % (tp * colmul) || (c.emb_dim / tp) % colmul || c.vocab_size % tp)
             return fail("config: hidden_dim / emb_dim / vocab_size do not split %d ways for this wtype", tp);
     }
+    if ((c.flags & LLMF90_FLAG_CLS_Q6K) && (c.emb_dim % 256 || c.emb_dim > 12288))
+        return fail("config: a Q6_K classifier needs emb_dim to be a multiple of 256 (and at most 12288)");
     *hs_out = hs; *tp_out = tp; *rank_out = rank;
     return 0;
 }
@@ -495,7 +500,8 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     E.cfg.tp_size = tp; E.cfg.tp_rank = rank;
     E.hs = hs; E.kv_mul = c.n_heads / c.n_kv_heads;
     E.n_sms = prop.multiProcessorCount;
-    E.use_stream = !(c.flags & LLMF90_FLAG_GRANULAR);
+    E.cls_q6k = (c.flags & LLMF90_FLAG_CLS_Q6K) != 0;
+    E.use_stream = !(c.flags & LLMF90_FLAG_GRANULAR) && !E.cls_q6k;
     E.prof = (c.flags & LLMF90_FLAG_PROFILE) != 0;
     if (const char *s = getenv("LLMF90_PROFILE")) E.prof = E.prof || atoi(s) != 0;
     const int emb = c.emb_dim, L = c.n_layers, V = c.vocab_size, wt = c.wtype;
@@ -524,18 +530,19 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
     CK(dalloc(&E.d_wo, (size_t)L * mbytes(emb, att)));
     CK(dalloc(&E.d_w13, (size_t)L * mbytes(2 * hid, emb)));
     CK(dalloc(&E.d_w2, (size_t)L * mbytes(emb, hid)));
-    CK(dalloc(&E.d_wcls, mbytes(Vl, emb)));
+    const size_t cls_bytes = E.cls_q6k ? (size_t)Vl * (emb / 256) * 210 : (size_t)Vl * rs_e;  // classifier bytes in HBM
+    CK(dalloc(&E.d_wcls, E.cls_q6k ? cls_bytes : mbytes(Vl, emb)));
     CK(dalloc(&E.d_rms_att, (size_t)L * emb));
     CK(dalloc(&E.d_rms_ffn, (size_t)L * emb));
     CK(dalloc(&E.d_rms_final, (size_t)emb));
-    E.weight_bytes = (size_t)V * rs_e + (size_t)Vl * rs_e +
+    E.weight_bytes = (size_t)V * rs_e + cls_bytes +
                      (size_t)L * ((size_t)nqkv * rs_e + (size_t)emb * rs_a + (size_t)2 * hid * rs_e + (size_t)emb * rs_h) +
                      (size_t)(2 * L + 1) * emb * 4;
     // algorithmic bytes per token on this GPU, host row sizes
     const size_t hb_e = host_row_bytes(wt, emb), hb_hf = host_row_bytes(wt, hid_full);
     E.active_bytes = (size_t)L * ((size_t)(nqkv + 2 * hid) * hb_e + (size_t)emb * host_row_bytes(wt, att) +
                                   (size_t)emb * host_row_bytes(wt, hid) + 2 * (size_t)emb * 4) +
-                     (size_t)Vl * hb_e + (size_t)emb * 4 + hb_e;
+                     (E.cls_q6k ? cls_bytes : (size_t)Vl * hb_e) + (size_t)emb * 4 + hb_e;
     if (E.use_stream) {
         // the fused kernel's plan comes first: the f32 / f16 matrices are laid out in the order it streams them
         int coop = 0, smem_optin = 0;
@@ -583,7 +590,10 @@ int llmf90_b200_init(const llmf90_b200_config *cfg, const void *tok_emb, const f
         };
         int rc = 0;
         rc |= upload_matrix(E.d_emb, tok_emb, wt, V, emb, V, 0, emb, 0, 0, 0, stage, stage_bytes);
-        rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, Vl, 0, emb, 0, rank * Vl, 0, stage, stage_bytes, tiled);
+        if (E.cls_q6k) {  // file-format super-blocks, consumed as they are
+            if (cudaMemcpy(E.d_wcls, wcls, cls_bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc |= fail("upload of the Q6_K classifier failed");
+        } else
+            rc |= upload_matrix(E.d_wcls, wcls, wt, V, emb, Vl, 0, emb, 0, rank * Vl, 0, stage, stage_bytes, tiled);
         if (!rc) rc |= to_tiles(4, E.d_wcls);
         for (int l = 0; l < L && !rc; l++) {
             const uint8_t *s_qkv = (const uint8_t *)wqkv + (size_t)l * nqkv_full * hb_e;
@@ -931,7 +941,7 @@ int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_
     if (n_sms <= 0 || smem_optin <= STREAM_STATIC_SMEM) return fail("plan: bad device description");
     int hs, tp, rank;
     if (check_config(*cfg, &hs, &tp, &rank)) return 1;
-    if (cfg->flags & LLMF90_FLAG_GRANULAR) return fail("plan: the granular forward has no ring plan");
+    if (cfg->flags & (LLMF90_FLAG_GRANULAR | LLMF90_FLAG_CLS_Q6K)) return fail("plan: the granular forward has no ring plan");
     const bool tiled = cfg->wtype == WT_Q4_0;
     const uint8_t *bases[5];
     for (int i = 0; i < 5; i++) bases[i] = reinterpret_cast<const uint8_t *>(LLMF90_PLAN_VBASE(i));
@@ -1003,6 +1013,19 @@ int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_
 int llmf90_b200_matvec(const void *w, int32_t wtype, int32_t rows, int32_t cols, const float *x, float *y)
 {
     if (!w || !x || !y || rows <= 0 || cols <= 0) return fail("matvec: bad argument");
+    if (wtype == LLMF90_WTYPE_Q6_K) {  // ggml super-blocks straight from the file
+        if (cols % 256 || cols > 12288) return fail("matvec: Q6_K needs cols to be a multiple of 256, at most 12288");
+        TmpStream t;
+        if (op_begin(t)) return 1;
+        uint8_t *d_w; float *d_x, *d_y;
+        if (op_buf(t, &d_w, (size_t)rows * (cols / 256) * 210, w)) return 1;
+        if (op_buf(t, &d_x, (size_t)cols, x)) return 1;
+        if (op_buf(t, &d_y, (size_t)rows, nullptr)) return 1;
+        CK(launch_matvec_q6k(d_w, rows, cols, d_x, d_y, t.s));
+        CK(cudaMemcpyAsync(y, d_y, (size_t)rows * 4, cudaMemcpyDeviceToHost, t.s));
+        CK(cudaStreamSynchronize(t.s));
+        return 0;
+    }
     if (wtype < 0 || wtype > 2) return fail("matvec: unknown wtype");
     const int colmul = wtype == WT_Q4_0 ? 32 : (wtype == WT_F16 ? 8 : 4);
     if (cols % colmul) return fail("matvec: cols must be a multiple of %d", colmul);

@@ -14,6 +14,7 @@ size_t row_bytes(int wtype, int n)
 {
     if (wtype == 0) return (size_t)n * 4;
     if (wtype == 1) return (size_t)n * 2;
+    if (wtype == 14) return (size_t)n / 256 * 210;  // Q6_K super-blocks
     return (size_t)n / 32 * 18;
 }
 
@@ -223,7 +224,14 @@ Model load_gguf(const std::string &path, bool verbose, bool print_offset)
     const int nqkv = e + 2 * kv;
     Weights &w = m.w;
     w.token_embedding_table.resize((size_t)V * rb_e);
-    w.wcls.resize((size_t)V * rb_e);
+    // output.weight: the model's type, or Q6_K -- llama.cpp's q4_0 files keep the classifier in ggml type 14, which
+    // the reference's type switch (read_ggml.f90:613-635) stops at; SURVEY.md 8f1
+    c.cls_wtype = (int)need("output.weight").type;
+    if (c.cls_wtype != wt && c.cls_wtype != 14)
+        throw std::runtime_error("Type not supported: output.weight has ggml tensor type " + std::to_string(c.cls_wtype) +
+                                 " (the model's type and Q6_K are)");
+    if (c.cls_wtype == 14 && e % 256) throw std::runtime_error("Q6_K output.weight needs an embedding length that is a multiple of 256");
+    w.wcls.resize((size_t)V * row_bytes(c.cls_wtype, e));
     w.wqkv.resize((size_t)L * nqkv * rb_e);
     w.wo.resize((size_t)L * e * rb_e);
     w.w13.resize((size_t)L * 2 * h * rb_e);
@@ -247,7 +255,7 @@ Model load_gguf(const std::string &path, bool verbose, bool print_offset)
         read_into(p + "ffn_down.weight", w.w2.data() + (size_t)l * e * rb_h, e, h, wt);
     }
     read_into("output_norm.weight", reinterpret_cast<uint8_t *>(w.rms_final_weight.data()), 1, e, 0);
-    read_into("output.weight", w.wcls.data(), V, e, wt);  // a separate classifier is required (:406)
+    read_into("output.weight", w.wcls.data(), V, e, c.cls_wtype);  // a separate classifier is required (:406)
 
     // ---- vocabulary: a leading U+2581 becomes one space (read_ggml.f90:483-503)
     if ((int)m.vocab.tokens.size() != V) throw std::runtime_error("key not found: tokenizer.ggml.tokens");

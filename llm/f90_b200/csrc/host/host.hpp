@@ -17,6 +17,7 @@ namespace llmhost {
 struct ModelConfig {  // type Config (weight_module.f90:28-31) + storage type
     int emb_dim = 0, hidden_dim = 0, n_layers = 0, n_heads = 0, n_kv_heads = 0, vocab_size = 0, seq_len = 0;
     int wtype = 0;  // 0 f32, 1 f16, 2 q4_0 (ggml tensor type ids)
+    int cls_wtype = 0;  // storage of wcls: wtype, or 14 (ggml Q6_K: the output.weight of stock llama.cpp q4_0 files)
 };
 
 // TransformerWeights (weight_module.f90:13-26) in the C view of the Fortran layout; 2-D tensors

@@ -47,7 +47,7 @@ int llmf90_host_get_config(const llmf90_host_model *m, llmf90_host_config *out)
 {
     if (!m || !out) return 1;
     const auto &c = m->m.cfg;
-    *out = {c.emb_dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads, c.vocab_size, c.seq_len, c.wtype};
+    *out = {c.emb_dim, c.hidden_dim, c.n_layers, c.n_heads, c.n_kv_heads, c.vocab_size, c.seq_len, c.wtype, c.cls_wtype};
     return 0;
 }
 

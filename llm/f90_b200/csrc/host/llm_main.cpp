@@ -128,6 +128,7 @@ int main(int argc, char **argv)
     cfg.seq_len = m.cfg.seq_len; cfg.wtype = m.cfg.wtype; cfg.device = a.device >= 0 ? a.device : a.tp_rank;
     cfg.tp_rank = a.tp_rank; cfg.tp_size = a.tp_size;
     cfg.flags = a.granular ? LLMF90_FLAG_GRANULAR : 0;
+    if (m.cfg.cls_wtype == 14) cfg.flags |= LLMF90_FLAG_CLS_Q6K;  // stock llama.cpp q4_0 file: Q6_K classifier
     if (llmf90_b200_init(&cfg, m.w.token_embedding_table.data(), m.w.rms_att_weight.data(), m.w.wqkv.data(),
                          m.w.wo.data(), m.w.rms_ffn_weight.data(), m.w.w13.data(), m.w.w2.data(),
                          m.w.rms_final_weight.data(), m.w.wcls.data()))

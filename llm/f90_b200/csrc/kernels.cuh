@@ -14,6 +14,8 @@ cudaError_t launch_softmax(const float *x, float *p, int n, int s, cudaStream_t 
 // y[r] = (residual ? residual[r] : 0) + dot(W[r,:], x), W in device row format
 cudaError_t launch_matvec(const uint8_t *W, int wtype, int rows, int cols, const float *x,
                           const float *residual, float *y, cudaStream_t st);
+// y[r] = dot(dequant(W[r,:]), x), W = rows x (cols / 256) ggml Q6_K super-blocks of 210 bytes (file format, no re-layout)
+cudaError_t launch_matvec_q6k(const uint8_t *W, int rows, int cols, const float *x, float *y, cudaStream_t st);
 // standalone RoPE with on-the-fly trig (llama2.f90:543-559); pos is read from *pos_dev if given
 cudaError_t launch_rope(float *q, float *k, int emb, int kv, int hs, int pos, cudaStream_t st);
 // rope table: tab[(p*hs/2 + j)] = (cos, sin)((p+1) * 10000^-((2j+1)/hs)),  p = 0..seq-1

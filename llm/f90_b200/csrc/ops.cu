@@ -154,6 +154,53 @@ cudaError_t launch_matvec(const uint8_t *W, int wtype, int rows, int cols, const
     return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------ Q6_K mat-vec (classifier of stock llama.cpp q4_0 files)
+// W is `rows` rows of cols / 256 ggml block_q6_K super-blocks, 210 bytes each, exactly as in the file:
+// ql[128] (low 4 bits) | qh[64] (high 2 bits) | int8 scales[16] | f16 d;  weight = d * scale * (q - 32).
+// One warp per row; for each super-block lane l takes the elements l, l + 32, l + 64, l + 96 of both halves (the
+// loop of ggml's dequantize_row_q6_K with l = lane): byte loads that are contiguous across the warp.  The product
+// d * scale * q is exact in f32 (11 + 7 + 6 bits), so this is the f32 dot product of the dequantised row.
+__global__ void __launch_bounds__(MV_WARPS * 32) matvec_q6k_kernel(const uint8_t *__restrict__ W, int rows, int cols,
+                                                                   const float *__restrict__ x, float *__restrict__ y)
+{
+    extern __shared__ __align__(16) float xs[];
+    for (int e = threadIdx.x; e < cols; e += blockDim.x) xs[e] = x[e];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * MV_WARPS + warp;
+    if (r >= rows) return;
+    const int nb = cols >> 8, is = lane >> 4;
+    const uint8_t *blk = W + (size_t)r * nb * 210;
+    float acc = 0.f;
+    for (int b = 0; b < nb; b++, blk += 210) {
+        const float d = __half2float(__ushort_as_half((unsigned short)(blk[208] | (blk[209] << 8))));
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint8_t *ql = blk + 64 * half, *qh = blk + 128 + 32 * half;
+            const int8_t *sc = reinterpret_cast<const int8_t *>(blk + 192 + 8 * half);
+            const float *xv = xs + b * 256 + 128 * half + lane;
+            const int l0 = ql[lane], l1 = ql[lane + 32], h = qh[lane];
+            const int q1 = ((l0 & 0xF) | (((h >> 0) & 3) << 4)) - 32;
+            const int q2 = ((l1 & 0xF) | (((h >> 2) & 3) << 4)) - 32;
+            const int q3 = ((l0 >> 4) | (((h >> 4) & 3) << 4)) - 32;
+            const int q4 = ((l1 >> 4) | (((h >> 6) & 3) << 4)) - 32;
+            acc = fmaf(d * (float)sc[is] * (float)q1, xv[0], acc);
+            acc = fmaf(d * (float)sc[is + 2] * (float)q2, xv[32], acc);
+            acc = fmaf(d * (float)sc[is + 4] * (float)q3, xv[64], acc);
+            acc = fmaf(d * (float)sc[is + 6] * (float)q4, xv[96], acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) y[r] = acc;
+}
+
+cudaError_t launch_matvec_q6k(const uint8_t *W, int rows, int cols, const float *x, float *y, cudaStream_t st)
+{
+    if (cols % 256 || (size_t)cols * 4 > 48 * 1024) return cudaErrorInvalidValue;  // 12288 columns of activations in default shared memory
+    matvec_q6k_kernel<<<(rows + MV_WARPS - 1) / MV_WARPS, MV_WARPS * 32, (size_t)cols * 4, st>>>(W, rows, cols, x, y);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ RoPE (llama2.f90:543-559)
 // Q1: exponent (2j+1)/hs (the reference's 1-based odd loop index through mod(i,head_size));
 // Q2: angle = pos * freq with the 1-based pos.  Accurate powf/cosf/sinf (no fast-math).

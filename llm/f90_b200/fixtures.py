@@ -13,7 +13,7 @@ from typing import Iterable
 
 import numpy as np
 
-from .layout import (Config, Weights, F32, F16, Q4_0, GGML_TYPE, QK4_0, row_bytes)
+from .layout import (Config, Weights, F32, F16, Q4_0, Q6_K, GGML_TYPE, QK4_0, QK_K, Q6_K_BLOCK_BYTES, row_bytes)
 
 GGUF_MAGIC = 1179993927  # read_ggml.f90:122
 GGUF_VERSION = 3
@@ -54,12 +54,61 @@ def dequantize_q4_0(b: np.ndarray, n: int) -> np.ndarray:
     return vals.reshape(rows, n)
 
 
+def quantize_q6_k(w: np.ndarray) -> np.ndarray:
+    """f32 [rows, n] -> uint8 [rows, n/256*210] ggml Q6_K blocks (ql[128] | qh[64] | int8 scales[16] | f16 d).
+    A plain round-to-nearest quantiser (ggml searches the sub-block scales; any valid encoding serves a
+    fixture): sub-block scale = max|x| / 31, d = max|scale| / 127, q = round(x / (d * sc)) in [-32, 31]."""
+    rows, n = w.shape
+    assert n % QK_K == 0
+    nb = n // QK_K
+    x = np.ascontiguousarray(w, np.float32).reshape(rows, nb, 16, 16)
+    s = np.abs(x).max(-1) / 31.0                              # [rows, nb, 16]
+    d = (s.max(-1) / 127.0).astype(np.float16)                # [rows, nb]
+    df = d.astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sc = np.where(df[..., None] > 0, np.rint(s / df[..., None]), 0).clip(-128, 127).astype(np.int8)
+        eff = df[..., None] * sc.astype(np.float32)
+        q = np.where(eff[..., None] != 0, np.rint(x / eff[..., None]), 0).clip(-32, 31).astype(np.int32) + 32
+    q = q.reshape(rows, nb, 2, 4, 32)                         # [half][group of 32: +0, +32, +64, +96][l]
+    ql = np.empty((rows, nb, 2, 64), np.uint8)
+    ql[..., :32] = (q[..., 0, :] & 0xF) | ((q[..., 2, :] & 0xF) << 4)
+    ql[..., 32:] = (q[..., 1, :] & 0xF) | ((q[..., 3, :] & 0xF) << 4)
+    qh = ((q[..., 0, :] >> 4) | ((q[..., 1, :] >> 4) << 2) | ((q[..., 2, :] >> 4) << 4) | ((q[..., 3, :] >> 4) << 6)).astype(np.uint8)
+    out = np.empty((rows, nb, Q6_K_BLOCK_BYTES), np.uint8)
+    out[..., 0:128] = ql.reshape(rows, nb, 128)
+    out[..., 128:192] = qh.reshape(rows, nb, 64)
+    out[..., 192:208] = sc.view(np.uint8)
+    out[..., 208:210] = d.view(np.uint8).reshape(rows, nb, 2)
+    return out.reshape(rows, nb * Q6_K_BLOCK_BYTES)
+
+
+def dequantize_q6_k(b: np.ndarray, n: int) -> np.ndarray:
+    """uint8 [rows, n/256*210] -> f32 [rows, n], exact (d * scale * (q - 32): at most 24 significant bits)."""
+    rows = b.shape[0]
+    nb = n // QK_K
+    blk = b.reshape(rows, nb, Q6_K_BLOCK_BYTES)
+    ql = blk[..., 0:128].reshape(rows, nb, 2, 64).astype(np.int32)
+    qh = blk[..., 128:192].reshape(rows, nb, 2, 32).astype(np.int32)
+    sc = blk[..., 192:208].copy().view(np.int8).reshape(rows, nb, 2, 8).astype(np.float32)
+    d = blk[..., 208:210].copy().view(np.float16).astype(np.float32).reshape(rows, nb, 1, 1, 1)
+    q = np.empty((rows, nb, 2, 4, 32), np.int32)
+    q[..., 0, :] = (ql[..., :32] & 0xF) | (((qh >> 0) & 3) << 4)
+    q[..., 1, :] = (ql[..., 32:] & 0xF) | (((qh >> 2) & 3) << 4)
+    q[..., 2, :] = (ql[..., :32] >> 4) | (((qh >> 4) & 3) << 4)
+    q[..., 3, :] = (ql[..., 32:] >> 4) | (((qh >> 6) & 3) << 4)
+    # element l of group g uses scale index l // 16 + 2 g of its half
+    scale = sc.reshape(rows, nb, 2, 4, 2)[..., None].repeat(16, -1).reshape(rows, nb, 2, 4, 32)
+    return ((d * scale) * (q - 32).astype(np.float32)).reshape(rows, n).astype(np.float32)
+
+
 def encode_matrix(w: np.ndarray, wtype: int) -> np.ndarray:
     """f32 [rows, n] -> storage array for ``wtype`` (f32 array, f16 array, or q4_0 bytes)."""
     if wtype == F32:
         return np.ascontiguousarray(w, dtype=np.float32)
     if wtype == F16:
         return np.ascontiguousarray(w.astype(np.float16))
+    if wtype == Q6_K:
+        return quantize_q6_k(w)
     return quantize_q4_0(w)
 
 
@@ -69,6 +118,8 @@ def decode_matrix(a: np.ndarray, wtype: int, n: int) -> np.ndarray:
         return a.reshape(-1, n).astype(np.float32)
     if wtype == F16:
         return a.reshape(-1, n).astype(np.float32)
+    if wtype == Q6_K:
+        return dequantize_q6_k(a.reshape(-1, row_bytes(Q6_K, n)), n)
     return dequantize_q4_0(a.reshape(-1, row_bytes(Q4_0, n)), n)
 
 
@@ -103,9 +154,10 @@ def synth_tensors(cfg: Config, seed: int = 0) -> dict[str, np.ndarray]:
     return t
 
 
-def fuse_tensors(cfg: Config, t: dict[str, np.ndarray]) -> Weights:
+def fuse_tensors(cfg: Config, t: dict[str, np.ndarray], cls_wtype: int | None = None) -> Weights:
     """GGUF-named f32 tensors -> ``Weights`` in the fused weight_module layout, stored as
-    ``cfg.wtype`` (the same mapping load_ggml performs, read_ggml.f90:238-410)."""
+    ``cfg.wtype`` (the same mapping load_ggml performs, read_ggml.f90:238-410); ``cls_wtype`` = Q6_K stores
+    output.weight the way llama.cpp's q4_0 files do."""
     L, wt = cfg.n_layers, cfg.wtype
     enc = lambda a: encode_matrix(a, wt)
 
@@ -115,6 +167,7 @@ def fuse_tensors(cfg: Config, t: dict[str, np.ndarray]) -> Weights:
 
     return Weights(
         cfg,
+        cls_wtype=cls_wtype,
         token_embedding_table=enc(t["token_embd.weight"]),
         rms_att_weight=np.stack([t[f"blk.{l}.attn_norm.weight"] for l in range(L)]),
         wqkv=per_layer(["attn_q", "attn_k", "attn_v"]),
@@ -123,7 +176,7 @@ def fuse_tensors(cfg: Config, t: dict[str, np.ndarray]) -> Weights:
         w13=per_layer(["ffn_gate", "ffn_up"]),
         w2=per_layer(["ffn_down"]),
         rms_final_weight=t["output_norm.weight"],
-        wcls=enc(t["output.weight"]),
+        wcls=encode_matrix(t["output.weight"], wt if cls_wtype is None else cls_wtype),
     )
 
 
@@ -308,7 +361,7 @@ def _kv(key: str, vtype: int, payload: bytes) -> bytes:
 
 def write_gguf(path: str, cfg: Config, tensors: dict[str, np.ndarray],
                vocab: list[bytes] | None = None, scores: np.ndarray | None = None,
-               alignment: int = ALIGNMENT, name: str = "synthetic") -> None:
+               alignment: int = ALIGNMENT, name: str = "synthetic", cls_wtype: int | None = None) -> None:
     """Write a GGUF v3 file.  ``tensors`` are f32 arrays by GGUF name; 2-D ones are stored as
     ``cfg.wtype``, 1-D ones as f32.  Framing per read_ggml.f90:112-196,600-718."""
     if vocab is None:
@@ -341,7 +394,8 @@ def write_gguf(path: str, cfg: Config, tensors: dict[str, np.ndarray],
     infos, blobs, off = [], [], 0
     for tname, a in tensors.items():
         if a.ndim == 2:
-            ttype, data = GGML_TYPE[cfg.wtype], encode_matrix(a, cfg.wtype)
+            wt = cls_wtype if (tname == "output.weight" and cls_wtype is not None) else cfg.wtype
+            ttype, data = GGML_TYPE[wt], encode_matrix(a, wt)
             dims = (a.shape[1], a.shape[0])  # innermost (contraction) dimension first
         else:
             ttype, data = GGML_TYPE[F32], np.ascontiguousarray(a, dtype=np.float32)
@@ -367,4 +421,4 @@ def write_synth_gguf(path: str, cfg: Config, seed: int = 0, **kw) -> Weights:
     """Write a synthetic model to ``path`` and return the fused ``Weights`` it must load to."""
     t = synth_tensors(cfg, seed)
     write_gguf(path, cfg, t, **kw)
-    return fuse_tensors(cfg, t)
+    return fuse_tensors(cfg, t, cls_wtype=kw.get("cls_wtype"))

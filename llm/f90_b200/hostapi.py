@@ -21,7 +21,7 @@ class HostError(RuntimeError):
 
 class CHostConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("emb_dim", "hidden_dim", "n_layers", "n_heads", "n_kv_heads",
-                                         "vocab_size", "seq_len", "wtype")]
+                                         "vocab_size", "seq_len", "wtype", "cls_wtype")]
 
 
 _lib = None
@@ -70,7 +70,8 @@ class HostModel:
             raise HostError(self.L.llmf90_host_last_error().decode(errors="replace"))
         cc = CHostConfig()
         self.L.llmf90_host_get_config(self.h, C.byref(cc))
-        self.cfg = Config(**{n: getattr(cc, n) for n, _ in CHostConfig._fields_})
+        self.cfg = Config(**{n: getattr(cc, n) for n, _ in CHostConfig._fields_ if n != "cls_wtype"})
+        self.cls_wtype = int(cc.cls_wtype)
         self.data_offset = int(self.L.llmf90_host_data_offset(self.h))
 
     def close(self):
@@ -93,7 +94,9 @@ class HostModel:
         arrs = {}
         for i, f in enumerate(names):
             arrs[f] = self._tensor(i, np.float32 if f.startswith("rms") else dt).copy()
-        return Weights(self.cfg, **arrs)
+        if self.cls_wtype != wt:  # Q6_K classifier: raw 210-byte blocks
+            arrs["wcls"] = self._tensor(8, np.uint8).copy()
+        return Weights(self.cfg, cls_wtype=self.cls_wtype, **arrs)
 
     def vocab(self) -> tuple[list[bytes], np.ndarray]:
         toks, scores = [], np.empty(self.cfg.vocab_size, np.float32)

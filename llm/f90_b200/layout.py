@@ -28,9 +28,11 @@ import numpy as np
 F32, F16, Q4_0 = 0, 1, 2
 WTYPE_NAMES = {F32: "f32", F16: "f16", Q4_0: "q4_0"}
 WTYPE_BY_NAME = {v: k for k, v in WTYPE_NAMES.items()}
-GGML_TYPE = {F32: 0, F16: 1, Q4_0: 2}  # ggml tensor type ids used in GGUF tensor infos
+GGML_TYPE = {F32: 0, F16: 1, Q4_0: 2, 14: 14}  # ggml tensor type ids used in GGUF tensor infos (14 = Q6_K)
 QK4_0 = 32  # load.f90:8 (qk4)
 Q4_0_BLOCK_BYTES = 18
+Q6_K = 14  # ggml type 14: only as the storage of wcls (the output.weight of stock llama.cpp q4_0 files)
+QK_K, Q6_K_BLOCK_BYTES = 256, 210
 
 
 @dataclass(frozen=True)
@@ -78,6 +80,9 @@ def row_bytes(wtype: int, n: int) -> int:
         return 4 * n
     if wtype == F16:
         return 2 * n
+    if wtype == Q6_K:
+        assert n % QK_K == 0
+        return n // QK_K * Q6_K_BLOCK_BYTES
     assert n % QK4_0 == 0
     return n // QK4_0 * Q4_0_BLOCK_BYTES
 
@@ -108,8 +113,10 @@ class Weights:
     FIELDS = ("token_embedding_table", "rms_att_weight", "wqkv", "wo", "rms_ffn_weight",
               "w13", "w2", "rms_final_weight", "wcls")
 
-    def __init__(self, cfg: Config, **arrays: np.ndarray):
+    def __init__(self, cfg: Config, cls_wtype: int | None = None, **arrays: np.ndarray):
         self.cfg = cfg
+        # storage of wcls: the model's wtype, or Q6_K (ggml type 14) for a stock llama.cpp q4_0 file
+        self.cls_wtype = cfg.wtype if cls_wtype is None else cls_wtype
         for f in self.FIELDS:
             a = np.ascontiguousarray(arrays[f])
             setattr(self, f, a)
@@ -125,7 +132,7 @@ class Weights:
             "wo": L * e * rb_e,
             "w13": L * 2 * h * rb_e,
             "w2": L * e * rb_h,
-            "wcls": V * rb_e,
+            "wcls": V * row_bytes(self.cls_wtype, e),
             "rms_att_weight": L * e * 4,
             "rms_ffn_weight": L * e * 4,
             "rms_final_weight": e * 4,

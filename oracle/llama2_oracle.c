@@ -49,6 +49,7 @@
 #define ORACLE_F32 0
 #define ORACLE_F16 1
 #define ORACLE_Q4_0 2
+#define ORACLE_Q6_K 14 /* ggml type 14: the output.weight of stock llama.cpp q4_0 files (classifier only) */
 
 typedef struct {
     int emb_dim, hidden_dim, n_layers, n_heads, n_kv_heads, vocab_size, seq_len;
@@ -69,6 +70,7 @@ typedef struct {
     double times[5];    /* ms per bucket, llama2.f90:526-638 */
     /* scratch */
     float *x, *xb, *qkv, *hb13, *row;
+    int cls_type;       /* storage of wcls: c.wtype, or ORACLE_Q6_K (oracle_set_cls_type) */
 } oracle_model;
 
 static float f16_table[65536];
@@ -110,6 +112,7 @@ size_t oracle_row_bytes(int wtype, int n)
 {
     if (wtype == ORACLE_F32) return (size_t)n * 4;
     if (wtype == ORACLE_F16) return (size_t)n * 2;
+    if (wtype == ORACLE_Q6_K) return (size_t)(n / 256) * 210;
     return (size_t)(n / 32) * 18;
 }
 
@@ -123,6 +126,33 @@ void oracle_dequant_row(const void *src, int wtype, int n, float *dst)
         f16_init();
         const uint16_t *h = (const uint16_t *)src;
         for (int i = 0; i < n; i++) dst[i] = f16_table[h[i]];
+    } else if (wtype == ORACLE_Q6_K) {
+        /* ggml block_q6_K, 256 weights in 210 bytes: ql[128] low 4 bits, qh[64] high 2 bits, 16 int8
+         * sub-block scales, f16 super-scale d; weight = d * scale * (q - 32) with q the 6-bit value
+         * (public ggml format: ggml-quants.c dequantize_row_q6_K; checked against gguf.quants in
+         * tests/test_oracle.py).  d * scale * q has at most 11 + 7 + 6 = 24 significant bits: exact in f32. */
+        f16_init();
+        const uint8_t *b = (const uint8_t *)src;
+        for (int blk = 0; blk < n / 256; blk++, b += 210) {
+            const uint8_t *ql = b, *qh = b + 128;
+            const int8_t *sc = (const int8_t *)(b + 192);
+            uint16_t dh;
+            memcpy(&dh, b + 208, 2);
+            const float d = f16_table[dh];
+            for (int half = 0; half < 2; half++, dst += 128, ql += 64, qh += 32, sc += 8) {
+                for (int l = 0; l < 32; l++) {
+                    const int is = l / 16;
+                    const int q1 = (int)((ql[l] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32;
+                    const int q2 = (int)((ql[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
+                    const int q3 = (int)((ql[l] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32;
+                    const int q4 = (int)((ql[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
+                    dst[l] = d * (float)sc[is] * (float)q1;
+                    dst[l + 32] = d * (float)sc[is + 2] * (float)q2;
+                    dst[l + 64] = d * (float)sc[is + 4] * (float)q3;
+                    dst[l + 96] = d * (float)sc[is + 6] * (float)q4;
+                }
+            }
+        }
     } else {
         f16_init();
         const uint8_t *b = (const uint8_t *)src;
@@ -241,6 +271,7 @@ oracle_model *oracle_create(const oracle_cfg *cfg, const void *tok_emb, const fl
     if (m->c.n_threads < 1) m->c.n_threads = 1;
     m->tok_emb = tok_emb; m->rms_att = rms_att; m->wqkv = wqkv; m->wo = wo;
     m->rms_ffn = rms_ffn; m->w13 = w13; m->w2 = w2; m->rms_final = rms_final; m->wcls = wcls;
+    m->cls_type = cfg->wtype;
     const int hs = cfg->emb_dim / cfg->n_heads;
     const int kv = cfg->n_kv_heads * hs;
     /* llama2.f90:311-319: caches allocated at seq_len and zeroed */
@@ -256,6 +287,9 @@ oracle_model *oracle_create(const oracle_cfg *cfg, const void *tok_emb, const fl
     f16_init();
     return m;
 }
+
+/* the classifier tensor is stored in another ggml type than the rest (Q6_K output.weight of a q4_0 file) */
+void oracle_set_cls_type(oracle_model *m, int type) { m->cls_type = type; }
 
 void oracle_free(oracle_model *m)
 {
@@ -357,7 +391,7 @@ int oracle_transformer(oracle_model *m, int token, int pos, float *logits)
     /* :627-636  final norm + classifier */
     t = now_ms();
     oracle_rmsnorm(x, m->rms_final, emb, x);
-    matvec_rows(m->wcls, wt, V, emb, x, logits, nt);
+    matvec_rows(m->wcls, m->cls_type, V, emb, x, logits, nt);
     m->times[4] += now_ms() - t;
     return 0;
 }

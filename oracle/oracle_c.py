@@ -40,6 +40,7 @@ def lib(arch: str = "x86-64-v3") -> C.CDLL:
     L.oracle_create.restype = vp
     L.oracle_create.argtypes = [C.POINTER(OracleCfg)] + [vp] * 9
     L.oracle_free.argtypes = [vp]
+    L.oracle_set_cls_type.argtypes = [vp, C.c_int]
     L.oracle_reset.argtypes = [vp]
     L.oracle_transformer.restype = C.c_int
     L.oracle_transformer.argtypes = [vp, C.c_int, C.c_int, fp]
@@ -83,6 +84,8 @@ class Oracle:
                                       ptr(weights.rms_att_weight), ptr(weights.wqkv), ptr(weights.wo),
                                       ptr(weights.rms_ffn_weight), ptr(weights.w13), ptr(weights.w2),
                                       ptr(weights.rms_final_weight), ptr(weights.wcls))
+        if getattr(weights, "cls_wtype", c.wtype) != c.wtype:  # Q6_K output.weight of a q4_0 file
+            self.L.oracle_set_cls_type(self.h, weights.cls_wtype)
 
     def close(self):
         if self.h:

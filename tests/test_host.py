@@ -258,3 +258,24 @@ def test_loader_survives_truncated_and_corrupted_files(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     n, ok, err = (int(x) for x in r.stdout.split("FUZZ")[1].split())
     assert ok + err == n and err >= 48  # every truncation fails cleanly; a flipped weight byte may still load
+
+
+def test_loader_accepts_a_q6_k_output_weight(tmp_path):
+    """Stock llama.cpp q4_0 files keep output.weight in Q6_K (ggml type 14), where the reference's type switch
+    stops (read_ggml.f90:613-635): the loader hands the super-blocks through unchanged and says so."""
+    from llm.f90_b200.layout import Q6_K, Q4_0
+    cfg = Config(emb_dim=256, hidden_dim=352, n_layers=2, n_heads=4, n_kv_heads=2, vocab_size=300, seq_len=32, wtype=Q4_0)
+    p = str(tmp_path / "m.gguf")
+    want = fx.write_synth_gguf(p, cfg, seed=3, cls_wtype=Q6_K)
+    m = hostapi.HostModel(p)
+    assert m.cfg == cfg and m.cls_wtype == Q6_K
+    got = m.weights()
+    assert got.cls_wtype == Q6_K and got.wcls.nbytes == cfg.vocab_size * 210
+    for f in got.FIELDS:
+        assert np.array_equal(getattr(got, f).view(np.uint8).ravel(), getattr(want, f).view(np.uint8).ravel()), f
+    m.close()
+    # any other classifier type is still refused with the reference's message
+    bad = str(tmp_path / "bad.gguf")
+    fx.write_synth_gguf(bad, Config(**{**cfg.asdict(), "wtype": F32}), seed=3, cls_wtype=Q4_0)
+    with pytest.raises(hostapi.HostError, match="Type not supported"):
+        hostapi.HostModel(bad)

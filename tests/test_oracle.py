@@ -172,3 +172,39 @@ def test_forced_prompt_then_greedy():
     o2 = oc.Oracle(w)
     assert np.array_equal(o2.transformer(2, 1), lg[0])
     assert np.array_equal(o2.transformer(40, 2), lg[1])
+
+
+# ------------------------------------------------------------------ Q6_K classifier
+def test_q6_k_codec_matches_gguf_quants():
+    """The oracle's and the fixtures' Q6_K dequantisation against the `gguf` package's (a third implementation of
+    the public ggml block format), bit for bit -- on quantised rows and on arbitrary block bytes."""
+    from gguf import quants, GGMLQuantizationType as T
+    from llm.f90_b200.layout import Q6_K
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal((9, 768)) * 0.05).astype(np.float32)
+    q = fx.quantize_q6_k(x)
+    ref = quants.dequantize(q, T.Q6_K)
+    assert np.array_equal(fx.dequantize_q6_k(q, 768), ref)
+    assert np.array_equal(np.stack([oc.dequant_row(q[i], Q6_K, 768) for i in range(9)]), ref)
+    assert np.abs(ref - x).max() < 0.03 * np.abs(x).max()  # it is a 6-bit quantiser
+    raw = rng.integers(0, 256, (6, 630), dtype=np.uint8)
+    for b in range(3):  # finite super-scales
+        raw[:, 210 * b + 208:210 * b + 210] = np.array([0.37 * (b + 1) * (-1) ** b], np.float16).view(np.uint8)
+    ref = quants.dequantize(raw, T.Q6_K)
+    assert np.array_equal(fx.dequantize_q6_k(raw, 768), ref)
+    assert np.array_equal(np.stack([oc.dequant_row(raw[i], Q6_K, 768) for i in range(6)]), ref)
+
+
+def test_oracle_q6_k_classifier_equals_the_dequantised_f32_classifier():
+    """Q6_K dequantises exactly to f32, so a model with a Q6_K output.weight must give the very logits of the same
+    model with that tensor stored as the dequantised f32 values."""
+    from llm.f90_b200.layout import Q6_K
+    cfg = Config(emb_dim=256, hidden_dim=352, n_layers=2, n_heads=4, n_kv_heads=2, vocab_size=300, seq_len=32, wtype=F32)
+    t = fx.synth_tensors(cfg, 4)
+    wq = fx.fuse_tensors(cfg, t, cls_wtype=Q6_K)
+    t2 = dict(t)
+    t2["output.weight"] = fx.dequantize_q6_k(wq.wcls.reshape(cfg.vocab_size, -1), cfg.emb_dim)
+    wf = fx.fuse_tensors(cfg, t2)
+    a, b = oc.Oracle(wq), oc.Oracle(wf)
+    for pos, tok in enumerate([2, 17, 250], 1):
+        assert np.array_equal(a.transformer(tok, pos), b.transformer(tok, pos))
