@@ -98,6 +98,14 @@ int llmf90_b200_init(const llmf90_b200_config *cfg,
  * logits[vocab_size] is host memory. */
 int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits);
 
+/* transformer() and the pick of the next token in one call, the pick made on the device: maxloc for
+ * temperature == 0 (llama2.f90:388), otherwise softmax(logits / temperature) and the CDF walk against the uniform
+ * number r in [0, 1) that the caller draws (llama2.f90:390-391, :428-447; the reference draws it with
+ * random_number).  Returns the 1-based token in *next_token; the logits stay in HBM (4 bytes come back instead of
+ * vocab_size floats).  The probabilities are summed in f32 like the reference's, in chunks instead of one chain:
+ * the pick equals the sequential walk's unless r lies within rounding (~1e-6) of a CDF boundary. */
+int llmf90_b200_transformer_sample(int32_t token, int32_t pos, float temperature, float r, int32_t *next_token);
+
 /* s%times(1:5) in milliseconds, accumulated since init/reset (llama2.f90:526-638, :407-410).
  * With LLMF90_FLAG_PROFILE (or LLMF90_PROFILE=1) the five buckets come from the kernel's phase
  * timers; without it (the default, faster kernel) and on the granular path the whole forward pass

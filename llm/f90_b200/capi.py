@@ -28,6 +28,7 @@ EXPORTS = [
     "llmf90_b200_tp_export", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
     "llmf90_b200_bench_device_loop", "llmf90_b200_phase_times", "llmf90_b200_debug_trace",
     "llmf90_b200_plan", "llmf90_b200_prefill", "llmf90_b200_debug_read_kv", "llmf90_b200_matmul",
+    "llmf90_b200_transformer_sample",
 ]
 
 
@@ -97,6 +98,7 @@ def load() -> C.CDLL:
     L.llmf90_b200_tp_connect.argtypes = [vp, C.c_int32]
     L.llmf90_b200_get_stats.argtypes = [C.POINTER(CStats)]
     L.llmf90_b200_bench_device_loop.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp]
+    L.llmf90_b200_transformer_sample.argtypes = [C.c_int32, C.c_int32, C.c_float, C.c_float, ip]
     L.llmf90_b200_prefill.argtypes = [ip, C.c_int32, C.c_int32]
     L.llmf90_b200_debug_read_kv.argtypes = [C.c_int32, C.c_int32, fp, fp]
     L.llmf90_b200_matmul.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, C.c_int32, fp]
@@ -163,6 +165,12 @@ class Engine:
             out = np.empty(self.cfg.vocab_size, np.float32)
         _check(self.L.llmf90_b200_transformer(token, pos, _fp(out)))
         return out
+
+    def transformer_sample(self, token: int, pos: int, temperature: float, r: float) -> int:
+        """transformer() + the pick of the next token on the device (maxloc, or softmax / T + CDF walk against r)."""
+        nxt = C.c_int32(0)
+        _check(self.L.llmf90_b200_transformer_sample(token, pos, temperature, r, C.byref(nxt)))
+        return nxt.value
 
     def prefill(self, tokens, pos0: int = 1) -> None:
         """KV rows of positions pos0.. for the input tokens, as one batched tcgen05 pass (llama2.f90:379-385)."""

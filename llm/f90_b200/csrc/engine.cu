@@ -777,6 +777,30 @@ int llmf90_b200_transformer(int32_t token, int32_t pos, float *logits)
     return 0;
 }
 
+int llmf90_b200_transformer_sample(int32_t token, int32_t pos, float temperature, float r, int32_t *next_token)
+{
+    if (!E.ready) return fail("llmf90_b200_transformer_sample: engine not initialised");
+    if (!E.peers_ready) return fail("tensor-parallel engine: call llmf90_b200_tp_connect first");
+    if (token < 1 || token > E.cfg.vocab_size) return fail("token %d out of range 1..%d", token, E.cfg.vocab_size);
+    if (pos < 1 || pos > E.cfg.seq_len) return fail("pos %d out of range 1..%d", pos, E.cfg.seq_len);
+    if (!next_token || !(temperature >= 0.f)) return fail("transformer_sample: bad argument");
+    CK(cudaEventRecord(E.ev0, E.st));
+    if (enqueue_forward(token, pos, false, nullptr, nullptr)) return 1;
+    CK(cudaEventRecord(E.ev1, E.st));
+    // the pick is made next to the logits: maxloc for temperature 0 (llama2.f90:388), else softmax(logits / T) and
+    // the CDF walk against r (:390-391, :428-447); 4 bytes come back instead of the vocabulary's logits
+    if (temperature == 0.f) CK(launch_argmax(logits_dev(), E.cfg.vocab_size, E.d_amax, E.st));
+    else CK(launch_sample(logits_dev(), E.cfg.vocab_size, temperature, r, E.d_amax, E.st));
+    E.launches += 1;
+    CK(cudaMemcpyAsync(E.h_tokpos + 8, E.d_amax, 4, cudaMemcpyDeviceToHost, E.st));
+    CK(cudaStreamSynchronize(E.st));
+    if (check_peers()) return 1;
+    *next_token = E.h_tokpos[8];
+    CK(cudaEventElapsedTime(&E.last_ms, E.ev0, E.ev1));
+    if (!E.use_stream || !E.prof) E.host_times[3] += E.last_ms;
+    return 0;
+}
+
 int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t *out, int32_t n_ctas)
 {
     if (!E.ready || !E.use_stream) return fail("debug_trace: needs the fused streaming engine");

@@ -21,6 +21,7 @@ struct Args {  // type args (llama2.f90:7-14), defaults :26-32
     bool verbose = false, ak = false;
     int n = 256;
     int device = -1, granular = 0;
+    bool host_sampler = false;  // extension: copy the logits back and pick on the host, like the reference
     // extension: tensor parallelism, one `llm` process per GPU started with the same flags plus its
     // --tp-rank; the ranks meet in --tp-dir (a fresh directory on a shared file system)
     int tp_size = 1, tp_rank = 0;
@@ -51,6 +52,7 @@ Args parse_args(int argc, char **argv)
         else if (f == "--ak") { a.ak = true; i += 1; }
         else if (f == "--device") { a.device = atoi(val().c_str()); i += 2; }       // extension
         else if (f == "--granular") { a.granular = 1; i += 1; }                     // extension
+        else if (f == "--host-sampler") { a.host_sampler = true; i += 1; }          // extension
         else if (f == "--tp-size") { a.tp_size = atoi(val().c_str()); i += 2; }     // extension
         else if (f == "--tp-rank") { a.tp_rank = atoi(val().c_str()); i += 2; }     // extension
         else if (f == "--tp-dir") { a.tp_dir = val(); i += 2; }                     // extension
@@ -151,10 +153,21 @@ int main(int argc, char **argv)
     bool started = false;
     int token = 2;  // <s>, 1-based (llama2.f90:376)
     for (int pos = 1; pos <= seq_len; pos++) {
-        if (llmf90_b200_transformer(token, pos, logits.data())) die(llmf90_b200_last_error());
-        if (pos <= (int)prompt_tokens.size()) token = prompt_tokens[pos - 1];
-        else if (a.temperature == 0.f) token = llmhost::argmax1(logits.data(), m.cfg.vocab_size);
-        else token = llmhost::sample_cdf(logits.data(), m.cfg.vocab_size, a.temperature, uni(rng), scratch);
+        if (a.host_sampler) {
+            // the reference's own shape: logits to the host, pick there (llama2.f90:380-392)
+            if (llmf90_b200_transformer(token, pos, logits.data())) die(llmf90_b200_last_error());
+            if (pos <= (int)prompt_tokens.size()) token = prompt_tokens[pos - 1];
+            else if (a.temperature == 0.f) token = llmhost::argmax1(logits.data(), m.cfg.vocab_size);
+            else token = llmhost::sample_cdf(logits.data(), m.cfg.vocab_size, a.temperature, uni(rng), scratch);
+        } else {
+            // default: maxloc / softmax(logits / T) + CDF walk next to the logits on the device; only the token
+            // comes back.  The uniform number is drawn here, once per sampled position, like random_number (:433).
+            const bool forced = pos <= (int)prompt_tokens.size();
+            const float r = (!forced && a.temperature != 0.f) ? uni(rng) : 0.f;
+            int32_t next = 0;
+            if (llmf90_b200_transformer_sample(token, pos, a.temperature, r, &next)) die(llmf90_b200_last_error());
+            token = forced ? prompt_tokens[pos - 1] : next;
+        }
         if (talk) {
             const std::string &piece = m.vocab.tokens[token - 1];
             fwrite(piece.data(), 1, piece.size(), stdout);

@@ -35,6 +35,9 @@ cudaError_t launch_swiglu(const float *h13, float *hb, int hid, cudaStream_t st)
 // out[0] = 1-based index of the first maximum (maxloc, llama2.f90:388); also tokpos update
 cudaError_t launch_argmax(const float *v, int n, int *out_token, cudaStream_t st);
 
+// out[0] = 1-based index sampled from softmax(v / temperature) by the CDF walk against r (llama2.f90:390-391, :428-447)
+cudaError_t launch_sample(const float *v, int n, float temperature, float r, int *out_token, cudaStream_t st);
+
 // ---------------------------------------------------------------- upload helpers (ops.cu)
 // dst row r (device format) = src row rowmap(r), columns [col0, col0+ncols) of a host-format
 // matrix already copied to the device.  map_kind: 0 identity (+row0), 1 interleave halves

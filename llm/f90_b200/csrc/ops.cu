@@ -435,6 +435,93 @@ cudaError_t launch_argmax(const float *v, int n, int *out_token, cudaStream_t st
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ softmax(logits / T) + CDF walk (llama2.f90:390-391, :428-447)
+// The reference divides the logits by the temperature, takes the softmax and returns the first index whose
+// running sum of probabilities exceeds a uniform r (the last index if none does).  Here one CTA does it next to
+// the logits, so a sampled token costs a 4-byte copy instead of the vocabulary's logits: max and sum block-wide,
+// then every thread sums the probabilities of its CONTIGUOUS chunk, a block-wide scan of the 1024 chunk sums finds
+// the chunk in which the running sum crosses r, and that thread walks its chunk element by element.  The sums
+// are f32 like the reference's but associate differently (chunk sums instead of one long chain): the pick can
+// differ from the sequential walk only when r lies within rounding (~1e-6) of a boundary of the CDF.
+__global__ void __launch_bounds__(1024) sample_kernel(const float *__restrict__ logits, int n, float temperature, float r,
+                                                      int *__restrict__ out)
+{
+    __shared__ float red[32];
+    __shared__ float bcast;
+    __shared__ float chunk_incl[1024];
+    __shared__ int pick;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mx = -INFINITY;
+    for (int i = tid; i < n; i += 1024) mx = fmaxf(mx, logits[i] / temperature);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (warp == 0) {
+        float t = warp_max(red[lane]);
+        if (lane == 0) bcast = t;
+    }
+    __syncthreads();
+    mx = bcast;
+    float sum = 0.f;
+    for (int i = tid; i < n; i += 1024) sum += expf(logits[i] / temperature - mx);
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        float t = warp_sum(red[lane]);
+        if (lane == 0) bcast = t;
+    }
+    if (tid == 0) pick = n;  // the reference's fallback: the last index (llama2.f90:444)
+    __syncthreads();
+    sum = bcast;
+    // chunk sums and their inclusive scan (warp scan, then the 32 warp totals)
+    const int c = (n + 1023) / 1024, i0 = tid * c, i1 = min(n, i0 + c);
+    float cs = 0.f;
+    for (int i = i0; i < i1; i++) cs += expf(logits[i] / temperature - mx) / sum;
+    float incl = cs;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    __syncthreads();
+    if (lane == 31) red[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        float w = red[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        red[lane] = w;  // inclusive totals of warps 0 .. lane
+    }
+    __syncthreads();
+    incl += warp > 0 ? red[warp - 1] : 0.f;
+    chunk_incl[tid] = incl;
+    __syncthreads();
+    // the first chunk whose inclusive sum exceeds r holds the answer (the running sum is non-decreasing)
+    const float before = tid > 0 ? chunk_incl[tid - 1] : 0.f;
+    if (r < incl && !(r < before) && i0 < n) {
+        float cdf = before;
+        int ans = i1;  // not reached: r < incl means the walk crosses inside the chunk (up to rounding)
+        for (int i = i0; i < i1; i++) {
+            cdf += expf(logits[i] / temperature - mx) / sum;
+            if (r < cdf) { ans = i + 1; break; }
+        }
+        pick = min(ans, n);
+    }
+    __syncthreads();
+    if (tid == 0) out[0] = pick;
+}
+
+cudaError_t launch_sample(const float *logits, int n, float temperature, float r, int *out_token, cudaStream_t st)
+{
+    sample_kernel<<<1, 1024, 0, st>>>(logits, n, temperature, r, out_token);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ upload re-layout
 __device__ __forceinline__ int map_row(int r, int map_kind, int row0, int half)
 {

@@ -61,10 +61,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 }
 // shared-memory matrix descriptor, K-major, no swizzle: core matrices (8 rows x 16 bytes, 128 contiguous bytes)
 // `lbo` bytes apart along K and `sbo` bytes apart along M / N; version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint64_t ver = 1ull << 46)
 {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | ver;
 }
 // D[tmem] (+)= A[smem desc] . B[smem desc], kind::f16 (f16 inputs, f32 accumulate), issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -106,7 +106,7 @@ struct GemmArgs {
     int kc, cps;           // k-chunks in total, k-chunks per split (grid.y = ceil(kc / cps))
     int nst;               // pipeline stages
     int tmem_cols;         // power of two >= max(32, ppad)
-    int swap_lbo;          // debug knob: exchange the two descriptor strides
+    int swap_lbo;          // debug knob (LLMF90_UMMA_SWAP_LBO): bit 0 exchanges the two descriptor strides, bit 1 clears the version field
 };
 
 template <int NPW>  // weight planes: 1 (f16 weights) or 2 (hi + lo of f32 / q4_0 weights)
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(PF_THREADS) umma_gemm_kernel(const GemmArgs a)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(a.ppad >> 3) << 17) | ((uint32_t)(PF_TILE_M >> 4) << 24);
             // core matrices: along K (the "leading" offset) a whole column of rows apart, along M / N 128 bytes
             uint32_t a_lbo = PF_TILE_M * 16, a_sbo = 128, b_lbo = (uint32_t)a.ppad * 16u, b_sbo = 128;
-            if (a.swap_lbo) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+            const uint64_t ver = (a.swap_lbo & 2) ? 0ull : (1ull << 46);
+            if (a.swap_lbo & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
             uint32_t acc = 0;
             for (int c = c0, i = 0; c < c1; c++, i++) {
                 const int s = i % a.nst, u = i / a.nst;
@@ -163,11 +164,11 @@ __global__ void __launch_bounds__(PF_THREADS) umma_gemm_kernel(const GemmArgs a)
 #pragma unroll
                 for (int k = 0; k < PF_BK / 16; k++) {  // one tcgen05.mma covers 16 contraction elements = 2 core matrices
                     const uint32_t ak = sa + (uint32_t)k * 2u * (PF_TILE_M * 16), bk = sb + (uint32_t)k * 2u * ((uint32_t)a.ppad * 16u);
-                    const uint64_t a_hi = umma_desc(ak, a_lbo, a_sbo);
-                    const uint64_t b_hi = umma_desc(bk, b_lbo, b_sbo), b_lo = umma_desc(bk + b_plane, b_lbo, b_sbo);
+                    const uint64_t a_hi = umma_desc(ak, a_lbo, a_sbo, ver);
+                    const uint64_t b_hi = umma_desc(bk, b_lbo, b_sbo, ver), b_lo = umma_desc(bk + b_plane, b_lbo, b_sbo, ver);
                     umma_f16(tmem, a_hi, b_lo, idesc, acc);
                     acc = 1;
-                    if (NPW == 2) umma_f16(tmem, umma_desc(ak + PF_A_PLANE, a_lbo, a_sbo), b_hi, idesc, 1u);
+                    if (NPW == 2) umma_f16(tmem, umma_desc(ak + PF_A_PLANE, a_lbo, a_sbo, ver), b_hi, idesc, 1u);
                     umma_f16(tmem, a_hi, b_hi, idesc, 1u);
                 }
                 umma_commit(&empty[s]);  // the stage's operands have been read when these MMAs complete

@@ -77,9 +77,70 @@ def case_greedy(shape, wt, n_prompt, n):
             "ms": float(ms)}
 
 
+def case_q6k_matvec(rows, cols):
+    from llm.f90_b200.layout import Q6_K
+    rng = np.random.default_rng(rows + cols)
+    enc = fx.quantize_q6_k((rng.standard_normal((rows, cols)) / np.sqrt(cols)).astype(np.float32))
+    x = rng.standard_normal(cols).astype(np.float32)
+    ref = fx.dequantize_q6_k(enc, cols).astype(np.float64) @ x.astype(np.float64)
+    return {"rel_err": rel(capi.matvec(enc, Q6_K, rows, cols, x), ref)}
+
+
+def case_q6k_model(wt):
+    from oracle import oracle_c as oc
+    from llm.f90_b200.layout import Q6_K
+    cfg = Config(**SMALL, wtype=wt)
+    w = fx.fuse_tensors(cfg, fx.synth_tensors(cfg, 11), cls_wtype=Q6_K)
+    prompt, n = [21, 22, 23, 24, 25], 24
+    ref_toks, ref_lg, _ = oc.Oracle(w).generate(prompt, n, want_logits=True)
+    with capi.Engine(w) as eng:
+        toks, lg = capi.host_generate(eng, prompt, n, want_logits=True)
+    return {"logit_err": max(rel(lg[i], ref_lg[i]) for i in range(n)), "same": bool((toks == ref_toks).all())}
+
+
+def case_sample(shape, wt):
+    """transformer_sample against the sequential CDF walk of the host mirror on the same logits."""
+    from llm.f90_b200 import hostapi
+    cfg = Config(**SHAPES[shape], wtype=wt)
+    w = fx.synth_weights(cfg, 7)
+    rng = np.random.default_rng(1)
+    bad, near, n = [], 0, 0
+    with capi.Engine(w) as eng:
+        tok = 2
+        for pos in range(1, 25):
+            lg = eng.transformer(tok, pos).copy()
+            for T in (0.0, 0.7, 1.3):
+                r = float(rng.random())
+                got = eng.transformer_sample(tok, pos, T, r)   # same position again: the cache row is rewritten with the same values
+                want = hostapi.argmax(lg) if T == 0 else hostapi.sample(lg, T, r)
+                n += 1
+                if got != want:
+                    z = lg.astype(np.float64) / T
+                    p = np.exp(z - z.max()); cdf = np.cumsum(p / p.sum())
+                    if np.abs(cdf - r).min() < 1e-5:
+                        near += 1
+                    else:
+                        bad.append((pos, T, r, int(got), int(want)))
+            tok = int(lg.argmax()) + 1
+    return {"n": n, "mismatch_near_boundary": near, "bad": bad[:5], "ok": not bad}
+
+
 def main(argv):
     kind = argv[0]
-    if kind == "matmul":
+    if kind == "multi":  # several cases in one process: "kind args..." strings
+        for spec in argv[1:]:
+            try:
+                main(spec.split())
+            except Exception as e:  # keep going: the later cases may still tell something
+                print(json.dumps({"case": spec, "error": repr(e)[:400]}), flush=True)
+        return
+    if kind == "q6k_matvec":
+        out = case_q6k_matvec(int(argv[1]), int(argv[2]))
+    elif kind == "q6k_model":
+        out = case_q6k_model(int(argv[1]))
+    elif kind == "sample":
+        out = case_sample(argv[1], int(argv[2]))
+    elif kind == "matmul":
         out = case_matmul(int(argv[1]), int(argv[2]), int(argv[3]), int(argv[4]))
     elif kind == "prefill":
         out = case_prefill(argv[1], int(argv[2]), int(argv[3]))
@@ -92,6 +153,7 @@ def main(argv):
 
 
 if __name__ == "__main__":
-    import __graft_entry__ as ge
-    ge.build()
+    if not os.environ.get("LLMF90_WORKER_NO_BUILD"):
+        import __graft_entry__ as ge
+        ge.build()
     main(sys.argv[1:])
