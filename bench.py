@@ -230,7 +230,8 @@ def tp1_same_workload(model: str, wtype: str, steps: int, local_rank: int, timeo
     vis = [d for d in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if d]
     env["CUDA_VISIBLE_DEVICES"] = vis[local_rank] if local_rank < len(vis) else str(local_rank)
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--model", model, "--wtype", wtype,
-           "--steps", str(max(1, min(steps, 5))), "--warmup", "3", "--no-cpu-baseline", "--no-tp1"]
+           "--steps", str(max(1, min(steps, 5))), "--warmup", "3", "--no-cpu-baseline", "--no-tp1",
+           "--no-prefill"]  # like the tensor-parallel run: every position one decode launch
     try:
         out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s).stdout
         for ln in reversed(out.strip().splitlines()):
@@ -254,6 +255,8 @@ def main():
     ap.add_argument("--model", default=None)
     ap.add_argument("--wtype", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true",
+                    help="N = 1: run the prompt positions through the per-token kernel too (default: one batched tcgen05 pass)")
     ap.add_argument("--cpu-sample-pos", type=int, default=0, help="positions of the CPU sample (0 = auto)")
     ap.add_argument("--no-tp1", action="store_true", help="N > 1: skip the one-GPU run of the same workload")
     ap.add_argument("--force-tp1", action="store_true", help="N = 1: run the child measurement anyway (test hook)")
@@ -334,7 +337,10 @@ def main():
 
     w = fx.synth_weights_tiled(cfg, 0)
     prompt = prompt_tokens(cfg)
-    eng = capi.make_engine(w, device=dev, tp_rank=rank, tp_size=world)
+    # one GPU: the forced prompt positions are one batched pass on the tensor cores (llmf90_b200_prefill; their
+    # logits are dead values in the reference, llama2.f90:383-385); tensor-parallel runs take them token by token
+    use_prefill = world == 1 and not a.no_prefill
+    eng = capi.make_engine(w, device=dev, tp_rank=rank, tp_size=world, prefill=use_prefill)
     act_bytes = active_weight_bytes(cfg)
 
     def barrier():
@@ -369,16 +375,29 @@ def main():
         tot_ms = float(t.item())
     value = a.steps * N_POS / (tot_ms / 1000.0)
     ref_formula = a.steps * (N_POS - 1) / (sum(after_first) / 1000.0)
+    # the decode kernel on its own for the roofline: N_POS launches of it (positions 1..N_POS fed with their own
+    # picks), CUDA events on the engine's stream inside the library; with the prompt pass on, `value` is not
+    # N_POS launches of one kernel any more
+    decode_ms = []
+    for _ in range(max(1, min(a.steps, 5))):
+        eng.reset()
+        decode_ms.append(eng.bench_device_loop(2, 1, N_POS))
+    decode_launch_ms = float(sum(decode_ms)) / (len(decode_ms) * N_POS)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([decode_launch_ms], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        decode_launch_ms = float(t.item())
 
     # ---- e2e: the reference-facing per-token call with host logits
     for _ in range(2):
         eng.reset()
-        capi.host_generate(eng, prompt, N_POS)
+        capi.host_generate(eng, prompt, N_POS, prefill=use_prefill)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(a.steps, 5))
     for _ in range(e2e_steps):
-        toks_h, _ = capi.host_generate(eng, prompt, N_POS)
+        toks_h, _ = capi.host_generate(eng, prompt, N_POS, prefill=use_prefill)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -396,7 +415,8 @@ def main():
 
     peak, peak_src = peaks()
     st = eng.stats()
-    per_launch_ms = tot_ms / max(1, a.steps * N_POS)
+    per_launch_ms = decode_launch_ms
+    n_pf = min(len(prompt), N_POS - 1) if use_prefill else 0
     per_gpu_bytes = st["active_bytes_per_token"]
     achieved = per_gpu_bytes / (per_launch_ms / 1000.0) / 1e9
     line = {
@@ -406,17 +426,24 @@ def main():
         "config": {**config_of(f"tp{world}", len(prompt)),
                    "l2": f"inputs larger than L2: {act_bytes / 1e6:.0f} MB of weights streamed per token vs 126 MB L2",
                    "tokens_per_s_reference_formula": ref_formula,
+                   "prompt_pass": (f"positions 1..{n_pf} (BOS + forced prompt) in one batched tcgen05 pass "
+                                   f"(llmf90_b200_prefill), positions {n_pf + 1}..{N_POS} one decode launch each"
+                                   if n_pf else "every position one decode launch"),
+                   "decode_only_tokens_per_s": 1000.0 / decode_launch_ms,
                    "wall_ms_timed_region": wall_ms},
         "clocks": clk.summary(),
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8 * N_POS,
-                "d2h_bytes_per_step": 4 * cfg.vocab_size * N_POS, "steps": e2e_steps,
-                "api": "llmf90_b200_transformer(token,pos,logits) per position, host argmax",
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8 * (N_POS - n_pf) + 4 * n_pf,
+                "d2h_bytes_per_step": 4 * cfg.vocab_size * (N_POS - n_pf), "steps": e2e_steps,
+                "api": ("llmf90_b200_prefill(prompt positions) + " if n_pf else "") +
+                       "llmf90_b200_transformer(token,pos,logits) per position, host argmax",
                 "tokens_match_device_loop": tokens_agree},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(model, wtype), "peak_source": peak_src,
                      "kernel": "stream_decode_kernel (1 launch = 1 token)" if st["stream_slots"] else "granular graph",
-                     "algorithmic_bytes_per_launch": int(per_gpu_bytes), "launch_ms": per_launch_ms},
+                     "algorithmic_bytes_per_launch": int(per_gpu_bytes), "launch_ms": per_launch_ms,
+                     "timed": f"{len(decode_ms)} x {N_POS} launches of the decode kernel alone (llmf90_b200_bench_device_loop), "
+                              "CUDA events on the engine's stream"},
     }
     if model == "tinyllama" and wtype == "f32":
         # the one throughput figure the reference publishes; another workload

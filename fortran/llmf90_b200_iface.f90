@@ -10,6 +10,9 @@ module llmf90_b200
         implicit none
 
         integer(c_int32_t), parameter :: LLMF90_WTYPE_F32 = 0, LLMF90_WTYPE_F16 = 1, LLMF90_WTYPE_Q4_0 = 2
+        ! flags: granular kernels, per-phase timers, batched prompt pass, Q6_K output.weight
+        integer(c_int32_t), parameter :: LLMF90_FLAG_GRANULAR = 1, LLMF90_FLAG_PROFILE = 2, LLMF90_FLAG_PREFILL = 4, &
+                & LLMF90_FLAG_CLS_Q6K = 8
 
         ! mirror of `llmf90_b200_config`; the first seven fields are type Config (weight_module.f90:28-31)
         type, bind(C) :: b200_config
@@ -94,6 +97,26 @@ module llmf90_b200
                         integer(c_int32_t), value :: emb, kv, head_size, pos
                         integer(c_int) :: rc
                 end function b200_rope
+
+                ! the forced prompt positions (llama2.f90:379-385) as one batched pass: fills the KV cache for the
+                ! input tokens at positions pos0 .. pos0 + n_tokens - 1 (needs LLMF90_FLAG_PREFILL)
+                function b200_prefill(tokens, n_tokens, pos0) bind(C, name="llmf90_b200_prefill") result(rc)
+                        import :: c_int, c_int32_t
+                        integer(c_int32_t), intent(in) :: tokens(*)
+                        integer(c_int32_t), value :: n_tokens, pos0
+                        integer(c_int) :: rc
+                end function b200_prefill
+
+                ! transformer() + maxloc (temperature == 0, llama2.f90:388) or softmax(logits / temperature) + the
+                ! CDF walk of `sample` against r (llama2.f90:390-391, :428-447) on the device; r from random_number
+                function b200_transformer_sample(token, pos, temperature, r, next_token) &
+                                & bind(C, name="llmf90_b200_transformer_sample") result(rc)
+                        import :: c_int, c_int32_t, c_float
+                        integer(c_int32_t), value :: token, pos
+                        real(c_float), value :: temperature, r
+                        integer(c_int32_t), intent(out) :: next_token
+                        integer(c_int) :: rc
+                end function b200_transformer_sample
         end interface
 
 contains

@@ -162,7 +162,10 @@ class Engine:
     def transformer(self, token: int, pos: int, out: np.ndarray | None = None) -> np.ndarray:
         """logits = transformer(token, pos) with 1-based token/pos (llama2.f90:380)."""
         if out is None:
-            out = np.empty(self.cfg.vocab_size, np.float32)
+            # one buffer for the engine's lifetime: the library page-locks the array it is given in place, and a
+            # fresh array per call would mean one registration per token (and stale ones over freed memory)
+            _check(self.L.llmf90_b200_transformer(token, pos, _fp(self._logits)))
+            return self._logits.copy()
         _check(self.L.llmf90_b200_transformer(token, pos, _fp(out)))
         return out
 
@@ -236,15 +239,22 @@ class Engine:
         self.close()
 
 
-def host_generate(engine: Engine, prompt_tokens, n: int, want_logits: bool = False):
+def host_generate(engine: Engine, prompt_tokens, n: int, want_logits: bool = False, prefill: bool = False):
     """The reference's token loop (llama2.f90:376-393, temperature 0) driving the C ABI one
-    token at a time with host logits -- what the Fortran host does."""
+    token at a time with host logits -- what the Fortran host does.  prefill=True: the forced prompt
+    positions (inputs BOS, prompt[:-1]; their logits are never looked at, llama2.f90:383-385) go through
+    llmf90_b200_prefill as one batched pass and the loop starts at the first position whose logits are used."""
     V = engine.cfg.vocab_size
     toks = np.empty(n, np.int32)
-    lg_all = np.empty((n, V), np.float32) if want_logits else None
+    lg_all = np.full((n, V), np.nan, np.float32) if want_logits else None
     buf = np.empty(V, np.float32)
     token = 2
-    for pos in range(1, n + 1):
+    m = min(len(prompt_tokens), n - 1) if prefill else 0
+    if m >= 1:
+        engine.prefill([2] + [int(t) for t in prompt_tokens[:m - 1]], 1)
+        toks[:m] = prompt_tokens[:m]
+        token = int(prompt_tokens[m - 1])
+    for pos in range(m + 1, n + 1):
         engine.transformer(token, pos, buf)
         if want_logits:
             lg_all[pos - 1] = buf
@@ -307,11 +317,11 @@ def rope(q: np.ndarray, k: np.ndarray, head_size: int, pos: int):
 
 
 def make_engine(weights: Weights, device: int = 0, tp_rank: int = 0, tp_size: int = 1,
-                granular: bool = False) -> Engine:
+                granular: bool = False, prefill: bool = False) -> Engine:
     """Single GPU, or one tensor-parallel rank of `tp_size` (one process per GPU).  For tp_size > 1
     torch.distributed must be initialised: it carries the 64-byte IPC handles, nothing else -- the
     all-reduces of the forward run inside the decode kernel over NVLink peer stores."""
-    eng = Engine(weights, device=device, granular=granular, tp_rank=tp_rank, tp_size=tp_size)
+    eng = Engine(weights, device=device, granular=granular, tp_rank=tp_rank, tp_size=tp_size, prefill=prefill)
     if tp_size > 1:
         import torch.distributed as dist
         handles: list = [None] * tp_size

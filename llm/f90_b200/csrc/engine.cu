@@ -288,6 +288,15 @@ int enqueue_forward(int token, int pos, bool device_loop, const int *forced, int
     return 0;
 }
 
+// llmf90_b200_transformer page-locks the caller's logits array in place (one registration for the whole token
+// loop).  A caller that frees that array leaves a stale registration behind, and a later cudaMemcpy whose host
+// range overlaps only part of it fails with "invalid argument": every entry point that copies to or from OTHER
+// caller memory drops the registration first (the next transformer call registers again).
+void drop_logits_registration()
+{
+    if (E.reg_logits) { cudaHostUnregister(E.reg_logits); E.reg_logits = nullptr; }
+}
+
 // after a stream synchronisation: did a kernel give up waiting for a tensor-parallel peer?
 int check_peers()
 {
@@ -446,6 +455,7 @@ constexpr int STREAM_STATIC_SMEM = 3072;  // the kernel's static shared memory (
 namespace {
 int prefill_positions(const int32_t *tokens, int n, int pos0, float *ms)
 {
+    drop_logits_registration();
     const int maxp = prefill_max_positions();
     const PrefillRun r{E.d_emb, E.d_rms_att, E.d_rms_ffn, E.d_rope, E.d_kc, E.d_vc};
     CK(cudaEventRecord(E.ev0, E.st));
@@ -806,6 +816,7 @@ int llmf90_b200_debug_trace(int32_t token, int32_t pos, int32_t layer, uint64_t 
     if (!E.ready || !E.use_stream) return fail("debug_trace: needs the fused streaming engine");
     if (!E.peers_ready) return fail("tensor-parallel engine: call llmf90_b200_tp_connect first");
     if (!out || n_ctas < E.plan.grid) return fail("debug_trace: buffer must hold %d x 128 entries", E.plan.grid);
+    drop_logits_registration();
     unsigned long long *d = nullptr;
     CK(cudaMalloc((void **)&d, (size_t)E.plan.grid * 128 * 8));
     CK(cudaMemset(d, 0, (size_t)E.plan.grid * 128 * 8));
@@ -826,6 +837,7 @@ int llmf90_b200_phase_times(float *ms, int32_t n)
     if (!E.ready) return fail("engine not initialised");
     if (!ms || n < 1) return fail("phase_times: bad argument");
     unsigned long long c[PH_COUNT + 2];
+    drop_logits_registration();
     CK(cudaStreamSynchronize(E.st));
     CK(cudaMemcpy(c, E.d_times, sizeof c, cudaMemcpyDeviceToHost));
     // cycles -> ms with the kernel's own (globaltimer ns / clock64 cycles) ratio
@@ -868,6 +880,7 @@ int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, 
     if (!E.peers_ready) return fail("tensor-parallel engine: call llmf90_b200_tp_connect first");
     if (n < 1 || n > E.cfg.seq_len) return fail("n %d out of range 1..%d", n, E.cfg.seq_len);
     if (n_prompt < 0 || (n_prompt > 0 && !prompt_tokens)) return fail("bad prompt");
+    drop_logits_registration();
     std::vector<int> forced(E.cfg.seq_len, 0);
     for (int i = 0; i < n_prompt && i < n; i++) {
         if (prompt_tokens[i] < 1 || prompt_tokens[i] > E.cfg.vocab_size) return fail("prompt token out of range");
@@ -888,6 +901,8 @@ int llmf90_b200_generate_greedy(const int32_t *prompt_tokens, int32_t n_prompt, 
         if (device_loop(prompt_tokens[m - 1], m + 1, n - m, E.d_forced, E.d_out_tokens, nullptr, &loop_ms)) return 1;
         CK(cudaMemcpy(out_tokens, E.d_out_tokens, (size_t)n * 4, cudaMemcpyDeviceToHost));
         for (int i = 0; i < m; i++) out_tokens[i] = prompt_tokens[i];
+        E.loop_total_ms = pf_ms + loop_ms;  // the stats describe the whole generation: the prompt pass and the loop
+        E.loop_after_first_ms = pf_ms + loop_ms;
         if (elapsed_ms) *elapsed_ms = pf_ms + loop_ms;  // every position is inside: there is no separate first token to leave out
         return 0;
     }
@@ -918,6 +933,7 @@ int llmf90_b200_debug_read_kv(int32_t layer, int32_t pos, float *k, float *v)
 {
     if (!E.ready) return fail("engine not initialised");
     if (layer < 0 || layer >= E.cfg.n_layers || pos < 1 || pos > E.cfg.seq_len || !k || !v) return fail("read_kv: bad argument");
+    drop_logits_registration();
     CK(cudaStreamSynchronize(E.st));
     const size_t off = ((size_t)layer * E.cfg.seq_len + (size_t)(pos - 1)) * E.kv;
     CK(cudaMemcpy(k, E.d_kc + off, (size_t)E.kv * 4, cudaMemcpyDeviceToHost));

@@ -498,7 +498,7 @@ cudaError_t prefill_create(Prefill **out, const PrefillDims &d, int n_sms)
         pf->N[i] = N[i]; pf->K[i] = K[i];
         pf->mt[i] = cdiv(N[i], PF_TILE_M); pf->kc[i] = cdiv(K[i], PF_BK);
         // K splits: enough CTAs to cover the SMs, at most PF_MAX_SPLIT, every split non-empty
-        int want = std::max(1, std::min({n_sms / pf->mt[i], PF_MAX_SPLIT, pf->kc[i]}));
+        int want = std::max(1, std::min({(n_sms + pf->mt[i] / 2) / pf->mt[i], PF_MAX_SPLIT, pf->kc[i]}));
         pf->cps[i] = cdiv(pf->kc[i], want);
         pf->nsplit[i] = cdiv(pf->kc[i], pf->cps[i]);
         pf->layer_bytes[i] = (size_t)pf->mt[i] * pf->kc[i] * pf->npw * PF_A_PLANE;
@@ -608,7 +608,7 @@ cudaError_t prefill_gemm_op(const uint8_t *w_host_format, int wtype, int N, int 
 {
     if (P < 1 || P > PF_MAXP) return cudaErrorInvalidValue;
     const int npw = wtype == WT_F16 ? 1 : 2, mt = cdiv(N, PF_TILE_M), kc = cdiv(K, PF_BK), ppad = (P + 15) & ~15;
-    const int want = std::max(1, std::min({n_sms / mt, PF_MAX_SPLIT, kc}));
+    const int want = std::max(1, std::min({(n_sms + mt / 2) / mt, PF_MAX_SPLIT, kc}));
     const int cps = cdiv(kc, want), nsplit = cdiv(kc, cps);
     uint8_t *A = nullptr, *B = nullptr;
     float *Y = nullptr;

@@ -46,7 +46,10 @@ def prompt_for(cfg, n_prompt, seed=3):
 def case_prefill(shape, wt, n_prompt):
     """KV rows of every layer and the logits of the next position: batched pass vs the per-token path."""
     cfg = Config(**SHAPES[shape], wtype=wt)
-    w = fx.synth_weights(cfg, 11) if shape in ("tiny", "small", "mha") else fx.synth_weights_fast(cfg, 11)
+    if shape in ("tiny", "small", "mha"):
+        w = fx.synth_weights(cfg, 11)
+    else:  # large shapes: the quick generators of the benchmark
+        w = fx.synth_weights_tiled(cfg, 0) if shape == "tinyllama" else fx.synth_weights_fast(cfg, 11)
     toks = [2] + prompt_for(cfg, n_prompt)  # inputs of positions 1 .. n_prompt + 1
     with capi.Engine(w, prefill=True) as eng:
         for p in range(n_prompt):
