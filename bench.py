@@ -407,6 +407,22 @@ def main():
         e2e_s = float(t.item())
     e2e = e2e_steps * N_POS / e2e_s
     tokens_agree = bool((np.asarray(toks_h) == np.asarray(toks)).all())
+    # the same host-driven loop with the pick made on the device (llmf90_b200_transformer_sample, temperature 0):
+    # 4 bytes come back per position instead of the logits.  Reported beside e2e, not as e2e.
+    eng.reset()
+    capi.host_generate_device_pick(eng, prompt, N_POS, prefill=use_prefill)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        toks_p = capi.host_generate_device_pick(eng, prompt, N_POS, prefill=use_prefill)
+    barrier()
+    pick_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([pick_s], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pick_s = float(t.item())
+    pick_agree = bool((np.asarray(toks_p) == np.asarray(toks)).all())
 
     if rank != 0:
         barrier()
@@ -436,7 +452,11 @@ def main():
                 "d2h_bytes_per_step": 4 * cfg.vocab_size * (N_POS - n_pf), "steps": e2e_steps,
                 "api": ("llmf90_b200_prefill(prompt positions) + " if n_pf else "") +
                        "llmf90_b200_transformer(token,pos,logits) per position, host argmax",
-                "tokens_match_device_loop": tokens_agree},
+                "tokens_match_device_loop": tokens_agree,
+                "device_pick": {"value": e2e_steps * N_POS / pick_s, "unit": "tokens/s",
+                                "api": "llmf90_b200_transformer_sample(token,pos,0,r,&next) per position: maxloc next to "
+                                       "the logits, 4 bytes back",
+                                "d2h_bytes_per_step": 4 * (N_POS - n_pf), "tokens_match_device_loop": pick_agree}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(model, wtype), "peak_source": peak_src,

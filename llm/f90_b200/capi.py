@@ -263,6 +263,27 @@ def host_generate(engine: Engine, prompt_tokens, n: int, want_logits: bool = Fal
     return toks, lg_all
 
 
+def host_generate_device_pick(engine: Engine, prompt_tokens, n: int, temperature: float = 0.0, rng=None,
+                              prefill: bool = False) -> np.ndarray:
+    """The same token loop with the pick made next to the logits (llmf90_b200_transformer_sample): one call per
+    position, the token comes back instead of the logits.  rng draws the uniform number of a sampled position, in
+    the host, like random_number at llama2.f90:433."""
+    toks = np.empty(n, np.int32)
+    token = 2
+    m = min(len(prompt_tokens), n - 1) if prefill else 0
+    if m >= 1:
+        engine.prefill([2] + [int(t) for t in prompt_tokens[:m - 1]], 1)
+        toks[:m] = prompt_tokens[:m]
+        token = int(prompt_tokens[m - 1])
+    for pos in range(m + 1, n + 1):
+        forced = pos <= len(prompt_tokens)
+        r = float(rng.random()) if (rng is not None and temperature != 0 and not forced) else 0.0
+        nxt = engine.transformer_sample(token, pos, temperature, r)
+        token = int(prompt_tokens[pos - 1]) if forced else nxt
+        toks[pos - 1] = token
+    return toks
+
+
 def plan(cfg: Config, tp_rank: int = 0, tp_size: int = 1, n_sms: int = B200_SMS,
          smem_optin: int = B200_SMEM_OPTIN):
     """llmf90_b200_plan: the fused kernel's grid / ring / per-CTA stage lists for a configuration,

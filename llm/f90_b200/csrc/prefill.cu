@@ -271,11 +271,12 @@ __global__ void pf_embed_kernel(const uint8_t *__restrict__ table, int wtype, in
 
 // x[p] += sum of the partial products of the previous GEMM (residual add, llama2.f90:606, :621), then
 // B operand = rmsnorm(x[p]) * w (llama2.f90:450-457).  One CTA per padded position; rows >= P are zeros.
-__global__ void __launch_bounds__(256) pf_rmsnorm_pack_kernel(float *__restrict__ X, const float *__restrict__ w, int emb,
+constexpr int PF_NORM_THREADS = 1024;
+__global__ void __launch_bounds__(PF_NORM_THREADS) pf_rmsnorm_pack_kernel(float *__restrict__ X, const float *__restrict__ w, int emb,
                                                               const float *__restrict__ Y, int nsplit, int P, int ppad,
                                                               int kpad, uint8_t *__restrict__ B)
 {
-    __shared__ float red[8];
+    __shared__ float red[PF_NORM_THREADS / 32];
     __shared__ float s_xn;
     const int p = blockIdx.x;
     if (p >= P) {
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(256) pf_rmsnorm_pack_kernel(float *__restrict_
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
-        for (int i = 0; i < 8; i++) t += red[i];
+        for (int i = 0; i < PF_NORM_THREADS / 32; i++) t += red[i];
         s_xn = sqrtf(t / (float)emb + 1e-5f);
     }
     __syncthreads();
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) pf_rmsnorm_pack_kernel(float *__restrict_
 }
 
 // RoPE on q and k with the decode path's table (quirks Q1 / Q2), KV append at cache row pos0 - 1 + p
-// (llama2.f90:543-565); q goes to Q[p][emb].  One CTA per position, one thread per pair of q | k | v.
+// (llama2.f90:543-565); q goes to Q[p][emb].  grid = (positions, chunks of pairs), one thread per pair of q | k | v.
 __global__ void pf_rope_kv_kernel(const float *__restrict__ Y, int nsplit, int ppad, int emb, int kv, int hs,
                                   const float2 *__restrict__ tab, int pos0, float *__restrict__ Q,
                                   float *__restrict__ kc_layer, float *__restrict__ vc_layer)
@@ -320,7 +321,7 @@ __global__ void pf_rope_kv_kernel(const float *__restrict__ Y, int nsplit, int p
     const int p = blockIdx.x, N = emb + 2 * kv, half = hs >> 1;
     const int row = pos0 - 1 + p;  // 0-based cache row
     const int nq = emb >> 1, nk = kv >> 1;
-    for (int i = threadIdx.x; i < nq + 2 * nk; i += blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < nq + 2 * nk; i += gridDim.y * blockDim.x) {
         if (i < nq) {
             const float2 cs = tab[(size_t)row * half + i % half];
             const float a = sum_parts(Y, nsplit, ppad, N, p, 2 * i), b = sum_parts(Y, nsplit, ppad, N, p, 2 * i + 1);
@@ -418,12 +419,12 @@ __global__ void __launch_bounds__(PF_ATT_THREADS) pf_attention_kernel(
 }
 
 // hb = silu(W1 x) * (W3 x) (llama2.f90:613-616) from the partial products of the W1|W3 GEMM (rows W1 then W3,
-// the host order) into the packed B operand of the W2 GEMM.  grid = ppad.
+// the host order) into the packed B operand of the W2 GEMM.  grid = (ppad, chunks of 8-element units).
 __global__ void __launch_bounds__(256) pf_swiglu_pack_kernel(const float *__restrict__ Y, int nsplit, int P, int ppad, int hid,
                                                              int kpad, uint8_t *__restrict__ B)
 {
     const int p = blockIdx.x;
-    for (int k8 = threadIdx.x; k8 < kpad / 8; k8 += blockDim.x) {
+    for (int k8 = blockIdx.y * blockDim.x + threadIdx.x; k8 < kpad / 8; k8 += gridDim.y * blockDim.x) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -575,11 +576,11 @@ cudaError_t prefill_run(Prefill *pf, const PrefillRun &r, int n, int pos0, cudaS
     for (int l = 0; l < d.L; l++) {
         float *kc = r.kc + (size_t)l * d.seq * d.kv, *vc = r.vc + (size_t)l * d.seq * d.kv;
         // rmsnorm (+ the previous layer's W2 residual) -> QKV
-        pf_rmsnorm_pack_kernel<<<ppad, 256, 0, st>>>(pf->X, r.rms_att + (size_t)l * d.emb, d.emb, pf->Y, l ? pf->nsplit[3] : 0, n,
+        pf_rmsnorm_pack_kernel<<<ppad, PF_NORM_THREADS, 0, st>>>(pf->X, r.rms_att + (size_t)l * d.emb, d.emb, pf->Y, l ? pf->nsplit[3] : 0, n,
                                                      ppad, kpad_e, pf->B);
         PF_CK(cudaGetLastError());
         PF_CK(run_gemm(pf, 0, l, n, ppad, st));
-        pf_rope_kv_kernel<<<n, 256, 0, st>>>(pf->Y, pf->nsplit[0], ppad, d.emb, d.kv, d.hs, r.rope_tab, pos0, pf->Q, kc, vc);
+        pf_rope_kv_kernel<<<dim3(n, cdiv(d.emb / 2 + d.kv, 256)), 256, 0, st>>>(pf->Y, pf->nsplit[0], ppad, d.emb, d.kv, d.hs, r.rope_tab, pos0, pf->Q, kc, vc);
         PF_CK(cudaGetLastError());
         if (l == d.L - 1) break;  // the last layer's attention / FFN only feed logits nobody reads (llama2.f90:383-385)
         pf_attention_kernel<<<dim3(d.H, ppad), PF_ATT_THREADS, (size_t)(pos0 + n) * 4, st>>>(pf->Q, kc, vc, pos0, n, ppad, d.emb,
@@ -587,11 +588,11 @@ cudaError_t prefill_run(Prefill *pf, const PrefillRun &r, int n, int pos0, cudaS
         PF_CK(cudaGetLastError());
         PF_CK(run_gemm(pf, 1, l, n, ppad, st));
         // residual + rmsnorm -> W1|W3 -> SwiGLU -> W2
-        pf_rmsnorm_pack_kernel<<<ppad, 256, 0, st>>>(pf->X, r.rms_ffn + (size_t)l * d.emb, d.emb, pf->Y, pf->nsplit[1], n, ppad,
+        pf_rmsnorm_pack_kernel<<<ppad, PF_NORM_THREADS, 0, st>>>(pf->X, r.rms_ffn + (size_t)l * d.emb, d.emb, pf->Y, pf->nsplit[1], n, ppad,
                                                      kpad_e, pf->B);
         PF_CK(cudaGetLastError());
         PF_CK(run_gemm(pf, 2, l, n, ppad, st));
-        pf_swiglu_pack_kernel<<<ppad, 256, 0, st>>>(pf->Y, pf->nsplit[2], n, ppad, d.hid, kpad_h, pf->B);
+        pf_swiglu_pack_kernel<<<dim3(ppad, cdiv(kpad_h / 8, 256)), 256, 0, st>>>(pf->Y, pf->nsplit[2], n, ppad, d.hid, kpad_h, pf->B);
         PF_CK(cudaGetLastError());
         PF_CK(run_gemm(pf, 3, l, n, ppad, st));
     }
