@@ -379,15 +379,13 @@ def main():
     # picks), CUDA events on the engine's stream inside the library; with the prompt pass on, `value` is not
     # N_POS launches of one kernel any more
     decode_ms = []
-    for _ in range(max(1, min(a.steps, 5))):
-        eng.reset()
-        decode_ms.append(eng.bench_device_loop(2, 1, N_POS))
-    decode_launch_ms = float(sum(decode_ms)) / (len(decode_ms) * N_POS)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([decode_launch_ms], device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        decode_launch_ms = float(t.item())
+    if use_prefill:
+        for _ in range(max(1, min(a.steps, 5))):
+            eng.reset()
+            decode_ms.append(eng.bench_device_loop(2, 1, N_POS))
+        decode_launch_ms = float(sum(decode_ms)) / (len(decode_ms) * N_POS)
+    else:
+        decode_launch_ms = tot_ms / max(1, a.steps * N_POS)  # every position of the timed region is one decode launch
 
     # ---- e2e: the reference-facing per-token call with host logits
     for _ in range(2):
@@ -409,20 +407,16 @@ def main():
     tokens_agree = bool((np.asarray(toks_h) == np.asarray(toks)).all())
     # the same host-driven loop with the pick made on the device (llmf90_b200_transformer_sample, temperature 0):
     # 4 bytes come back per position instead of the logits.  Reported beside e2e, not as e2e.
-    eng.reset()
-    capi.host_generate_device_pick(eng, prompt, N_POS, prefill=use_prefill)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        toks_p = capi.host_generate_device_pick(eng, prompt, N_POS, prefill=use_prefill)
-    barrier()
-    pick_s = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([pick_s], device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pick_s = float(t.item())
-    pick_agree = bool((np.asarray(toks_p) == np.asarray(toks)).all())
+    pick = None
+    if world == 1:
+        eng.reset()
+        capi.host_generate_device_pick(eng, prompt, N_POS, prefill=use_prefill)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            toks_p = capi.host_generate_device_pick(eng, prompt, N_POS, prefill=use_prefill)
+        barrier()
+        pick = (e2e_steps * N_POS / (time.perf_counter() - t0), bool((np.asarray(toks_p) == np.asarray(toks)).all()))
 
     if rank != 0:
         barrier()
@@ -452,19 +446,21 @@ def main():
                 "d2h_bytes_per_step": 4 * cfg.vocab_size * (N_POS - n_pf), "steps": e2e_steps,
                 "api": ("llmf90_b200_prefill(prompt positions) + " if n_pf else "") +
                        "llmf90_b200_transformer(token,pos,logits) per position, host argmax",
-                "tokens_match_device_loop": tokens_agree,
-                "device_pick": {"value": e2e_steps * N_POS / pick_s, "unit": "tokens/s",
-                                "api": "llmf90_b200_transformer_sample(token,pos,0,r,&next) per position: maxloc next to "
-                                       "the logits, 4 bytes back",
-                                "d2h_bytes_per_step": 4 * (N_POS - n_pf), "tokens_match_device_loop": pick_agree}},
+                "tokens_match_device_loop": tokens_agree},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(model, wtype), "peak_source": peak_src,
                      "kernel": "stream_decode_kernel (1 launch = 1 token)" if st["stream_slots"] else "granular graph",
                      "algorithmic_bytes_per_launch": int(per_gpu_bytes), "launch_ms": per_launch_ms,
-                     "timed": f"{len(decode_ms)} x {N_POS} launches of the decode kernel alone (llmf90_b200_bench_device_loop), "
-                              "CUDA events on the engine's stream"},
+                     "timed": (f"{len(decode_ms)} x {N_POS} launches of the decode kernel alone (llmf90_b200_bench_device_loop), "
+                               "CUDA events on the engine's stream") if decode_ms else
+                              f"the {a.steps} x {N_POS} decode launches of the timed region, CUDA events on the engine's stream"},
     }
+    if pick:
+        line["e2e"]["device_pick"] = {"value": pick[0], "unit": "tokens/s",
+                                      "api": "llmf90_b200_transformer_sample(token,pos,0,r,&next) per position: maxloc next to "
+                                             "the logits, 4 bytes back",
+                                      "d2h_bytes_per_step": 4 * (N_POS - n_pf), "tokens_match_device_loop": pick[1]}
     if model == "tinyllama" and wtype == "f32":
         # the one throughput figure the reference publishes; another workload
         # (-n 96, sampled, unspecified CPU), so it is quoted, not divided into vs_baseline

@@ -239,6 +239,22 @@ typedef struct llmf90_b200_sched_stage {   /* one bulk copy (cp.async.bulk) */
 int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_optin,
                      llmf90_b200_plan_info *info, llmf90_b200_sched_stage *sched, int64_t sched_entries);
 
+/* ---- the batched prompt pass's plan for a configuration, computed WITHOUT a device ----
+ * One entry per GEMM of a layer (0 QKV, 1 Wo, 2 W1|W3, 3 W2) for a pass over n_pos positions (1..128): the
+ * grid (m_tiles x n_splits CTAs: 128 weight rows x a range of 64-element contraction chunks), the TMEM columns
+ * of the accumulator, the shared-memory pipeline, and the bytes of the operand-order weight copy and of the
+ * K-split partial products.  The CPU test-suite checks with it that the splits cover every chunk exactly once,
+ * that the pipeline fits a B200 SM (227 KB, 512 TMEM columns) and what the flag costs in HBM (tests/test_plan.py). */
+typedef struct llmf90_b200_prefill_gemm {
+    int32_t rows, cols, planes;
+    int32_t m_tiles, k_chunks, chunks_per_split, n_splits;
+    int32_t ppad, tmem_cols;
+    int32_t stages, stage_bytes, smem_bytes;
+    uint64_t weight_bytes;   /* per layer */
+    uint64_t partial_bytes;
+} llmf90_b200_prefill_gemm;
+int llmf90_b200_prefill_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t n_pos, llmf90_b200_prefill_gemm out[4]);
+
 /* device-resident variant used for the HBM-resident measurement: runs `n_steps` forwards for
  * positions pos0..pos0+n_steps-1 feeding each one the greedy pick of the previous one, without
  * any host<->device traffic; returns the device time in ms. */

@@ -28,7 +28,7 @@ EXPORTS = [
     "llmf90_b200_tp_export", "llmf90_b200_tp_connect", "llmf90_b200_get_stats",
     "llmf90_b200_bench_device_loop", "llmf90_b200_phase_times", "llmf90_b200_debug_trace",
     "llmf90_b200_plan", "llmf90_b200_prefill", "llmf90_b200_debug_read_kv", "llmf90_b200_matmul",
-    "llmf90_b200_transformer_sample",
+    "llmf90_b200_transformer_sample", "llmf90_b200_prefill_plan",
 ]
 
 
@@ -54,6 +54,12 @@ class CPlanInfo(C.Structure):
                 ("tile_chunks", C.c_int32 * 5), ("tile_warps", C.c_int32 * 5), ("reserved0", C.c_int32),
                 ("matrix_bytes", C.c_uint64 * 5),
                 ("vector_bytes", C.c_uint64), ("emb_row_bytes", C.c_uint64)]
+
+
+class CPrefillGemm(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("rows", "cols", "planes", "m_tiles", "k_chunks", "chunks_per_split", "n_splits",
+                                         "ppad", "tmem_cols", "stages", "stage_bytes", "smem_bytes")] + \
+               [("weight_bytes", C.c_uint64), ("partial_bytes", C.c_uint64)]
 
 
 SCHED_DTYPE = np.dtype([("src", np.uint64), ("bytes", np.uint32), ("layer_stride16", np.uint32),
@@ -99,6 +105,7 @@ def load() -> C.CDLL:
     L.llmf90_b200_get_stats.argtypes = [C.POINTER(CStats)]
     L.llmf90_b200_bench_device_loop.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp]
     L.llmf90_b200_transformer_sample.argtypes = [C.c_int32, C.c_int32, C.c_float, C.c_float, ip]
+    L.llmf90_b200_prefill_plan.argtypes = [C.POINTER(CConfig), C.c_int32, C.c_int32, C.POINTER(CPrefillGemm)]
     L.llmf90_b200_prefill.argtypes = [ip, C.c_int32, C.c_int32]
     L.llmf90_b200_debug_read_kv.argtypes = [C.c_int32, C.c_int32, fp, fp]
     L.llmf90_b200_matmul.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, fp, C.c_int32, fp]
@@ -308,6 +315,15 @@ def matvec(w: np.ndarray, wtype: int, rows: int, cols: int, x: np.ndarray) -> np
     w = np.ascontiguousarray(w)
     _check(load().llmf90_b200_matvec(w.ctypes.data_as(C.c_void_p), wtype, rows, cols, _fp(x), _fp(y)))
     return y
+
+
+def prefill_plan(cfg: Config, n_pos: int, n_sms: int = B200_SMS) -> list[dict]:
+    """The four GEMMs of a batched prompt pass over n_pos positions, computed without a device."""
+    cc = CConfig(cfg.emb_dim, cfg.hidden_dim, cfg.n_layers, cfg.n_heads, cfg.n_kv_heads, cfg.vocab_size, cfg.seq_len,
+                 cfg.wtype, 0, 0, 1, FLAG_PREFILL)
+    out = (CPrefillGemm * 4)()
+    _check(load().llmf90_b200_prefill_plan(C.byref(cc), n_sms, n_pos, out))
+    return [{n: int(getattr(g, n)) for n, _ in CPrefillGemm._fields_} for g in out]
 
 
 def matmul(w: np.ndarray, wtype: int, rows: int, cols: int, x: np.ndarray) -> np.ndarray:

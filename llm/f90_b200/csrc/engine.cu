@@ -1048,6 +1048,24 @@ int llmf90_b200_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t smem_
     return rc;
 }
 
+int llmf90_b200_prefill_plan(const llmf90_b200_config *cfg, int32_t n_sms, int32_t n_pos, llmf90_b200_prefill_gemm out[4])
+{
+    if (!cfg || !out) return fail("prefill_plan: null argument");
+    if (n_sms <= 0 || n_pos < 1 || n_pos > prefill_max_positions()) return fail("prefill_plan: n_sms > 0 and n_pos in 1..%d", prefill_max_positions());
+    int hs, tp, rank;
+    if (check_config(*cfg, &hs, &tp, &rank)) return 1;
+    if (tp > 1) return fail("prefill_plan: the batched prompt pass is single-GPU");
+    const int emb = cfg->emb_dim, hid = cfg->hidden_dim, kv = cfg->n_kv_heads * hs;
+    const int N[4] = {emb + 2 * kv, emb, 2 * hid, emb}, K[4] = {emb, emb, emb, hid};
+    for (int i = 0; i < 4; i++) {
+        PrefillGemmGeom g;
+        prefill_gemm_geometry(N[i], K[i], cfg->wtype, n_sms, n_pos, &g);
+        out[i] = {g.rows, g.cols, g.planes, g.m_tiles, g.k_chunks, g.chunks_per_split, g.n_splits, g.ppad, g.tmem_cols,
+                  g.stages, g.stage_bytes, g.smem_bytes, g.weight_bytes, g.partial_bytes};
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------- operator wrappers
 
 int llmf90_b200_matvec(const void *w, int32_t wtype, int32_t rows, int32_t cols, const float *x, float *y)

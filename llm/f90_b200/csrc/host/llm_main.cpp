@@ -22,6 +22,7 @@ struct Args {  // type args (llama2.f90:7-14), defaults :26-32
     int n = 256;
     int device = -1, granular = 0;
     bool host_sampler = false;  // extension: copy the logits back and pick on the host, like the reference
+    bool prefill = false;       // extension: the prompt positions as one batched tensor-core pass (single GPU)
     // extension: tensor parallelism, one `llm` process per GPU started with the same flags plus its
     // --tp-rank; the ranks meet in --tp-dir (a fresh directory on a shared file system)
     int tp_size = 1, tp_rank = 0;
@@ -53,6 +54,7 @@ Args parse_args(int argc, char **argv)
         else if (f == "--device") { a.device = atoi(val().c_str()); i += 2; }       // extension
         else if (f == "--granular") { a.granular = 1; i += 1; }                     // extension
         else if (f == "--host-sampler") { a.host_sampler = true; i += 1; }          // extension
+        else if (f == "--prefill") { a.prefill = true; i += 1; }                    // extension
         else if (f == "--tp-size") { a.tp_size = atoi(val().c_str()); i += 2; }     // extension
         else if (f == "--tp-rank") { a.tp_rank = atoi(val().c_str()); i += 2; }     // extension
         else if (f == "--tp-dir") { a.tp_dir = val(); i += 2; }                     // extension
@@ -131,6 +133,7 @@ int main(int argc, char **argv)
     cfg.tp_rank = a.tp_rank; cfg.tp_size = a.tp_size;
     cfg.flags = a.granular ? LLMF90_FLAG_GRANULAR : 0;
     if (m.cfg.cls_wtype == 14) cfg.flags |= LLMF90_FLAG_CLS_Q6K;  // stock llama.cpp q4_0 file: Q6_K classifier
+    if (a.prefill && a.tp_size == 1) cfg.flags |= LLMF90_FLAG_PREFILL;
     if (llmf90_b200_init(&cfg, m.w.token_embedding_table.data(), m.w.rms_att_weight.data(), m.w.wqkv.data(),
                          m.w.wo.data(), m.w.rms_ffn_weight.data(), m.w.w13.data(), m.w.w2.data(),
                          m.w.rms_final_weight.data(), m.w.wcls.data()))
@@ -152,7 +155,25 @@ int main(int argc, char **argv)
     clk::time_point t_start{};
     bool started = false;
     int token = 2;  // <s>, 1-based (llama2.f90:376)
-    for (int pos = 1; pos <= seq_len; pos++) {
+    int first_pos = 1, timed_positions = seq_len - 1;  // the reference's clock starts after the first token (:399-401)
+    if ((cfg.flags & LLMF90_FLAG_PREFILL) && !prompt_tokens.empty() && seq_len > 1) {
+        t_start = clk::now(); started = true; timed_positions = seq_len;  // here every position is inside the clock
+        // The forced positions 1..np (inputs <s>, prompt[0..np-2]) only leave KV rows behind -- their picks are
+        // overwritten by the prompt (llama2.f90:383-385) -- so they are one batched pass; the loop starts at np + 1.
+        const int np = std::min((int)prompt_tokens.size(), seq_len - 1);
+        std::vector<int32_t> in(np);
+        in[0] = 2;
+        for (int i = 1; i < np; i++) in[i] = prompt_tokens[i - 1];
+        if (llmf90_b200_prefill(in.data(), np, 1)) die(llmf90_b200_last_error());
+        for (int i = 0; i < np && talk; i++) {  // the reference prints the forced tokens as it goes (:395)
+            const std::string &piece = m.vocab.tokens[prompt_tokens[i] - 1];
+            fwrite(piece.data(), 1, piece.size(), stdout);
+        }
+        fflush(stdout);
+        token = prompt_tokens[np - 1];
+        first_pos = np + 1;
+    }
+    for (int pos = first_pos; pos <= seq_len; pos++) {
         if (a.host_sampler) {
             // the reference's own shape: logits to the host, pick there (llama2.f90:380-392)
             if (llmf90_b200_transformer(token, pos, logits.data())) die(llmf90_b200_last_error());
@@ -178,7 +199,7 @@ int main(int argc, char **argv)
     const double ms = std::chrono::duration<double, std::milli>(clk::now() - t_start).count();
     if (talk) {
         printf("\n Inference time:  %g  seconds\n", ms / 1000.0);
-        printf(" %g tokens/second\n", 1000.0 * (seq_len - 1) / ms);
+        printf(" %g tokens/second\n", 1000.0 * timed_positions / ms);
         printf(" Timings\n");
         float t[5] = {0, 0, 0, 0, 0};
         llmf90_b200_times(t);

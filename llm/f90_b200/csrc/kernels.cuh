@@ -174,6 +174,18 @@ struct PrefillRun {
     float *kc, *vc;                      // [L][seq][kv]
 };
 struct Prefill;
+// geometry of one GEMM of the pass (host-side arithmetic only: also what llmf90_b200_prefill_plan reports)
+struct PrefillGemmGeom {
+    int rows, cols;          // weight rows N, contraction length K
+    int planes;              // f16 planes of the weights: 1 (f16 storage) or 2 (hi + lo of f32 / q4_0)
+    int m_tiles, k_chunks;   // tiles of 128 rows, chunks of 64 contraction elements (both padded with zeros)
+    int chunks_per_split, n_splits;  // grid = m_tiles x n_splits; split s takes chunks [s * cps, min(k_chunks, (s + 1) * cps))
+    int ppad, tmem_cols;     // positions padded to 16; TMEM columns allocated (power of two >= 32)
+    int stages, stage_bytes, smem_bytes;
+    unsigned long long weight_bytes;   // operand-order copy of one layer of this matrix
+    unsigned long long partial_bytes;  // Y[n_splits][ppad][rows] f32
+};
+void prefill_gemm_geometry(int rows, int cols, int wtype, int n_sms, int n_pos, PrefillGemmGeom *g);
 size_t prefill_weight_bytes(const PrefillDims &d);   // HBM the operand-order copy of the layer matrices takes
 cudaError_t prefill_create(Prefill **out, const PrefillDims &d, int n_sms);
 void prefill_destroy(Prefill *pf);

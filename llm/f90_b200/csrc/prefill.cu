@@ -463,6 +463,26 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 // ------------------------------------------------------------------ host side
+void prefill_gemm_geometry(int rows, int cols, int wtype, int n_sms, int n_pos, PrefillGemmGeom *g)
+{
+    g->rows = rows; g->cols = cols;
+    g->planes = wtype == WT_F16 ? 1 : 2;
+    g->m_tiles = cdiv(rows, PF_TILE_M); g->k_chunks = cdiv(cols, PF_BK);
+    // K splits: enough CTAs to cover the SMs (rounded to the nearest whole number of splits), at most PF_MAX_SPLIT,
+    // every split non-empty
+    const int want = std::max(1, std::min({(n_sms + g->m_tiles / 2) / g->m_tiles, PF_MAX_SPLIT, g->k_chunks}));
+    g->chunks_per_split = cdiv(g->k_chunks, want);
+    g->n_splits = cdiv(g->k_chunks, g->chunks_per_split);
+    g->ppad = (std::max(1, std::min(n_pos, PF_MAXP)) + 15) & ~15;
+    g->tmem_cols = 32;
+    while (g->tmem_cols < g->ppad) g->tmem_cols *= 2;
+    g->stage_bytes = g->planes * PF_A_PLANE + g->ppad * 256;
+    g->stages = std::max(2, std::min({PF_MAX_STAGES, (200 * 1024) / g->stage_bytes, g->chunks_per_split}));
+    g->smem_bytes = g->stages * g->stage_bytes + (2 * PF_MAX_STAGES + 1) * 8 + 16;
+    g->weight_bytes = (unsigned long long)g->m_tiles * g->k_chunks * g->planes * PF_A_PLANE;
+    g->partial_bytes = (unsigned long long)g->n_splits * g->ppad * rows * 4ull;
+}
+
 struct Prefill {
     PrefillDims d{};
     int npw = 2, n_sms = 148, swap_lbo = 0;
@@ -496,13 +516,12 @@ cudaError_t prefill_create(Prefill **out, const PrefillDims &d, int n_sms)
     int kmax = 0;
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 4 && e == cudaSuccess; i++) {
+        PrefillGemmGeom g;
+        prefill_gemm_geometry(N[i], K[i], d.wtype, n_sms, PF_MAXP, &g);
         pf->N[i] = N[i]; pf->K[i] = K[i];
-        pf->mt[i] = cdiv(N[i], PF_TILE_M); pf->kc[i] = cdiv(K[i], PF_BK);
-        // K splits: enough CTAs to cover the SMs, at most PF_MAX_SPLIT, every split non-empty
-        int want = std::max(1, std::min({(n_sms + pf->mt[i] / 2) / pf->mt[i], PF_MAX_SPLIT, pf->kc[i]}));
-        pf->cps[i] = cdiv(pf->kc[i], want);
-        pf->nsplit[i] = cdiv(pf->kc[i], pf->cps[i]);
-        pf->layer_bytes[i] = (size_t)pf->mt[i] * pf->kc[i] * pf->npw * PF_A_PLANE;
+        pf->mt[i] = g.m_tiles; pf->kc[i] = g.k_chunks;
+        pf->cps[i] = g.chunks_per_split; pf->nsplit[i] = g.n_splits;
+        pf->layer_bytes[i] = (size_t)g.weight_bytes;
         ymax = std::max(ymax, (size_t)pf->nsplit[i] * PF_MAXP * N[i]);
         kmax = std::max(kmax, pf->kc[i] * PF_BK);
         e = cudaMalloc((void **)&pf->W[i], pf->layer_bytes[i] * d.L);
@@ -549,14 +568,14 @@ static cudaError_t run_gemm(Prefill *pf, int matrix, int layer, int P, int ppad,
     a.A = pf->W[matrix] + (size_t)layer * pf->layer_bytes[matrix];
     a.B = pf->B; a.Y = pf->Y;
     a.N = pf->N[matrix]; a.P = P; a.ppad = ppad;
-    a.kc = pf->kc[matrix]; a.cps = pf->cps[matrix];
-    a.tmem_cols = 32;
-    while (a.tmem_cols < ppad) a.tmem_cols *= 2;
+    PrefillGemmGeom g;
+    prefill_gemm_geometry(pf->N[matrix], pf->K[matrix], pf->d.wtype, pf->n_sms, P, &g);
+    a.kc = g.k_chunks; a.cps = g.chunks_per_split;
+    a.tmem_cols = g.tmem_cols;
     a.swap_lbo = pf->swap_lbo;
-    const int st_bytes = pf->npw * PF_A_PLANE + ppad * 256;
-    a.nst = std::max(2, std::min({PF_MAX_STAGES, (200 * 1024) / st_bytes, a.cps}));
-    const size_t smem = (size_t)a.nst * st_bytes + (2 * PF_MAX_STAGES + 1) * 8 + 16;
-    const dim3 grid(pf->mt[matrix], pf->nsplit[matrix]);
+    a.nst = g.stages;
+    const size_t smem = (size_t)g.smem_bytes;
+    const dim3 grid(g.m_tiles, g.n_splits);
     if (pf->npw == 1) umma_gemm_kernel<1><<<grid, PF_THREADS, smem, st>>>(a);
     else umma_gemm_kernel<2><<<grid, PF_THREADS, smem, st>>>(a);
     return cudaGetLastError();
@@ -608,9 +627,9 @@ cudaError_t prefill_gemm_op(const uint8_t *w_host_format, int wtype, int N, int 
                             int n_sms, cudaStream_t st)
 {
     if (P < 1 || P > PF_MAXP) return cudaErrorInvalidValue;
-    const int npw = wtype == WT_F16 ? 1 : 2, mt = cdiv(N, PF_TILE_M), kc = cdiv(K, PF_BK), ppad = (P + 15) & ~15;
-    const int want = std::max(1, std::min({(n_sms + mt / 2) / mt, PF_MAX_SPLIT, kc}));
-    const int cps = cdiv(kc, want), nsplit = cdiv(kc, cps);
+    PrefillGemmGeom g;
+    prefill_gemm_geometry(N, K, wtype, n_sms, P, &g);
+    const int npw = g.planes, mt = g.m_tiles, kc = g.k_chunks, ppad = g.ppad, cps = g.chunks_per_split, nsplit = g.n_splits;
     uint8_t *A = nullptr, *B = nullptr;
     float *Y = nullptr;
     cudaError_t e = cudaMalloc((void **)&A, (size_t)mt * kc * npw * PF_A_PLANE);
@@ -623,12 +642,10 @@ cudaError_t prefill_gemm_op(const uint8_t *w_host_format, int wtype, int N, int 
         pf_pack_rows_kernel<<<ppad, 256, 0, st>>>(x, P, ppad, K, kc * PF_BK, B);
         GemmArgs a{};
         a.A = A; a.B = B; a.Y = Y; a.N = N; a.P = P; a.ppad = ppad; a.kc = kc; a.cps = cps;
-        a.tmem_cols = 32;
-        while (a.tmem_cols < ppad) a.tmem_cols *= 2;
+        a.tmem_cols = g.tmem_cols;
         if (const char *s = getenv("LLMF90_UMMA_SWAP_LBO")) a.swap_lbo = atoi(s);
-        const int st_bytes = npw * PF_A_PLANE + ppad * 256;
-        a.nst = std::max(2, std::min({PF_MAX_STAGES, (200 * 1024) / st_bytes, cps}));
-        const size_t smem = (size_t)a.nst * st_bytes + (2 * PF_MAX_STAGES + 1) * 8 + 16;
+        a.nst = g.stages;
+        const size_t smem = (size_t)g.smem_bytes;
         if (npw == 1) umma_gemm_kernel<1><<<dim3(mt, nsplit), PF_THREADS, smem, st>>>(a);
         else umma_gemm_kernel<2><<<dim3(mt, nsplit), PF_THREADS, smem, st>>>(a);
         pf_sum_kernel<<<148, 256, 0, st>>>(Y, nsplit, P, ppad, N, y);

@@ -60,3 +60,28 @@ def test_prefill_matches_per_token_path(wt):
 def test_generate_greedy_with_prefill_matches_oracle():
     for o in run_cases([f"greedy small {wt} 9 40" for wt in WT] + ["greedy small 0 60 40"]):  # prompt longer than the run
         assert o["same"], o
+
+
+def test_cli_with_prefill_prints_the_oracles_text(tmp_path):
+    """`llm --prefill`: the prompt as one batched pass, then the token loop -- the same text as the oracle driven by
+    the same file and prompt (and as `llm` without the flag)."""
+    import numpy as np
+    from llm.f90_b200 import fixtures as fx, hostapi
+    from llm.f90_b200.layout import Config, SMALL
+    from oracle import oracle_c as oc
+    cfg = Config(**SMALL, wtype=Q4_0)
+    p = str(tmp_path / "m.gguf")
+    w = fx.write_synth_gguf(p, cfg, seed=12)
+    m = hostapi.HostModel(p)
+    vocab, _ = m.vocab()
+    prompt = "the cat sat on the mat and"
+    ptoks = m.encode(prompt)
+    m.close()
+    n = 32
+    ref_toks, _, _ = oc.Oracle(w).generate(ptoks, n)
+    want = b"".join(vocab[t - 1] for t in ref_toks)
+    for extra in (["--prefill"], ["--prefill", "--host-sampler"]):
+        r = subprocess.run([hostapi.LLM_BIN, "-m", p, "-n", str(n), "-p", prompt, "-t", "0"] + extra, capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+        text = r.stdout.split(b"\n Inference time:")[0].split(b"\n", 1)[1]
+        assert text == want, extra

@@ -113,3 +113,50 @@ def test_plan_balance_is_within_one_unit():
             unit = 16 if wt == WT_Q4_0 else 2
             per_unit = info["matrix_bytes"][k] / (((rows + unit - 1) // unit))
             assert per_cta.max() - per_cta.min() <= per_unit + 1e-6
+
+
+# ------------------------------------------------------------------ the batched prompt pass (prefill.cu)
+@pytest.mark.parametrize("wt", [WT_F32, WT_F16, WT_Q4_0], ids=["f32", "f16", "q4_0"])
+@pytest.mark.parametrize("shape", ["small", "odd", "tinyllama", "llama2-7b"])
+@pytest.mark.parametrize("n_pos", [1, 16, 37, 128])
+def test_prefill_plan_fits_a_b200_sm_and_covers_every_chunk(shape, wt, n_pos):
+    """llmf90_b200_prefill_plan (no device): every GEMM's K splits cover the contraction chunks exactly once and none is
+    empty, the accumulator fits tensor memory, the pipeline the opt-in shared memory, the operand-order copy has the
+    bytes of its f16 planes, and the grid reaches the SMs wherever the matrix has the work for it."""
+    from llm.f90_b200.layout import TINYLLAMA, LLAMA2_7B, SMALL
+    dims = {"small": SMALL, "tinyllama": TINYLLAMA, "llama2-7b": LLAMA2_7B,
+            "odd": dict(emb_dim=160, hidden_dim=416, n_layers=2, n_heads=5, n_kv_heads=5, vocab_size=300, seq_len=64)}[shape]
+    cfg = Config(**dims, wtype=wt)
+    gemms = capi.prefill_plan(cfg, n_pos)
+    e, h, kv = cfg.emb_dim, cfg.hidden_dim, cfg.kv_head_size
+    assert [(g["rows"], g["cols"]) for g in gemms] == [(e + 2 * kv, e), (e, e), (2 * h, e), (e, h)]
+    for g in gemms:
+        assert g["planes"] == (1 if wt == WT_F16 else 2)
+        assert g["m_tiles"] * 128 >= g["rows"] > (g["m_tiles"] - 1) * 128
+        assert g["k_chunks"] * 64 >= g["cols"] > (g["k_chunks"] - 1) * 64
+        cps, ns = g["chunks_per_split"], g["n_splits"]
+        assert 1 <= ns <= 16 and (ns - 1) * cps < g["k_chunks"] <= ns * cps        # exact cover, last split non-empty
+        assert g["ppad"] % 16 == 0 and n_pos <= g["ppad"] < n_pos + 16
+        assert g["tmem_cols"] in (32, 64, 128) and g["tmem_cols"] >= g["ppad"]       # of 512 columns per SM
+        assert g["stage_bytes"] == g["planes"] * 16384 + g["ppad"] * 256
+        assert 2 <= g["stages"] <= 8 and g["smem_bytes"] <= capi.B200_SMEM_OPTIN
+        assert g["weight_bytes"] == g["m_tiles"] * g["k_chunks"] * g["planes"] * 16384
+        assert g["partial_bytes"] == ns * g["ppad"] * g["rows"] * 4
+        ctas = g["m_tiles"] * ns
+        # small matrices are split along K until they cover at least half of the 148 SMs (or cannot be split further),
+        # never beyond two waves
+        assert ctas >= 0.5 * 148 or cps == -(-g["k_chunks"] // min(16, g["k_chunks"]))
+        assert ctas <= max(2 * 148, g["m_tiles"])
+
+
+def test_prefill_plan_cost_of_the_flag():
+    """The second copy of the layer matrices: TinyLlama f32 as hi + lo f16 planes = its f32 layer bytes, f16 one plane."""
+    from llm.f90_b200.layout import TINYLLAMA
+    for wt, planes in ((WT_F32, 2), (WT_F16, 1), (WT_Q4_0, 2)):
+        cfg = Config(**TINYLLAMA, wtype=wt)
+        total = cfg.n_layers * sum(g["weight_bytes"] for g in capi.prefill_plan(cfg, 16))
+        e, h, kv = cfg.emb_dim, cfg.hidden_dim, cfg.kv_head_size
+        elems = cfg.n_layers * ((e + 2 * kv) * e + e * e + 2 * h * e + e * h)
+        assert total == elems * 2 * planes  # TinyLlama's dimensions are multiples of 128 / 64: no padding
+    with pytest.raises(capi.EngineError):
+        capi.prefill_plan(Config(**TINYLLAMA), 129)
