@@ -60,11 +60,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // shared-memory matrix descriptor, K-major, no swizzle: core matrices (8 rows x 16 bytes, 128 contiguous bytes)
-// `lbo` bytes apart along K and `sbo` bytes apart along M / N; version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint64_t ver = 1ull << 46)
+// `lbo` bytes apart along K (the "leading" offset) and `sbo` bytes apart along M / N (the "stride" offset); version 1
+// (sm_100).  The first hardware run tried the other reading of the two offsets as well: it faults.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
 {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | ver;
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 // D[tmem] (+)= A[smem desc] . B[smem desc], kind::f16 (f16 inputs, f32 accumulate), issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -106,7 +107,6 @@ struct GemmArgs {
     int kc, cps;           // k-chunks in total, k-chunks per split (grid.y = ceil(kc / cps))
     int nst;               // pipeline stages
     int tmem_cols;         // power of two >= max(32, ppad)
-    int swap_lbo;          // debug knob (LLMF90_UMMA_SWAP_LBO): bit 0 exchanges the two descriptor strides, bit 1 clears the version field
 };
 
 template <int NPW>  // weight planes: 1 (f16 weights) or 2 (hi + lo of f32 / q4_0 weights)
@@ -152,9 +152,7 @@ __global__ void __launch_bounds__(PF_THREADS) umma_gemm_kernel(const GemmArgs a)
             // instruction descriptor: D f32 (bit 4), A / B f16 K-major (zeros), N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | ((uint32_t)(a.ppad >> 3) << 17) | ((uint32_t)(PF_TILE_M >> 4) << 24);
             // core matrices: along K (the "leading" offset) a whole column of rows apart, along M / N 128 bytes
-            uint32_t a_lbo = PF_TILE_M * 16, a_sbo = 128, b_lbo = (uint32_t)a.ppad * 16u, b_sbo = 128;
-            const uint64_t ver = (a.swap_lbo & 2) ? 0ull : (1ull << 46);
-            if (a.swap_lbo & 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+            const uint32_t a_lbo = PF_TILE_M * 16, a_sbo = 128, b_lbo = (uint32_t)a.ppad * 16u, b_sbo = 128;
             uint32_t acc = 0;
             for (int c = c0, i = 0; c < c1; c++, i++) {
                 const int s = i % a.nst, u = i / a.nst;
@@ -164,11 +162,11 @@ __global__ void __launch_bounds__(PF_THREADS) umma_gemm_kernel(const GemmArgs a)
 #pragma unroll
                 for (int k = 0; k < PF_BK / 16; k++) {  // one tcgen05.mma covers 16 contraction elements = 2 core matrices
                     const uint32_t ak = sa + (uint32_t)k * 2u * (PF_TILE_M * 16), bk = sb + (uint32_t)k * 2u * ((uint32_t)a.ppad * 16u);
-                    const uint64_t a_hi = umma_desc(ak, a_lbo, a_sbo, ver);
-                    const uint64_t b_hi = umma_desc(bk, b_lbo, b_sbo, ver), b_lo = umma_desc(bk + b_plane, b_lbo, b_sbo, ver);
+                    const uint64_t a_hi = umma_desc(ak, a_lbo, a_sbo);
+                    const uint64_t b_hi = umma_desc(bk, b_lbo, b_sbo), b_lo = umma_desc(bk + b_plane, b_lbo, b_sbo);
                     umma_f16(tmem, a_hi, b_lo, idesc, acc);
                     acc = 1;
-                    if (NPW == 2) umma_f16(tmem, umma_desc(ak + PF_A_PLANE, a_lbo, a_sbo, ver), b_hi, idesc, 1u);
+                    if (NPW == 2) umma_f16(tmem, umma_desc(ak + PF_A_PLANE, a_lbo, a_sbo), b_hi, idesc, 1u);
                     umma_f16(tmem, a_hi, b_hi, idesc, 1u);
                 }
                 umma_commit(&empty[s]);  // the stage's operands have been read when these MMAs complete
@@ -485,7 +483,7 @@ void prefill_gemm_geometry(int rows, int cols, int wtype, int n_sms, int n_pos, 
 
 struct Prefill {
     PrefillDims d{};
-    int npw = 2, n_sms = 148, swap_lbo = 0;
+    int npw = 2, n_sms = 148;
     // per matrix (0 QKV, 1 Wo, 2 W1|W3, 3 W2): rows, contraction length, tiles, k-chunks, bytes per layer, K splits
     int N[4] = {}, K[4] = {}, mt[4] = {}, kc[4] = {}, cps[4] = {}, nsplit[4] = {};
     size_t layer_bytes[4] = {};
@@ -510,7 +508,6 @@ cudaError_t prefill_create(Prefill **out, const PrefillDims &d, int n_sms)
     Prefill *pf = new Prefill;
     pf->d = d; pf->n_sms = n_sms;
     pf->npw = d.wtype == WT_F16 ? 1 : 2;
-    if (const char *s = getenv("LLMF90_UMMA_SWAP_LBO")) pf->swap_lbo = atoi(s);
     const int N[4] = {d.nqkv, d.emb, 2 * d.hid, d.emb}, K[4] = {d.emb, d.emb, d.emb, d.hid};
     size_t ymax = 0;
     int kmax = 0;
@@ -572,7 +569,6 @@ static cudaError_t run_gemm(Prefill *pf, int matrix, int layer, int P, int ppad,
     prefill_gemm_geometry(pf->N[matrix], pf->K[matrix], pf->d.wtype, pf->n_sms, P, &g);
     a.kc = g.k_chunks; a.cps = g.chunks_per_split;
     a.tmem_cols = g.tmem_cols;
-    a.swap_lbo = pf->swap_lbo;
     a.nst = g.stages;
     const size_t smem = (size_t)g.smem_bytes;
     const dim3 grid(g.m_tiles, g.n_splits);
@@ -643,7 +639,6 @@ cudaError_t prefill_gemm_op(const uint8_t *w_host_format, int wtype, int N, int 
         GemmArgs a{};
         a.A = A; a.B = B; a.Y = Y; a.N = N; a.P = P; a.ppad = ppad; a.kc = kc; a.cps = cps;
         a.tmem_cols = g.tmem_cols;
-        if (const char *s = getenv("LLMF90_UMMA_SWAP_LBO")) a.swap_lbo = atoi(s);
         a.nst = g.stages;
         const size_t smem = (size_t)g.smem_bytes;
         if (npw == 1) umma_gemm_kernel<1><<<dim3(mt, nsplit), PF_THREADS, smem, st>>>(a);
