@@ -253,8 +253,16 @@ __device__ __forceinline__ void store_b8(uint8_t *B, int ppad, int p, int k8, co
 // sum of the K-split partial products of element (p, n), in split order
 __device__ __forceinline__ float sum_parts(const float *Y, int nsplit, int ppad, int N, int p, int n)
 {
+    // four loads in flight per step (a partial is an L2 round trip); the additions keep the split order
+    const float *y = Y + (size_t)p * N + n;
+    const size_t st = (size_t)ppad * N;
     float v = 0.f;
-    for (int s = 0; s < nsplit; s++) v += Y[((size_t)s * ppad + p) * N + n];
+    int s = 0;
+    for (; s + 4 <= nsplit; s += 4, y += 4 * st) {
+        const float a0 = y[0], a1 = y[st], a2 = y[2 * st], a3 = y[3 * st];
+        v += a0; v += a1; v += a2; v += a3;
+    }
+    for (; s < nsplit; s++, y += st) v += y[0];
     return v;
 }
 
