@@ -5,6 +5,10 @@ forever must not take the whole pytest session with it.
     python tests/prefill_worker.py matmul  <wtype> <rows> <cols> <n_pos>
     python tests/prefill_worker.py prefill <shape> <wtype> <n_prompt>
     python tests/prefill_worker.py greedy  <shape> <wtype> <n_prompt> <n>
+    python tests/prefill_worker.py q6k_matvec <rows> <cols> | q6k_model <wtype> | sample <shape> <wtype>
+    python tests/prefill_worker.py multi "<case> <args>" "<case> <args>" ...     (several cases, one process)
+
+Also what the hardware check scripts tools/gpu_r02b.sh .. use directly (LLMF90_WORKER_NO_BUILD=1 skips the build check).
 """
 import json
 import os
