@@ -208,3 +208,14 @@ def test_oracle_q6_k_classifier_equals_the_dequantised_f32_classifier():
     a, b = oc.Oracle(wq), oc.Oracle(wf)
     for pos, tok in enumerate([2, 17, 250], 1):
         assert np.array_equal(a.transformer(tok, pos), b.transformer(tok, pos))
+
+
+def test_q6_k_golden_vectors():
+    """The committed gguf.quants vectors (tests/golden/make_q6k_golden.py): no third-party package needed at test time."""
+    import os
+    from llm.f90_b200.layout import Q6_K
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "q6k_golden.npz"))
+    blocks, values = g["blocks"], g["values"]
+    n = values.shape[1]
+    assert np.array_equal(fx.dequantize_q6_k(blocks, n), values)
+    assert np.array_equal(np.stack([oc.dequant_row(np.ascontiguousarray(blocks[i]), Q6_K, n) for i in range(len(blocks))]), values)
