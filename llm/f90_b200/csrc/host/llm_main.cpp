@@ -174,7 +174,7 @@ int main(int argc, char **argv)
         first_pos = np + 1;
     }
     for (int pos = first_pos; pos <= seq_len; pos++) {
-        if (a.host_sampler) {
+        if (a.host_sampler || a.tp_size > 1) {  // (tensor-parallel runs keep the path their tests cover: logits on every rank, host pick)
             // the reference's own shape: logits to the host, pick there (llama2.f90:380-392)
             if (llmf90_b200_transformer(token, pos, logits.data())) die(llmf90_b200_last_error());
             if (pos <= (int)prompt_tokens.size()) token = prompt_tokens[pos - 1];
